@@ -1,0 +1,120 @@
+"""Pin oracle/nerf_oracle.py against vectors produced by the unmodified reference (tests/golden/make_golden.py).
+
+CPU only.  On the machine/torch build that generated the fixtures the match is bit-exact (same ATen kernels in
+the same order); elsewhere GEMM blocking may differ, so the asserted tolerances are the reference's own fp32
+noise, not zero.
+"""
+import numpy as np
+import torch
+
+from conftest import load_npz
+from oracle import nerf_oracle as O
+
+NET = O.NetCfg()
+torch.set_num_threads(8)
+
+
+def close(a, b, atol, rtol=0.0):
+    a, b = torch.as_tensor(a).float(), torch.as_tensor(b).float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs()
+    assert bool((err <= atol + rtol * b.abs()).all()), float(err.max())
+
+
+def test_raygen_and_ndc():
+    g = load_npz("golden_raygen.npz")
+    o, d = O.get_ray_bundle(int(g["H"]), int(g["W"]), float(g["focal"]), g["pose"])
+    close(o, g["origin"], 0)
+    close(d, g["dirs"], 1e-7)
+    on, dn = O.ndc_rays(int(g["H"]), int(g["W"]), float(g["focal"]), 1.0, o[None, None, :].expand(12, 10, 3), d)
+    close(on, g["ndc_o"], 1e-6)
+    close(dn, g["ndc_d"], 1e-6)
+    for ang, p in zip(g["poses120_angles"], g["poses120"]):
+        close(O.pose_spherical(float(ang), -30.0, 4.0), p, 0)
+
+
+def test_stage_vectors():
+    g = load_npz("golden_stages.npz")
+    close(O.positional_encoding(g["pe_in_xyz"], 10), g["pe_xyz"], 0)
+    close(O.positional_encoding(g["pe_in_dir"], 4), g["pe_dir"], 0)
+    close(O.sample_pdf_forward(g["pdf_t"], g["pdf_w"], 128), g["pdf_out"], 0)
+    close(O.ray_sample_interval(64, 5, torch.tensor(2.0), torch.tensor(6.0), lindisp=True), g["t_lindisp"], 0)
+    close(O.ray_sample_interval(64, 5, torch.linspace(0.5, 1.5, 5), torch.linspace(3.0, 7.0, 5)), g["t_perray"], 0)
+    for tag, wb in (("vr", False), ("vrw", True)):
+        b = O.volume_render(g["vr_raw"], g["vr_t"], g["vr_dirs"], white_background=wb)
+        close(b.rgb_map, g[f"{tag}_rgb"], 1e-7)
+        close(b.weights, g[f"{tag}_weights"], 0)
+        close(b.mask_weights, g[f"{tag}_mask_weights"], 0)
+        close(b.acc_map, g[f"{tag}_acc"], 1e-7)
+        close(b.disp_map, g[f"{tag}_disp"], 1e-7)
+        close(b.depth_map, g[f"{tag}_depth"], 1e-6)
+
+
+def test_lego_nerf_pipeline(lego):
+    g = load_npz("golden_lego_nerf.npz")
+    assert NET.flops_per_point() == 1186816 and NET.flops_per_point(True) == 982528
+    rc = O.RenderCfg()
+    bc, bf, t_c, t_f = O.nerf_forward(lego["coarse"], lego["fine"], NET, NET, rc, g["origin"], g["dirs"],
+                                      g["bounds"][0], g["bounds"][1], u=lego["u"])
+    close(t_c, g["t_coarse"], 0)
+    close(bc.rgb_map, g["coarse_rgb"], 2e-6)
+    close(bc.weights, g["coarse_weights"], 2e-5)
+    # teacher-forced fine pass on the reference's own t_fine
+    p_f = O.intervals_to_ray_points(g["t_fine"], g["dirs"], g["origin"])
+    raw_f = O.flexible_nerf_forward(lego["fine"], NET, p_f, g["dirs"][:, None, :].expand_as(p_f))
+    close(raw_f[..., :3], g["raw_fine"][..., :3], 1e-4)
+    close(raw_f[..., 3], g["raw_fine"][..., 3], 1e-2, 1e-4)
+    b = O.volume_render(g["raw_fine"], g["t_fine"], g["dirs"])
+    close(b.rgb_map, g["fine_rgb"], 1e-6)
+    close(b.acc_map, g["fine_acc"], 1e-6)
+    close(b.disp_map, g["fine_disp"], 1e-6)
+    # end to end (not teacher forced): within the reference's own fp32-vs-fp64 floor (5.7e-4)
+    close(t_f, g["t_fine"], 5e-4)
+    close(bf.rgb_map, g["fine_rgb"], 6e-4)
+    # per-point
+    close(O.sample_points(lego["fine"], NET, g["pts"], g["pdirs"])[:, :3], g["sample_points_fine"][:, :3], 1e-4)
+    close(O.sample_points(lego["fine"], NET, g["pts"], g["pdirs"])[:, 3], g["sample_points_fine"][:, 3], 1e-2, 1e-4)
+    close(O.sample_points(lego["coarse"], NET, g["pts"], g["pdirs"])[:, 3], g["sample_points_coarse"][:, 3], 1e-2, 1e-4)
+
+
+def test_lego_grid_and_iso(lego):
+    g = load_npz("golden_lego_grid.npz")
+    res, limit = int(g["res"]), float(g["limit"])
+    pts = O.grid_points(limit, res)
+    close(pts.view(res, res, res, 3)[3, 5, 7], torch.stack([g["lin"][3], g["lin"][5], g["lin"][7]]), 0)
+    rad = O.extract_radiance(lego["fine"], NET, limit, res, batch_size=4096)
+    close(rad[..., :3], g["radiance"][..., :3], 1e-4)
+    close(rad[..., 3], g["radiance"][..., 3], 1e-2, 1e-4)
+    iso = O.extract_iso_level(g["radiance"][..., 3].numpy(), float(g["iso_level"]))
+    assert np.float32(iso) == np.float32(g["iso_value"])
+    v = np.array([[0.0, 10.0, 20.0]], dtype=np.float32)
+    np.testing.assert_allclose(O.rescale_vertices(v, 1.2, 20), 1.2 * (v / 10.0 - 1.0))
+
+
+def test_lego_buff_pipeline(buff):
+    g = load_npz("golden_lego_buff.npz")
+    rc = O.RenderCfg(num_coarse=192, num_fine=0)
+    z, mask = O.batch_ray_voxel_intersect(buff["voxels"], g["origin"][None], g["dirs"], g["bounds"][0], g["bounds"][1], 192)
+    assert bool((mask == g["ray_mask"]).all())
+    assert int(mask.sum()) >= 60 and int((~mask).sum()) >= 2      # both branches exercised
+    close(z[mask], g["z"][mask], 0)
+    b, t, m2 = O.buff_forward(buff["coarse"], NET, rc, buff["voxels"], g["origin"][None], g["dirs"], g["bounds"][0], g["bounds"][1])
+    close(t, g["z"], 0)
+    close(b.rgb_map, g["out_rgb"], 5e-6)
+    close(b.acc_map, g["out_acc"], 5e-6)
+    close(b.disp_map, g["out_disp"], 5e-6)
+    close(b.mask_weights, g["out_mask_weights"], 0)
+
+
+def test_fern_ndc_pipeline(fern):
+    g = load_npz("golden_fern_nerf.npz")
+    rc = O.RenderCfg()
+    bc, bf, t_c, t_f = O.nerf_forward(fern["coarse"], fern["fine"], NET, NET, rc, g["origins"], g["dirs"],
+                                      g["bounds"][0], g["bounds"][1], u=fern["u"])
+    close(t_c, g["t_coarse"], 0)
+    close(bc.rgb_map, g["coarse_rgb"], 5e-6)
+    close(t_f, g["t_fine"], 5e-4)
+    close(bf.rgb_map, g["fine_rgb"], 6e-4)
+    p_f = O.intervals_to_ray_points(g["t_fine"], g["dirs"], g["origins"])
+    raw_f = O.flexible_nerf_forward(fern["fine"], NET, p_f, g["dirs"][:, None, :].expand_as(p_f))
+    close(raw_f[..., :3], g["raw_fine"][..., :3], 1e-4)
