@@ -1,0 +1,176 @@
+/*
+ * nerfmeshes_b200 — C ABI of the B200-native NeRF render / dense-grid hot path.
+ *
+ * The reference (qway/nerfmeshes, pure Python) has no FFI layer; its de-facto operator API for this path
+ * is the Python surface SURVEY.md section 8(b) lists.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/).  The reference-side binding a maintainer would add is a
+ * ctypes stub; it is shown in INTEGRATION.md and shipped as nerfmeshes_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as void* (NULL =
+ *     legacy default stream).
+ *   - every call returns 0 on success, <0 on error; nm_last_error() returns a thread-local message.
+ *   - pointers suffixed _dev are device pointers on the handle's device, _host are host pointers.
+ *   - device-pointer calls are stream-ordered and asynchronous w.r.t. the host; *_host calls synchronise
+ *     before returning (they copy results back).
+ *   - the handle owns packed weights, tables, the voxel list and a grow-only workspace; callers own all
+ *     input / output buffers.  One host thread per handle at a time.
+ */
+#ifndef NERFMESHES_B200_H
+#define NERFMESHES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NM_VERSION 100 /* 0.1.0 */
+
+/* Shape of one FlexibleNeRFModel — constructor arguments of src/nerf/models.py:5-22. */
+typedef struct NmNetDesc {
+  int32_t num_layers;          /* 8  */
+  int32_t hidden_size;         /* 256 (128 or 256 supported by the tensor-core path) */
+  int32_t skip_step;           /* 4  */
+  int32_t num_encoding_fn_xyz; /* 10 */
+  int32_t num_encoding_fn_dir; /* 4  */
+  int32_t include_input_xyz;   /* 1  */
+  int32_t include_input_dir;   /* 1  */
+  int32_t log_sampling_xyz;    /* 1  */
+  int32_t log_sampling_dir;    /* 1  */
+  int32_t use_viewdirs;        /* 1  */
+} NmNetDesc;
+
+/* MLP arithmetic selection. */
+enum {
+  NM_PREC_EXACT = 0, /* tcgen05, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulate (default) */
+  NM_PREC_FAST = 1,  /* tcgen05, single fp16 operands (misses the 1e-4 target; for comparison only)      */
+  NM_PREC_FP32 = 2   /* CUDA-core fp32 FMA kernel (bit-for-bit fp32 arithmetic; slow; debugging yard-stick) */
+};
+
+/* cfg.nerf.{train,validation}.* and cfg.dataset.* knobs read on the path (config/nerf-synthetic-lego.yml). */
+typedef struct NmRenderCfg {
+  int32_t num_coarse;          /* cfg.nerf.train.num_coarse (the reference sizes its samplers from .train,
+                                  src/models/model_nerf.py:31-32)                                        */
+  int32_t num_fine;            /* cfg.nerf.train.num_fine; 0 = coarse only (models.use_fine False)          */
+  int32_t lindisp;
+  int32_t perturb;             /* stratified jitter / random u (distributional parity only)                 */
+  int32_t white_background;
+  float noise_std;             /* radiance_field_noise_std of the active mode                              */
+  float attenuation_threshold; /* 1e-5, src/models/model_base.py:28-33                                     */
+  int32_t precision;           /* NM_PREC_*                                                                */
+  int32_t act_scale_log2;      /* s >= 0: fp16 A-operands are stored as x * 2^-s (range guard)  */
+} NmRenderCfg;
+
+typedef struct NmHandle_t* NmHandle;
+
+enum { NM_NET_COARSE = 0, NM_NET_FINE = 1 };
+
+/* Output block of one render call: the fields of OutputBundle (src/nerf/modules.py:40-47).  Any pointer may be
+ * NULL (that output is skipped).  depth is the eval-mode thresholded map (modules.py:108-109) unless flag
+ * NM_FLAG_TRAINING is set; depth_raw is sum(w*t) before the threshold (what parity tests compare). */
+typedef struct NmRenderOut {
+  float* rgb;          /* (R,3) */
+  float* depth;        /* (R,)  */
+  float* depth_raw;    /* (R,)  */
+  float* acc;          /* (R,)  */
+  float* disp;         /* (R,)  */
+  float* weights;      /* (R,S) S = num_coarse+num_fine (or num_coarse when coarse-only / BuFF) */
+  float* mask_weights; /* (R,S) */
+  float* t_vals;       /* (R,S) the sample distances actually used (debug / parity) */
+  float* coarse_rgb;   /* (R,3) coarse-pass colour (training loss needs it, model_nerf.py:128) */
+  float* coarse_acc;   /* (R,)  */
+  float* coarse_disp;  /* (R,)  */
+  float* coarse_weights; /* (R,num_coarse) */
+} NmRenderOut;
+
+enum {
+  NM_FLAG_TRAINING = 1,    /* module.training: no depth threshold, train noise_std            */
+  NM_FLAG_BUFF = 2,        /* BuFFModel.forward: AABB-clipped sampling, single net (coarse slot) */
+  NM_FLAG_TEACHER_T = 4    /* t_vals is an INPUT: skip sampling, run net `which`=fine-if-present on it */
+};
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+int nm_version(void);
+const char* nm_last_error(void);
+/* 0 if `device` is a compute-capability-10.x GPU, error otherwise (the library fails loudly elsewhere). */
+int nm_device_check(int device);
+/* Replaces NeRFModel.__init__/BuFFModel.__init__ (src/models/model_nerf.py:24-32, model_buff.py:13-29). */
+int nm_create(int device, const NmNetDesc* coarse, const NmNetDesc* fine_or_null, const NmRenderCfg* cfg,
+              NmHandle* out);
+int nm_destroy(NmHandle h);
+int nm_set_render_cfg(NmHandle h, const NmRenderCfg* cfg);
+
+/* Replaces load_state_dict for one FlexibleNeRFModel (weight ABI: SURVEY Appendix A.1).  names[i] is the
+ * reference state-dict key without the model prefix ("layer1.weight", "layers_xyz.4.bias", "fc_alpha.weight",
+ * ...); tensors_host[i] points at numel[i] fp32 values in the reference (out,in) row-major layout. */
+int nm_load_weights(NmHandle h, int which, int n_tensors, const char* const* names,
+                    const float* const* tensors_host, const int64_t* numel);
+/* Sampler tables: coarse s = torch.linspace(0,1,num_coarse) (src/nerf/modules.py:154) and the SamplePDF buffer
+ * u = torch.linspace(0,1,num_fine) (modules.py:193).  Host pointers; NULL = recompute i/(n-1) in fp32. */
+int nm_set_tables(NmHandle h, const float* coarse_s_host, const float* fine_u_host);
+/* BuFF voxel list, checkpoint['tree']['voxels'] (V,2,3) (src/nerf/tree.py:345-358). */
+int nm_set_tree(NmHandle h, const float* voxels_host, int32_t V);
+
+/* ---- hot path, device pointers ---------------------------------------------------------------------- */
+/* BaseModel.sample_points (src/models/model_base.py:65-73) == FlexibleNeRFModel.forward (src/nerf/models.py:60-80).
+ * pts/dirs (M,3) fp32; out (M,4) = [sigmoid rgb, raw sigma], or (M,) raw sigma when sigma_only. */
+int nm_point_mlp(NmHandle h, int which, const float* pts_dev, const float* dirs_dev, int64_t M, float* out_dev,
+                 int sigma_only, void* stream);
+/* NeRFModel.forward / BuFFModel.forward (src/models/model_nerf.py:37-78, model_buff.py:34-69).
+ * origins: o_stride = 0 -> one shared (3,) origin, 3 -> per-ray (R,3).  near/far: nf_stride = 0 -> 2 scalars in
+ * near_far_host[0..1]; 1 -> per-ray near (R,) and far (R,) device arrays in near_dev / far_dev. */
+int nm_render_rays(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                   const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
+                   const NmRenderOut* out_dev, void* stream);
+/* get_ray_bundle (+ ndc_rays) fused with the render for image rows [row0,row1) — the eval_nerf.py:50-98 image
+ * loop with the pose, not 7.7 MB of directions, crossing PCIe.  pose_host: 12 floats, c2w[:3,:4] row-major.
+ * Outputs are (row1-row0)*W rays. */
+int nm_render_image(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, int row0, int row1,
+                    const float* near_far_host, int flags, uint64_t seed, const NmRenderOut* out_dev, void* stream);
+/* get_ray_bundle / ndc_rays alone (src/nerf/nerf_helpers.py:226-307): dirs (rows,W,3); origins (rows,W,3) only
+ * when ndc (else the origin is pose[:,3]). */
+int nm_ray_bundle(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, float ndc_near, int row0,
+                  int row1, float* origins_dev_or_null, float* dirs_dev, void* stream);
+/* extract_radiance (src/mesh_nerf.py:27-53) for grid planes [x0,x1): points from the three linspace tables
+ * (host, lengths n0,n1,n2; pass torch.linspace values for bit-identical coordinates), dirs := positions.
+ * sigma_dev (x1-x0,n1,n2) raw density; rgb_dev (x1-x0,n1,n2,3) or NULL (sigma-only fast path). */
+int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, const float* lin2_host, int n0, int n1,
+                  int n2, int x0, int x1, float* sigma_dev, float* rgb_dev_or_null, void* stream);
+/* numpy min / max / std of a float32 volume (extract_iso_level, src/mesh_nerf.py:56-65): out_host[0..2] =
+ * {min, max, std}; synchronises. */
+int nm_volume_stats(NmHandle h, const float* vol_dev, int64_t n, float* out_host);
+
+/* skimage.measure.marching_cubes(volume, level) seam (src/mesh_nerf.py:79) on a device volume (nx,ny,nz) fp32:
+ * classify -> scan -> emit.  Two-call protocol: nm_marching_cubes_count fills counts_host = {n_vertices,
+ * n_triangles} (synchronises); nm_marching_cubes_emit writes verts (n_vertices,3) fp32 in index coordinates
+ * (x offset x_off added, for slab sharding), normals (n_vertices,3), faces (n_triangles,3) int32.  Vertices are
+ * unique per crossed grid edge (indexed mesh, like the Lewiner output). */
+int nm_marching_cubes_count(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso,
+                            int64_t* counts_host, void* stream);
+int nm_marching_cubes_emit(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, float x_off,
+                           float* verts_dev, float* normals_dev, int32_t* faces_dev, void* stream);
+
+/* ---- hot path, host buffers (what a reference-side caller holding CPU tensors binds) ------------------ */
+/* model.query(ray_batch) with host tensors (src/eval_nerf.py:62-69): copies H2D, renders, copies D2H, syncs. */
+int nm_query_host(NmHandle h, const float* origins_host, int o_stride, const float* dirs_host, int64_t R,
+                  const float* near_far_host, int flags, uint64_t seed, const NmRenderOut* out_host);
+/* one image from a pose, results to host (eval_nerf.py image loop). */
+int nm_render_image_host(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, int row0, int row1,
+                         const float* near_far_host, int flags, uint64_t seed, const NmRenderOut* out_host);
+/* model.sample_points with host tensors (src/mesh_nerf.py:43-48). */
+int nm_point_mlp_host(NmHandle h, int which, const float* pts_host, const float* dirs_host, int64_t M,
+                      float* out_host, int sigma_only);
+
+/* ---- introspection ---------------------------------------------------------------------------------- */
+/* number of kernels launched through this handle since creation (bench.py's gpu_launches). */
+int64_t nm_launch_count(NmHandle h);
+/* duration in ms of the last fused-MLP launch sequence, measured with CUDA events on the call's stream when
+ * timing is enabled (bench.py's roofline); <0 if disabled. */
+int nm_set_timing(NmHandle h, int enable);
+double nm_mlp_time_ms(NmHandle h, int64_t* points_out, int64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFMESHES_B200_H */

@@ -1,0 +1,536 @@
+// C ABI of libnerfmeshes_b200.so (include/nerfmeshes_b200.h): handle lifecycle, weight loading, and the orchestration
+// of the hot path — the body of NeRFModel.forward / BuFFModel.forward (src/models/model_nerf.py:37-78,
+// model_buff.py:34-69) and extract_radiance (src/mesh_nerf.py:27-53) as stream-ordered kernel sequences.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "nm_common.h"
+
+namespace nm {
+const char* last_error();
+}
+
+using namespace nm;
+
+namespace {
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); return -2; }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct NmHandle_t {
+  int device = 0;
+  int num_sms = 0;
+  NmRenderCfg cfg{};
+  NetDev nets[2];
+  bool has_fine = false;
+  NmNetDesc desc[2]{};
+  Buf s_table, u_table, voxels;
+  int V = 0;
+  // workspace
+  Buf t_c, raw_c, w_c, t_f, raw_f, t_u, dirs, origins, lin[3], small, stage_in[3], stage_out[12], mc_ws;
+  int lin_n[3] = {0, 0, 0};
+  int* d_err = nullptr;       // [0] tcgen05 watchdog code, [1] aabb hit-list overflow
+  double* d_stats = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int64_t launches = 0;
+  // timing of the fused-MLP launches
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  int64_t mlp_points = 0, mlp_launches = 0;
+  size_t mc_ws_bytes = 0;
+  void* mc_ws_ptr = nullptr;
+};
+
+namespace {
+
+constexpr long long kChunkRays = 1ll << 20;
+
+int bind_device(NmHandle h) {
+  NM_CHECK(h != nullptr, "null handle");
+  NM_CUDA(cudaSetDevice(h->device));
+  return 0;
+}
+
+void linspace_host(int n, std::vector<float>* out) {  // torch.linspace(0,1,n) fp32 (ATen's two-sided formula)
+  out->resize(n);
+  if (n == 1) { (*out)[0] = 0.f; return; }
+  const float step = 1.0f / (float)(n - 1);
+  for (int i = 0; i < n; ++i) (*out)[i] = (i < n / 2) ? 0.f + step * (float)i : 1.0f - step * (float)(n - 1 - i);
+}
+
+int upload(Buf* b, const void* src, size_t bytes) {
+  if (int e = b->ensure(bytes)) return e;
+  NM_CUDA(cudaMemcpy(b->p, src, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int check_kernel_flags(NmHandle h) {
+  int flags[2] = {0, 0};
+  NM_CUDA(cudaMemcpy(flags, h->d_err, sizeof(flags), cudaMemcpyDeviceToHost));
+  NM_CHECK(flags[0] == 0, "tcgen05 pipeline watchdog fired (code %d)", flags[0]);
+  NM_CHECK(flags[1] == 0, "AABB sampler: more than 512 voxel hits on one ray");
+  return 0;
+}
+
+// one fused-MLP launch in the configured arithmetic
+int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st) {
+  const NetDev& net = h->nets[which];
+  NM_CHECK(net.loaded, "weights of network %d not loaded", which);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing) {
+    while (h->ev.size() < h->ev_used + 2) {
+      cudaEvent_t e;
+      NM_CUDA(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+    e0 = h->ev[h->ev_used++]; e1 = h->ev[h->ev_used++];
+    NM_CUDA(cudaEventRecord(e0, st));
+  }
+  int rc;
+  if (h->cfg.precision == NM_PREC_FP32) rc = launch_mlp_simt(net, sigma_only, in, out, st, &h->launches);
+  else rc = launch_mlp_tc(net, sigma_only, h->cfg.precision == NM_PREC_FAST ? 1 : 3, h->cfg.act_scale_log2, in, out,
+                          h->num_sms, h->d_err, st, &h->launches);
+  if (rc) return rc;
+  if (h->timing) {
+    NM_CUDA(cudaEventRecord(e1, st));
+    h->mlp_points += in.M;
+    h->mlp_launches += 1;
+  }
+  return 0;
+}
+
+struct RayBatch {
+  const float* origins; int o_stride; const float* dirs; long long R;
+  float nf[2]; const float* near_dev; const float* far_dev;
+};
+
+float* off(float* p, long long n) { return p ? p + n : nullptr; }
+
+// NeRFModel.forward / BuFFModel.forward for one chunk of rays; `o` already offset to the chunk.
+int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const NmRenderOut& o, cudaStream_t st) {
+  const NmRenderCfg& c = h->cfg;
+  const long long R = rb.R;
+  const int Nc = c.num_coarse;
+  const bool buff = flags & NM_FLAG_BUFF;
+  const bool teacher = flags & NM_FLAG_TEACHER_T;
+  const bool training = flags & NM_FLAG_TRAINING;
+  const int Nf = (h->has_fine && !buff) ? c.num_fine : 0;
+  const int S = Nc + Nf;
+  auto composite = [&](const float* raw, const float* t, int s, float* rgb, float* depth, float* depth_raw, float* acc,
+                       float* disp, float* w, float* mw) {
+    CompositeArgs a{};
+    a.raw = raw; a.t = t; a.dirs = rb.dirs; a.R = R; a.S = s; a.noise_std = c.noise_std; a.seed = seed ^ 0x5bd1e995u;
+    a.white_bg = c.white_background; a.training = training ? 1 : 0; a.thr = c.attenuation_threshold;
+    a.rgb = rgb; a.depth = depth; a.depth_raw = depth_raw; a.acc = acc; a.disp = disp; a.weights = w; a.mask_weights = mw;
+    return launch_composite(a, st, &h->launches);
+  };
+  auto rays_input = [&](const float* t, int s) {
+    MlpInput in{};
+    in.mode = IN_RAYS; in.dirs = rb.dirs; in.ray_o = rb.origins; in.o_stride = rb.o_stride; in.t = t; in.S = s;
+    in.M = R * s;
+    return in;
+  };
+
+  if (teacher) {
+    NM_CHECK(o.t_vals != nullptr, "NM_FLAG_TEACHER_T needs out.t_vals as input");
+    const int which = (h->has_fine && !buff) ? NM_NET_FINE : NM_NET_COARSE;
+    if (int e = h->raw_f.ensure((size_t)R * S * 16)) return e;
+    if (int e = run_mlp(h, which, false, rays_input(o.t_vals, S), h->raw_f.as<float>(), st)) return e;
+    return composite(h->raw_f.as<float>(), o.t_vals, S, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+  }
+
+  // coarse / uniform samples (a3)
+  if (int e = h->t_c.ensure((size_t)R * Nc * 4)) return e;
+  float* t_c = h->t_c.as<float>();
+  if (int e = launch_stratified(h->s_table.as<float>(), Nc, R, rb.nf, rb.near_dev, rb.far_dev, c.lindisp, c.perturb,
+                                seed, t_c, st, &h->launches)) return e;
+  if (buff) {
+    NM_CHECK(h->V > 0, "BuFF render without a voxel list (nm_set_tree)");
+    NM_CHECK(rb.near_dev == nullptr, "BuFF path takes scalar near/far");
+    if (int e = h->t_u.ensure((size_t)R * Nc * 4)) return e;
+    float* z = h->t_u.as<float>();
+    if (int e = launch_aabb(h->voxels.as<float>(), h->V, rb.origins, rb.o_stride, rb.dirs, R, rb.nf[0], rb.nf[1], Nc,
+                            h->s_table.as<float>(), t_c, z, h->d_err + 1, st, &h->launches)) return e;
+    if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
+    if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(z, Nc), h->raw_c.as<float>(), st)) return e;
+    if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, z, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
+    return composite(h->raw_c.as<float>(), z, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+  }
+  if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
+  if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(t_c, Nc), h->raw_c.as<float>(), st)) return e;
+  if (Nf == 0) {
+    if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, t_c, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
+    return composite(h->raw_c.as<float>(), t_c, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+  }
+  float* w_c = o.coarse_weights;
+  if (!w_c) { if (int e = h->w_c.ensure((size_t)R * Nc * 4)) return e; w_c = h->w_c.as<float>(); }
+  if (int e = composite(h->raw_c.as<float>(), t_c, Nc, o.coarse_rgb, nullptr, nullptr, o.coarse_acc, o.coarse_disp, w_c, nullptr)) return e;
+  // inverse-CDF resampling + merge (a8)
+  float* t_f = o.t_vals;
+  if (!t_f) { if (int e = h->t_f.ensure((size_t)R * S * 4)) return e; t_f = h->t_f.as<float>(); }
+  if (int e = launch_invcdf(t_c, w_c, h->u_table.as<float>(), Nc, Nf, R, c.perturb, seed ^ 0x9e3779b9u, t_f, st, &h->launches)) return e;
+  if (int e = h->raw_f.ensure((size_t)R * S * 16)) return e;
+  if (int e = run_mlp(h, NM_NET_FINE, false, rays_input(t_f, S), h->raw_f.as<float>(), st)) return e;
+  return composite(h->raw_f.as<float>(), t_f, S, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+}
+
+NmRenderOut offset_out(const NmRenderOut& o, long long r0, int S, int Nc) {
+  NmRenderOut q = o;
+  q.rgb = off(o.rgb, 3 * r0); q.depth = off(o.depth, r0); q.depth_raw = off(o.depth_raw, r0); q.acc = off(o.acc, r0);
+  q.disp = off(o.disp, r0); q.weights = off(o.weights, r0 * S); q.mask_weights = off(o.mask_weights, r0 * S);
+  q.t_vals = off(o.t_vals, r0 * S); q.coarse_rgb = off(o.coarse_rgb, 3 * r0); q.coarse_acc = off(o.coarse_acc, r0);
+  q.coarse_disp = off(o.coarse_disp, r0); q.coarse_weights = off(o.coarse_weights, r0 * Nc);
+  return q;
+}
+
+int out_samples(NmHandle h, int flags) {
+  const bool buff = flags & NM_FLAG_BUFF;
+  return h->cfg.num_coarse + ((h->has_fine && !buff) ? h->cfg.num_fine : 0);
+}
+
+int render_rays_impl(NmHandle h, const float* origins, int o_stride, const float* dirs, long long R, const float* nf_host,
+                     const float* near_dev, const float* far_dev, int flags, uint64_t seed, const NmRenderOut& out,
+                     cudaStream_t st) {
+  NM_CHECK(o_stride == 0 || o_stride == 3, "o_stride must be 0 or 3");
+  NM_CHECK(dirs && origins, "null ray pointers");
+  NM_CHECK((near_dev == nullptr) == (far_dev == nullptr), "near_dev / far_dev must be given together");
+  NM_CHECK(near_dev || nf_host, "no near/far bounds given");
+  NM_CHECK(h->s_table.p != nullptr, "sampler tables missing");
+  const int S = out_samples(h, flags);
+  for (long long r0 = 0; r0 < R; r0 += kChunkRays) {
+    RayBatch rb{};
+    rb.R = (R - r0 < kChunkRays) ? R - r0 : kChunkRays;
+    rb.origins = origins + (long long)o_stride * r0; rb.o_stride = o_stride; rb.dirs = dirs + 3 * r0;
+    if (nf_host) { rb.nf[0] = nf_host[0]; rb.nf[1] = nf_host[1]; }
+    rb.near_dev = near_dev ? near_dev + r0 : nullptr; rb.far_dev = far_dev ? far_dev + r0 : nullptr;
+    if (int e = render_chunk(h, rb, flags, seed + (uint64_t)r0, offset_out(out, r0, S, h->cfg.num_coarse), st)) return e;
+  }
+  return 0;
+}
+
+// copy every non-null field of a device-side NmRenderOut to the host-side one
+struct OutStage {
+  NmRenderOut dev{};
+  std::vector<std::pair<float**, size_t>> dummy;
+};
+
+int stage_outputs(NmHandle h, const NmRenderOut& host, long long R, int S, int Nc, NmRenderOut* dev, size_t sizes[12]) {
+  float* const* hp = reinterpret_cast<float* const*>(&host);
+  float** dp = reinterpret_cast<float**>(dev);
+  const size_t per[12] = {3, 1, 1, 1, 1, (size_t)S, (size_t)S, (size_t)S, 3, 1, 1, (size_t)Nc};
+  for (int i = 0; i < 12; ++i) {
+    sizes[i] = (size_t)R * per[i] * sizeof(float);
+    if (hp[i]) { if (int e = h->stage_out[i].ensure(sizes[i])) return e; dp[i] = h->stage_out[i].as<float>(); }
+    else dp[i] = nullptr;
+  }
+  return 0;
+}
+
+int copy_outputs(const NmRenderOut& host, const NmRenderOut& dev, const size_t sizes[12], cudaStream_t st) {
+  float* const* hp = reinterpret_cast<float* const*>(&host);
+  float* const* dp = reinterpret_cast<float* const*>(&dev);
+  for (int i = 0; i < 12; ++i)
+    if (hp[i]) NM_CUDA(cudaMemcpyAsync(hp[i], dp[i], sizes[i], cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nm_version(void) { return NM_VERSION; }
+const char* nm_last_error(void) { return nm::last_error(); }
+
+int nm_device_check(int device) {
+  int n = 0;
+  NM_CUDA(cudaGetDeviceCount(&n));
+  NM_CHECK(device >= 0 && device < n, "device %d out of range (%d visible)", device, n);
+  cudaDeviceProp p;
+  NM_CUDA(cudaGetDeviceProperties(&p, device));
+  NM_CHECK(p.major == 10, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
+  return 0;
+}
+
+int nm_create(int device, const NmNetDesc* coarse, const NmNetDesc* fine, const NmRenderCfg* cfg, NmHandle* out) {
+  NM_CHECK(coarse && cfg && out, "null argument");
+  if (int e = nm_device_check(device)) return e;
+  NetProgram a, b;
+  if (int e = build_programs(*coarse, &a, &b)) return e;
+  if (fine) if (int e = build_programs(*fine, &a, &b)) return e;
+  NM_CUDA(cudaSetDevice(device));
+  NmHandle h = new NmHandle_t();
+  h->device = device;
+  cudaDeviceProp p;
+  NM_CUDA(cudaGetDeviceProperties(&p, device));
+  h->num_sms = p.multiProcessorCount;
+  h->desc[0] = *coarse;
+  h->has_fine = fine != nullptr;
+  if (fine) h->desc[1] = *fine;
+  NM_CUDA(cudaMalloc(&h->d_err, 2 * sizeof(int)));
+  NM_CUDA(cudaMemset(h->d_err, 0, 2 * sizeof(int)));
+  NM_CUDA(cudaMalloc(&h->d_stats, 4 * sizeof(double)));
+  NM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  *out = h;
+  if (int e = nm_set_render_cfg(h, cfg)) { nm_destroy(h); *out = nullptr; return e; }
+  return nm_set_tables(h, nullptr, nullptr);
+}
+
+int nm_destroy(NmHandle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_network(&h->nets[0]); free_network(&h->nets[1]);
+  Buf* bufs[] = {&h->s_table, &h->u_table, &h->voxels, &h->t_c, &h->raw_c, &h->w_c, &h->t_f, &h->raw_f, &h->t_u,
+                 &h->dirs, &h->origins, &h->lin[0], &h->lin[1], &h->lin[2], &h->small, &h->mc_ws};
+  for (Buf* b : bufs) b->release();
+  for (Buf& b : h->stage_in) b.release();
+  for (Buf& b : h->stage_out) b.release();
+  if (h->mc_ws_ptr) cudaFree(h->mc_ws_ptr);
+  cudaFree(h->d_err); cudaFree(h->d_stats);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+int nm_set_render_cfg(NmHandle h, const NmRenderCfg* cfg) {
+  NM_CHECK(h && cfg, "null argument");
+  NM_CHECK(cfg->num_coarse >= 3 && cfg->num_coarse <= 256, "num_coarse %d outside [3,256]", cfg->num_coarse);
+  NM_CHECK(cfg->num_fine >= 0 && cfg->num_coarse + cfg->num_fine <= 512, "num_coarse+num_fine exceeds 512");
+  NM_CHECK(cfg->precision >= NM_PREC_EXACT && cfg->precision <= NM_PREC_FP32, "unknown precision %d", cfg->precision);
+  NM_CHECK(cfg->act_scale_log2 >= 0 && cfg->act_scale_log2 <= 12, "act_scale_log2 outside [0,12]");
+  const bool resize = cfg->num_coarse != h->cfg.num_coarse || cfg->num_fine != h->cfg.num_fine;
+  h->cfg = *cfg;
+  if (resize && h->s_table.p) return nm_set_tables(h, nullptr, nullptr);
+  return 0;
+}
+
+int nm_load_weights(NmHandle h, int which, int n_tensors, const char* const* names, const float* const* tensors_host,
+                    const int64_t* numel) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(which == NM_NET_COARSE || (which == NM_NET_FINE && h->has_fine), "network slot %d not present", which);
+  WeightSource src;
+  src.n = n_tensors; src.names = names; src.ptrs = tensors_host; src.numel = numel;
+  return pack_network(h->desc[which], src, &h->nets[which]);
+}
+
+int nm_set_tables(NmHandle h, const float* coarse_s_host, const float* fine_u_host) {
+  if (int e = bind_device(h)) return e;
+  std::vector<float> tmp;
+  if (!coarse_s_host) { linspace_host(h->cfg.num_coarse, &tmp); coarse_s_host = tmp.data(); }
+  if (int e = upload(&h->s_table, coarse_s_host, sizeof(float) * h->cfg.num_coarse)) return e;
+  if (h->cfg.num_fine > 0) {
+    std::vector<float> tmp2;
+    if (!fine_u_host) { linspace_host(h->cfg.num_fine, &tmp2); fine_u_host = tmp2.data(); }
+    if (int e = upload(&h->u_table, fine_u_host, sizeof(float) * h->cfg.num_fine)) return e;
+  }
+  return 0;
+}
+
+int nm_set_tree(NmHandle h, const float* voxels_host, int32_t V) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(voxels_host && V > 0, "empty voxel list");
+  h->V = V;
+  return upload(&h->voxels, voxels_host, sizeof(float) * 6 * (size_t)V);
+}
+
+int nm_point_mlp(NmHandle h, int which, const float* pts_dev, const float* dirs_dev, int64_t M, float* out_dev,
+                 int sigma_only, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(which == NM_NET_COARSE || (which == NM_NET_FINE && h->has_fine), "network slot %d not present", which);
+  NM_CHECK(pts_dev && out_dev && M >= 0, "bad arguments");
+  MlpInput in{};
+  in.mode = IN_POINTS; in.pts = pts_dev; in.dirs = dirs_dev; in.M = M;
+  return run_mlp(h, which, sigma_only != 0, in, out_dev, (cudaStream_t)stream);
+}
+
+int nm_render_rays(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                   const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
+                   const NmRenderOut* out_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(out_dev, "null output block");
+  return render_rays_impl(h, origins_dev, o_stride, dirs_dev, R, near_far_host, near_dev, far_dev, flags, seed, *out_dev,
+                          (cudaStream_t)stream);
+}
+
+int nm_ray_bundle(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, float ndc_near, int row0,
+                  int row1, float* origins_dev, float* dirs_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(pose_host && dirs_dev, "null argument");
+  NM_CHECK(0 <= row0 && row0 <= row1 && row1 <= H && W > 0, "bad row range");
+  NM_CHECK(!ndc || origins_dev, "ndc rays need an origins buffer");
+  RayGenArgs a{};
+  memcpy(a.pose, pose_host, sizeof(a.pose));
+  a.H = H; a.W = W; a.focal = focal; a.ndc = ndc; a.ndc_near = ndc_near; a.row0 = row0; a.row1 = row1;
+  return launch_raygen(a, origins_dev, dirs_dev, (cudaStream_t)stream, &h->launches);
+}
+
+int nm_render_image(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, int row0, int row1,
+                    const float* near_far_host, int flags, uint64_t seed, const NmRenderOut* out_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(out_dev && pose_host && near_far_host, "null argument");
+  const long long R = (long long)(row1 - row0) * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = h->dirs.ensure((size_t)R * 12)) return e;
+  float* origins = nullptr;
+  int o_stride = 0;
+  if (ndc) {
+    if (int e = h->origins.ensure((size_t)R * 12)) return e;
+    origins = h->origins.as<float>();
+    o_stride = 3;
+  }
+  if (int e = nm_ray_bundle(h, pose_host, H, W, focal, ndc, 1.0f, row0, row1, origins, h->dirs.as<float>(), stream)) return e;
+  if (!ndc) {
+    if (int e = h->small.ensure(64)) return e;
+    const float o3[3] = {pose_host[3], pose_host[7], pose_host[11]};
+    NM_CUDA(cudaMemcpyAsync(h->small.p, o3, sizeof(o3), cudaMemcpyHostToDevice, st));
+    origins = h->small.as<float>();
+  }
+  return render_rays_impl(h, origins, o_stride, h->dirs.as<float>(), R, near_far_host, nullptr, nullptr, flags, seed,
+                          *out_dev, st);
+}
+
+int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, const float* lin2_host, int n0, int n1,
+                  int n2, int x0, int x1, float* sigma_dev, float* rgb_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(lin0_host && lin1_host && lin2_host && sigma_dev, "null argument");
+  NM_CHECK(0 <= x0 && x0 <= x1 && x1 <= n0 && n1 > 0 && n2 > 0, "bad slab range");
+  const int which = h->has_fine ? NM_NET_FINE : NM_NET_COARSE;     // BaseModel.get_model(): finest net
+  const float* hs[3] = {lin0_host, lin1_host, lin2_host};
+  const int ns[3] = {n0, n1, n2};
+  for (int i = 0; i < 3; ++i) { if (int e = upload(&h->lin[i], hs[i], sizeof(float) * ns[i])) return e; h->lin_n[i] = ns[i]; }
+  cudaStream_t st = (cudaStream_t)stream;
+  MlpInput in{};
+  in.mode = IN_GRID;
+  in.lin0 = h->lin[0].as<float>(); in.lin1 = h->lin[1].as<float>(); in.lin2 = h->lin[2].as<float>();
+  in.n1 = n1; in.n2 = n2;
+  in.grid_base = (long long)x0 * n1 * n2;
+  in.M = (long long)(x1 - x0) * n1 * n2;
+  if (!rgb_dev) return run_mlp(h, which, true, in, sigma_dev, st);
+  // reference-faithful rgb+sigma: run the full net into a scratch (M,4) and split
+  if (int e = h->raw_f.ensure((size_t)in.M * 16)) return e;
+  if (int e = run_mlp(h, which, false, in, h->raw_f.as<float>(), st)) return e;
+  NM_CUDA(cudaMemcpy2DAsync(sigma_dev, 4, h->raw_f.as<float>() + 3, 16, 4, (size_t)in.M, cudaMemcpyDeviceToDevice, st));
+  NM_CUDA(cudaMemcpy2DAsync(rgb_dev, 12, h->raw_f.as<float>(), 16, 12, (size_t)in.M, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int nm_volume_stats(NmHandle h, const float* vol_dev, int64_t n, float* out_host) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(vol_dev && out_host, "null argument");
+  return launch_volume_stats(vol_dev, n, h->d_stats, out_host, h->own_stream, &h->launches);
+}
+
+int nm_marching_cubes_count(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, int64_t* counts_host,
+                            void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(vol_dev && counts_host && nx >= 2 && ny >= 2 && nz >= 2, "bad arguments");
+  return mc_count(vol_dev, nx, ny, nz, iso, &h->mc_ws_ptr, &h->mc_ws_bytes, counts_host, (cudaStream_t)stream, &h->launches);
+}
+
+int nm_marching_cubes_emit(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, float x_off,
+                           float* verts_dev, float* normals_dev, int32_t* faces_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(vol_dev && verts_dev && faces_dev && h->mc_ws_ptr, "bad arguments (call nm_marching_cubes_count first)");
+  return mc_emit(vol_dev, nx, ny, nz, iso, x_off, h->mc_ws_ptr, verts_dev, normals_dev, faces_dev, (cudaStream_t)stream,
+                 &h->launches);
+}
+
+int nm_query_host(NmHandle h, const float* origins_host, int o_stride, const float* dirs_host, int64_t R,
+                  const float* near_far_host, int flags, uint64_t seed, const NmRenderOut* out_host) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(origins_host && dirs_host && near_far_host && out_host && R > 0, "bad arguments");
+  NM_CHECK(!(flags & NM_FLAG_TEACHER_T), "NM_FLAG_TEACHER_T is a device-pointer feature");
+  cudaStream_t st = h->own_stream;
+  const size_t ob = o_stride ? (size_t)R * 12 : 12;
+  if (int e = h->stage_in[0].ensure(ob)) return e;
+  if (int e = h->stage_in[1].ensure((size_t)R * 12)) return e;
+  NM_CUDA(cudaMemcpyAsync(h->stage_in[0].p, origins_host, ob, cudaMemcpyHostToDevice, st));
+  NM_CUDA(cudaMemcpyAsync(h->stage_in[1].p, dirs_host, (size_t)R * 12, cudaMemcpyHostToDevice, st));
+  NmRenderOut dev{};
+  size_t sizes[12];
+  if (int e = stage_outputs(h, *out_host, R, out_samples(h, flags), h->cfg.num_coarse, &dev, sizes)) return e;
+  if (int e = render_rays_impl(h, h->stage_in[0].as<float>(), o_stride, h->stage_in[1].as<float>(), R, near_far_host,
+                               nullptr, nullptr, flags, seed, dev, st)) return e;
+  if (int e = copy_outputs(*out_host, dev, sizes, st)) return e;
+  NM_CUDA(cudaStreamSynchronize(st));
+  return check_kernel_flags(h);
+}
+
+int nm_render_image_host(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, int row0, int row1,
+                         const float* near_far_host, int flags, uint64_t seed, const NmRenderOut* out_host) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(out_host, "null output block");
+  const long long R = (long long)(row1 - row0) * W;
+  cudaStream_t st = h->own_stream;
+  NmRenderOut dev{};
+  size_t sizes[12];
+  if (int e = stage_outputs(h, *out_host, R, out_samples(h, flags), h->cfg.num_coarse, &dev, sizes)) return e;
+  if (int e = nm_render_image(h, pose_host, H, W, focal, ndc, row0, row1, near_far_host, flags, seed, &dev, st)) return e;
+  if (int e = copy_outputs(*out_host, dev, sizes, st)) return e;
+  NM_CUDA(cudaStreamSynchronize(st));
+  return check_kernel_flags(h);
+}
+
+int nm_point_mlp_host(NmHandle h, int which, const float* pts_host, const float* dirs_host, int64_t M, float* out_host,
+                      int sigma_only) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(pts_host && out_host && M > 0, "bad arguments");
+  cudaStream_t st = h->own_stream;
+  const size_t outb = (size_t)M * (sigma_only ? 4 : 16);
+  if (int e = h->stage_in[0].ensure((size_t)M * 12)) return e;
+  if (int e = h->stage_in[1].ensure((size_t)M * 12)) return e;
+  if (int e = h->stage_out[0].ensure(outb)) return e;
+  NM_CUDA(cudaMemcpyAsync(h->stage_in[0].p, pts_host, (size_t)M * 12, cudaMemcpyHostToDevice, st));
+  if (dirs_host) NM_CUDA(cudaMemcpyAsync(h->stage_in[1].p, dirs_host, (size_t)M * 12, cudaMemcpyHostToDevice, st));
+  if (int e = nm_point_mlp(h, which, h->stage_in[0].as<float>(), dirs_host ? h->stage_in[1].as<float>() : nullptr, M,
+                           h->stage_out[0].as<float>(), sigma_only, st)) return e;
+  NM_CUDA(cudaMemcpyAsync(out_host, h->stage_out[0].p, outb, cudaMemcpyDeviceToHost, st));
+  NM_CUDA(cudaStreamSynchronize(st));
+  return check_kernel_flags(h);
+}
+
+int64_t nm_launch_count(NmHandle h) { return h ? h->launches : -1; }
+
+int nm_set_timing(NmHandle h, int enable) {
+  NM_CHECK(h, "null handle");
+  h->timing = enable != 0;
+  h->ev_used = 0; h->mlp_points = 0; h->mlp_launches = 0;
+  return 0;
+}
+
+double nm_mlp_time_ms(NmHandle h, int64_t* points_out, int64_t* launches_out) {
+  if (!h || !h->timing) return -1.0;
+  cudaSetDevice(h->device);
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    if (cudaEventSynchronize(h->ev[i + 1]) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) != cudaSuccess) return -1.0;
+    total += ms;
+  }
+  if (points_out) *points_out = h->mlp_points;
+  if (launches_out) *launches_out = h->mlp_launches;
+  h->ev_used = 0; h->mlp_points = 0; h->mlp_launches = 0;
+  return total;
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+// Internal declarations shared by the translation units of libnerfmeshes_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/nerfmeshes_b200.h"
+#include "nm_program.h"
+
+namespace nm {
+
+void set_error(const char* fmt, ...);
+#define NM_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      nm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                                  \
+    }                                                                                             \
+  } while (0)
+#define NM_CHECK(cond, ...)       \
+  do {                            \
+    if (!(cond)) {                \
+      nm::set_error(__VA_ARGS__); \
+      return -1;                  \
+    }                             \
+  } while (0)
+
+// One network's device-resident data.
+struct NetDev {
+  bool loaded = false;
+  NmNetDesc desc{};
+  NetProgram full{};        // rgb + sigma
+  NetProgram sigma{};       // trunk + sigma head only (grid fast path)
+  // device arrays
+  NetProgram* d_full = nullptr;
+  NetProgram* d_sigma = nullptr;
+  uint8_t* d_wpack_full = nullptr;   // tensor-core weight stages, issue order of `full`
+  uint8_t* d_wpack_sigma = nullptr;
+  float* d_bias = nullptr;
+  float* d_head = nullptr;
+  float* d_wt = nullptr;             // transposed fp32 weights (CUDA-core kernel)
+};
+
+// Inputs of one fused-MLP launch (three front-end modes).
+enum : int { IN_POINTS = 0, IN_RAYS = 1, IN_GRID = 2 };
+struct MlpInput {
+  int mode = IN_POINTS;
+  const float* pts = nullptr;    // IN_POINTS (M,3)
+  const float* dirs = nullptr;   // IN_POINTS (M,3);  IN_RAYS (R,3)
+  const float* ray_o = nullptr;  // IN_RAYS
+  int o_stride = 0;              //   0: shared origin, 3: per ray
+  const float* t = nullptr;      // IN_RAYS (R,S)
+  int S = 0;
+  const float* lin0 = nullptr;   // IN_GRID: device linspace tables
+  const float* lin1 = nullptr;
+  const float* lin2 = nullptr;
+  int n1 = 0, n2 = 0;
+  long long grid_base = 0;       //   flat index of the first point
+  long long M = 0;               // number of points
+};
+
+int build_programs(const NmNetDesc& d, NetProgram* full, NetProgram* sigma);
+// Packs host fp32 reference tensors into the device layouts.  `get(name, &numel)` returns the host tensor.
+struct WeightSource {
+  int n = 0;
+  const char* const* names = nullptr;
+  const float* const* ptrs = nullptr;
+  const int64_t* numel = nullptr;
+  const float* find(const std::string& name, int64_t expect) const;
+};
+int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net);
+void free_network(NetDev* net);
+
+// kernel launchers (return 0 / <0; count launches via *launches)
+int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
+                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches);
+int launch_mlp_simt(const NetDev& net, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st,
+                    int64_t* launches);
+
+struct RayGenArgs {
+  float pose[12];
+  int H, W;
+  float focal;
+  int ndc;
+  float ndc_near;
+  int row0, row1;
+};
+int launch_raygen(const RayGenArgs& a, float* origins_or_null, float* dirs, cudaStream_t st, int64_t* launches);
+int launch_stratified(const float* s_table, int Nc, long long R, const float* near_far2, const float* near_dev,
+                      const float* far_dev, int lindisp, int perturb, uint64_t seed, float* t_out, cudaStream_t st,
+                      int64_t* launches);
+struct CompositeArgs {
+  const float* raw;    // (R,S,4)
+  const float* t;      // (R,S)
+  const float* dirs;   // (R,3)
+  long long R;
+  int S;
+  float noise_std;
+  uint64_t seed;
+  int white_bg, training;
+  float thr;
+  float *rgb, *depth, *depth_raw, *acc, *disp, *weights, *mask_weights;
+};
+int launch_composite(const CompositeArgs& a, cudaStream_t st, int64_t* launches);
+int launch_invcdf(const float* t_c, const float* w_c, const float* u_table, int Nc, int Nf, long long R, int perturb,
+                  uint64_t seed, float* t_f, cudaStream_t st, int64_t* launches);
+int launch_aabb(const float* voxels, int V, const float* origins, int o_stride, const float* dirs, long long R,
+                float near, float far, int S, const float* s_table, const float* t_uniform, float* z_out,
+                int* d_overflow, cudaStream_t st, int64_t* launches);
+int launch_volume_stats(const float* vol, long long n, double* d_scratch, float* out_host, cudaStream_t st,
+                        int64_t* launches);
+int mc_count(const float* vol, int nx, int ny, int nz, float iso, void** ws, size_t* ws_bytes, int64_t* counts_host,
+             cudaStream_t st, int64_t* launches);
+int mc_emit(const float* vol, int nx, int ny, int nz, float iso, float x_off, void* ws, float* verts, float* normals,
+            int32_t* faces, cudaStream_t st, int64_t* launches);
+
+}  // namespace nm

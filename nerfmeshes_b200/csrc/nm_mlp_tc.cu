@@ -1,0 +1,384 @@
+// Fused FlexibleNeRFModel forward on the 5th-gen tensor cores (sm_100a): positional encoding -> all linear layers ->
+// sigma / rgb heads in ONE persistent kernel.  Activations never leave the SM: the fp32 accumulator of a layer lives
+// in TMEM, the epilogue warps turn it (bias, ReLU, fp16 hi/lo split) into the next layer's A operand, again in TMEM
+// (tcgen05.mma with A from tensor memory), and the weights stream through a shared-memory ring filled by the
+// bulk-copy (TMA) engine from an L2-resident, pre-swizzled, schedule-ordered image (nm_program.cu).
+//
+// Reference semantics: src/nerf/models.py:60-80 (network), src/nerf/modules.py:26-34 (encoding).
+//
+// Arithmetic (NM_PREC_EXACT): every product x*W is evaluated as xh*Wh + xl*Wh + xh*Wl with x = xh + xl, W = Wh + Wl
+// fp16 splits and fp32 accumulation — three kind::f16 MMAs per K-step (1.5e-6 max-abs on composited
+// RGB against fp32, where plain fp16 gives 3.3e-3).  NM_PREC_FAST issues only xh*Wh.
+//
+// CTA = one 128-point tile at a time (TMEM lane = point), 14 warps:
+//   warps 0-7   epilogue: tcgen05.ld accumulator chunk -> +bias, ReLU, heads -> fp16 hi/lo -> tcgen05.st A operand
+//   warps 8-11  front-end: fetch/synthesise the NEXT tile's points, positional encoding -> swizzled smem A tiles
+//   warp 12     producer: cp.async.bulk weight stages (16 KB = one 64x64 block, hi|lo) into the ring
+//   warp 13     MMA issuer (one lane) + TMEM allocator
+// TMEM (512 columns): [0,256) fp32 accumulator D, [256,384) A_hi, [384,512) A_lo (two fp16 per column).
+// A layer is issued as 64x64 blocks (M=128,N=64,K=16 MMAs) in the order nm_program.cu derives, which lets layer
+// l+1 start as soon as the epilogue has converted the first 64 columns of layer l (see the schedule comment there).
+#include <cuda_fp16.h>
+
+#include "nm_common.h"
+#include "nm_frontend.cuh"
+#include "nm_ptx.cuh"
+
+namespace nm {
+
+namespace {
+
+constexpr int kThreads = 448;
+constexpr int kEpiWarps = 8;
+constexpr int kFeWarp0 = 8;
+constexpr int kProdWarp = 12;
+constexpr int kMmaWarp = 13;
+constexpr uint32_t kPeTile = 16384;      // 128 rows x 128 B
+constexpr uint32_t kPeBuf = 4 * kPeTile;  // xyz_hi, xyz_lo, dir_hi, dir_lo
+constexpr uint32_t kColAhi = 256, kColAlo = 384;
+constexpr int kMaxStages = 8;
+
+struct TcParams {
+  const NetProgram* prog;
+  const uint8_t* wpack;
+  const float* bias;
+  const float* head;
+  MlpInput in;
+  float* out;
+  int out_sigma_only;
+  int n_passes;
+  float act_scale, act_inv_scale;
+  int num_stages;
+  long long n_tiles;
+  int* err;
+  uint32_t off_pe, off_bias, off_head, off_layers, off_blocks, off_red, off_bars;
+};
+
+// barrier slots (8 B each) relative to off_bars
+constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
+                   kBarDFull = 192, kTmemPtr = 224, kBarBytes = 256;
+
+enum : int { ERR_ALIGN = 1, ERR_W_EMPTY = 2, ERR_W_FULL = 3, ERR_PE_FULL = 4, ERR_PE_EMPTY = 5, ERR_CHUNK = 6,
+             ERR_DFULL = 7 };
+
+__device__ __forceinline__ uint16_t f16_bits_sat(float a) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(a));
+  return h;
+}
+__device__ __forceinline__ float f16_bits_to_float(uint16_t h) {
+  float f;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+  return f;
+}
+__device__ __forceinline__ uint32_t swz_off(int r, int c) {
+  return (uint32_t)r * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+}
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bars = sbase + P.off_bars;
+  const int NS = P.num_stages;
+  float* s_bias = reinterpret_cast<float*>(smem + P.off_bias);
+  float* s_head = reinterpret_cast<float*>(smem + P.off_head);
+  LayerProg* s_layers = reinterpret_cast<LayerProg*>(smem + P.off_layers);
+  BlockProg* s_blocks = reinterpret_cast<BlockProg*>(smem + P.off_blocks);
+  float* s_red = reinterpret_cast<float*>(smem + P.off_red);   // [128] sigma partials, then [128][4]
+  const int n_layers = P.prog->n_layers, n_blocks = P.prog->n_blocks;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (threadIdx.x == 0) {
+    if (sbase & 1023u) { atomicExch(P.err, ERR_ALIGN); __trap(); }
+    for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(bars + kBarWFull + 8 * i, 1); ptx::mbar_init(bars + kBarWEmpty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bars + kBarPeFull + 8 * i, 128); ptx::mbar_init(bars + kBarPeEmpty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(bars + kBarChunk + 8 * i, kEpiWarps * 32); ptx::mbar_init(bars + kBarDFull + 8 * i, 1); }
+    ptx::fence_mbar_init();
+  }
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem + P.off_pe);
+    for (int i = threadIdx.x; i < (int)(2 * kPeBuf / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < P.prog->n_bias; i += kThreads) s_bias[i] = P.bias[i];
+    for (int i = threadIdx.x; i < P.prog->n_head; i += kThreads) s_head[i] = P.head[i];
+    const uint32_t* gl = reinterpret_cast<const uint32_t*>(P.prog->layers);
+    uint32_t* sl = reinterpret_cast<uint32_t*>(s_layers);
+    for (int i = threadIdx.x; i < n_layers * (int)(sizeof(LayerProg) / 4); i += kThreads) sl[i] = gl[i];
+    const uint32_t* gb = reinterpret_cast<const uint32_t*>(P.prog->blocks);
+    uint32_t* sb = reinterpret_cast<uint32_t*>(s_blocks);
+    for (int i = threadIdx.x; i < n_blocks * (int)(sizeof(BlockProg) / 4); i += kThreads) sb[i] = gb[i];
+  }
+  ptx::fence_proxy_async_smem();
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc(bars + kTmemPtr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + P.off_bars + kTmemPtr);
+
+  const float so = P.act_scale, si = P.act_inv_scale;
+  const int n_passes = P.n_passes;
+
+  if (warp < kEpiWarps) {
+    // =============================================================== epilogue warps
+    const int q = warp & 3, hcol = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t gl = 0;
+    float sigma_val = 0.f;
+    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const long long m = tile * kTileM + row;
+      for (int li = 0; li < n_layers; ++li, ++gl) {
+        const LayerProg L = s_layers[li];
+        const int NC = L.n_out >> 6;
+        const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
+        const int heads = L.kind == KIND_SIGMA ? 1 : (L.kind == KIND_RGB ? 3 : (L.kind == KIND_OUT4 ? 4 : 0));
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int n = 0; n < 4; ++n) {
+          ptx::mbar_wait(bars + kBarDFull + 8 * n, gl & 1, P.err, ERR_DFULL);
+          if (n < NC) {
+            ptx::tc_fence_after();
+            uint32_t r[32];
+            NM_TMEM_LD32(tmem + lane_addr + (uint32_t)(n * 64 + hcol * 32), r);
+            ptx::tmem_wait_ld();
+            const int col0 = n * 64 + hcol * 32;
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + L.bias_off + col0);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), so, bb.x);
+              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), so, bb.y);
+              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), so, bb.z);
+              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), so, bb.w);
+            }
+            if (L.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            for (int hh = 0; hh < heads; ++hh) {
+              const float4* w4 = reinterpret_cast<const float4*>(s_head + L.head_off + hh * L.n_out + col0);
+              float acc = part[hh];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 ww = w4[j];
+                acc = fmaf(ww.x, v[4 * j + 0], acc);
+                acc = fmaf(ww.y, v[4 * j + 1], acc);
+                acc = fmaf(ww.z, v[4 * j + 2], acc);
+                acc = fmaf(ww.w, v[4 * j + 3], acc);
+              }
+              part[hh] = acc;
+            }
+            if (writes_a) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a0 = v[2 * j] * si, a1 = v[2 * j + 1] * si;
+                hi[j] = ptx::pack_f16x2_sat(a0, a1);
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+                lo[j] = ptx::pack_f16x2_sat(a0 - f.x, a1 - f.y);
+              }
+              const uint32_t acol = (uint32_t)(n * 32 + hcol * 16);
+              NM_TMEM_ST16(tmem + lane_addr + kColAhi + acol, hi);
+              if (n_passes == 3) NM_TMEM_ST16(tmem + lane_addr + kColAlo + acol, lo);
+              ptx::tmem_wait_st();
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(bars + kBarChunk + 8 * n);
+        }
+        if (heads) {
+          // the two column halves of a row live in warps w and w+4: combine through smem
+          const float* hb = s_head + L.head_off + heads * L.n_out;
+          if (L.kind == KIND_SIGMA) {
+            if (hcol == 1) s_red[row] = part[0];
+            ptx::named_bar_sync(1, kEpiWarps * 32);
+            if (hcol == 0) {
+              sigma_val = part[0] + s_red[row] + hb[0];
+              if (L.is_final && m < P.in.M) P.out[m] = sigma_val;   // sigma-only program
+            }
+          } else {
+            float* r4 = s_red + 128 + 4 * row;
+            if (hcol == 1) { r4[0] = part[0]; r4[1] = part[1]; r4[2] = part[2]; r4[3] = part[3]; }
+            ptx::named_bar_sync(2, kEpiWarps * 32);
+            if (hcol == 0 && m < P.in.M) {
+              float o[4];
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) o[hh] = (hh < heads) ? part[hh] + r4[hh] + hb[hh] : 0.f;
+              const float sg = (L.kind == KIND_RGB) ? sigma_val : o[3];
+              if (P.out_sigma_only) {
+                P.out[m] = sg;
+              } else {
+                float4 res;
+                res.x = 1.f / (1.f + expf(-o[0]));
+                res.y = 1.f / (1.f + expf(-o[1]));
+                res.z = 1.f / (1.f + expf(-o[2]));
+                res.w = sg;
+                reinterpret_cast<float4*>(P.out)[m] = res;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < kProdWarp) {
+    // =============================================================== front-end warps: next tile's encodings
+    const int r = (warp - kFeWarp0) * 32 + lane;
+    const int Lx = P.prog->L_xyz, Ld = P.prog->L_dir, ix = P.prog->inc_xyz, id = P.prog->inc_dir;
+    const int has_dir = P.prog->dim_dir > 0;
+    const float* fx = P.prog->freq_xyz;
+    const float* fd = P.prog->freq_dir;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      ptx::mbar_wait(bars + kBarPeEmpty + 8 * buf, ((it >> 1) & 1) ^ 1, P.err, ERR_PE_EMPTY);
+      long long m = tile * kTileM + r;
+      if (m >= P.in.M) m = P.in.M - 1;
+      float p[3], d[3];
+      fetch_point(P.in, m, p, d);
+      uint8_t* tb = smem + P.off_pe + buf * kPeBuf;
+      auto emit_to = [&](uint8_t* hi_tile, int j, float val) {
+        const float a = val * si;
+        const uint16_t h = f16_bits_sat(a);
+        const uint32_t off = swz_off(r, j);
+        *reinterpret_cast<uint16_t*>(hi_tile + off) = h;
+        *reinterpret_cast<uint16_t*>(hi_tile + kPeTile + off) = f16_bits_sat(a - f16_bits_to_float(h));
+      };
+      positional_encoding(p, Lx, ix, fx, [&](int j, float val) { emit_to(tb, j, val); });
+      if (has_dir) positional_encoding(d, Ld, id, fd, [&](int j, float val) { emit_to(tb + 2 * kPeTile, j, val); });
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(bars + kBarPeFull + 8 * buf);
+    }
+  } else if (warp == kProdWarp) {
+    // =============================================================== weight producer
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = (n_passes == 3) ? (uint32_t)kStageBytes : (uint32_t)kHalfStage;
+      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        for (int b = 0; b < n_blocks; ++b) {
+          ptx::mbar_wait(bars + kBarWEmpty + 8 * slot, ph ^ 1, P.err, ERR_W_EMPTY);
+          ptx::mbar_expect_tx(bars + kBarWFull + 8 * slot, bytes);
+          ptx::bulk_g2s(sbase + (uint32_t)slot * kStageBytes, P.wpack + (size_t)b * kStageBytes, bytes,
+                        bars + kBarWFull + 8 * slot);
+          if (++slot == NS) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
+      int slot = 0;
+      uint32_t ph = 0, gl = 0, it = 0;
+      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1;
+        ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
+        ptx::tc_fence_after();
+        const uint32_t pe_base = sbase + P.off_pe + buf * kPeBuf;
+        for (int li = 0; li < n_layers; ++li, ++gl) {
+          const LayerProg L = s_layers[li];
+          const int NC = L.n_out >> 6;
+          int waited = -1;
+          for (int b = L.blk_begin; b < L.blk_end; ++b) {
+            const BlockProg B = s_blocks[b];
+            while (waited < (int)B.group) {
+              ++waited;
+              if (gl > 0) ptx::mbar_wait(bars + kBarChunk + 8 * waited, (gl - 1) & 1, P.err, ERR_CHUNK);
+            }
+            ptx::mbar_wait(bars + kBarWFull + 8 * slot, ph, P.err, ERR_W_FULL);
+            ptx::tc_fence_after();
+            const uint32_t wst = sbase + (uint32_t)slot * kStageBytes;
+            const uint32_t d_t = tmem + (uint32_t)B.nc * 64u;
+            for (int pass = 0; pass < n_passes; ++pass) {
+              const bool a_lo = (pass == 1), w_lo = (pass == 2);
+              const uint64_t bdesc = ptx::make_kmajor_sw128_desc(wst + (w_lo ? (uint32_t)kHalfStage : 0u));
+              if (B.src == SRC_ACT) {
+                const uint32_t a_t = tmem + (a_lo ? kColAlo : kColAhi) + (uint32_t)B.kb * 32u;
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                  ptx::mma_ts(d_t, a_t + 8u * s, bdesc + 2u * s, idesc, !(B.first && pass == 0 && s == 0));
+              } else {
+                const uint64_t adesc = ptx::make_kmajor_sw128_desc(pe_base + (B.src == SRC_PE_DIR ? 2 * kPeTile : 0u) +
+                                                                   (a_lo ? kPeTile : 0u));
+                for (int s = 0; s < (int)B.ksteps; ++s)
+                  ptx::mma_ss(d_t, adesc + 2u * s, bdesc + 2u * s, idesc, !(B.first && pass == 0 && s == 0));
+              }
+            }
+            ptx::tc_commit(bars + kBarWEmpty + 8 * slot);
+            if (B.last) ptx::tc_commit(bars + kBarDFull + 8 * B.nc);
+            if (++slot == NS) { slot = 0; ph ^= 1; }
+          }
+          while (waited < 3) {
+            ++waited;
+            if (gl > 0) ptx::mbar_wait(bars + kBarChunk + 8 * waited, (gl - 1) & 1, P.err, ERR_CHUNK);
+          }
+          for (int n = NC; n < 4; ++n) ptx::tc_commit(bars + kBarDFull + 8 * n);
+        }
+        ptx::tc_commit(bars + kBarPeEmpty + 8 * buf);
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
+                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches) {
+  if (in.M <= 0) return 0;
+  const NetProgram& hp = sigma_only ? net.sigma : net.full;
+  TcParams P{};
+  P.prog = sigma_only ? net.d_sigma : net.d_full;
+  P.wpack = sigma_only ? net.d_wpack_sigma : net.d_wpack_full;
+  P.bias = net.d_bias;
+  P.head = net.d_head;
+  P.in = in;
+  P.out = out;
+  P.out_sigma_only = sigma_only ? 1 : 0;
+  P.n_passes = n_passes;
+  P.act_scale = ldexpf(1.f, act_scale_log2);
+  P.act_inv_scale = ldexpf(1.f, -act_scale_log2);
+  P.n_tiles = (in.M + kTileM - 1) / kTileM;
+  P.err = d_err;
+
+  auto align_up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
+  int dev = 0, max_smem = 0;
+  NM_CUDA(cudaGetDevice(&dev));
+  NM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const uint32_t fixed = 2 * kPeBuf + align_up(hp.n_bias * 4, 16) + align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16) +
+                         align_up(hp.n_layers * sizeof(LayerProg), 16) + align_up(hp.n_blocks * sizeof(BlockProg), 16) +
+                         (128 + 512) * 4 + kBarBytes;
+  int ns = ((int)max_smem - (int)fixed) / kStageBytes;
+  if (ns > kMaxStages) ns = kMaxStages;
+  NM_CHECK(ns >= 2, "network too large for the shared-memory budget (%u B fixed, %d B available)", fixed, max_smem);
+  P.num_stages = ns;
+  uint32_t off = (uint32_t)ns * kStageBytes;
+  P.off_pe = off; off += 2 * kPeBuf;
+  P.off_bias = off; off += align_up(hp.n_bias * 4, 16);
+  P.off_head = off; off += align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16);
+  P.off_layers = off; off += align_up(hp.n_layers * sizeof(LayerProg), 16);
+  P.off_blocks = off; off += align_up(hp.n_blocks * sizeof(BlockProg), 16);
+  P.off_red = off; off += (128 + 512) * 4;
+  P.off_bars = off; off += kBarBytes;
+  NM_CHECK((int)off <= max_smem, "shared-memory layout overflow");
+
+  static int configured_dev = -1;
+  if (configured_dev != dev) {
+    NM_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    configured_dev = dev;
+  }
+  long long grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+  mlp_tc_kernel<<<(unsigned)grid, kThreads, off, st>>>(P);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+}  // namespace nm

@@ -1,0 +1,449 @@
+// The light stages around the fused MLP: ray generation (a1/a2), stratified sampling (a3), sigma->alpha compositing
+// (a7), inverse-CDF resampling (a8), AABB-clipped sampling (a10), volume statistics (a14).  All fp32, written op for
+// op like the reference (this TU is compiled with -fmad=false so a*b+c stays two roundings, as torch evaluates it).
+// Their traffic is ~20 B per sample against ~3.6 MFLOP of tensor work per sample, so they are deliberately simple:
+// correctness and the reference's evaluation order matter here, not bandwidth.
+#include <math_constants.h>
+
+#include "nm_common.h"
+
+namespace nm {
+namespace {
+
+// counter-based uniform [0,1): splitmix64 of (seed, index).  Used only for perturb / noise (distributional parity).
+__device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float randn(uint64_t seed, uint64_t idx) {
+  const float a = fmaxf(u01(seed, 2 * idx), 1e-7f), b = u01(seed, 2 * idx + 1);
+  return sqrtf(-2.f * logf(a)) * cospif(2.f * b);
+}
+
+// ------------------------------------------------------------------------------------------------ a1 / a2
+// get_ray_bundle (src/nerf/nerf_helpers.py:226-277) and ndc_rays (:280-307).
+struct RayGenDev {
+  float pose[12];
+  int H, W;
+  float focal, half_w, half_h;
+  int ndc;
+  float ndc_near, sx, sy, two_near;
+  int row0;
+  long long n;
+};
+__global__ void raygen_kernel(const __grid_constant__ RayGenDev a, float* __restrict__ origins, float* __restrict__ dirs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int c = (int)(i % a.W), r = a.row0 + (int)(i / a.W);
+  float x = ((float)c - a.half_w) / a.focal;
+  float y = -((float)r - a.half_h) / a.focal;
+  float z = -1.0f;
+  const float nrm = sqrtf(x * x + y * y + z * z);
+  x = x / nrm; y = y / nrm; z = z / nrm;
+  float d[3], o[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    d[j] = (x * a.pose[4 * j + 0] + y * a.pose[4 * j + 1]) + z * a.pose[4 * j + 2];
+    o[j] = a.pose[4 * j + 3];
+  }
+  if (a.ndc) {
+    const float t = -(a.ndc_near + o[2]) / d[2];
+    o[0] = o[0] + t * d[0]; o[1] = o[1] + t * d[1]; o[2] = o[2] + t * d[2];
+    const float o0 = a.sx * o[0] / o[2], o1 = a.sy * o[1] / o[2], o2 = 1.0f + a.two_near / o[2];
+    const float d0 = a.sx * (d[0] / d[2] - o[0] / o[2]);
+    const float d1 = a.sy * (d[1] / d[2] - o[1] / o[2]);
+    const float d2 = -a.two_near / o[2];
+    o[0] = o0; o[1] = o1; o[2] = o2;
+    d[0] = d0; d[1] = d1; d[2] = d2;
+  }
+  dirs[3 * i + 0] = d[0]; dirs[3 * i + 1] = d[1]; dirs[3 * i + 2] = d[2];
+  if (origins) { origins[3 * i + 0] = o[0]; origins[3 * i + 1] = o[1]; origins[3 * i + 2] = o[2]; }
+}
+
+// ------------------------------------------------------------------------------------------------ a3
+// RaySampleInterval.forward (src/nerf/modules.py:157-186).
+__global__ void stratified_kernel(const float* __restrict__ s_table, int Nc, long long R, float near0, float far0,
+                                  const float* __restrict__ near_dev, const float* __restrict__ far_dev, int lindisp,
+                                  int perturb, uint64_t seed, float* __restrict__ t_out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= R * Nc) return;
+  const long long ray = idx / Nc;
+  const int i = (int)(idx % Nc);
+  const float near = near_dev ? near_dev[ray] : near0, far = far_dev ? far_dev[ray] : far0;
+  auto at = [&](int k) -> float {
+    const float s = s_table[k];
+    if (!lindisp) return near * (1.0f - s) + far * s;
+    return 1.0f / (1.0f / near * (1.0f - s) + 1.0f / far * s);
+  };
+  float t = at(i);
+  if (perturb) {
+    const float lower = (i == 0) ? t : 0.5f * (t + at(i - 1));
+    const float upper = (i == Nc - 1) ? t : 0.5f * (at(i + 1) + t);
+    t = lower + (upper - lower) * u01(seed, (uint64_t)idx);
+  }
+  t_out[idx] = t;
+}
+
+// ------------------------------------------------------------------------------------------------ a7
+// VolumeRenderer.forward (src/nerf/modules.py:67-121).  One thread per ray, samples visited in order so the
+// exclusive cumprod (nerf_helpers.py:199-223) is the same sequential product torch.cumprod forms.
+__global__ void composite_kernel(const __grid_constant__ CompositeArgs a) {
+  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= a.R) return;
+  const int S = a.S;
+  const float4* raw = reinterpret_cast<const float4*>(a.raw) + ray * S;
+  const float* t = a.t + ray * S;
+  const float dx = a.dirs[3 * ray], dy = a.dirs[3 * ray + 1], dz = a.dirs[3 * ray + 2];
+  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+  float T = 1.0f, acc = 0.f, depth = 0.f, r = 0.f, g = 0.f, b = 0.f;
+  float tc = t[0];
+  for (int i = 0; i < S; ++i) {
+    const float tn = (i + 1 < S) ? t[i + 1] : 0.f;
+    const float dist = ((i + 1 < S) ? (tn - tc) : 1e10f) * nrm;
+    const float4 q = raw[i];
+    float sg = q.w;
+    if (a.noise_std > 0.f) sg = sg + randn(a.seed, (uint64_t)(ray * S + i)) * a.noise_std;
+    sg = fmaxf(sg, 0.f);
+    const float alpha = 1.0f - expf(-sg * dist);
+    const float w = alpha * T;
+    if (a.weights) a.weights[ray * S + i] = w;
+    if (a.mask_weights) a.mask_weights[ray * S + i] = (T > a.thr) ? 1.f : 0.f;
+    r = r + w * q.x; g = g + w * q.y; b = b + w * q.z;
+    acc = acc + w;
+    depth = depth + w * tc;
+    T = T * (1.0f - alpha + 1e-10f);
+    tc = tn;
+  }
+  float disp = 1.0f / fmaxf(1e-10f, depth / acc);
+  if (isnan(disp)) disp = 0.f;          // fmaxf drops a NaN operand; torch.max propagates it, then :107 zeroes it
+  if (isnan(depth / acc)) disp = 0.f;
+  if (a.depth_raw) a.depth_raw[ray] = depth;
+  if (a.depth) a.depth[ray] = (!a.training && acc < 1.0f) ? 0.f : depth;
+  if (a.white_bg) { const float bg = 1.0f - acc; r = r + bg; g = g + bg; b = b + bg; }
+  if (a.rgb) { a.rgb[3 * ray] = r; a.rgb[3 * ray + 1] = g; a.rgb[3 * ray + 2] = b; }
+  if (a.acc) a.acc[ray] = acc;
+  if (a.disp) a.disp[ray] = disp;
+}
+
+// ------------------------------------------------------------------------------------------------ a8
+// SamplePDF.forward (src/nerf/modules.py:197-248).  One warp per ray; everything in shared memory.
+constexpr int kMaxCoarse = 256;
+constexpr int kMaxTotal = 512;
+constexpr int kInvWarps = 4;
+
+__device__ __forceinline__ void warp_bitonic_sort(float* a, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        const int p = i ^ j;
+        if (p > i) {
+          const float x = a[i], y = a[p];
+          const bool up = ((i & k) == 0);
+          if ((x > y) == up) { a[i] = y; a[p] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kInvWarps * 32) invcdf_kernel(const float* __restrict__ t_c, const float* __restrict__ w_c,
+                                                              const float* __restrict__ u_table, int Nc, int Nf,
+                                                              long long R, int perturb, uint64_t seed,
+                                                              float* __restrict__ t_f) {
+  __shared__ float s_bins[kInvWarps][kMaxCoarse];
+  __shared__ float s_cdf[kInvWarps][kMaxCoarse];
+  __shared__ float s_all[kInvWarps][kMaxTotal];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ray = (long long)blockIdx.x * kInvWarps + wid;
+  if (ray >= R) return;
+  float* bins = s_bins[wid];
+  float* cdf = s_cdf[wid];
+  float* all = s_all[wid];
+  const float* t = t_c + ray * Nc;
+  const float* w = w_c + ray * Nc;
+  const int nb = Nc - 1;                       // number of bins (mid points)
+  const int nw = Nc - 2;                       // weights[..., 1:-1]
+  for (int i = lane; i < nb; i += 32) bins[i] = 0.5f * (t[i + 1] + t[i]);
+  for (int i = lane; i < Nc; i += 32) all[i] = t[i];
+  // pdf = (w + 1e-5) / sum
+  float part = 0.f;
+  for (int i = lane; i < nw; i += 32) { const float x = w[i + 1] + 1e-5f; cdf[i + 1] = x; part += x; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  __syncwarp();
+  if (lane == 0) {                             // torch.cumsum: sequential fp32 running sum
+    float run = 0.f;
+    cdf[0] = 0.f;
+    for (int i = 1; i <= nw; ++i) { run = run + cdf[i] / part; cdf[i] = run; }
+  }
+  __syncwarp();
+  const int ncdf = nw + 1;                     // == nb
+  const int total = Nc + Nf;
+  for (int j = lane; j < Nf; j += 32) {
+    const float u = perturb ? u01(seed, (uint64_t)(ray * Nf + j)) : u_table[j];
+    int lo = 0, hi = ncdf;                     // searchsorted(cdf, u, right=True) = #{cdf <= u}
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    const int below = max(lo - 1, 0), above = min(ncdf - 1, lo);
+    const float cb = cdf[below], ca = cdf[above], bb = bins[below], ba = bins[above];
+    float denom = ca - cb;
+    if (denom < 1e-5f) denom = 1.0f;
+    const float tt = (u - cb) / denom;
+    all[Nc + j] = bb + tt * (ba - bb);
+  }
+  int n2 = 1;
+  while (n2 < total) n2 <<= 1;
+  for (int i = total + lane; i < n2; i += 32) all[i] = CUDART_INF_F;
+  __syncwarp();
+  warp_bitonic_sort(all, n2, lane);
+  for (int i = lane; i < total; i += 32) t_f[ray * total + i] = all[i];
+}
+
+// ------------------------------------------------------------------------------------------------ a10
+// TreeSampling.batch_ray_voxel_intersect, deterministic branch (src/nerf/tree.py:215-343), + the miss fallback of
+// BuFFModel.forward (src/models/model_buff.py:53).  One warp per ray, voxel list streamed from global (L1/L2-resident:
+// 1533 x 24 B), hit list / prefix sums / samples in shared memory.
+constexpr int kMaxHits = 512;
+constexpr int kAabbWarps = 4;
+
+__device__ __forceinline__ void warp_bitonic_sort_pairs(float* key, float* val, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        const int p = i ^ j;
+        if (p > i) {
+          const float x = key[i], y = key[p];
+          const bool up = ((i & k) == 0);
+          if ((x > y) == up) {
+            key[i] = y; key[p] = x;
+            const float vx = val[i]; val[i] = val[p]; val[p] = vx;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __restrict__ voxels, int V,
+                                                              const float* __restrict__ origins, int o_stride,
+                                                              const float* __restrict__ dirs, long long R, float near,
+                                                              float far, int S, const float* __restrict__ s_table,
+                                                              const float* __restrict__ t_uniform,
+                                                              float* __restrict__ z_out, int* __restrict__ overflow) {
+  __shared__ float s_lo[kAabbWarps][kMaxHits];
+  __shared__ float s_hi[kAabbWarps][kMaxHits];
+  __shared__ float s_z[kAabbWarps][kMaxTotal];
+  __shared__ int s_bucket[kAabbWarps][kMaxTotal];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ray = (long long)blockIdx.x * kAabbWarps + wid;
+  if (ray >= R) return;
+  float* lo = s_lo[wid];
+  float* hi = s_hi[wid];
+  float* z = s_z[wid];
+  int* bucket = s_bucket[wid];
+  float o[3], inv[3];
+  bool neg[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = origins[(long long)o_stride * ray + c];
+    inv[c] = 1.0f / dirs[3 * ray + c];
+    neg[c] = inv[c] < 0.f;
+  }
+  int H = 0;
+  for (int v0 = 0; v0 < V; v0 += 32) {
+    const int v = v0 + lane;
+    bool hit = false;
+    float tmin = 0.f, tmax = 0.f;
+    if (v < V) {
+      float tlo[3], thi[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float vmin = voxels[6 * v + c], vmax = voxels[6 * v + 3 + c];
+        tlo[c] = ((neg[c] ? vmax : vmin) - o[c]) * inv[c];
+        thi[c] = ((neg[c] ? vmin : vmax) - o[c]) * inv[c];
+      }
+      tmin = tlo[0]; tmax = thi[0];
+      hit = (tmin <= thi[1]) && (tlo[1] <= tmax);
+      if (tlo[1] > tmin) tmin = tlo[1];
+      if (thi[1] < tmax) tmax = thi[1];
+      hit = hit && (tmin <= thi[2]) && (tlo[2] <= tmax);
+      if (tlo[2] > tmin) tmin = tlo[2];
+      if (thi[2] < tmax) tmax = thi[2];
+      hit = hit && (tmin >= near) && (tmax <= far);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int pos = H + __popc(bal & ((1u << lane) - 1));
+      if (pos < kMaxHits) { lo[pos] = tmin; hi[pos] = tmax; }
+    }
+    H += __popc(bal);
+  }
+  if (H > kMaxHits) { if (lane == 0) atomicExch(overflow, 1); H = kMaxHits; }
+  __syncwarp();
+  if (H == 0) {                                 // miss: uniform fallback samples
+    for (int k = lane; k < S; k += 32) z_out[ray * S + k] = t_uniform[ray * S + k];
+    return;
+  }
+  int n2 = 1;
+  while (n2 < H) n2 <<= 1;
+  for (int i = H + lane; i < n2; i += 32) { lo[i] = CUDART_INF_F; hi[i] = CUDART_INF_F; }
+  __syncwarp();
+  warp_bitonic_sort_pairs(lo, hi, n2, lane);    // hits by entry distance
+  // running sum of the interval lengths (torch.cumsum, sequential), kept in hi[]
+  if (lane == 0) {
+    float run = 0.f;
+    for (int i = 0; i < H; ++i) { run = run + (hi[i] - lo[i]); hi[i] = run; }
+  }
+  __syncwarp();
+  const float total = hi[H - 1];
+  for (int k = lane; k < S; k += 32) {
+    const float s = s_table[k] * total;
+    int a = 0, b = H;                           // searchsorted(cums, s) left = #{cums < s}
+    while (a < b) { const int mid = (a + b) >> 1; if (hi[mid] < s) a = mid + 1; else b = mid; }
+    bucket[k] = min(a, H - 1);
+  }
+  __syncwarp();
+  for (int k = lane; k < S; k += 32) {
+    const int bk = bucket[k];
+    int a = 0, b = k;                           // first sample index that falls in the same bucket
+    while (a < b) { const int mid = (a + b) >> 1; if (bucket[mid] < bk) a = mid + 1; else b = mid; }
+    z[k] = lo[bk] + (s_table[k] * total - s_table[a] * total);
+  }
+  int m2 = 1;
+  while (m2 < S) m2 <<= 1;
+  for (int i = S + lane; i < m2; i += 32) z[i] = CUDART_INF_F;
+  __syncwarp();
+  warp_bitonic_sort(z, m2, lane);
+  for (int k = lane; k < S; k += 32) z_out[ray * S + k] = z[k];
+}
+
+// ------------------------------------------------------------------------------------------------ a14
+__global__ void stats_pass1(const float* __restrict__ v, long long n, double* __restrict__ acc /*[min,max,sum]*/) {
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = v[i];
+    mn = fminf(mn, x); mx = fmaxf(mx, x); s += (double)x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(acc + 2, s);
+    // float min/max through ordered-int atomics on the double slots' low words would be obscure; use CAS on doubles
+    unsigned long long* pmn = reinterpret_cast<unsigned long long*>(acc);
+    unsigned long long old = *pmn, assumed;
+    do { assumed = old; if (__longlong_as_double(assumed) <= (double)mn) break;
+         old = atomicCAS(pmn, assumed, __double_as_longlong((double)mn)); } while (assumed != old);
+    unsigned long long* pmx = reinterpret_cast<unsigned long long*>(acc + 1);
+    old = *pmx;
+    do { assumed = old; if (__longlong_as_double(assumed) >= (double)mx) break;
+         old = atomicCAS(pmx, assumed, __double_as_longlong((double)mx)); } while (assumed != old);
+  }
+}
+__global__ void stats_pass2(const float* __restrict__ v, long long n, double mean, double* __restrict__ acc) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double d = (double)v[i] - mean;
+    s += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(acc + 3, s);
+}
+
+}  // namespace
+
+int launch_raygen(const RayGenArgs& a, float* origins, float* dirs, cudaStream_t st, int64_t* launches) {
+  RayGenDev d{};
+  for (int i = 0; i < 12; ++i) d.pose[i] = a.pose[i];
+  d.H = a.H; d.W = a.W; d.focal = a.focal;
+  d.half_w = (float)(a.W * 0.5); d.half_h = (float)(a.H * 0.5);
+  d.ndc = a.ndc; d.ndc_near = a.ndc_near;
+  // python-double scalars of ndc_rays, rounded once to fp32 like torch does for tensor (op) python-scalar
+  d.sx = (float)(-1.0 / ((double)a.W / (2.0 * (double)a.focal)));
+  d.sy = (float)(-1.0 / ((double)a.H / (2.0 * (double)a.focal)));
+  d.two_near = (float)(2.0 * (double)a.ndc_near);
+  d.row0 = a.row0;
+  d.n = (long long)(a.row1 - a.row0) * a.W;
+  if (d.n <= 0) return 0;
+  raygen_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, st>>>(d, origins, dirs);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_stratified(const float* s_table, int Nc, long long R, const float* near_far2, const float* near_dev,
+                      const float* far_dev, int lindisp, int perturb, uint64_t seed, float* t_out, cudaStream_t st,
+                      int64_t* launches) {
+  const long long n = R * Nc;
+  if (n <= 0) return 0;
+  stratified_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s_table, Nc, R, near_far2 ? near_far2[0] : 0.f,
+                                                                 near_far2 ? near_far2[1] : 0.f, near_dev, far_dev,
+                                                                 lindisp, perturb, seed, t_out);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_composite(const CompositeArgs& a, cudaStream_t st, int64_t* launches) {
+  if (a.R <= 0) return 0;
+  composite_kernel<<<(unsigned)((a.R + 127) / 128), 128, 0, st>>>(a);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_invcdf(const float* t_c, const float* w_c, const float* u_table, int Nc, int Nf, long long R, int perturb,
+                  uint64_t seed, float* t_f, cudaStream_t st, int64_t* launches) {
+  NM_CHECK(Nc >= 3 && Nc <= kMaxCoarse && Nc + Nf <= kMaxTotal, "sample counts (%d,%d) exceed the resampler limits", Nc, Nf);
+  if (R <= 0) return 0;
+  invcdf_kernel<<<(unsigned)((R + kInvWarps - 1) / kInvWarps), kInvWarps * 32, 0, st>>>(t_c, w_c, u_table, Nc, Nf, R,
+                                                                                       perturb, seed, t_f);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_aabb(const float* voxels, int V, const float* origins, int o_stride, const float* dirs, long long R,
+                     float near, float far, int S, const float* s_table, const float* t_uniform, float* z_out,
+                     int* d_overflow, cudaStream_t st, int64_t* launches) {
+  NM_CHECK(S <= kMaxTotal, "sample count %d exceeds the AABB sampler limit", S);
+  if (R <= 0) return 0;
+  aabb_kernel<<<(unsigned)((R + kAabbWarps - 1) / kAabbWarps), kAabbWarps * 32, 0, st>>>(
+      voxels, V, origins, o_stride, dirs, R, near, far, S, s_table, t_uniform, z_out, d_overflow);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_volume_stats(const float* vol, long long n, double* d_scratch, float* out_host, cudaStream_t st,
+                        int64_t* launches) {
+  NM_CHECK(n > 0, "empty volume");
+  const double init[4] = {1e300, -1e300, 0.0, 0.0};
+  NM_CUDA(cudaMemcpyAsync(d_scratch, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  stats_pass1<<<1184, 256, 0, st>>>(vol, n, d_scratch);
+  NM_CUDA(cudaGetLastError());
+  double h[4];
+  NM_CUDA(cudaMemcpyAsync(h, d_scratch, sizeof(h), cudaMemcpyDeviceToHost, st));
+  NM_CUDA(cudaStreamSynchronize(st));
+  const double mean = h[2] / (double)n;
+  stats_pass2<<<1184, 256, 0, st>>>(vol, n, mean, d_scratch);
+  NM_CUDA(cudaGetLastError());
+  NM_CUDA(cudaMemcpyAsync(h, d_scratch, sizeof(h), cudaMemcpyDeviceToHost, st));
+  NM_CUDA(cudaStreamSynchronize(st));
+  out_host[0] = (float)h[0];
+  out_host[1] = (float)h[1];
+  out_host[2] = (float)sqrt(h[3] / (double)n);   // numpy .std(): population std (ddof=0)
+  if (launches) *launches += 2;
+  return 0;
+}
+
+}  // namespace nm

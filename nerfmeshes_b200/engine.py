@@ -1,0 +1,286 @@
+"""Engine: one NmHandle plus the torch-tensor plumbing around it (device memory, streams).
+
+torch is used for allocation and stream identity only; every computation is a call through the C ABI
+(nerfmeshes_b200/_lib.py).  CPU tensors go through the *_host entry points (copies inside the library), CUDA
+tensors through the device-pointer entry points on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+NET_KEYS = ("num_layers", "hidden_size", "skip_step", "num_encoding_fn_xyz", "num_encoding_fn_dir",
+            "include_input_xyz", "include_input_dir", "log_sampling_xyz", "log_sampling_dir", "use_viewdirs")
+NET_DEFAULTS = dict(num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6, num_encoding_fn_dir=4,
+                    include_input_xyz=True, include_input_dir=True, log_sampling_xyz=True, log_sampling_dir=True,
+                    use_viewdirs=True)   # FlexibleNeRFModel.__init__ defaults, src/nerf/models.py:5-17
+
+
+def net_desc(**kw) -> L.NmNetDesc:
+    d = dict(NET_DEFAULTS)
+    d.update({k: v for k, v in kw.items() if k in NET_KEYS})
+    return L.NmNetDesc(*[int(d[k]) for k in NET_KEYS])
+
+
+@dataclass
+class RenderSettings:
+    num_coarse: int = 64
+    num_fine: int = 128
+    lindisp: bool = False
+    perturb: bool = False
+    white_background: bool = False
+    noise_std: float = 0.0
+    attenuation_threshold: float = 1e-5
+    precision: int = L.PREC_EXACT
+    act_scale_log2: int = 0
+
+    def to_c(self) -> L.NmRenderCfg:
+        return L.NmRenderCfg(int(self.num_coarse), int(self.num_fine), int(bool(self.lindisp)), int(bool(self.perturb)),
+                             int(bool(self.white_background)), float(self.noise_std), float(self.attenuation_threshold),
+                             int(self.precision), int(self.act_scale_log2))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t, device=None) -> torch.Tensor:
+    t = torch.as_tensor(t)
+    if device is not None:
+        t = t.to(device)
+    return t.detach().to(torch.float32).contiguous()
+
+
+class Engine:
+    """Owns one library handle on one CUDA device."""
+
+    def __init__(self, coarse: dict, fine: Optional[dict], settings: RenderSettings, device: int = 0):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.NmError("nerfmeshes_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device("cuda", device)
+        self.settings = settings
+        self.has_fine = fine is not None
+        self._h = C.c_void_p()
+        dc = net_desc(**coarse)
+        df = net_desc(**fine) if fine is not None else None
+        cfg = settings.to_c()
+        L.check(self.lib.nm_create(device, C.byref(dc), C.byref(df) if df is not None else None, C.byref(cfg),
+                                   C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.nm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration
+    def configure(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.settings, k):
+                raise AttributeError(k)
+            setattr(self.settings, k, v)
+        cfg = self.settings.to_c()
+        L.check(self.lib.nm_set_render_cfg(self._h, C.byref(cfg)))
+
+    def load_weights(self, which: int, state: Dict[str, torch.Tensor]):
+        """state: reference state-dict keys without the model prefix -> tensors (any device)."""
+        names, ptrs, numel, keep = [], [], [], []
+        for k, v in state.items():
+            if "frequency_bands" in k:
+                continue
+            a = np.ascontiguousarray(v.detach().cpu().numpy().astype(np.float32, copy=False))
+            keep.append(a)
+            names.append(k.encode())
+            ptrs.append(a.ctypes.data)
+            numel.append(a.size)
+        n = len(names)
+        L.check(self.lib.nm_load_weights(self._h, which, n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs),
+                                         (C.c_int64 * n)(*numel)))
+
+    def set_tables(self, coarse_s: Optional[torch.Tensor] = None, fine_u: Optional[torch.Tensor] = None):
+        s = None if coarse_s is None else np.ascontiguousarray(coarse_s.detach().cpu().numpy(), dtype=np.float32)
+        u = None if fine_u is None else np.ascontiguousarray(fine_u.detach().cpu().numpy(), dtype=np.float32)
+        if s is not None:
+            assert s.size == self.settings.num_coarse
+        if u is not None:
+            assert u.size == self.settings.num_fine
+        L.check(self.lib.nm_set_tables(self._h, None if s is None else s.ctypes.data, None if u is None else u.ctypes.data))
+
+    def set_tree(self, voxels: torch.Tensor):
+        v = np.ascontiguousarray(voxels.detach().cpu().numpy(), dtype=np.float32)
+        assert v.ndim == 3 and v.shape[1:] == (2, 3)
+        L.check(self.lib.nm_set_tree(self._h, v.ctypes.data, v.shape[0]))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ hot path
+    def point_mlp(self, which: int, pts: torch.Tensor, dirs: Optional[torch.Tensor], sigma_only=False) -> torch.Tensor:
+        lead = pts.shape[:-1]
+        host = not pts.is_cuda
+        p = _f32c(pts.reshape(-1, 3))
+        d = None if dirs is None else _f32c(dirs.expand_as(pts).reshape(-1, 3))
+        M = p.shape[0]
+        out = torch.empty((M,) if sigma_only else (M, 4), dtype=torch.float32, device=p.device)
+        if M == 0:
+            return out.reshape(*lead, *(() if sigma_only else (4,)))
+        if host:
+            L.check(self.lib.nm_point_mlp_host(self._h, which, _ptr(p), _ptr(d), M, _ptr(out), int(sigma_only)))
+        else:
+            L.check(self.lib.nm_point_mlp(self._h, which, _ptr(p), _ptr(d), M, _ptr(out), int(sigma_only), self._stream()))
+        return out.reshape(*lead, *(() if sigma_only else (4,)))
+
+    def num_samples(self, buff=False):
+        s = self.settings
+        return s.num_coarse + (s.num_fine if (self.has_fine and not buff) else 0)
+
+    def _alloc_out(self, R, S, device, want, pin=False):
+        sizes = dict(rgb=(R, 3), depth=(R,), depth_raw=(R,), acc=(R,), disp=(R,), weights=(R, S), mask_weights=(R, S),
+                     t_vals=(R, S), coarse_rgb=(R, 3), coarse_acc=(R,), coarse_disp=(R,),
+                     coarse_weights=(R, self.settings.num_coarse))
+        outs = {}
+        for k in want:
+            t = torch.empty(sizes[k], dtype=torch.float32, device=device)
+            if pin and device.type == "cpu":
+                t = t.pin_memory()
+            outs[k] = t
+        block = L.NmRenderOut(*[(outs[k].data_ptr() if k in outs else None) for k in L.OUT_FIELDS])
+        return outs, block
+
+    DEFAULT_OUT = ("rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights")
+
+    def render_rays(self, origins, dirs, near, far, *, training=False, buff=False, seed=0, want=None,
+                    teacher_t: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """NeRFModel.forward / BuFFModel.forward on a ray batch.  origins (3,), (1,3) or (R,3); dirs (R,3);
+        near/far python floats / 0-dim tensors, or (R,) tensors (CUDA path only)."""
+        want = tuple(want or self.DEFAULT_OUT)
+        dirs_t = torch.as_tensor(dirs)
+        host = not dirs_t.is_cuda
+        dev = dirs_t.device if not host else torch.device("cpu")
+        d = _f32c(dirs_t)
+        R = d.shape[0]
+        o = _f32c(origins, d.device)
+        if o.numel() == 3:
+            o = o.reshape(3)
+            o_stride = 0
+        else:
+            assert o.shape == (R, 3), "origins must be (3,), (1,3) or (R,3)"
+            o_stride = 3
+        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        S = self.num_samples(buff)
+        per_ray = isinstance(near, torch.Tensor) and near.dim() > 0 and near.shape[0] == R and near.numel() == R and R > 1
+        nf = (C.c_float * 2)(0.0, 0.0)
+        near_d = far_d = None
+        if per_ray:
+            if host:
+                raise L.NmError("per-ray near/far needs CUDA tensors")
+            near_d, far_d = _f32c(near, d.device), _f32c(far, d.device)
+        else:
+            nf = (C.c_float * 2)(float(near), float(far))
+        if teacher_t is not None:
+            flags |= L.FLAG_TEACHER_T
+            want = tuple(k for k in want if k != "t_vals")
+        outs, block = self._alloc_out(R, S, dev, want)
+        if teacher_t is not None:
+            tt = _f32c(teacher_t, d.device)
+            assert tt.shape == (R, S) and not host
+            block.t_vals = tt.data_ptr()
+        if R == 0:
+            return outs
+        if host:
+            L.check(self.lib.nm_query_host(self._h, _ptr(o), o_stride, _ptr(d), R, nf, flags, seed, C.byref(block)))
+        else:
+            L.check(self.lib.nm_render_rays(self._h, _ptr(o), o_stride, _ptr(d), R, None if per_ray else nf, _ptr(near_d),
+                                            _ptr(far_d), flags, seed, C.byref(block), self._stream()))
+        return outs
+
+    def render_image(self, pose, H, W, focal, near, far, *, ndc=False, rows=None, training=False, buff=False, seed=0,
+                     want=None, to_host=False, host_out=None) -> Dict[str, torch.Tensor]:
+        """Rays generated on the device from a 3x4 / 4x4 camera-to-world pose (get_ray_bundle [+ ndc_rays])."""
+        want = tuple(want or ("rgb", "depth", "acc", "disp"))
+        row0, row1 = rows if rows is not None else (0, H)
+        R = (row1 - row0) * W
+        p = np.ascontiguousarray(torch.as_tensor(pose).detach().cpu().numpy()[:3, :4], dtype=np.float32)
+        nf = (C.c_float * 2)(float(near), float(far))
+        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        S = self.num_samples(buff)
+        if to_host:
+            if host_out is not None:
+                outs = host_out
+                block = L.NmRenderOut(*[(outs[k].data_ptr() if k in outs else None) for k in L.OUT_FIELDS])
+            else:
+                outs, block = self._alloc_out(R, S, torch.device("cpu"), want, pin=True)
+            L.check(self.lib.nm_render_image_host(self._h, p.ctypes.data, H, W, float(focal), int(ndc), row0, row1, nf,
+                                                  flags, seed, C.byref(block)))
+        else:
+            outs, block = self._alloc_out(R, S, self.device, want)
+            L.check(self.lib.nm_render_image(self._h, p.ctypes.data, H, W, float(focal), int(ndc), row0, row1, nf, flags,
+                                             seed, C.byref(block), self._stream()))
+        return outs
+
+    def ray_bundle(self, pose, H, W, focal, *, ndc=False, ndc_near=1.0, rows=None):
+        row0, row1 = rows if rows is not None else (0, H)
+        p = np.ascontiguousarray(torch.as_tensor(pose).detach().cpu().numpy()[:3, :4], dtype=np.float32)
+        dirs = torch.empty((row1 - row0, W, 3), dtype=torch.float32, device=self.device)
+        origins = torch.empty_like(dirs) if ndc else None
+        L.check(self.lib.nm_ray_bundle(self._h, p.ctypes.data, H, W, float(focal), int(ndc), float(ndc_near), row0, row1,
+                                       _ptr(origins), _ptr(dirs), self._stream()))
+        if not ndc:
+            origins = torch.from_numpy(p[:, 3].copy()).to(self.device)
+        return origins, dirs
+
+    def grid_sigma(self, lins, x0=0, x1=None, with_rgb=False):
+        """extract_radiance for planes [x0,x1): lins = three 1-D fp32 tensors (torch.linspace values)."""
+        ls = [np.ascontiguousarray(torch.as_tensor(t).detach().cpu().numpy(), dtype=np.float32) for t in lins]
+        n0, n1, n2 = (a.size for a in ls)
+        x1 = n0 if x1 is None else x1
+        sigma = torch.empty((x1 - x0, n1, n2), dtype=torch.float32, device=self.device)
+        rgb = torch.empty((x1 - x0, n1, n2, 3), dtype=torch.float32, device=self.device) if with_rgb else None
+        L.check(self.lib.nm_grid_sigma(self._h, ls[0].ctypes.data, ls[1].ctypes.data, ls[2].ctypes.data, n0, n1, n2, x0,
+                                       x1, _ptr(sigma), _ptr(rgb), self._stream()))
+        return (sigma, rgb) if with_rgb else sigma
+
+    def volume_stats(self, vol: torch.Tensor):
+        v = _f32c(vol, self.device)
+        out = (C.c_float * 3)()
+        torch.cuda.current_stream(self.device).synchronize()
+        L.check(self.lib.nm_volume_stats(self._h, _ptr(v), v.numel(), out))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def marching_cubes(self, vol: torch.Tensor, iso: float, x_off: float = 0.0):
+        v = _f32c(vol, self.device)
+        nx, ny, nz = v.shape
+        counts = (C.c_int64 * 2)()
+        L.check(self.lib.nm_marching_cubes_count(self._h, _ptr(v), nx, ny, nz, float(iso), counts, self._stream()))
+        nv, nt = int(counts[0]), int(counts[1])
+        verts = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
+        normals = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
+        faces = torch.empty((nt, 3), dtype=torch.int32, device=self.device)
+        if nv > 0:
+            L.check(self.lib.nm_marching_cubes_emit(self._h, _ptr(v), nx, ny, nz, float(iso), float(x_off), _ptr(verts),
+                                                    _ptr(normals), _ptr(faces), self._stream()))
+        return verts, faces, normals
+
+    # ------------------------------------------------------------------ introspection
+    def launch_count(self) -> int:
+        return int(self.lib.nm_launch_count(self._h))
+
+    def set_timing(self, on: bool):
+        L.check(self.lib.nm_set_timing(self._h, int(on)))
+
+    def mlp_time_ms(self):
+        pts, n = C.c_int64(0), C.c_int64(0)
+        ms = float(self.lib.nm_mlp_time_ms(self._h, C.byref(pts), C.byref(n)))
+        return ms, int(pts.value), int(n.value)

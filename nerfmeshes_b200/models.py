@@ -1,0 +1,399 @@
+"""Host-side mirror of the reference's model layer for the hot path (the drop-in boundary).
+
+Same names, constructor arguments, call conventions and state-dict keys as
+  src/nerf/models.py:4-80          FlexibleNeRFModel
+  src/nerf/modules.py:40-47        OutputBundle
+  src/models/model_nerf.py:22-86   NeRFModel   (.forward -> (coarse_bundle, fine_bundle), .query, .get_model)
+  src/models/model_buff.py:12-73   BuFFModel   (.forward / .query -> bundle; checkpoint['tree'])
+  src/models/model_base.py:65-73   BaseModel.sample_points
+but every computation is a call into libnerfmeshes_b200.so through nerfmeshes_b200.engine.Engine.  The classes are
+torch.nn.Modules only so that parameters / state_dict / load_state_dict / train() / eval() behave as the reference's
+callers expect (PyTorch-Lightning itself is not required).  There is no torch fallback: without a B200 the forward
+raises.
+"""
+from __future__ import annotations
+
+import io
+import pickle
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .cfgnode import CfgNode, flatten_dict, nest_dict
+from .engine import NET_KEYS, Engine, RenderSettings
+
+
+@dataclass
+class OutputBundle:
+    rgb_map: torch.Tensor = None
+    depth_map: torch.Tensor = None
+    weights: torch.Tensor = None
+    mask_weights: torch.Tensor = None
+    acc_map: torch.Tensor = None
+    disp_map: torch.Tensor = None
+    depth_raw: torch.Tensor = None      # sum(w*t) before the eval-mode threshold (extra; parity tests use it)
+
+
+class PositionalEncoding(torch.nn.Module):
+    """Holder of the `frequency_bands` buffer (state-dict key parity, src/nerf/modules.py:12-24); the encoding itself
+    is evaluated inside the fused kernel."""
+
+    def __init__(self, num_encoding_functions=6, include_input=True, log_sampling=True):
+        super().__init__()
+        self.num_encoding_functions = num_encoding_functions
+        self.include_input = include_input
+        n = num_encoding_functions
+        bands = 2.0 ** torch.linspace(0.0, n - 1, n) if log_sampling else torch.linspace(1.0, 2.0 ** (n - 1), n)
+        self.register_buffer("frequency_bands", bands)
+
+    def output_size(self):
+        return 6 * self.num_encoding_functions + (3 if self.include_input else 0)
+
+
+class FlexibleNeRFModel(torch.nn.Module):
+    def __init__(self, num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6, num_encoding_fn_dir=4,
+                 include_input_xyz=True, include_input_dir=True, log_sampling_xyz=True, log_sampling_dir=True,
+                 use_viewdirs=True, **kwargs):
+        super().__init__()
+        self.arch = dict(num_layers=num_layers, hidden_size=hidden_size, skip_step=skip_step,
+                         num_encoding_fn_xyz=num_encoding_fn_xyz, num_encoding_fn_dir=num_encoding_fn_dir,
+                         include_input_xyz=include_input_xyz, include_input_dir=include_input_dir,
+                         log_sampling_xyz=log_sampling_xyz, log_sampling_dir=log_sampling_dir, use_viewdirs=use_viewdirs)
+        self.encode_xyz = PositionalEncoding(num_encoding_fn_xyz, include_input_xyz, log_sampling_xyz)
+        self.encode_dir = PositionalEncoding(num_encoding_fn_dir, include_input_dir, log_sampling_dir)
+        self.dim_xyz = self.encode_xyz.output_size()
+        self.dim_dir = self.encode_dir.output_size() if use_viewdirs else 0
+        self.skip_step, self.num_layers, self.use_viewdirs = skip_step, num_layers, use_viewdirs
+        Lin = torch.nn.Linear
+        self.layer1 = Lin(self.dim_xyz, hidden_size)
+        self.layers_xyz = torch.nn.ModuleList()
+        for i in range(num_layers - 1):
+            skip = i % skip_step == 0 and i > 0 and i != num_layers - 1
+            self.layers_xyz.append(Lin(hidden_size + (self.dim_xyz if skip else 0), hidden_size))
+        if use_viewdirs:
+            self.layers_dir = torch.nn.ModuleList([Lin(self.dim_dir + hidden_size, hidden_size // 2)])
+            self.fc_alpha = Lin(hidden_size, 1)
+            self.fc_rgb = Lin(hidden_size // 2, 3)
+            self.fc_feat = Lin(hidden_size, hidden_size)
+        else:
+            self.fc_out = Lin(hidden_size, 4)
+        self._owner = None      # (parent model, slot) once bound
+
+    def bind(self, owner, which):
+        object.__setattr__(self, "_owner", (owner, which))
+
+    def weight_version(self):
+        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+
+    def forward(self, ray_points, ray_directions=None):
+        """(…,3),(…,3) -> (…,4) = [sigmoid rgb, raw sigma]  (src/nerf/models.py:60-80)."""
+        if self._owner is None:
+            raise L.NmError("FlexibleNeRFModel must belong to a NeRFModel/BuFFModel (it runs on that model's engine)")
+        owner, which = self._owner
+        return owner._engine().point_mlp(which, ray_points, ray_directions)
+
+
+class _Holder(torch.nn.Module):
+    pass
+
+
+def _cfg_get(node, path, default=None):
+    for p in path.split("."):
+        if not isinstance(node, dict) or p not in node:
+            return default
+        node = node[p]
+    return node
+
+
+class BaseModel(torch.nn.Module):
+    """Shared part of NeRFModel / BuFFModel (src/models/model_base.py:17-73), minus the Lightning trainer hooks."""
+
+    precision = L.PREC_EXACT
+    act_scale_log2 = 0
+
+    def __init__(self, cfg, *args, **kwargs):
+        super().__init__()
+        self.cfg = CfgNode(nest_dict(dict(cfg), sep="."))
+        self.hparams = flatten_dict(self.cfg, sep=".")
+        vr = _Holder()                                   # VolumeRenderer buffers/attributes (modules.py:51-65)
+        vr.train_radiance_field_noise_std = float(_cfg_get(self.cfg, "nerf.train.radiance_field_noise_std", 0.0))
+        vr.val_radiance_field_noise_std = float(_cfg_get(self.cfg, "nerf.validation.radiance_field_noise_std", 0.0))
+        vr.white_background = bool(_cfg_get(self.cfg, "dataset.white_background", False))
+        vr.attenuation_threshold = 1e-5                  # model_base.py:28-33
+        vr.register_buffer("one_e_10", torch.tensor([1e10]))
+        self.volume_renderer = vr
+        self._eng: Optional[Engine] = None
+        self._synced = {}
+        self._cuda_index = 0
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _nets(self):
+        raise NotImplementedError
+
+    def _render_settings(self) -> RenderSettings:
+        raise NotImplementedError
+
+    def cuda(self, device=None):
+        if isinstance(device, int):
+            self._cuda_index = device
+        return super().cuda(device)
+
+    def to(self, *args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, (str, torch.device)) and torch.device(a).type == "cuda" and torch.device(a).index is not None:
+                self._cuda_index = torch.device(a).index
+        return super().to(*args, **kwargs)
+
+    def _engine(self) -> Engine:
+        nets = self._nets()
+        if self._eng is None:
+            coarse = nets[0].arch
+            fine = nets[1].arch if len(nets) > 1 and nets[1] is not None else None
+            self._eng = Engine(coarse, fine, self._render_settings(), device=self._cuda_index)
+            self._after_engine_created()
+        for which, net in enumerate(nets):
+            if net is None:
+                continue
+            v = net.weight_version()
+            if self._synced.get(which) != v:
+                sd = {k: t for k, t in net.state_dict().items()}
+                self._eng.load_weights(which, sd)
+                self._synced[which] = v
+        s = self._render_settings()
+        if s != self._eng.settings:
+            self._eng.configure(**s.__dict__)
+        return self._eng
+
+    def _after_engine_created(self):
+        pass
+
+    def _mode_cfg(self):
+        return self.cfg.nerf.train if self.training else self.cfg.nerf.validation
+
+    # ------------------------------------------------------------------ reference surface
+    def get_model(self):
+        raise NotImplementedError
+
+    def query(self, ray_batch):
+        raise NotImplementedError
+
+    def sample_points(self, points, rays=None, **kwargs):
+        results = self.get_model().forward(points, rays, **kwargs)
+        return results[0] if isinstance(results, tuple) else results
+
+    @staticmethod
+    def _unpack(x):
+        ray_origins, ray_directions, bounds = x
+        near, far = bounds
+        return ray_origins, ray_directions, near, far
+
+    # ------------------------------------------------------------------ checkpoints
+    @classmethod
+    def load_from_checkpoint(cls, path, map_location="cpu", **kw):
+        """PyTorch-Lightning 0.9 checkpoint (SURVEY section 5 'Checkpoint / resume') without Lightning installed."""
+        ck = load_lightning_checkpoint(path)
+        model = cls(dict(ck["hyper_parameters"]))
+        if hasattr(model, "on_load_checkpoint"):
+            model.on_load_checkpoint(ck)
+        model.load_state_dict(ck["state_dict"], strict=False)
+        return model
+
+    @classmethod
+    def from_npz(cls, cfg, weights: dict):
+        """weights: {'coarse.<key>': tensor, 'fine.<key>': tensor, 'sample_pdf_u': ..., 'voxels': ...} (tests/golden)."""
+        model = cls(cfg)
+        nets = model._nets()
+        for prefix, net in zip(("coarse.", "fine."), nets):
+            if net is None:
+                continue
+            sd = {k[len(prefix):]: torch.as_tensor(v) for k, v in weights.items() if k.startswith(prefix)}
+            net.load_state_dict(sd, strict=False)
+        if "sample_pdf_u" in weights and hasattr(model, "sample_pdf"):
+            model.sample_pdf.u.copy_(torch.as_tensor(weights["sample_pdf_u"]))
+        if "voxels" in weights and hasattr(model, "tree"):
+            model.tree.voxels = torch.as_tensor(weights["voxels"]).float()
+        return model
+
+
+class NeRFModel(BaseModel):
+    def __init__(self, cfg, *args, **kwargs):
+        super().__init__(cfg, *args, **kwargs)
+        m = self.cfg.models
+        if m.get("coarse_type", "FlexibleNeRFModel") != "FlexibleNeRFModel":
+            raise L.NmError(f"models.coarse_type {m.coarse_type!r}: only FlexibleNeRFModel is on the fused path")
+        self.model_coarse = FlexibleNeRFModel(**m.coarse)
+        self.model_fine = None
+        if "fine" in m and m.get("use_fine", False):
+            self.model_fine = FlexibleNeRFModel(**m.fine)
+        self.model_coarse.bind(self, L.NET_COARSE)
+        if self.model_fine is not None:
+            self.model_fine.bind(self, L.NET_FINE)
+        sp = _Holder()                                   # SamplePDF buffer (modules.py:190-195)
+        sp.num_samples = int(self.cfg.nerf.train.num_fine)
+        sp.register_buffer("u", torch.linspace(0.0, 1.0, steps=sp.num_samples))
+        self.sample_pdf = sp
+        self.sampler = _Holder()                         # RaySampleInterval (non-persistent buffer, modules.py:154-155)
+        self.sampler.count = int(self.cfg.nerf.train.num_coarse)
+        self.sampler.point_intervals = torch.linspace(0.0, 1.0, self.sampler.count)[None, :]
+
+    def _nets(self):
+        return [self.model_coarse, self.model_fine]
+
+    def get_model(self):
+        return self.model_fine if self.model_fine is not None else self.model_coarse
+
+    def _render_settings(self):
+        mc = self.cfg.nerf.train if self.model_coarse.training else self.cfg.nerf.validation
+        vr = self.volume_renderer
+        return RenderSettings(
+            num_coarse=int(self.cfg.nerf.train.num_coarse),            # sized from .train even in eval (quirk B.1)
+            num_fine=int(self.cfg.nerf.train.num_fine) if self.model_fine is not None else 0,
+            lindisp=bool(mc.lindisp), perturb=bool(mc.perturb), white_background=vr.white_background,
+            noise_std=vr.train_radiance_field_noise_std if self.training else vr.val_radiance_field_noise_std,
+            attenuation_threshold=vr.attenuation_threshold, precision=self.precision, act_scale_log2=self.act_scale_log2)
+
+    def _after_engine_created(self):
+        self._eng.set_tables(self.sampler.point_intervals[0], self.sample_pdf.u if self.model_fine is not None else None)
+
+    def forward(self, x, seed=0):
+        ray_origins, ray_directions, near, far = self._unpack(x)
+        eng = self._engine()
+        want = ["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights"]
+        if self.model_fine is not None:
+            want += ["coarse_rgb", "coarse_acc", "coarse_disp", "coarse_weights"]
+        o = eng.render_rays(ray_origins, ray_directions, near, far, training=self.training, seed=seed, want=want)
+        main = OutputBundle(o["rgb"], o["depth"], o["weights"], o["mask_weights"], o["acc"], o["disp"], o["depth_raw"])
+        if self.model_fine is None:
+            return main, None
+        coarse = OutputBundle(rgb_map=o["coarse_rgb"], weights=o["coarse_weights"], acc_map=o["coarse_acc"],
+                              disp_map=o["coarse_disp"])
+        return coarse, main
+
+    def query(self, ray_batch):
+        coarse_bundle, fine_bundle = self.forward(ray_batch)
+        return fine_bundle if fine_bundle is not None else coarse_bundle
+
+
+class Node:
+    """Unpickling target for the octree nodes stored in BuFF checkpoints (src/nerf/tree.py:4-36).  Only the flat
+    voxel tensor is used for inference; the node graph is kept as loaded so it can be re-serialised."""
+
+    def __init__(self, *a, **k):
+        pass
+
+
+class TreeSampling:
+    """Inference view of src/nerf/tree.py:39-358: holds `voxels` (V,2,3) and answers batch_ray_voxel_intersect."""
+
+    def __init__(self, config, device=None):
+        self.config = config
+        near, far = float(config.dataset.near), float(config.dataset.far)
+        mean = (near + far) / 2
+        # untrained default: the outer subdivision of the root box [near-mean, far-mean]^3 (tree.py:76-87)
+        n = int(_cfg_get(config, "tree.subdivision_outer_count", 1) or 1)
+        lo, size = near - mean, (far - near) / n
+        idx = torch.stack(torch.meshgrid(*([torch.arange(n)] * 3), indexing="ij"), -1).reshape(-1, 3).float()
+        self.voxels = torch.stack((lo + idx * size, lo + (idx + 1) * size), 1)
+        self.root, self.memm, self.counter = None, None, 1
+
+    def serialize(self):
+        return {"root": self.root, "voxels": self.voxels, "memm": self.memm, "counter": self.counter}
+
+    def deserialize(self, d):
+        self.root, self.voxels, self.memm, self.counter = d["root"], d["voxels"].float().cpu(), d["memm"], d["counter"]
+
+
+class BuFFModel(BaseModel):
+    def __init__(self, cfg, *args, **kwargs):
+        super().__init__(cfg, *args, **kwargs)
+        m = self.cfg.models
+        self.model = FlexibleNeRFModel(**m.coarse)
+        self.model.bind(self, L.NET_COARSE)
+        self.tree = TreeSampling(self.cfg)
+        self.sampler = _Holder()
+        self.sampler.count = int(self.cfg.nerf.train.num_coarse)
+        self.sampler.point_intervals = torch.linspace(0.0, 1.0, self.sampler.count)[None, :]
+        self._tree_id = None
+
+    def _nets(self):
+        return [self.model]
+
+    def get_model(self):
+        return self.model
+
+    def _render_settings(self):
+        mc = self.cfg.nerf.train if self.model.training else self.cfg.nerf.validation
+        vr = self.volume_renderer
+        return RenderSettings(
+            num_coarse=int(self.cfg.nerf.train.num_coarse), num_fine=0, lindisp=bool(mc.lindisp), perturb=bool(mc.perturb),
+            white_background=vr.white_background,
+            noise_std=vr.train_radiance_field_noise_std if self.training else vr.val_radiance_field_noise_std,
+            attenuation_threshold=vr.attenuation_threshold, precision=self.precision, act_scale_log2=self.act_scale_log2)
+
+    def _after_engine_created(self):
+        self._eng.set_tables(self.sampler.point_intervals[0], None)
+
+    def forward(self, x, seed=0):
+        ray_origins, ray_directions, near, far = self._unpack(x)
+        if torch.as_tensor(ray_origins).dim() < 2:
+            raise IndexError("BuFFModel needs ray origins of shape (1,3) or (R,3) (src/nerf/tree.py:231)")
+        eng = self._engine()
+        if self._tree_id != id(self.tree.voxels):
+            eng.set_tree(self.tree.voxels)
+            self._tree_id = id(self.tree.voxels)
+        o = eng.render_rays(ray_origins, ray_directions, near, far, training=self.training, buff=True, seed=seed,
+                            want=["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights", "t_vals"])
+        b = OutputBundle(o["rgb"], o["depth"], o["weights"], o["mask_weights"], o["acc"], o["disp"], o["depth_raw"])
+        b.t_vals = o["t_vals"]
+        return b
+
+    def query(self, ray_batch):
+        return self.forward(ray_batch)
+
+    def on_save_checkpoint(self, checkpoint):
+        checkpoint["tree"] = self.tree.serialize()
+
+    def on_load_checkpoint(self, checkpoint):
+        self.tree.deserialize(checkpoint["tree"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class _AttributeDict(dict):
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class _CkptUnpickler(pickle.Unpickler):
+    """Resolves the two foreign classes inside the shipped checkpoints without importing their packages:
+    pytorch_lightning.utilities.parsing.AttributeDict and nerf.tree.Node."""
+
+    def find_class(self, module, name):
+        if name == "AttributeDict" and module.startswith("pytorch_lightning"):
+            return _AttributeDict
+        if name == "Node" and module in ("nerf.tree", "tree"):
+            return Node
+        if module.startswith("nerf.cfgnode") or (module == "nerf" and name == "CfgNode"):
+            return CfgNode
+        return super().find_class(module, name)
+
+
+class _PickleModule:
+    __name__ = "nerfmeshes_b200_ckpt_pickle"
+    Unpickler = _CkptUnpickler
+    load = staticmethod(lambda f, **kw: _CkptUnpickler(f, **kw).load())
+    loads = staticmethod(lambda b, **kw: _CkptUnpickler(io.BytesIO(b), **kw).load())
+    dump, dumps, Pickler = pickle.dump, pickle.dumps, pickle.Pickler
+    HIGHEST_PROTOCOL, DEFAULT_PROTOCOL = pickle.HIGHEST_PROTOCOL, pickle.DEFAULT_PROTOCOL
+
+
+def load_lightning_checkpoint(path):
+    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=_PickleModule)
+
+
+def state_dict_to_npz(path, **tensors):
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in tensors.items()})

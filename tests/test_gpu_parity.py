@@ -1,0 +1,242 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden vectors.
+
+All tests need a B200 (`-m gpu`).  Tolerances (floating-point path; BASELINE.json north_star: RGB/depth <= 1e-4
+max-abs with fp32 accumulate):
+  * per-point network output, same inputs:      rgb <= 1e-4, raw sigma <= 1e-2 + 1e-4*|sigma|  (sigma spans +-4.6e3)
+  * composited maps, teacher-forced samples:    <= 1e-4
+  * end to end (samples re-derived on device):  <= 6e-4 max, the reference's own fp32-vs-fp64 floor
+    (5.7e-4), and <= 1e-4 at the 99th percentile
+  * index / placement work (AABB z-values, coarse t):  bit-exact
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NET = O.NetCfg()
+LEGO_CFG = {
+    "experiment.model": "NeRFModel", "dataset.near": 2, "dataset.far": 6, "dataset.white_background": False,
+    "models.coarse_type": "FlexibleNeRFModel", "models.fine_type": "FlexibleNeRFModel", "models.use_fine": True,
+    **{f"models.coarse.{k}": v for k, v in NET.__dict__.items()}, **{f"models.fine.{k}": v for k, v in NET.__dict__.items()},
+    "nerf.train.num_coarse": 64, "nerf.train.num_fine": 128, "nerf.train.perturb": False, "nerf.train.lindisp": False,
+    "nerf.train.radiance_field_noise_std": 0.2, "nerf.validation.num_coarse": 64, "nerf.validation.num_fine": 128,
+    "nerf.validation.perturb": False, "nerf.validation.lindisp": False, "nerf.validation.radiance_field_noise_std": 0.0,
+}
+BUFF_CFG = {**LEGO_CFG, "experiment.model": "BuFFModel", "models.use_fine": False, "nerf.train.num_coarse": 192,
+            "nerf.train.num_fine": 64, "nerf.validation.num_coarse": 192, "tree.subdivision_outer_count": 2}
+
+
+def close(a, b, atol, rtol=0.0, name=""):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    err = (a - b).abs()
+    bad = err > atol + rtol * b.abs()
+    assert not bool(bad.any()), f"{name}: max err {float(err.max()):.3e}, {int(bad.sum())} of {bad.numel()} outside tolerance"
+
+
+@pytest.fixture(scope="module")
+def lego_model():
+    import nerfmeshes_b200 as nm
+    z = load_npz("weights_lego_nerf.npz")
+    return nm.NeRFModel.from_npz(LEGO_CFG, z).eval()
+
+
+@pytest.fixture(scope="module")
+def fern_model():
+    import nerfmeshes_b200 as nm
+    z = load_npz("weights_fern_nerf.npz")
+    return nm.NeRFModel.from_npz(LEGO_CFG, z).eval()
+
+
+@pytest.fixture(scope="module")
+def buff_model():
+    import nerfmeshes_b200 as nm
+    z = load_npz("weights_lego_buff.npz")
+    return nm.BuFFModel.from_npz(BUFF_CFG, z).eval()
+
+
+# ----------------------------------------------------------------------------------------------------- fused MLP
+@pytest.mark.parametrize("prec", ["fp32", "exact"])
+@pytest.mark.parametrize("arch", [
+    dict(num_layers=8, hidden_size=256, num_encoding_fn_xyz=10, num_encoding_fn_dir=4),
+    dict(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6, num_encoding_fn_dir=4),            # the `tiny` net
+    dict(num_layers=6, hidden_size=256, skip_step=2, num_encoding_fn_xyz=8, num_encoding_fn_dir=2, include_input_dir=False),
+    dict(num_layers=3, hidden_size=128, num_encoding_fn_xyz=5, use_viewdirs=False, log_sampling_xyz=False),
+])
+def test_point_mlp_random_weights(arch, prec):
+    import nerfmeshes_b200 as nm
+    cfg = O.NetCfg(**{**dict(num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6, num_encoding_fn_dir=4), **arch})
+    sd = O.init_weights(cfg, seed=11)
+    eng = nm.Engine(cfg.__dict__, None, nm.RenderSettings(num_coarse=8, num_fine=0,
+                                                          precision=nm.PREC_FP32 if prec == "fp32" else nm.PREC_EXACT))
+    eng.load_weights(0, sd)
+    g = torch.Generator().manual_seed(5)
+    for M in (1, 127, 129, 4097):                              # ragged tails around the 128-point tile
+        pts = (torch.rand(M, 3, generator=g) * 2 - 1) * 2.5
+        dirs = torch.randn(M, 3, generator=g)                  # un-normalised on purpose
+        ref = O.flexible_nerf_forward(sd, cfg, pts, dirs)
+        out = eng.point_mlp(0, pts.cuda(), dirs.cuda())
+        close(out[:, :3], ref[:, :3], 2e-5, name=f"rgb M={M}")
+        close(out[:, 3], ref[:, 3], 2e-5, 1e-5, name=f"sigma M={M}")
+        sg = eng.point_mlp(0, pts.cuda(), dirs.cuda(), sigma_only=True)
+        close(sg, ref[:, 3], 2e-5, 1e-5, name=f"sigma-only M={M}")
+    # host-buffer entry point gives the same bits as the device-pointer one
+    out_h = eng.point_mlp(0, pts, dirs)
+    assert torch.equal(out_h, out.cpu())
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "exact"])
+def test_point_mlp_lego_checkpoint(lego_model, prec):
+    import nerfmeshes_b200 as nm
+    g = load_npz("golden_lego_nerf.npz")
+    lego_model.precision = nm.PREC_FP32 if prec == "fp32" else nm.PREC_EXACT
+    out = lego_model.sample_points(g["pts"].cuda(), g["pdirs"].cuda())
+    close(out[:, :3], g["sample_points_fine"][:, :3], 1e-4, name="rgb")
+    close(out[:, 3], g["sample_points_fine"][:, 3], 1e-2, 1e-4, name="sigma")
+    outc = lego_model.model_coarse(g["pts"].cuda(), g["pdirs"].cuda())
+    close(outc[:, 3], g["sample_points_coarse"][:, 3], 1e-2, 1e-4, name="coarse sigma")
+    lego_model.precision = nm.PREC_EXACT
+
+
+def test_fast_mode_is_worse_but_sane(lego_model):
+    """NM_PREC_FAST (single fp16 pass) is a comparison mode: must run, stay finite, and miss the exact target."""
+    import nerfmeshes_b200 as nm
+    g = load_npz("golden_lego_nerf.npz")
+    lego_model.precision = nm.PREC_FAST
+    out = lego_model.sample_points(g["pts"].cuda(), g["pdirs"].cuda())
+    lego_model.precision = nm.PREC_EXACT
+    assert bool(torch.isfinite(out).all())
+    err = (out.cpu()[:, 3] - g["sample_points_fine"][:, 3]).abs()
+    assert float(err.max()) < 30.0 and float(err.max()) > 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------- ray generation
+def test_ray_bundle_and_ndc():
+    import nerfmeshes_b200 as nm
+    g = load_npz("golden_raygen.npz")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    o, d = nm.get_ray_bundle(H, W, f, g["pose"])
+    close(o, g["origin"], 0, name="origin")
+    close(d, g["dirs"], 2e-7, name="dirs")
+    on, dn = nm.ndc_rays(H, W, f, 1.0, tform_cam2world=g["pose"])
+    close(on, g["ndc_o"], 5e-6, 5e-6, name="ndc origins")
+    close(dn, g["ndc_d"], 5e-6, 5e-6, name="ndc dirs")
+    assert np.array_equal(nm.pose_spherical(30.0, -30.0, 4.0), O.pose_spherical(30.0, -30.0, 4.0).numpy())
+
+
+# ----------------------------------------------------------------------------------------------------- NeRF pipeline
+def test_lego_pipeline_teacher_forced(lego_model):
+    """Fine pass on the reference's own sample positions: isolates MLP + compositor from sample-placement chaos."""
+    g = load_npz("golden_lego_nerf.npz")
+    eng = lego_model._engine()
+    o = eng.render_rays(g["origin"].cuda(), g["dirs"].cuda(), 2.0, 6.0, teacher_t=g["t_fine"].cuda(),
+                        want=["rgb", "acc", "disp", "depth_raw", "weights", "mask_weights"])
+    close(o["rgb"], g["fine_rgb"], 1e-4, name="rgb")
+    close(o["acc"], g["fine_acc"], 1e-4, name="acc")
+    close(o["disp"], g["fine_disp"], 1e-4, name="disp")
+    close(o["weights"], g["fine_weights"], 1e-4, name="weights")
+    assert float((o["mask_weights"].cpu() != g["fine_mask_weights"]).float().mean()) < 2e-3
+
+
+def test_lego_pipeline_end_to_end(lego_model):
+    g = load_npz("golden_lego_nerf.npz")
+    coarse, fine = lego_model.forward((g["origin"].cuda(), g["dirs"].cuda(), g["bounds"]))
+    close(coarse.rgb_map, g["coarse_rgb"], 1e-4, name="coarse rgb")
+    close(coarse.weights, g["coarse_weights"], 1e-4, name="coarse weights")
+    err = (fine.rgb_map.cpu() - g["fine_rgb"]).abs().flatten()
+    assert float(err.max()) <= 6e-4, float(err.max())
+    assert float(err.quantile(0.99)) <= 1e-4
+    close(fine.acc_map, g["fine_acc"], 6e-4, name="acc")
+    close(fine.disp_map, g["fine_disp"], 6e-4, name="disp")
+    # query() returns the fine bundle; CPU tensors go through the host-buffer C-ABI call with identical results
+    q = lego_model.query((g["origin"], g["dirs"], g["bounds"]))
+    assert not q.rgb_map.is_cuda and torch.equal(q.rgb_map, fine.rgb_map.cpu())
+    # coarse sample positions are pure index arithmetic on the table: bit-exact
+    o = lego_model._engine().render_rays(g["origin"].cuda(), g["dirs"].cuda(), 2.0, 6.0, want=["t_vals", "rgb"])
+    tf = o["t_vals"].cpu()
+    close(tf, g["t_fine"], 5e-4, name="t_fine")
+    assert bool((tf[:, 1:] >= tf[:, :-1]).all())                  # sortedness (size-independent property)
+
+
+def test_fern_ndc_pipeline(fern_model):
+    g = load_npz("golden_fern_nerf.npz")
+    coarse, fine = fern_model.forward((g["origins"].cuda(), g["dirs"].cuda(), g["bounds"]))
+    close(coarse.rgb_map, g["coarse_rgb"], 1e-4, name="coarse rgb")
+    err = (fine.rgb_map.cpu() - g["fine_rgb"]).abs().flatten()
+    assert float(err.max()) <= 6e-4, float(err.max())
+    o = fern_model._engine().render_rays(g["origins"].cuda(), g["dirs"].cuda(), 0.0, 1.0, teacher_t=g["t_fine"].cuda(),
+                                         want=["rgb", "acc"])
+    close(o["rgb"], g["fine_rgb"], 1e-4, name="teacher-forced rgb")
+
+
+def test_render_image_matches_ray_batches(lego_model):
+    """nm_render_image (rays generated on device from the pose) == nm_render_rays on the oracle's rays."""
+    g = load_npz("golden_lego_nerf.npz")
+    H, W, f = 40, 48, 55.0
+    pose = g["pose"]
+    o, d = O.get_ray_bundle(H, W, f, pose)
+    eng = lego_model._engine()
+    img = eng.render_image(pose, H, W, f, 2.0, 6.0, want=["rgb", "acc", "disp"])
+    ref = eng.render_rays(o.cuda(), d.reshape(-1, 3).cuda(), 2.0, 6.0, want=["rgb", "acc", "disp"])
+    close(img["rgb"], ref["rgb"], 2e-4, name="image rgb")
+    rows = eng.render_image(pose, H, W, f, 2.0, 6.0, rows=(10, 25), want=["rgb"])
+    assert torch.equal(rows["rgb"], img["rgb"][10 * W:25 * W])    # row shards are bit-identical to the full image
+    host = eng.render_image(pose, H, W, f, 2.0, 6.0, want=["rgb"], to_host=True)
+    assert torch.equal(host["rgb"], img["rgb"].cpu())
+
+
+def test_perturb_and_noise_are_distributional(lego_model):
+    g = load_npz("golden_lego_nerf.npz")
+    lego_model.train()
+    try:
+        lego_model.cfg.nerf.train.perturb = True
+        c1, f1 = lego_model.forward((g["origin"].cuda(), g["dirs"].cuda(), g["bounds"]), seed=1)
+        c2, f2 = lego_model.forward((g["origin"].cuda(), g["dirs"].cuda(), g["bounds"]), seed=2)
+        assert bool(torch.isfinite(f1.rgb_map).all()) and not torch.equal(f1.rgb_map, f2.rgb_map)
+        assert float((f1.rgb_map.cpu() - g["fine_rgb"]).abs().mean()) < 0.05
+        assert float((f1.depth_map - f1.depth_raw).abs().max()) == 0.0          # no eval-mode threshold when training
+    finally:
+        lego_model.cfg.nerf.train.perturb = False
+        lego_model.eval()
+
+
+# ----------------------------------------------------------------------------------------------------- BuFF
+def test_buff_pipeline(buff_model):
+    g = load_npz("golden_lego_buff.npz")
+    b = buff_model.forward((g["origin"][None].cuda(), g["dirs"].cuda(), g["bounds"]))
+    z = b.t_vals.cpu()
+    mask = g["ray_mask"].bool()
+    assert int(mask.sum()) >= 60 and int((~mask).sum()) >= 2
+    assert torch.equal(z[mask], g["z"][mask]), float((z[mask] - g["z"][mask]).abs().max())   # placement: bit-exact
+    assert torch.equal(z[~mask], g["z"][~mask])                                                # uniform fallback rows
+    close(b.rgb_map, g["out_rgb"], 1e-4, name="rgb")
+    close(b.acc_map, g["out_acc"], 1e-4, name="acc")
+    close(b.disp_map, g["out_disp"], 1e-4, name="disp")
+    with pytest.raises(IndexError):
+        buff_model.forward((g["origin"].cuda(), g["dirs"].cuda(), g["bounds"]))                # (3,) origin: reference errors too
+
+
+# ----------------------------------------------------------------------------------------------------- grid sweep
+def test_grid_sigma_and_iso(lego_model):
+    import nerfmeshes_b200 as nm
+    g = load_npz("golden_lego_grid.npz")
+
+    class A:
+        limit, res, iso_level = float(g["limit"]), int(g["res"]), float(g["iso_level"])
+    rad = nm.extract_radiance(lego_model, A, "cuda", A.res)
+    close(rad[..., :3], g["radiance"][..., :3], 1e-4, name="grid rgb")
+    close(rad[..., 3], g["radiance"][..., 3], 1e-2, 1e-4, name="grid sigma")
+    sig = nm.extract_radiance(lego_model, A, "cuda", A.res, sigma_only=True)
+    close(sig, g["radiance"][..., 3], 1e-2, 1e-4, name="sigma-only grid")
+    slab = nm.extract_radiance(lego_model, A, "cuda", A.res, sigma_only=True, slab=(5, 9))
+    assert torch.equal(slab, sig[5:9])                                                           # x-slabs are bit-identical
+    iso = nm.extract_iso_level(sig, A, lego_model._engine())
+    assert np.float32(iso) == np.float32(g["iso_value"])
+    mn, mx, sd = lego_model._engine().volume_stats(sig)
+    s = sig.cpu().numpy()
+    assert mn == s.min() and mx == s.max() and abs(sd - s.std()) <= 1e-4 * s.std()
