@@ -162,6 +162,13 @@ int nm_render_image_host(NmHandle h, const float* pose_host, int H, int W, float
 int nm_point_mlp_host(NmHandle h, int which, const float* pts_host, const float* dirs_host, int64_t M,
                       float* out_host, int sigma_only);
 
+/* ---- host-only debugging aid (no CUDA): the layer program + tensor-core weight stream nm_load_weights would
+ * upload, for CPU tests of the schedule / swizzle logic.  program_out receives the internal NetProgram struct
+ * (nerfmeshes_b200/csrc/nm_program.h). */
+int nm_debug_pack(const NmNetDesc* desc, int n_tensors, const char* const* names, const float* const* tensors_host,
+                  const int64_t* numel, int sigma_only, void* program_out, size_t program_cap, uint8_t* pack_out,
+                  size_t pack_cap, size_t* pack_need);
+
 /* ---- introspection ---------------------------------------------------------------------------------- */
 /* number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t nm_launch_count(NmHandle h);

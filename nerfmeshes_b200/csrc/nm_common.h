@@ -73,6 +73,8 @@ struct WeightSource {
 };
 int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net);
 void free_network(NetDev* net);
+int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, NetProgram* prog, uint8_t* out, size_t cap,
+               size_t* need);
 
 // kernel launchers (return 0 / <0; count launches via *launches)
 int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,

@@ -212,6 +212,20 @@ static int pack_stream(const NetProgram& p, const std::vector<LayerNames>& names
   return 0;
 }
 
+// Host-only view of the packer for CPU tests of the schedule / swizzle logic (no CUDA calls).
+int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, NetProgram* prog, uint8_t* out, size_t cap,
+               size_t* need) {
+  std::vector<LayerNames> names;
+  if (int e = build_one(d, sigma_only, prog, &names)) return e;
+  *need = (size_t)prog->n_blocks * kStageBytes;
+  if (!out) return 0;
+  NM_CHECK(cap >= *need, "buffer too small");
+  std::vector<uint8_t> pk;
+  if (int e = pack_stream(*prog, names, src, &pk)) return e;
+  memcpy(out, pk.data(), pk.size());
+  return 0;
+}
+
 void free_network(NetDev* net) {
   cudaFree(net->d_full); cudaFree(net->d_sigma); cudaFree(net->d_wpack_full); cudaFree(net->d_wpack_sigma);
   cudaFree(net->d_bias); cudaFree(net->d_head); cudaFree(net->d_wt);

@@ -1,0 +1,229 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, fails loudly without a GPU, and the
+host logic (layer program, tensor-core schedule, weight swizzle/packing, config containers, checkpoint reader)
+is right.  No GPU compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_npz, net_weights
+from oracle import nerf_oracle as O
+
+import nerfmeshes_b200 as nm
+from nerfmeshes_b200 import _lib as L
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    hdr = open(os.path.join(ROOT, "include", "nerfmeshes_b200.h")).read()
+    declared = set(re.findall(r"\b(nm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(L.exported_symbols()) == declared
+    assert lib.nm_version() == 100
+
+
+def test_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = L.load()
+    assert lib.nm_device_check(0) != 0 and lib.nm_last_error()
+    with pytest.raises(L.NmError):
+        nm.Engine(dict(O.NetCfg().__dict__), None, nm.RenderSettings())
+    cfg = {"models.coarse_type": "FlexibleNeRFModel", "models.use_fine": False, **{f"models.coarse.{k}": v for k, v in O.NetCfg().__dict__.items()},
+           "nerf.train.num_coarse": 64, "nerf.train.num_fine": 0, "nerf.train.perturb": False, "nerf.train.lindisp": False,
+           "nerf.validation.perturb": False, "nerf.validation.lindisp": False, "dataset.near": 2, "dataset.far": 6}
+    m = nm.NeRFModel(cfg).eval()
+    with pytest.raises(L.NmError):                       # no silent CPU fallback on the product path
+        m.query((torch.zeros(3), torch.randn(4, 3), torch.tensor([2.0, 6.0])))
+
+
+# ------------------------------------------------------------------------------------------ program + packing
+class LayerProg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_out", "k_act", "pe_src", "k_pe", "relu", "kind", "is_final", "bias_off",
+                                         "head_off", "blk_begin", "blk_end", "wt_off")]
+
+
+class BlockProg(C.Structure):
+    _fields_ = [(n, C.c_uint8) for n in ("src", "kb", "nc", "ksteps", "group", "first", "last", "pad")]
+
+
+class NetProgram(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_layers", "n_blocks", "hidden", "dim_xyz", "dim_dir", "L_xyz", "L_dir", "inc_xyz",
+                                         "inc_dir", "n_bias", "n_head")] + \
+               [("freq_xyz", C.c_float * 16), ("freq_dir", C.c_float * 16), ("layers", LayerProg * 24), ("blocks", BlockProg * 256)]
+
+
+def debug_pack(cfg: O.NetCfg, sd, sigma_only=False):
+    lib = L.load()
+    desc = nm.engine.net_desc(**cfg.__dict__)
+    names = [k.encode() for k in sd]
+    arrs = [np.ascontiguousarray(v.numpy(), dtype=np.float32) for v in sd.values()]
+    n = len(names)
+    prog = NetProgram()
+    need = C.c_size_t(0)
+    args = (C.byref(desc), n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*[a.ctypes.data for a in arrs]),
+            (C.c_int64 * n)(*[a.size for a in arrs]), int(sigma_only), C.byref(prog), C.sizeof(prog))
+    L.check(lib.nm_debug_pack(*args, None, 0, C.byref(need)))
+    buf = np.zeros(need.value, dtype=np.uint8)
+    L.check(lib.nm_debug_pack(*args, buf.ctypes.data, buf.size, C.byref(need)))
+    return prog, buf
+
+
+def unswizzle(tile_bytes):
+    """8 KB stage half -> (64 rows, 64 k) fp16, inverse of the 128B-swizzled K-major layout."""
+    t = tile_bytes.view(np.float16).reshape(64, 8, 8)            # row, 16-byte chunk position, 8 halfs
+    out = np.empty((64, 64), dtype=np.float16)
+    for r in range(64):
+        for c in range(8):
+            out[r, c * 8:(c + 1) * 8] = t[r, c ^ (r & 7)]
+    return out
+
+
+WEIGHT_NAMES = {0: "layer1"}
+
+
+def layer_weight_names(cfg: O.NetCfg, sigma_only):
+    names = ["layer1"] + [f"layers_xyz.{i}" for i in range(cfg.num_layers - 1)]
+    if cfg.use_viewdirs and not sigma_only:
+        names += ["fc_feat", "layers_dir.0"]
+    return names
+
+
+@pytest.mark.parametrize("arch,sigma_only", [
+    (dict(), False), (dict(), True),
+    (dict(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6), False),
+    (dict(num_layers=6, hidden_size=256, skip_step=2, num_encoding_fn_xyz=8, num_encoding_fn_dir=2, include_input_dir=False), False),
+    (dict(num_layers=3, hidden_size=128, num_encoding_fn_xyz=5, use_viewdirs=False), False),
+    (dict(num_layers=1, hidden_size=128, num_encoding_fn_xyz=4, use_viewdirs=False), False),
+])
+def test_schedule_and_packing_reproduce_each_linear_layer(arch, sigma_only):
+    """Replays the tensor-core block schedule on the CPU with the packed (un-swizzled) hi+lo stages and checks
+    (i) every accumulator chunk is started exactly once and finished exactly once, (ii) each block only uses inputs
+    the previous layer's epilogue has released (group rule), (iii) the in-place A-operand rule, and (iv) the result
+    equals x @ W.T for the reference weights to fp16-split precision."""
+    cfg = O.NetCfg(**{**O.NetCfg().__dict__, **arch})
+    sd = O.init_weights(cfg, seed=3)
+    prog, pack = debug_pack(cfg, sd, sigma_only)
+    names = layer_weight_names(cfg, sigma_only)
+    assert prog.n_layers == len(names)
+    assert prog.dim_xyz == cfg.dim_xyz and prog.dim_dir == cfg.dim_dir
+    np.testing.assert_array_equal(np.array(prog.freq_xyz[:cfg.num_encoding_fn_xyz]),
+                                  O.frequency_bands(cfg.num_encoding_fn_xyz, cfg.log_sampling_xyz).numpy())
+    rng = np.random.default_rng(0)
+    total_blocks = 0
+    for li, wname in enumerate(names):
+        Lp = prog.layers[li]
+        W = sd[wname + ".weight"].numpy().astype(np.float64)
+        assert W.shape == (Lp.n_out, Lp.k_act + Lp.k_pe)
+        x_act = rng.standard_normal((128, Lp.k_act))
+        x_pe = rng.standard_normal((128, Lp.k_pe))
+        D = np.full((128, Lp.n_out), np.nan)
+        done = [False] * 4
+        seen = set()
+        last_of_chunk = {}
+        for b in range(Lp.blk_begin, Lp.blk_end):
+            B = prog.blocks[b]
+            st = pack[b * 16384:(b + 1) * 16384]
+            w = unswizzle(st[:8192]).astype(np.float64) + unswizzle(st[8192:]).astype(np.float64)      # (64 n, 64 k)
+            if B.src == 0:
+                a = x_act[:, B.kb * 64:(B.kb + 1) * 64]
+                assert B.group >= max(B.kb, B.nc) and B.ksteps == 4
+                key = ("act", B.kb, B.nc)
+            else:
+                assert B.src == Lp.pe_src and B.kb == 0 and B.group >= B.nc
+                a = np.zeros((128, 64)); a[:, :Lp.k_pe] = x_pe
+                assert B.ksteps * 16 >= Lp.k_pe
+                assert not w[:, B.ksteps * 16:].any()            # K columns the kernel skips hold zeros
+                key = ("pe", 0, B.nc)
+            assert key not in seen
+            seen.add(key)
+            blk = a @ w.T
+            cols = slice(B.nc * 64, (B.nc + 1) * 64)
+            assert not done[B.nc]
+            if B.first:
+                assert np.isnan(D[:, cols]).all()
+                D[:, cols] = blk
+            else:
+                assert not np.isnan(D[:, cols]).any()
+                D[:, cols] += blk
+            if B.last:
+                done[B.nc] = True
+                last_of_chunk[B.nc] = b
+        assert all(done[:Lp.n_out // 64])
+        assert len(seen) == (Lp.k_act // 64 + (1 if Lp.pe_src else 0)) * (Lp.n_out // 64)
+        ref = np.concatenate([x_act, x_pe], 1) @ W.T
+        np.testing.assert_allclose(D, ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+        # in-place A operand: all readers of activation K-block n are issued no later than the block that completes chunk n
+        for b in range(Lp.blk_begin, Lp.blk_end):
+            B = prog.blocks[b]
+            if B.src == 0 and B.kb in last_of_chunk:
+                assert b <= last_of_chunk[B.kb]
+        total_blocks += Lp.blk_end - Lp.blk_begin
+    assert total_blocks == prog.n_blocks
+    if not arch and not sigma_only:
+        assert prog.n_blocks == 146            # 2.39 MB of fp16 hi+lo stages per 8x256 network
+
+
+def test_heads_and_flags():
+    cfg = O.NetCfg()
+    prog, _ = debug_pack(cfg, O.init_weights(cfg, 1))
+    kinds = [prog.layers[i].kind for i in range(prog.n_layers)]
+    assert kinds == [0] * 7 + [1, 0, 2]                              # sigma head on layers_xyz.6, rgb head on layers_dir.0
+    assert [prog.layers[i].relu for i in range(prog.n_layers)] == [0] + [1] * 9     # layer1 has no activation
+    assert [prog.layers[i].pe_src for i in range(prog.n_layers)] == [1, 0, 0, 0, 0, 1, 0, 0, 0, 2]   # skip at layers_xyz.4
+    assert prog.layers[prog.n_layers - 1].is_final == 1 and prog.layers[9].n_out == 128
+    sig, _ = debug_pack(cfg, O.init_weights(cfg, 1), sigma_only=True)
+    assert sig.n_layers == 8 and sig.layers[7].is_final == 1 and sig.layers[7].kind == 1
+
+
+def test_unsupported_shapes_are_rejected():
+    lib = L.load()
+    bad = nm.engine.net_desc(**{**O.NetCfg().__dict__, "hidden_size": 192})
+    prog, need = NetProgram(), C.c_size_t(0)
+    rc = lib.nm_debug_pack(C.byref(bad), 0, None, None, None, 0, C.byref(prog), C.sizeof(prog), None, 0, C.byref(need))
+    assert rc != 0 and b"hidden_size" in lib.nm_last_error()
+
+
+# ------------------------------------------------------------------------------------------ host mirror
+def test_cfgnode_roundtrip():
+    flat = {"a.b.c": 1, "a.b.d": 2, "e": 3}
+    nested = nm.nest_dict(flat)
+    assert nested == {"a": {"b": {"c": 1, "d": 2}}, "e": 3}
+    node = nm.CfgNode(nested)
+    assert node.a.b.d == 2 and node.e == 3
+    assert nm.flatten_dict(node) == flat
+    with pytest.raises(AttributeError):
+        node.missing
+
+
+def test_model_state_dict_matches_reference_checkpoint_keys():
+    """The weight ABI: our modules expose exactly the reference's state-dict keys and shapes."""
+    from test_gpu_parity import LEGO_CFG, BUFF_CFG
+    z = load_npz("weights_lego_nerf.npz")
+    m = nm.NeRFModel.from_npz(LEGO_CFG, z)
+    sd = m.state_dict()
+    for prefix, key in (("model_coarse.", "coarse"), ("model_fine.", "fine")):
+        for k, v in net_weights(z, key).items():
+            assert torch.equal(sd[prefix + k], v), k
+    assert "sample_pdf.u" in sd and "volume_renderer.one_e_10" in sd and "model_coarse.encode_xyz.frequency_bands" in sd
+    assert torch.equal(sd["sample_pdf.u"], z["sample_pdf_u"])
+    zb = load_npz("weights_lego_buff.npz")
+    b = nm.BuFFModel.from_npz(BUFF_CFG, zb)
+    assert b.tree.voxels.shape == (1533, 2, 3) and "model.layers_xyz.4.weight" in b.state_dict()
+    assert m.get_model() is m.model_fine and b.get_model() is b.model
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/pretrained"), reason="reference checkpoints not on this machine")
+def test_lightning_checkpoint_reader():
+    p = "/root/reference/pretrained/{}/default/version_0/checkpoints/model_last.ckpt"
+    m = nm.NeRFModel.load_from_checkpoint(p.format("colab-lego-nerf-high-res"))
+    z = load_npz("weights_lego_nerf.npz")
+    assert torch.equal(m.model_fine.layers_xyz[4].weight.data, z["fine.layers_xyz.4.weight"])
+    assert m.cfg.nerf.train.num_coarse == 64 and m.cfg.experiment.model == "NeRFModel"
+    b = nm.BuFFModel.load_from_checkpoint(p.format("buff-synthetic-lego"))
+    assert torch.equal(b.tree.voxels, load_npz("weights_lego_buff.npz")["voxels"])
