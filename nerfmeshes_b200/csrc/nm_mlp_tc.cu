@@ -11,7 +11,8 @@
 // RGB against fp32, where plain fp16 gives 3.3e-3).  NM_PREC_FAST issues only xh*Wh.
 //
 // CTA = one 128-point tile at a time (TMEM lane = point), 14 warps:
-//   warps 0-7   epilogue: tcgen05.ld accumulator chunk -> +bias, ReLU, heads -> fp16 hi/lo -> tcgen05.st A operand
+//   warps 0-7   epilogue (two sets of 4, one warp per TMEM lane quarter; set s converts accumulator chunks s, s+2):
+//               tcgen05.ld chunk -> +bias, ReLU, heads -> fp16 hi/lo -> tcgen05.st A operand
 //   warps 8-11  front-end: fetch/synthesise the NEXT tile's points, positional encoding -> swizzled smem A tiles
 //   warp 12     producer: cp.async.bulk weight stages (16 KB = one 64x64 block, hi|lo) into the ring
 //   warp 13     MMA issuer (one lane) + TMEM allocator
@@ -19,6 +20,8 @@
 // A layer is issued as 64x64 blocks (M=128,N=64,K=16 MMAs) in the order nm_program.cu derives, which lets layer
 // l+1 start as soon as the epilogue has converted the first 64 columns of layer l (see the schedule comment there).
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "nm_common.h"
 #include "nm_frontend.cuh"
@@ -51,6 +54,7 @@ struct TcParams {
   int num_stages;
   long long n_tiles;
   int* err;
+  int dbg;   // bring-up switches (env NM_TC_DEBUG): 1 = no MMA issue, 2 = no epilogue math, 4 = no weight copies
   uint32_t off_pe, off_bias, off_head, off_layers, off_blocks, off_red, off_bars;
 };
 
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     if (sbase & 1023u) { atomicExch(P.err, ERR_ALIGN); __trap(); }
     for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(bars + kBarWFull + 8 * i, 1); ptx::mbar_init(bars + kBarWEmpty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bars + kBarPeFull + 8 * i, 128); ptx::mbar_init(bars + kBarPeEmpty + 8 * i, 1); }
-    for (int i = 0; i < 4; ++i) { ptx::mbar_init(bars + kBarChunk + 8 * i, kEpiWarps * 32); ptx::mbar_init(bars + kBarDFull + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(bars + kBarChunk + 8 * i, 4); ptx::mbar_init(bars + kBarDFull + 8 * i, 1); }
     ptx::fence_mbar_init();
   }
   {
@@ -136,61 +140,69 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
         const int heads = L.kind == KIND_SIGMA ? 1 : (L.kind == KIND_RGB ? 3 : (L.kind == KIND_OUT4 ? 4 : 0));
         float part[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int n = 0; n < 4; ++n) {
+        // Warp set `hcol` (warps 4*hcol..4*hcol+3, one per TMEM lane quarter) owns accumulator chunks hcol and hcol+2:
+        // the two sets convert neighbouring chunks concurrently, so the commit -> wake -> convert -> arrive latency of
+        // one chunk overlaps the next chunk's instead of adding to it.
+        for (int nn = 0; nn < 2; ++nn) {
+          const int n = hcol + 2 * nn;
           ptx::mbar_wait(bars + kBarDFull + 8 * n, gl & 1, P.err, ERR_DFULL);
-          if (n < NC) {
+          if (n < NC && !(P.dbg & 2)) {
             ptx::tc_fence_after();
-            uint32_t r[32];
-            NM_TMEM_LD32(tmem + lane_addr + (uint32_t)(n * 64 + hcol * 32), r);
-            ptx::tmem_wait_ld();
-            const int col0 = n * 64 + hcol * 32;
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + L.bias_off + col0);
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = b4[j];
-              v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), so, bb.x);
-              v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), so, bb.y);
-              v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), so, bb.z);
-              v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), so, bb.w);
-            }
-            if (L.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            for (int hh = 0; hh < heads; ++hh) {
-              const float4* w4 = reinterpret_cast<const float4*>(s_head + L.head_off + hh * L.n_out + col0);
-              float acc = part[hh];
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r[32];
+              const int col0 = n * 64 + half * 32;
+              NM_TMEM_LD32(tmem + lane_addr + (uint32_t)col0, r);
+              ptx::tmem_wait_ld();
+              const float4* b4 = reinterpret_cast<const float4*>(s_bias + L.bias_off + col0);
+              float v[32];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 ww = w4[j];
-                acc = fmaf(ww.x, v[4 * j + 0], acc);
-                acc = fmaf(ww.y, v[4 * j + 1], acc);
-                acc = fmaf(ww.z, v[4 * j + 2], acc);
-                acc = fmaf(ww.w, v[4 * j + 3], acc);
+                const float4 bb = b4[j];
+                v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), so, bb.x);
+                v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), so, bb.y);
+                v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), so, bb.z);
+                v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), so, bb.w);
               }
-              part[hh] = acc;
-            }
-            if (writes_a) {
-              uint32_t hi[16], lo[16];
+              if (L.relu) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float a0 = v[2 * j] * si, a1 = v[2 * j + 1] * si;
-                hi[j] = ptx::pack_f16x2_sat(a0, a1);
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
-                lo[j] = ptx::pack_f16x2_sat(a0 - f.x, a1 - f.y);
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
               }
-              const uint32_t acol = (uint32_t)(n * 32 + hcol * 16);
-              NM_TMEM_ST16(tmem + lane_addr + kColAhi + acol, hi);
-              if (n_passes == 3) NM_TMEM_ST16(tmem + lane_addr + kColAlo + acol, lo);
-              ptx::tmem_wait_st();
+              for (int hh = 0; hh < heads; ++hh) {
+                const float4* w4 = reinterpret_cast<const float4*>(s_head + L.head_off + hh * L.n_out + col0);
+                float acc = part[hh];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 ww = w4[j];
+                  acc = fmaf(ww.x, v[4 * j + 0], acc);
+                  acc = fmaf(ww.y, v[4 * j + 1], acc);
+                  acc = fmaf(ww.z, v[4 * j + 2], acc);
+                  acc = fmaf(ww.w, v[4 * j + 3], acc);
+                }
+                part[hh] = acc;
+              }
+              if (writes_a) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float a0 = v[2 * j] * si, a1 = v[2 * j + 1] * si;
+                  hi[j] = ptx::pack_f16x2_sat(a0, a1);
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+                  lo[j] = ptx::pack_f16x2_sat(a0 - f.x, a1 - f.y);
+                }
+                const uint32_t acol = (uint32_t)(n * 32 + half * 16);
+                NM_TMEM_ST16(tmem + lane_addr + kColAhi + acol, hi);
+                if (n_passes == 3) NM_TMEM_ST16(tmem + lane_addr + kColAlo + acol, lo);
+              }
             }
+            if (writes_a) ptx::tmem_wait_st();
           }
           ptx::tc_fence_before();
-          ptx::mbar_arrive(bars + kBarChunk + 8 * n);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bars + kBarChunk + 8 * n);
         }
         if (heads) {
-          // the two column halves of a row live in warps w and w+4: combine through smem
+          // the two chunk sets of a row live in warps w and w+4: combine their partial dot products through smem
           const float* hb = s_head + L.head_off + heads * L.n_out;
           if (L.kind == KIND_SIGMA) {
             if (hcol == 1) s_red[row] = part[0];
@@ -260,9 +272,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         for (int b = 0; b < n_blocks; ++b) {
           ptx::mbar_wait(bars + kBarWEmpty + 8 * slot, ph ^ 1, P.err, ERR_W_EMPTY);
-          ptx::mbar_expect_tx(bars + kBarWFull + 8 * slot, bytes);
-          ptx::bulk_g2s(sbase + (uint32_t)slot * kStageBytes, P.wpack + (size_t)b * kStageBytes, bytes,
-                        bars + kBarWFull + 8 * slot);
+          if (P.dbg & 4) {
+            ptx::mbar_arrive(bars + kBarWFull + 8 * slot);
+          } else {
+            ptx::mbar_expect_tx(bars + kBarWFull + 8 * slot, bytes);
+            ptx::bulk_g2s(sbase + (uint32_t)slot * kStageBytes, P.wpack + (size_t)b * kStageBytes, bytes,
+                          bars + kBarWFull + 8 * slot);
+          }
           if (++slot == NS) { slot = 0; ph ^= 1; }
         }
       }
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             ptx::tc_fence_after();
             const uint32_t wst = sbase + (uint32_t)slot * kStageBytes;
             const uint32_t d_t = tmem + (uint32_t)B.nc * 64u;
-            for (int pass = 0; pass < n_passes; ++pass) {
+            for (int pass = 0; pass < ((P.dbg & 1) ? 0 : n_passes); ++pass) {
               const bool a_lo = (pass == 1), w_lo = (pass == 2);
               const uint64_t bdesc = ptx::make_kmajor_sw128_desc(wst + (w_lo ? (uint32_t)kHalfStage : 0u));
               if (B.src == SRC_ACT) {
@@ -347,6 +363,12 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.act_inv_scale = ldexpf(1.f, -act_scale_log2);
   P.n_tiles = (in.M + kTileM - 1) / kTileM;
   P.err = d_err;
+  {
+    const char* e = getenv("NM_TC_DEBUG");
+    P.dbg = e ? atoi(e) : 0;
+    const char* ns_env = getenv("NM_TC_STAGES");
+    (void)ns_env;
+  }
 
   auto align_up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
   int dev = 0, max_smem = 0;
@@ -357,6 +379,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
                          (128 + 512) * 4 + kBarBytes;
   int ns = ((int)max_smem - (int)fixed) / kStageBytes;
   if (ns > kMaxStages) ns = kMaxStages;
+  if (const char* e = getenv("NM_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v < ns) ns = v; }
   NM_CHECK(ns >= 2, "network too large for the shared-memory budget (%u B fixed, %d B available)", fixed, max_smem);
   P.num_stages = ns;
   uint32_t off = (uint32_t)ns * kStageBytes;

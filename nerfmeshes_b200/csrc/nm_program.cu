@@ -115,6 +115,7 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
     } else {
       add(h, h, 0, 0, 1, "fc_feat");
       LayerProg& D = add(h / 2, h, SRC_PE_DIR, p->dim_dir, 1, "layers_dir.0");
+      head = (head + 3) & ~3;                       // the epilogue reads head rows as float4
       D.kind = KIND_RGB; D.is_final = 1; D.head_off = head; head += 3 * (h / 2) + 3;
       names->back().head_w = "fc_rgb.weight"; names->back().head_b = "fc_rgb.bias";
     }
@@ -156,11 +157,7 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
       p->blocks[lastblk[n]].last = 1;
     }
     L.blk_end = nb;
-    // write-after-read invariant (see above), for the NEXT layer's readers of what this layer's epilogue writes
-    if (li + 1 < nl) {
-      const LayerProg& Nx = p->layers[li + 1];
-      (void)Nx;
-    }
+    // write-after-read invariant (see above): this layer's epilogue overwrites K-block n once chunk n is complete
     const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
     if (writes_a && KB > 0) {
       for (int n = 0; n < NC && n < KB; ++n)
