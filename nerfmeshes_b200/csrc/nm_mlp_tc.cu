@@ -10,15 +10,22 @@
 // fp16 splits and fp32 accumulation — three kind::f16 MMAs per K-step (1.5e-6 max-abs on composited
 // RGB against fp32, where plain fp16 gives 3.3e-3).  NM_PREC_FAST issues only xh*Wh.
 //
-// CTA = one 128-point tile at a time (TMEM lane = point), 14 warps:
+// CTA = one 128-point tile at a time (TMEM lane = point), 17 warps:
 //   warps 0-7   epilogue (two sets of 4, one warp per TMEM lane quarter; set s converts accumulator chunks s, s+2):
-//               tcgen05.ld chunk -> +bias, ReLU, heads -> fp16 hi/lo -> tcgen05.st A operand
+//               tcgen05.ld chunk -> +bias, ReLU, heads -> fp16 hi/lo -> tcgen05.st A operand -> zero the chunk
 //   warps 8-11  front-end: fetch/synthesise the NEXT tile's points, positional encoding -> swizzled smem A tiles
-//   warp 12     producer: cp.async.bulk weight stages (16 KB = one 64x64 block, hi|lo) into the ring
-//   warp 13     MMA issuer (one lane) + TMEM allocator
+//   warp 12     producer: cp.async.bulk weight stages (16 KB = one 64x64 block, hi|lo) into the ring; TMEM allocator
+//   warps 13-16 MMA issuers: schedule block b is issued by warp (b & 3), all lanes converged, one elected lane
+//               issuing.  Four issuers because one warp sustains only ~1 tcgen05.mma per 100 cycles while an
+//               M=128,N=64,K=16 MMA executes in 32 (tools/umma_bench.cu): four overlap to the execution rate.
 // TMEM (512 columns): [0,256) fp32 accumulator D, [256,384) A_hi, [384,512) A_lo (two fp16 per column).
 // A layer is issued as 64x64 blocks (M=128,N=64,K=16 MMAs) in the order nm_program.cu derives, which lets layer
-// l+1 start as soon as the epilogue has converted the first 64 columns of layer l (see the schedule comment there).
+// l+1 start as soon as the epilogue has converted the first 64 columns of layer l.  Because blocks of one
+// accumulator chunk come from different issuers (no cross-warp order), every MMA accumulates and the epilogue
+// re-zeroes a chunk after draining it.  mbarriers per layer transition:
+//   d_full[n]      (4 commits)  every issuer is done with accumulator chunk n           -> epilogue may drain it
+//   kb_free[k]     (4 commits)  every issuer is done reading activation K-block k       -> epilogue may overwrite it
+//   chunk_ready[n] (4 arrives)  chunk n drained + zeroed, K-block n of the new layer written -> issuers may use both
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -31,11 +38,11 @@ namespace nm {
 
 namespace {
 
-constexpr int kThreads = 448;
+constexpr int kThreads = 544;
 constexpr int kEpiWarps = 8;
 constexpr int kFeWarp0 = 8;
 constexpr int kProdWarp = 12;
-constexpr int kMmaWarp = 13;
+constexpr int kMmaWarp0 = 13;
 constexpr uint32_t kPeTile = 16384;      // 128 rows x 128 B
 constexpr uint32_t kPeBuf = 4 * kPeTile;  // xyz_hi, xyz_lo, dir_hi, dir_lo
 constexpr uint32_t kColAhi = 256, kColAlo = 384;
@@ -60,10 +67,10 @@ struct TcParams {
 
 // barrier slots (8 B each) relative to off_bars
 constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
-                   kBarDFull = 192, kTmemPtr = 224, kBarBytes = 256;
+                   kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kBarBytes = 320;
 
 enum : int { ERR_ALIGN = 1, ERR_W_EMPTY = 2, ERR_W_FULL = 3, ERR_PE_FULL = 4, ERR_PE_EMPTY = 5, ERR_CHUNK = 6,
-             ERR_DFULL = 7 };
+             ERR_DFULL = 7, ERR_KBFREE = 8 };
 
 __device__ __forceinline__ uint16_t f16_bits_sat(float a) {
   uint16_t h;
@@ -96,8 +103,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   if (threadIdx.x == 0) {
     if (sbase & 1023u) { atomicExch(P.err, ERR_ALIGN); __trap(); }
     for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(bars + kBarWFull + 8 * i, 1); ptx::mbar_init(bars + kBarWEmpty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bars + kBarPeFull + 8 * i, 128); ptx::mbar_init(bars + kBarPeEmpty + 8 * i, 1); }
-    for (int i = 0; i < 4; ++i) { ptx::mbar_init(bars + kBarChunk + 8 * i, 4); ptx::mbar_init(bars + kBarDFull + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(bars + kBarPeFull + 8 * i, 128); ptx::mbar_init(bars + kBarPeEmpty + 8 * i, kIssuers); }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(bars + kBarChunk + 8 * i, 4);
+      ptx::mbar_init(bars + kBarDFull + 8 * i, kIssuers);
+      ptx::mbar_init(bars + kBarKbFree + 8 * i, kIssuers);
+    }
     ptx::fence_mbar_init();
   }
   {
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     for (int i = threadIdx.x; i < n_blocks * (int)(sizeof(BlockProg) / 4); i += kThreads) sb[i] = gb[i];
   }
   ptx::fence_proxy_async_smem();
-  if (warp == kMmaWarp) {
+  if (warp == kProdWarp) {
     ptx::tmem_alloc(bars + kTmemPtr, 512);
     ptx::tmem_relinquish();
   }
@@ -121,6 +132,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + P.off_bars + kTmemPtr);
+  if (warp < kEpiWarps) {   // all MMAs accumulate: start from a zero accumulator
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0u;
+    const uint32_t base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) NM_TMEM_ST16(base + 16u * c, z);
+    ptx::tmem_wait_st();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
 
   const float so = P.act_scale, si = P.act_inv_scale;
   const int n_passes = P.n_passes;
@@ -190,13 +213,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
                   lo[j] = ptx::pack_f16x2_sat(a0 - f.x, a1 - f.y);
                 }
+                if (half == 0) ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
                 const uint32_t acol = (uint32_t)(n * 32 + half * 16);
                 NM_TMEM_ST16(tmem + lane_addr + kColAhi + acol, hi);
                 if (n_passes == 3) NM_TMEM_ST16(tmem + lane_addr + kColAlo + acol, lo);
               }
             }
-            if (writes_a) ptx::tmem_wait_st();
+            {   // hand the chunk back zeroed (issuers only ever accumulate)
+              uint32_t z[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) z[j] = 0u;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) NM_TMEM_ST16(tmem + lane_addr + (uint32_t)(n * 64 + 16 * c), z);
+            }
+            ptx::tmem_wait_st();
           }
+          if (!(n < NC && !(P.dbg & 2) && writes_a)) ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bars + kBarChunk + 8 * n);
@@ -284,26 +316,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       }
     }
   } else {
-    // =============================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
-      int slot = 0;
-      uint32_t ph = 0, gl = 0, it = 0;
-      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1;
-        ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
-        ptx::tc_fence_after();
-        const uint32_t pe_base = sbase + P.off_pe + buf * kPeBuf;
-        for (int li = 0; li < n_layers; ++li, ++gl) {
-          const LayerProg L = s_layers[li];
-          const int NC = L.n_out >> 6;
-          int waited = -1;
-          for (int b = L.blk_begin; b < L.blk_end; ++b) {
+    // =============================================================== MMA issuers (4 converged warps)
+    const int w = warp - kMmaWarp0;
+    const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
+    int slot = 0;
+    uint32_t ph = 0, gl = 0, it = 0;
+    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
+      ptx::tc_fence_after();
+      const uint32_t pe_base = sbase + P.off_pe + buf * kPeBuf;
+      for (int li = 0; li < n_layers; ++li, ++gl) {
+        const LayerProg L = s_layers[li];
+        const uint32_t none_d = (uint32_t)L.none_d >> (4 * w), none_k = (uint32_t)L.none_k >> (4 * w);
+        int waited = -1;
+        // Passing group g means the previous layer's chunk g is drained and its K-block g written; it is also the
+        // earliest phase-safe point for this issuer's "nothing to do" commits on index g.
+        auto pass_group = [&](int g) {
+          while (waited < g) {
+            ++waited;
+            if (gl > 0) ptx::mbar_wait(bars + kBarChunk + 8 * waited, (gl - 1) & 1, P.err, ERR_CHUNK);
+            if ((none_d >> waited) & 1u) ptx::tc_commit_elect(bars + kBarDFull + 8 * waited);
+            if ((none_k >> waited) & 1u) ptx::tc_commit_elect(bars + kBarKbFree + 8 * waited);
+          }
+        };
+        for (int b = L.blk_begin; b < L.blk_end; ++b) {
+          if ((b & (kIssuers - 1)) == w) {
             const BlockProg B = s_blocks[b];
-            while (waited < (int)B.group) {
-              ++waited;
-              if (gl > 0) ptx::mbar_wait(bars + kBarChunk + 8 * waited, (gl - 1) & 1, P.err, ERR_CHUNK);
-            }
+            pass_group((int)B.group);
             ptx::mbar_wait(bars + kBarWFull + 8 * slot, ph, P.err, ERR_W_FULL);
             ptx::tc_fence_after();
             const uint32_t wst = sbase + (uint32_t)slot * kStageBytes;
@@ -314,34 +354,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               if (B.src == SRC_ACT) {
                 const uint32_t a_t = tmem + (a_lo ? kColAlo : kColAhi) + (uint32_t)B.kb * 32u;
 #pragma unroll
-                for (int s = 0; s < 4; ++s)
-                  ptx::mma_ts(d_t, a_t + 8u * s, bdesc + 2u * s, idesc, !(B.first && pass == 0 && s == 0));
+                for (int s = 0; s < 4; ++s) ptx::mma_ts_elect(d_t, a_t + 8u * s, bdesc + 2u * s, idesc);
               } else {
                 const uint64_t adesc = ptx::make_kmajor_sw128_desc(pe_base + (B.src == SRC_PE_DIR ? 2 * kPeTile : 0u) +
                                                                    (a_lo ? kPeTile : 0u));
-                for (int s = 0; s < (int)B.ksteps; ++s)
-                  ptx::mma_ss(d_t, adesc + 2u * s, bdesc + 2u * s, idesc, !(B.first && pass == 0 && s == 0));
+                for (int s = 0; s < (int)B.ksteps; ++s) ptx::mma_ss_elect(d_t, adesc + 2u * s, bdesc + 2u * s, idesc);
               }
             }
-            ptx::tc_commit(bars + kBarWEmpty + 8 * slot);
-            if (B.last) ptx::tc_commit(bars + kBarDFull + 8 * B.nc);
-            if (++slot == NS) { slot = 0; ph ^= 1; }
+            ptx::tc_commit_elect(bars + kBarWEmpty + 8 * slot);
+            if (B.flags & 1) ptx::tc_commit_elect(bars + kBarDFull + 8 * B.nc);
+            if (B.flags & 2) ptx::tc_commit_elect(bars + kBarKbFree + 8 * B.kb);
           }
-          while (waited < 3) {
-            ++waited;
-            if (gl > 0) ptx::mbar_wait(bars + kBarChunk + 8 * waited, (gl - 1) & 1, P.err, ERR_CHUNK);
-          }
-          for (int n = NC; n < 4; ++n) ptx::tc_commit(bars + kBarDFull + 8 * n);
+          if (++slot == NS) { slot = 0; ph ^= 1; }
         }
-        ptx::tc_commit(bars + kBarPeEmpty + 8 * buf);
+        pass_group(3);
       }
+      ptx::tc_commit_elect(bars + kBarPeEmpty + 8 * buf);
     }
   }
 
   // ---------------------------------------------------------------- teardown
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, 512);
+  if (warp == kProdWarp) ptx::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace

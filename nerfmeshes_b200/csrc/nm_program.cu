@@ -139,7 +139,7 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
     auto push = [&](int src, int kb, int nc, int ksteps, int group) {
       BlockProg& B = p->blocks[nb];
       B.src = (uint8_t)src; B.kb = (uint8_t)kb; B.nc = (uint8_t)nc; B.ksteps = (uint8_t)ksteps; B.group = (uint8_t)group;
-      B.first = started[nc] ? 0 : 1; B.last = 0; B.pad = 0;
+      B.first = started[nc] ? 0 : 1; B.last = 0; B.flags = 0;
       started[nc] = 1; lastblk[nc] = nb; ++nb;
     };
     const int G = KB > NC ? KB : NC;
@@ -157,6 +157,21 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
       p->blocks[lastblk[n]].last = 1;
     }
     L.blk_end = nb;
+    // per-issuer bookkeeping (nm_mlp_tc.cu): which of an issuer's blocks is its last into each accumulator chunk /
+    // its last reader of each activation K-block, and which chunks / K-blocks it never touches in this layer
+    L.none_d = 0; L.none_k = 0;
+    for (int w = 0; w < kIssuers; ++w) {
+      int ld[4] = {-1, -1, -1, -1}, lk[4] = {-1, -1, -1, -1};
+      for (int b = L.blk_begin; b < L.blk_end; ++b) {
+        if ((b & (kIssuers - 1)) != w) continue;
+        ld[p->blocks[b].nc] = b;
+        if (p->blocks[b].src == SRC_ACT) lk[p->blocks[b].kb] = b;
+      }
+      for (int i = 0; i < 4; ++i) {
+        if (ld[i] >= 0) p->blocks[ld[i]].flags |= 1; else L.none_d |= 1 << (w * 4 + i);
+        if (lk[i] >= 0) p->blocks[lk[i]].flags |= 2; else L.none_k |= 1 << (w * 4 + i);
+      }
+    }
     // write-after-read invariant (see above): this layer's epilogue overwrites K-block n once chunk n is complete
     const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
     if (writes_a && KB > 0) {

@@ -11,6 +11,7 @@ constexpr int kMaxBlocks = 256;
 constexpr int kMaxFreq = 16;
 
 // tensor-core tiling constants
+constexpr int kIssuers = 4;           // MMA-issuing warps; schedule block b is issued by warp (b & 3)
 constexpr int kTileM = 128;          // points per tile (= TMEM lanes)
 constexpr int kChunk = 64;           // N-chunk / K-block width
 constexpr int kStageBytes = 16384;   // one weight stage: [hi 64x64 fp16 | lo 64x64 fp16], 128B-swizzled K-major
@@ -36,6 +37,9 @@ struct LayerProg {
   int32_t head_off;   // float offset into the head array: rows of the head weight then its bias
   int32_t blk_begin, blk_end;  // tensor-core block list
   int32_t wt_off;     // float offset into the transposed fp32 weights (CUDA-core kernel): Wt[k][n], k over [act|pe]
+  // tensor-core kernel, 4 issuing warps (block b belongs to issuer b & 3): bit (issuer*4 + i) set when that issuer has
+  // no block into accumulator chunk i (none_d) / no block reading activation K-block i (none_k) in this layer
+  int32_t none_d, none_k;
 };
 
 // One (K-block, N-chunk) step of the tensor-core schedule == one 16 KB weight stage.
@@ -45,9 +49,9 @@ struct BlockProg {
   uint8_t nc;      // N-chunk: accumulator columns nc*64..
   uint8_t ksteps;  // 1..4 MMAs of K=16
   uint8_t group;   // needs epilogue chunks 0..group of the previous layer done
-  uint8_t first;   // first block into this accumulator chunk (overwrite)
-  uint8_t last;    // last block into this accumulator chunk (commit d_full[nc])
-  uint8_t pad;
+  uint8_t first;   // first block into this accumulator chunk in schedule order (bookkeeping / CPU replay)
+  uint8_t last;    // last block into this accumulator chunk in schedule order
+  uint8_t flags;   // bit0: the issuer's (b & 3) last block into chunk nc; bit1: its last block reading K-block kb
 };
 
 struct NetProgram {

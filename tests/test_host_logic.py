@@ -45,11 +45,11 @@ def test_fails_loudly_without_gpu():
 # ------------------------------------------------------------------------------------------ program + packing
 class LayerProg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_out", "k_act", "pe_src", "k_pe", "relu", "kind", "is_final", "bias_off",
-                                         "head_off", "blk_begin", "blk_end", "wt_off")]
+                                         "head_off", "blk_begin", "blk_end", "wt_off", "none_d", "none_k")]
 
 
 class BlockProg(C.Structure):
-    _fields_ = [(n, C.c_uint8) for n in ("src", "kb", "nc", "ksteps", "group", "first", "last", "pad")]
+    _fields_ = [(n, C.c_uint8) for n in ("src", "kb", "nc", "ksteps", "group", "first", "last", "flags")]
 
 
 class NetProgram(C.Structure):
@@ -163,6 +163,16 @@ def test_schedule_and_packing_reproduce_each_linear_layer(arch, sigma_only):
             B = prog.blocks[b]
             if B.src == 0 and B.kb in last_of_chunk:
                 assert b <= last_of_chunk[B.kb]
+        # per-issuer bookkeeping: for every issuer w and index i exactly one of {a flagged block, the none bit}
+        for w in range(4):
+            mine = [b for b in range(Lp.blk_begin, Lp.blk_end) if (b & 3) == w]
+            for i in range(4):
+                fd = [b for b in mine if prog.blocks[b].nc == i and prog.blocks[b].flags & 1]
+                fk = [b for b in mine if prog.blocks[b].src == 0 and prog.blocks[b].kb == i and prog.blocks[b].flags & 2]
+                td = [b for b in mine if prog.blocks[b].nc == i]
+                tk = [b for b in mine if prog.blocks[b].src == 0 and prog.blocks[b].kb == i]
+                assert fd == td[-1:] and bool(Lp.none_d >> (w * 4 + i) & 1) == (not td)
+                assert fk == tk[-1:] and bool(Lp.none_k >> (w * 4 + i) & 1) == (not tk)
         total_blocks += Lp.blk_end - Lp.blk_begin
     assert total_blocks == prog.n_blocks
     if not arch and not sigma_only:
