@@ -169,6 +169,10 @@ int nm_debug_pack(const NmNetDesc* desc, int n_tensors, const char* const* names
                   const int64_t* numel, int sigma_only, void* program_out, size_t program_cap, uint8_t* pack_out,
                   size_t pack_cap, size_t* pack_need);
 
+/* Device-side error flags, readable even after a kernel trapped: out2[0] = tcgen05 pipeline watchdog code (0 = ok),
+ * out2[1] = AABB hit-list overflow. */
+int nm_kernel_flags(NmHandle h, int32_t* out2);
+
 /* ---- introspection ---------------------------------------------------------------------------------- */
 /* number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t nm_launch_count(NmHandle h);

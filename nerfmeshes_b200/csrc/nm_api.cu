@@ -46,7 +46,8 @@ struct NmHandle_t {
   // workspace
   Buf t_c, raw_c, w_c, t_f, raw_f, t_u, dirs, origins, lin[3], small, stage_in[3], stage_out[12], mc_ws;
   int lin_n[3] = {0, 0, 0};
-  int* d_err = nullptr;       // [0] tcgen05 watchdog code, [1] aabb hit-list overflow
+  int* d_err = nullptr;       // [0] tcgen05 watchdog code, [1] aabb hit-list overflow (device alias of h_err)
+  int* h_err = nullptr;       // mapped pinned host memory: still readable after a device-side trap
   double* d_stats = nullptr;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
@@ -83,8 +84,7 @@ int upload(Buf* b, const void* src, size_t bytes) {
 }
 
 int check_kernel_flags(NmHandle h) {
-  int flags[2] = {0, 0};
-  NM_CUDA(cudaMemcpy(flags, h->d_err, sizeof(flags), cudaMemcpyDeviceToHost));
+  const volatile int* flags = h->h_err;
   NM_CHECK(flags[0] == 0, "tcgen05 pipeline watchdog fired (code %d)", flags[0]);
   NM_CHECK(flags[1] == 0, "AABB sampler: more than 512 voxel hits on one ray");
   return 0;
@@ -284,8 +284,9 @@ int nm_create(int device, const NmNetDesc* coarse, const NmNetDesc* fine, const 
   h->desc[0] = *coarse;
   h->has_fine = fine != nullptr;
   if (fine) h->desc[1] = *fine;
-  NM_CUDA(cudaMalloc(&h->d_err, 2 * sizeof(int)));
-  NM_CUDA(cudaMemset(h->d_err, 0, 2 * sizeof(int)));
+  NM_CUDA(cudaHostAlloc(&h->h_err, 2 * sizeof(int), cudaHostAllocMapped));
+  h->h_err[0] = h->h_err[1] = 0;
+  NM_CUDA(cudaHostGetDevicePointer(&h->d_err, h->h_err, 0));
   NM_CUDA(cudaMalloc(&h->d_stats, 4 * sizeof(double)));
   NM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   *out = h;
@@ -304,7 +305,7 @@ int nm_destroy(NmHandle h) {
   for (Buf& b : h->stage_in) b.release();
   for (Buf& b : h->stage_out) b.release();
   if (h->mc_ws_ptr) cudaFree(h->mc_ws_ptr);
-  cudaFree(h->d_err); cudaFree(h->d_stats);
+  cudaFreeHost(h->h_err); cudaFree(h->d_stats);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -516,6 +517,13 @@ int nm_debug_pack(const NmNetDesc* desc, int n_tensors, const char* const* names
   WeightSource src;
   src.n = n_tensors; src.names = names; src.ptrs = tensors_host; src.numel = numel;
   return debug_pack(*desc, src, sigma_only != 0, reinterpret_cast<NetProgram*>(program_out), pack_out, pack_cap, pack_need);
+}
+
+int nm_kernel_flags(NmHandle h, int32_t* out2) {
+  NM_CHECK(h && out2, "null argument");
+  out2[0] = h->h_err[0];
+  out2[1] = h->h_err[1];
+  return 0;
 }
 
 int64_t nm_launch_count(NmHandle h) { return h ? h->launches : -1; }

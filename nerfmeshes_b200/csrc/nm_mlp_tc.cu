@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + P.off_bars + kTmemPtr);
-  if (warp < kEpiWarps) {   // all MMAs accumulate: start from a zero accumulator
+  if (warp < kEpiWarps && P.prog->accumulate_only) {   // all MMAs accumulate: start from a zero accumulator
     uint32_t z[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) z[j] = 0u;
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const int q = warp & 3, hcol = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool acc_only = P.prog->accumulate_only != 0;
     uint32_t gl = 0;
     float sigma_val = 0.f;
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 if (n_passes == 3) NM_TMEM_ST16(tmem + lane_addr + kColAlo + acol, lo);
               }
             }
-            {   // hand the chunk back zeroed (issuers only ever accumulate)
+            if (acc_only) {   // hand the chunk back zeroed (issuers only ever accumulate)
               uint32_t z[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) z[j] = 0u;
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   } else {
     // =============================================================== MMA issuers (4 converged warps)
     const int w = warp - kMmaWarp0;
+    const uint32_t acc_only = P.prog->accumulate_only ? 1u : 0u;
     const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
     int slot = 0;
     uint32_t ph = 0, gl = 0, it = 0;
@@ -341,8 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           }
         };
         for (int b = L.blk_begin; b < L.blk_end; ++b) {
-          if ((b & (kIssuers - 1)) == w) {
-            const BlockProg B = s_blocks[b];
+          const BlockProg B = s_blocks[b];
+          if ((int)(B.flags >> 4) == w) {
             pass_group((int)B.group);
             ptx::mbar_wait(bars + kBarWFull + 8 * slot, ph, P.err, ERR_W_FULL);
             ptx::tc_fence_after();
@@ -354,11 +356,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               if (B.src == SRC_ACT) {
                 const uint32_t a_t = tmem + (a_lo ? kColAlo : kColAhi) + (uint32_t)B.kb * 32u;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) ptx::mma_ts_elect(d_t, a_t + 8u * s, bdesc + 2u * s, idesc);
+                for (int s = 0; s < 4; ++s)
+                  ptx::mma_ts_elect(d_t, a_t + 8u * s, bdesc + 2u * s, idesc, acc_only | !(B.first && pass == 0 && s == 0));
               } else {
                 const uint64_t adesc = ptx::make_kmajor_sw128_desc(pe_base + (B.src == SRC_PE_DIR ? 2 * kPeTile : 0u) +
                                                                    (a_lo ? kPeTile : 0u));
-                for (int s = 0; s < (int)B.ksteps; ++s) ptx::mma_ss_elect(d_t, adesc + 2u * s, bdesc + 2u * s, idesc);
+                for (int s = 0; s < (int)B.ksteps; ++s)
+                  ptx::mma_ss_elect(d_t, adesc + 2u * s, bdesc + 2u * s, idesc, acc_only | !(B.first && pass == 0 && s == 0));
               }
             }
             ptx::tc_commit_elect(bars + kBarWEmpty + 8 * slot);

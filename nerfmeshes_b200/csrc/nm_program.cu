@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "nm_common.h"
@@ -127,6 +128,13 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
   // newly freed accumulator chunk) precedes the row part (all blocks reading the newly written K-block) so that,
   // MMAs executing in issue order, every reader of K-block n has retired before accumulator chunk n is handed to
   // the epilogue, which overwrites K-block n in place (TMEM A region is single-buffered).
+  // Issuer assignment.  policy 1 (default): the issuer owns an accumulator chunk, so a chunk's blocks are issued by
+  // one warp in schedule order -> deterministic accumulation order, first block overwrites.  policy 0: round-robin
+  // over the schedule (better balanced, but accumulation order across issuers is timing dependent, and the
+  // accumulator must be re-zeroed by the epilogue).  NM_TC_POLICY overrides, for experiments.
+  int policy = 1;
+  if (const char* e = getenv("NM_TC_POLICY")) policy = atoi(e) ? 1 : 0;
+  p->accumulate_only = policy == 0 ? 1 : 0;
   int nb = 0;
   for (int li = 0; li < nl; ++li) {
     LayerProg& L = p->layers[li];
@@ -160,10 +168,14 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
     // per-issuer bookkeeping (nm_mlp_tc.cu): which of an issuer's blocks is its last into each accumulator chunk /
     // its last reader of each activation K-block, and which chunks / K-blocks it never touches in this layer
     L.none_d = 0; L.none_k = 0;
+    for (int b = L.blk_begin; b < L.blk_end; ++b) {
+      const int issuer = policy == 0 ? (b & (kIssuers - 1)) : p->blocks[b].nc;
+      p->blocks[b].flags = (uint8_t)(issuer << 4);
+    }
     for (int w = 0; w < kIssuers; ++w) {
       int ld[4] = {-1, -1, -1, -1}, lk[4] = {-1, -1, -1, -1};
       for (int b = L.blk_begin; b < L.blk_end; ++b) {
-        if ((b & (kIssuers - 1)) != w) continue;
+        if ((p->blocks[b].flags >> 4) != w) continue;
         ld[p->blocks[b].nc] = b;
         if (p->blocks[b].src == SRC_ACT) lk[p->blocks[b].kb] = b;
       }

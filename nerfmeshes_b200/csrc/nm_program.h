@@ -11,7 +11,7 @@ constexpr int kMaxBlocks = 256;
 constexpr int kMaxFreq = 16;
 
 // tensor-core tiling constants
-constexpr int kIssuers = 4;           // MMA-issuing warps; schedule block b is issued by warp (b & 3)
+constexpr int kIssuers = 4;           // MMA-issuing warps; a block's issuer is BlockProg.flags >> 4
 constexpr int kTileM = 128;          // points per tile (= TMEM lanes)
 constexpr int kChunk = 64;           // N-chunk / K-block width
 constexpr int kStageBytes = 16384;   // one weight stage: [hi 64x64 fp16 | lo 64x64 fp16], 128B-swizzled K-major
@@ -37,7 +37,7 @@ struct LayerProg {
   int32_t head_off;   // float offset into the head array: rows of the head weight then its bias
   int32_t blk_begin, blk_end;  // tensor-core block list
   int32_t wt_off;     // float offset into the transposed fp32 weights (CUDA-core kernel): Wt[k][n], k over [act|pe]
-  // tensor-core kernel, 4 issuing warps (block b belongs to issuer b & 3): bit (issuer*4 + i) set when that issuer has
+  // tensor-core kernel, 4 issuing warps: bit (issuer*4 + i) set when that issuer has
   // no block into accumulator chunk i (none_d) / no block reading activation K-block i (none_k) in this layer
   int32_t none_d, none_k;
 };
@@ -51,7 +51,8 @@ struct BlockProg {
   uint8_t group;   // needs epilogue chunks 0..group of the previous layer done
   uint8_t first;   // first block into this accumulator chunk in schedule order (bookkeeping / CPU replay)
   uint8_t last;    // last block into this accumulator chunk in schedule order
-  uint8_t flags;   // bit0: the issuer's (b & 3) last block into chunk nc; bit1: its last block reading K-block kb
+  uint8_t flags;   // bit0: its issuer's last block into chunk nc; bit1: its issuer's last block reading K-block kb;
+                   // bits 4-5: issuer warp
 };
 
 struct NetProgram {
@@ -61,6 +62,7 @@ struct NetProgram {
   int32_t dim_xyz, dim_dir;      // true PE widths
   int32_t L_xyz, L_dir, inc_xyz, inc_dir;
   int32_t n_bias, n_head;        // floats
+  int32_t accumulate_only;       // 1: blocks of a chunk come from several issuers (no order): always accumulate, epilogue re-zeroes
   float freq_xyz[kMaxFreq];
   float freq_dir[kMaxFreq];
   LayerProg layers[kMaxLayers];

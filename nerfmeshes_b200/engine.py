@@ -274,6 +274,11 @@ class Engine:
         return verts, faces, normals
 
     # ------------------------------------------------------------------ introspection
+    def kernel_flags(self):
+        out = (C.c_int32 * 2)()
+        L.check(self.lib.nm_kernel_flags(self._h, out))
+        return int(out[0]), int(out[1])
+
     def launch_count(self) -> int:
         return int(self.lib.nm_launch_count(self._h))
 

@@ -54,7 +54,7 @@ class BlockProg(C.Structure):
 
 class NetProgram(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layers", "n_blocks", "hidden", "dim_xyz", "dim_dir", "L_xyz", "L_dir", "inc_xyz",
-                                         "inc_dir", "n_bias", "n_head")] + \
+                                         "inc_dir", "n_bias", "n_head", "accumulate_only")] + \
                [("freq_xyz", C.c_float * 16), ("freq_dir", C.c_float * 16), ("layers", LayerProg * 24), ("blocks", BlockProg * 256)]
 
 
@@ -165,7 +165,7 @@ def test_schedule_and_packing_reproduce_each_linear_layer(arch, sigma_only):
                 assert b <= last_of_chunk[B.kb]
         # per-issuer bookkeeping: for every issuer w and index i exactly one of {a flagged block, the none bit}
         for w in range(4):
-            mine = [b for b in range(Lp.blk_begin, Lp.blk_end) if (b & 3) == w]
+            mine = [b for b in range(Lp.blk_begin, Lp.blk_end) if (prog.blocks[b].flags >> 4) == w]
             for i in range(4):
                 fd = [b for b in mine if prog.blocks[b].nc == i and prog.blocks[b].flags & 1]
                 fk = [b for b in mine if prog.blocks[b].src == 0 and prog.blocks[b].kb == i and prog.blocks[b].flags & 2]
@@ -173,7 +173,10 @@ def test_schedule_and_packing_reproduce_each_linear_layer(arch, sigma_only):
                 tk = [b for b in mine if prog.blocks[b].src == 0 and prog.blocks[b].kb == i]
                 assert fd == td[-1:] and bool(Lp.none_d >> (w * 4 + i) & 1) == (not td)
                 assert fk == tk[-1:] and bool(Lp.none_k >> (w * 4 + i) & 1) == (not tk)
+        # default policy: the issuer owns the accumulator chunk (deterministic accumulation order)
+        assert all((prog.blocks[b].flags >> 4) == prog.blocks[b].nc for b in range(Lp.blk_begin, Lp.blk_end))
         total_blocks += Lp.blk_end - Lp.blk_begin
+    assert prog.accumulate_only == 0
     assert total_blocks == prog.n_blocks
     if not arch and not sigma_only:
         assert prog.n_blocks == 146            # 2.39 MB of fp16 hi+lo stages per 8x256 network
