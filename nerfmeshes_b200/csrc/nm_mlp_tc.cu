@@ -67,7 +67,7 @@ struct TcParams {
 
 // barrier slots (8 B each) relative to off_bars
 constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
-                   kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kBarBytes = 320;
+                   kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kLoadedCnt = 264, kBarBytes = 320;
 
 enum : int { ERR_ALIGN = 1, ERR_W_EMPTY = 2, ERR_W_FULL = 3, ERR_PE_FULL = 4, ERR_PE_EMPTY = 5, ERR_CHUNK = 6,
              ERR_DFULL = 7, ERR_KBFREE = 8 };
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       ptx::mbar_init(bars + kBarDFull + 8 * i, kIssuers);
       ptx::mbar_init(bars + kBarKbFree + 8 * i, kIssuers);
     }
+    *reinterpret_cast<volatile uint32_t*>(smem + P.off_bars + kLoadedCnt) = 0u;
     ptx::fence_mbar_init();
   }
   {
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // =============================================================== weight producer
     if (lane == 0) {
       int slot = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, issued = 0;
+      const uint32_t cnt_addr = bars + kLoadedCnt;
       const uint32_t bytes = (n_passes == 3) ? (uint32_t)kStageBytes : (uint32_t)kHalfStage;
       for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         for (int b = 0; b < n_blocks; ++b) {
@@ -312,6 +314,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             ptx::bulk_g2s(sbase + (uint32_t)slot * kStageBytes, P.wpack + (size_t)b * kStageBytes, bytes,
                           bars + kBarWFull + 8 * slot);
           }
+          // Publish how many stages have been armed.  The ring's mbarriers carry one parity bit, and an issuer whose
+          // consecutive blocks are more than NS apart in the schedule could otherwise look at a slot a full round early
+          // and mistake the previous round's completion for its own.
+          ++issued;
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(cnt_addr), "r"(issued) : "memory");
           if (++slot == NS) { slot = 0; ph ^= 1; }
         }
       }
@@ -322,7 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const uint32_t acc_only = P.prog->accumulate_only ? 1u : 0u;
     const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
     int slot = 0;
-    uint32_t ph = 0, gl = 0, it = 0;
+    uint32_t ph = 0, gl = 0, it = 0, gblock = 0;
+    const uint32_t cnt_addr = bars + kLoadedCnt;
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
       ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
@@ -346,6 +354,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           const BlockProg B = s_blocks[b];
           if ((int)(B.flags >> 4) == w) {
             pass_group((int)B.group);
+            {   // the producer must have armed this stage for THIS round before its parity means anything
+              uint32_t c;
+              long long t0 = clock64();
+              do {
+                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(c) : "r"(cnt_addr) : "memory");
+                if (c <= gblock && clock64() - t0 > 4000000000LL) { atomicExch(P.err, ERR_W_FULL + 100); __trap(); }
+              } while (c <= gblock);
+            }
             ptx::mbar_wait(bars + kBarWFull + 8 * slot, ph, P.err, ERR_W_FULL);
             ptx::tc_fence_after();
             const uint32_t wst = sbase + (uint32_t)slot * kStageBytes;
@@ -369,6 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             if (B.flags & 1) ptx::tc_commit_elect(bars + kBarDFull + 8 * B.nc);
             if (B.flags & 2) ptx::tc_commit_elect(bars + kBarKbFree + 8 * B.kb);
           }
+          ++gblock;
           if (++slot == NS) { slot = 0; ph ^= 1; }
         }
         pass_group(3);

@@ -1,0 +1,162 @@
+"""Functional simulation of the tcgen05 kernel's mbarrier protocol (nm_mlp_tc.cu) on the real layer program.
+
+Agents (producer, 4 MMA issuers, 2 epilogue sets, front-end) are generators that yield when they would block; a
+round-robin scheduler runs them until everyone finishes (ok) or nobody can move (deadlock -> prints who waits on what).
+Timing is not modelled, only ordering / phase correctness.  Commits are modelled as completing immediately.
+
+    NM_TC_POLICY=1 python tools/protocol_sim.py [--tiles 3] [--stages 5]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+class Bar:
+    def __init__(self, name, count):
+        self.name, self.count, self.pending, self.phase = name, count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0, f"{self.name}: too many arrivals in phase {self.phase}"
+        if self.pending == 0:
+            self.phase += 1
+            self.pending = self.count
+
+    def done(self, k):            # hardware semantics: try_wait.parity(k & 1) -- ONE parity bit, so a waiter that is two
+        return (self.phase & 1) != (k & 1)   # phases away from the barrier's current phase aliases (this is what is modelled)
+
+
+def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
+    L = [prog.layers[i] for i in range(prog.n_layers)]
+    w_full = [Bar(f"w_full{i}", 1) for i in range(NS)]
+    w_empty = [Bar(f"w_empty{i}", 1) for i in range(NS)]
+    pe_full = [Bar(f"pe_full{i}", 1) for i in range(2)]
+    pe_empty = [Bar(f"pe_empty{i}", 4) for i in range(2)]
+    chunk = [Bar(f"chunk_ready{i}", 1) for i in range(4)]       # one arrival per epilogue set (4 warps act together)
+    d_full = [Bar(f"d_full{i}", 4) for i in range(4)]
+    kb_free = [Bar(f"kb_free{i}", 4) for i in range(4)]
+    waiting = {}
+    armed = [0]
+    errors = []
+
+    def wait(me, bar, k):
+        while not bar.done(k):
+            waiting[me] = f"{bar.name} completion #{k} (phase now {bar.phase}, pending {bar.pending})"
+            yield
+        waiting.pop(me, None)
+
+    def producer():
+        g = 0
+        for t in range(tiles):
+            for b in range(prog.n_blocks):
+                slot, rnd = g % NS, g // NS
+                if rnd > 0:
+                    yield from wait("producer", w_empty[slot], rnd - 1)
+                w_full[slot].arrive()
+                g += 1
+                armed[0] = g
+
+    def frontend():
+        for t in range(tiles):
+            buf = t & 1
+            if t >= 2:
+                yield from wait("frontend", pe_empty[buf], t // 2 - 1)
+            pe_full[buf].arrive()
+
+    def issuer(w):
+        me = f"issuer{w}"
+        g = 0
+        gl = 0
+        for t in range(tiles):
+            buf = t & 1
+            yield from wait(me, pe_full[buf], t // 2)
+            for li, Lp in enumerate(L):
+                waited = -1
+
+                def pass_group(gr):
+                    nonlocal waited
+                    while waited < gr:
+                        waited += 1
+                        if gl > 0:
+                            yield from wait(me, chunk[waited], gl - 1)
+                        if (Lp.none_d >> (4 * w + waited)) & 1:
+                            d_full[waited].arrive()
+                        if (Lp.none_k >> (4 * w + waited)) & 1:
+                            kb_free[waited].arrive()
+                for b in range(Lp.blk_begin, Lp.blk_end):
+                    B = prog.blocks[b]
+                    slot, rnd = g % NS, g // NS
+                    if (B.flags >> 4) == w:
+                        yield from pass_group(B.group)
+                        while armed_counter and armed[0] <= g:
+                            waiting[me] = f"armed counter > {g}"
+                            yield
+                        yield from wait(me, w_full[slot], rnd)
+                        if w_full[slot].phase != rnd + 1:
+                            errors.append(f"{me}: consumed slot {slot} for block {g} (round {rnd}) while the barrier had completed {w_full[slot].phase} rounds")
+                        w_empty[slot].arrive()
+                        if B.flags & 1:
+                            d_full[B.nc].arrive()
+                        if B.flags & 2:
+                            kb_free[B.kb].arrive()
+                    g += 1
+                yield from pass_group(3)
+                gl += 1
+            pe_empty[buf].arrive()
+
+    def epilogue(s):
+        me = f"epi_set{s}"
+        gl = 0
+        for t in range(tiles):
+            for li, Lp in enumerate(L):
+                for nn in range(2):
+                    n = s + 2 * nn
+                    yield from wait(me, d_full[n], gl)
+                    yield from wait(me, kb_free[n], gl)
+                    chunk[n].arrive()
+                gl += 1
+
+    agents = {"producer": producer(), "frontend": frontend(), **{f"issuer{w}": issuer(w) for w in range(4)},
+              **{f"epi_set{s}": epilogue(s) for s in range(2)}}
+    alive = dict(agents)
+    steps = 0
+    while alive:
+        progressed = False
+        for name in list(alive):
+            before = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free),
+                      tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free))
+            try:
+                next(alive[name])
+            except StopIteration:
+                del alive[name]
+                progressed = True
+                continue
+            after = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free),
+                     tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free))
+            progressed |= before != after
+        steps += 1
+        if not progressed:
+            return False, dict(waiting, errors=errors[:3])
+    return (not errors), dict(errors=errors[:3])
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tiles", type=int, default=3)
+    ap.add_argument("--stages", type=int, default=5)
+    a = ap.parse_args()
+    from oracle import nerf_oracle as O
+    from test_host_logic import debug_pack
+    for arch in (dict(), dict(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6), dict(num_layers=3, hidden_size=128, use_viewdirs=False)):
+        cfg = O.NetCfg(**{**O.NetCfg().__dict__, **arch})
+        for sigma_only in (False, True):
+            prog, _ = debug_pack(cfg, O.init_weights(cfg, 1), sigma_only)
+            for ns in sorted({2, 3, a.stages}):
+                ok, who = simulate(prog, a.tiles, ns)
+                ok0, who0 = simulate(prog, a.tiles, ns, armed_counter=False)
+                print(f"arch={arch} sigma_only={sigma_only} stages={ns}: {'ok' if ok else 'FAIL ' + str(who)}"
+                      f"   [without the armed counter: {'ok' if ok0 else 'FAIL ' + str(who0)[:160]}]")
