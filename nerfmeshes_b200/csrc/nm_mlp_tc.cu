@@ -28,7 +28,9 @@
 //   chunk_ready[n] (4 arrives)  chunk n drained + zeroed, K-block n of the new layer written -> issuers may use both
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "nm_common.h"
 #include "nm_frontend.cuh"
@@ -61,6 +63,7 @@ struct TcParams {
   int num_stages;
   long long n_tiles;
   int* err;
+  unsigned long long* trace;   // NM_TC_TRACE: CTA 0 logs (kind, id, index, layer, t0..t3) records; trace[0] = count
   int dbg;   // bring-up switches (env NM_TC_DEBUG): 1 = no MMA issue, 2 = no epilogue math, 4 = no weight copies
   uint32_t off_pe, off_bias, off_head, off_layers, off_blocks, off_red, off_bars;
 };
@@ -81,6 +84,15 @@ __device__ __forceinline__ float f16_bits_to_float(uint16_t h) {
   float f;
   asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
   return f;
+}
+__device__ __forceinline__ void trace_rec(const TcParams& P, unsigned kind, unsigned id, unsigned idx, unsigned gl, long long t0,
+                                          long long t1, long long t2, long long t3) {
+  if (!P.trace || blockIdx.x != 0) return;
+  const unsigned long long slot = atomicAdd(P.trace, 1ull);
+  if (slot >= 60000ull) return;
+  unsigned long long* r = P.trace + 1 + slot * 5;
+  r[0] = ((unsigned long long)kind << 48) | ((unsigned long long)id << 40) | ((unsigned long long)idx << 24) | gl;
+  r[1] = (unsigned long long)t0; r[2] = (unsigned long long)t1; r[3] = (unsigned long long)t2; r[4] = (unsigned long long)t3;
 }
 __device__ __forceinline__ uint32_t swz_off(int r, int c) {
   return (uint32_t)r * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
@@ -170,7 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         // one chunk overlaps the next chunk's instead of adding to it.
         for (int nn = 0; nn < 2; ++nn) {
           const int n = hcol + 2 * nn;
+          const long long tr0 = P.trace ? clock64() : 0;
           ptx::mbar_wait(bars + kBarDFull + 8 * n, gl & 1, P.err, ERR_DFULL);
+          const long long tr1 = P.trace ? clock64() : 0;
+          long long tr2 = 0;
           if (n < NC && !(P.dbg & 2)) {
             ptx::tc_fence_after();
 #pragma unroll 1
@@ -215,7 +230,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
                   lo[j] = ptx::pack_f16x2_sat(a0 - f.x, a1 - f.y);
                 }
-                if (half == 0) ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
+                if (half == 0) {
+                  if (P.trace) tr2 = clock64();
+                  ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
+                }
                 const uint32_t acol = (uint32_t)(n * 32 + half * 16);
                 NM_TMEM_ST16(tmem + lane_addr + kColAhi + acol, hi);
                 if (n_passes == 3) NM_TMEM_ST16(tmem + lane_addr + kColAlo + acol, lo);
@@ -234,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bars + kBarChunk + 8 * n);
+          if (P.trace && (warp & 3) == 0 && lane == 0) trace_rec(P, 2, hcol, n, gl, tr0, tr1, tr2, clock64());
         }
         if (heads) {
           // the two chunk sets of a row live in warps w and w+4: combine their partial dot products through smem
@@ -353,7 +372,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         for (int b = L.blk_begin; b < L.blk_end; ++b) {
           const BlockProg B = s_blocks[b];
           if ((int)(B.flags >> 4) == w) {
+            const long long tr0 = P.trace ? clock64() : 0;
             pass_group((int)B.group);
+            const long long tr1 = P.trace ? clock64() : 0;
             {   // the producer must have armed this stage for THIS round before its parity means anything
               uint32_t c;
               long long t0 = clock64();
@@ -363,6 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               } while (c <= gblock);
             }
             ptx::mbar_wait(bars + kBarWFull + 8 * slot, ph, P.err, ERR_W_FULL);
+            const long long tr2 = P.trace ? clock64() : 0;
             ptx::tc_fence_after();
             const uint32_t wst = sbase + (uint32_t)slot * kStageBytes;
             const uint32_t d_t = tmem + (uint32_t)B.nc * 64u;
@@ -384,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             ptx::tc_commit_elect(bars + kBarWEmpty + 8 * slot);
             if (B.flags & 1) ptx::tc_commit_elect(bars + kBarDFull + 8 * B.nc);
             if (B.flags & 2) ptx::tc_commit_elect(bars + kBarKbFree + 8 * B.kb);
+            if (P.trace && lane == 0) trace_rec(P, 1, w, b, gl, tr0, tr1, tr2, clock64());
           }
           ++gblock;
           if (++slot == NS) { slot = 0; ph ^= 1; }
@@ -454,8 +477,21 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
     configured_dev = dev;
   }
   long long grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+  const char* trace_path = getenv("NM_TC_TRACE");
+  const size_t trace_words = 1 + 60000 * 5;
+  if (trace_path) {
+    NM_CUDA(cudaMalloc(&P.trace, trace_words * 8));
+    NM_CUDA(cudaMemset(P.trace, 0, trace_words * 8));
+  }
   mlp_tc_kernel<<<(unsigned)grid, kThreads, off, st>>>(P);
   NM_CUDA(cudaGetLastError());
+  if (trace_path) {   // debugging aid: synchronous dump of CTA 0's event log
+    NM_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> h(trace_words);
+    NM_CUDA(cudaMemcpy(h.data(), P.trace, trace_words * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), 8, trace_words, f); fclose(f); }
+    cudaFree(P.trace);
+  }
   if (launches) ++*launches;
   return 0;
 }
