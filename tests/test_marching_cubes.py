@@ -1,0 +1,116 @@
+"""Marching cubes (a15).  The reference's implementation is scikit-image 0.17.2's Lewiner extension, which is absent here:
+PARITY UNPINNED at that seam.  CPU tests pin the oracle's own invariants on analytic fields (the substitute
+checks SURVEY 8c prescribes); the GPU test requires the CUDA kernels to equal the oracle array-for-array, bit-for-bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mc
+
+
+def fields(n=40):
+    g = np.linspace(-1.2, 1.2, n, dtype=np.float32)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    sphere = (0.8 - np.sqrt(X * X + Y * Y + Z * Z)).astype(np.float32)
+    torus = (0.25 - np.sqrt((np.sqrt(X * X + Y * Y) - 0.7) ** 2 + Z * Z)).astype(np.float32)
+    two = np.maximum(0.35 - np.sqrt((X - 0.5) ** 2 + Y * Y + Z * Z), 0.35 - np.sqrt((X + 0.5) ** 2 + Y * Y + Z * Z)).astype(np.float32)
+    return dict(sphere=(sphere, 2), torus=(torus, 0), two_spheres=(two, 4)), g
+
+
+def edge_stats(f):
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    und, cnt = np.unique(np.sort(e, 1), axis=0, return_counts=True)
+    _, dcnt = np.unique(e, axis=0, return_counts=True)
+    return und.shape[0], cnt, dcnt
+
+
+@pytest.mark.parametrize("name", ["sphere", "torus", "two_spheres"])
+def test_oracle_topology_and_geometry(name):
+    fs, g = fields()
+    vol, euler = fs[name]
+    n = vol.shape[0]
+    v, f, nrm = mc.marching_cubes(vol, 0.0)
+    n_edges, cnt, dcnt = edge_stats(f)
+    assert set(cnt) == {2}, "closed manifold: every edge shared by exactly two triangles"
+    assert dcnt.max() == 1, "consistent orientation"
+    assert v.shape[0] - n_edges + f.shape[0] == euler
+    # every vertex lies on a grid edge whose end points straddle the iso value, strictly between them
+    frac = v - np.floor(v)
+    on_edge = (frac > 0).sum(1)
+    assert on_edge.max() <= 1
+    lo = np.floor(v).astype(int)
+    hi = np.minimum(lo + (frac > 0), n - 1)
+    a, b = vol[lo[:, 0], lo[:, 1], lo[:, 2]], vol[hi[:, 0], hi[:, 1], hi[:, 2]]
+    assert bool(((a > 0) != (b > 0))[on_edge == 1].all())
+    # within half a voxel of the analytic surface, and (signed-distance fields) the weighted mean IS the linear root
+    P = v / (n - 1) * 2.4 - 1.2
+    h = 2.4 / (n - 1)
+    if name == "sphere":
+        assert np.abs(np.linalg.norm(P, axis=1) - 0.8).max() < 0.5 * h
+        out = P / np.linalg.norm(P, axis=1, keepdims=True)
+        assert (np.sum(nrm * out, 1)).min() > 0.99                  # unit normals point to decreasing values (outward)
+        fn = np.cross(P[f[:, 1]] - P[f[:, 0]], P[f[:, 2]] - P[f[:, 0]])
+        assert (np.sum(fn * P[f].mean(1), 1) > 0).all()             # triangle winding agrees with the normals
+    np.testing.assert_allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-6)
+
+
+def test_oracle_slabs_reproduce_the_vertex_set():
+    """x-slab sharding: slabs with one overlapping plane give the same vertex set, bit for bit."""
+    vol = fields(36)[0]["torus"][0]
+    v, f, _ = mc.marching_cubes(vol, 0.0)
+    parts = []
+    for x0, x1 in ((0, 13), (13, 24), (24, 35)):
+        vs, fs_, _ = mc.marching_cubes(vol[x0:x1 + 1], 0.0, x_off=float(x0))
+        parts.append(vs)
+    allv = np.unique(np.concatenate(parts), axis=0)
+    assert np.array_equal(allv, np.unique(v, axis=0))
+
+
+def test_ragged_and_empty_inputs():
+    v, f, n = mc.marching_cubes(np.zeros((5, 4, 3), np.float32), 0.5)
+    assert v.shape == (0, 3) and f.shape == (0, 3)
+    vol = np.zeros((2, 2, 2), np.float32)
+    vol[0, 0, 0] = 1.0
+    v, f, n = mc.marching_cubes(vol, 0.5)
+    assert v.shape == (3, 3) and f.shape == (1, 3)
+    np.testing.assert_allclose(sorted(v.sum(1)), [0.5, 0.5, 0.5], atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sphere", "torus", "two_spheres", "noise", "ragged"])
+def test_cuda_equals_oracle_bit_for_bit(name):
+    import nerfmeshes_b200 as nm
+    from nerfmeshes_b200.nerf_api import _engine
+    if name == "noise":
+        vol, iso = np.random.default_rng(0).standard_normal((33, 20, 47)).astype(np.float32), 0.1
+    elif name == "ragged":
+        vol, iso = np.random.default_rng(1).standard_normal((3, 130, 2)).astype(np.float32) * 40, 32.0
+    else:
+        vol, iso = fields(48)[0][name][0], 0.0
+    v, f, n = mc.marching_cubes(vol, iso, x_off=3.0)
+    gv, gf, gn = _engine().marching_cubes(torch.from_numpy(vol).cuda(), iso, x_off=3.0)
+    assert np.array_equal(gv.cpu().numpy(), v)
+    assert np.array_equal(gf.cpu().numpy(), f)
+    assert np.array_equal(gn.cpu().numpy(), n)
+    sv, sf, sn, _ = nm.marching_cubes(vol, iso)                 # the skimage-shaped entry point
+    assert sv.shape == v.shape and sf.shape == f.shape
+
+
+@pytest.mark.gpu
+def test_extract_geometry_on_lego_grid():
+    """mesh_nerf.extract_geometry end to end on a small grid: sigma sweep -> iso clamp -> MC -> rescale; checked against
+    the oracle chain run on the same density."""
+    import nerfmeshes_b200 as nm
+    from conftest import load_npz
+    from test_gpu_parity import LEGO_CFG
+    from oracle import nerf_oracle as O
+    model = nm.NeRFModel.from_npz(LEGO_CFG, load_npz("weights_lego_nerf.npz")).eval()
+
+    class A:
+        limit, res, iso_level = 1.2, 40, 32.0
+    verts, tris, normals, density = nm.extract_geometry(model, "cuda", A)
+    iso = O.extract_iso_level(density, A.iso_level)
+    v, f, n = mc.marching_cubes(density, iso)
+    assert np.array_equal(tris.numpy(), f)
+    np.testing.assert_array_equal(verts.numpy(), (1.2 * (torch.from_numpy(v) / (A.res / 2.0) - 1.0)).numpy())
+    assert verts.shape[0] > 1000
