@@ -51,5 +51,7 @@ def extract_geometry(model, device, args):
     density = extract_radiance(model, args, device, args.res, sigma_only=True)
     iso_value = extract_iso_level(density, args, eng)
     verts, faces, normals = eng.marching_cubes(density, float(iso_value))
-    vertices = args.limit * (verts / (args.res / 2.0) - 1.0)          # keeps the reference's res/2 scale (:90)
-    return vertices.cpu(), faces.cpu(), normals.cpu(), density.cpu().numpy()
+    # the reference rescales CPU tensors (:82-90); do the same on the host so the rounding is identical (torch's CUDA
+    # division by a python scalar multiplies by the reciprocal, which differs in the last bit)
+    vertices = args.limit * (verts.cpu() / (args.res / 2.0) - 1.0)    # keeps the reference's res/2 scale (:90)
+    return vertices, faces.cpu(), normals.cpu(), density.cpu().numpy()
