@@ -229,10 +229,29 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # ---------------------------------------------------------------- secondary: 512^3 sigma sweep + marching cubes (configs[2])
+    from nerfmeshes_b200 import parallel as par
+    RES, LIMIT, ISO = 512, 1.2, 32.0
+    tiles = [torch.linspace(-LIMIT, LIMIT, RES) for _ in range(3)]
+    x0, x1 = par.slab_shard(RES, rank, world)
+    eng.grid_sigma(tiles, x0, min(x0 + 8, x1))                      # warm-up
+    barrier()
+    g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    g0.record()
+    sigma = eng.grid_sigma(tiles, x0, x1)                           # sigma-only fast path (rgb is discarded by the reference, mesh_nerf.py:73)
+    g1.record()
+    mv, mf, mn = eng.marching_cubes(sigma, ISO, x_off=float(x0))
+    g2.record()
+    barrier()
+    grid_ms, mc_ms = g0.elapsed_time(g1), g1.elapsed_time(g2)
+    n_mesh = torch.tensor([mv.shape[0], mf.shape[0]], dtype=torch.float64, device="cuda")
+    del sigma, mv, mf, mn
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, grid_ms, mc_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+        dist.all_reduce(n_mesh, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, grid_ms, mc_ms = (float(x) for x in t)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -248,6 +267,10 @@ def main():
         "e2e": {"value": rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(d_h.numel() * 4 + 12),
                 "d2h_bytes_per_step": int(H * W * 4 * 4), "api": "nm_query_host (model.query with CPU tensors)"},
         "gpu_launches": int(launches),
+        "grid": {"metric": "grid-voxels/sec", "value": RES ** 3 / ((grid_ms + mc_ms) * 1e-3), "unit": "voxels/s", "res": RES,
+                 "workload": "lego 512^3 sigma sweep (sigma-only trunk, 982,528 FLOP/voxel) + marching cubes iso=32, x-slabs across ranks",
+                 "sigma_sweep_ms": grid_ms, "marching_cubes_ms": mc_ms, "n_vertices": int(n_mesh[0]), "n_triangles": int(n_mesh[1]),
+                 "sweep_tflops": RES ** 3 * 982528 / (grid_ms * 1e-3) / 1e12},
         "roofline": {"bound": "tensor", "kernel": "mlp_tc_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None, "peak_source": peak_src,
                      "algorithmic_flop_per_point": FLOP_PER_POINT, "points_per_step": mlp_pts // max(a.steps, 1),

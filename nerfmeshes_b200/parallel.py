@@ -1,0 +1,107 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, independent units, ONE exchange step.
+
+Render: contiguous image-row shards, every rank generates its own rays from the 12-float pose; results are bit-identical
+to the single-GPU image (no cross-shard arithmetic), the exchange is one all_gather of the finished rows.
+Mesh: x-slabs of the density grid with one overlapping plane; per-slab marching cubes in global index coordinates; the
+exchange is an all_gather of the per-slab indexed meshes ("triangle soup", padded to the largest slab) plus three scalar
+all_reduces for the iso-level statistics (extract_iso_level, src/mesh_nerf.py:56-65).
+The collectives go through torch.distributed (NCCL on GPUs, gloo in the CPU tests); there is no data-path collective
+inside a shard's computation.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def row_shard(H: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [r0, r1) of rank `rank`: H split as evenly as possible, earlier ranks take the remainder."""
+    base, rem = divmod(H, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+def slab_shard(n0: int, rank: int, world: int) -> Tuple[int, int]:
+    """Planes [x0, x1) of the grid's slowest axis owned by `rank` such that the n0-1 cell layers are split evenly and
+    neighbouring slabs share one plane (cells between planes x1-1 and x1 belong to the next rank's first plane)."""
+    c0, c1 = row_shard(n0 - 1, rank, world)          # cell layers [c0, c1)
+    return c0, c1 + 1                                # planes c0 .. c1 inclusive
+
+
+def _all_gather_padded(t: torch.Tensor, group=None):
+    """all_gather of tensors whose first dimension differs per rank -> list of per-rank tensors."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c) for c in counts]
+    mx = max(counts)
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return [o[:c] for o, c in zip(out, counts)]
+
+
+def gather_rows(local: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """Concatenate per-rank row shards (rank order == row order) of every output map."""
+    return {k: torch.cat(_all_gather_padded(v.contiguous(), group), 0) for k, v in local.items()}
+
+
+def gather_mesh(verts: torch.Tensor, faces: torch.Tensor, normals: Optional[torch.Tensor] = None, group=None):
+    """Concatenate per-slab indexed meshes; face indices are shifted by the exclusive scan of the vertex counts.
+    Vertices on shared planes appear once per adjacent slab with identical bits (use torch.unique for the set)."""
+    vs = _all_gather_padded(verts.contiguous(), group)
+    fs = _all_gather_padded(faces.contiguous(), group)
+    ns = _all_gather_padded(normals.contiguous(), group) if normals is not None else None
+    off, shifted = 0, []
+    for v, f in zip(vs, fs):
+        shifted.append(f + off)
+        off += v.shape[0]
+    return torch.cat(vs, 0), torch.cat(shifted, 0), (torch.cat(ns, 0) if ns is not None else None)
+
+
+def global_stats(local_min: float, local_max: float, local_sum: float, local_sumsq_centered_fn, count: int, device, group=None):
+    """min / max / population std of a sharded volume: two rounds (mean first, then centred squares) so the result
+    matches the two-pass single-GPU computation."""
+    t = torch.tensor([local_min, -local_max], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    s = torch.tensor([local_sum, float(count)], dtype=torch.float64, device=device)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    mean = float(s[0] / s[1])
+    q = torch.tensor([local_sumsq_centered_fn(mean)], dtype=torch.float64, device=device)
+    dist.all_reduce(q, op=dist.ReduceOp.SUM, group=group)
+    return float(t[0]), float(-t[1]), math.sqrt(float(q[0]) / float(s[1]))
+
+
+def render_image_sharded(model, pose, H, W, focal, near, far, *, ndc=False, want=("rgb", "depth", "acc", "disp"), group=None):
+    """eval_nerf.py's image loop on N GPUs: this rank renders its rows, then one all_gather assembles the image."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    r0, r1 = row_shard(H, rank, world)
+    local = model._engine().render_image(pose, H, W, focal, near, far, ndc=ndc, rows=(r0, r1), want=list(want))
+    return gather_rows(local, group)
+
+
+def extract_geometry_sharded(model, args, group=None):
+    """mesh_nerf.extract_geometry on N GPUs: slab sigma sweep -> global iso statistics -> per-slab marching cubes ->
+    all_gather of the slab meshes.  Returns (vertices, triangles, normals) like the single-GPU function (vertices
+    rescaled to (-limit, limit)); the density grid stays sharded."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    eng = model._engine()
+    res = args.res
+    tiles = [torch.linspace(-args.limit, args.limit, res) for _ in range(3)]
+    x0, x1 = slab_shard(res, rank, world)
+    sigma = eng.grid_sigma(tiles, x0, x1)
+    own = sigma if rank == world - 1 else sigma[:-1]          # the shared plane is counted once
+    mn, mx, _ = eng.volume_stats(own)
+    s = float(own.double().sum())
+    smin, smax, sstd = global_stats(mn, mx, s, lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), sigma.device, group)
+    import numpy as np
+    iso = min(max(args.iso_level, np.float32(smin) + np.float32(sstd)), np.float32(smax) - np.float32(sstd))
+    v, f, n = eng.marching_cubes(sigma, float(iso), x_off=float(x0))
+    V, F, N = gather_mesh(v, f, n, group)
+    vertices = args.limit * (V.cpu() / (res / 2.0) - 1.0)
+    return vertices, F.cpu(), N.cpu(), float(iso)
