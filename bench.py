@@ -234,7 +234,9 @@ def main():
     RES, LIMIT, ISO = 512, 1.2, 32.0
     tiles = [torch.linspace(-LIMIT, LIMIT, RES) for _ in range(3)]
     x0, x1 = par.slab_shard(RES, rank, world)
-    eng.grid_sigma(tiles, x0, min(x0 + 8, x1))                      # warm-up
+    warm = eng.grid_sigma(tiles, x0, min(x0 + 8, x1))               # warm-up (kernel + workspace allocations)
+    eng.marching_cubes(torch.zeros((x1 - x0, RES, RES), device="cuda"), ISO)
+    del warm
     barrier()
     g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     g0.record()
