@@ -51,7 +51,7 @@ constexpr uint32_t kColAhi = 256, kColAlo = 384;
 constexpr int kMaxStages = 8;
 
 struct TcParams {
-  const NetProgram* prog;
+  NetProgram net;   // by value: lives in the constant bank, so the issuer warps index it with uniform registers
   const uint8_t* wpack;
   const float* bias;
   const float* head;
@@ -65,7 +65,7 @@ struct TcParams {
   int* err;
   unsigned long long* trace;   // NM_TC_TRACE: CTA 0 logs (kind, id, index, layer, t0..t3) records; trace[0] = count
   int dbg;   // bring-up switches (env NM_TC_DEBUG): 1 = no MMA issue, 2 = no epilogue math, 4 = no weight copies
-  uint32_t off_pe, off_bias, off_head, off_layers, off_blocks, off_red, off_bars;
+  uint32_t off_pe, off_bias, off_head, off_red, off_bars;
 };
 
 // barrier slots (8 B each) relative to off_bars
@@ -101,15 +101,14 @@ __device__ __forceinline__ uint32_t swz_off(int r, int c) {
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // broadcast from lane 0 so the compiler can prove the role / issuer index warp-uniform (uniform datapath, UR operands)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t bars = sbase + P.off_bars;
   const int NS = P.num_stages;
   float* s_bias = reinterpret_cast<float*>(smem + P.off_bias);
   float* s_head = reinterpret_cast<float*>(smem + P.off_head);
-  LayerProg* s_layers = reinterpret_cast<LayerProg*>(smem + P.off_layers);
-  BlockProg* s_blocks = reinterpret_cast<BlockProg*>(smem + P.off_blocks);
   float* s_red = reinterpret_cast<float*>(smem + P.off_red);   // [128] sigma partials, then [128][4]
-  const int n_layers = P.prog->n_layers, n_blocks = P.prog->n_blocks;
+  const int n_layers = P.net.n_layers, n_blocks = P.net.n_blocks;
 
   // ---------------------------------------------------------------- one-time setup
   if (threadIdx.x == 0) {
@@ -127,14 +126,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   {
     uint4* z = reinterpret_cast<uint4*>(smem + P.off_pe);
     for (int i = threadIdx.x; i < (int)(2 * kPeBuf / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < P.prog->n_bias; i += kThreads) s_bias[i] = P.bias[i];
-    for (int i = threadIdx.x; i < P.prog->n_head; i += kThreads) s_head[i] = P.head[i];
-    const uint32_t* gl = reinterpret_cast<const uint32_t*>(P.prog->layers);
-    uint32_t* sl = reinterpret_cast<uint32_t*>(s_layers);
-    for (int i = threadIdx.x; i < n_layers * (int)(sizeof(LayerProg) / 4); i += kThreads) sl[i] = gl[i];
-    const uint32_t* gb = reinterpret_cast<const uint32_t*>(P.prog->blocks);
-    uint32_t* sb = reinterpret_cast<uint32_t*>(s_blocks);
-    for (int i = threadIdx.x; i < n_blocks * (int)(sizeof(BlockProg) / 4); i += kThreads) sb[i] = gb[i];
+    for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) s_bias[i] = P.bias[i];
+    for (int i = threadIdx.x; i < P.net.n_head; i += kThreads) s_head[i] = P.head[i];
   }
   ptx::fence_proxy_async_smem();
   if (warp == kProdWarp) {
@@ -145,7 +138,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + P.off_bars + kTmemPtr);
-  if (warp < kEpiWarps && P.prog->accumulate_only) {   // all MMAs accumulate: start from a zero accumulator
+  if (threadIdx.x == 0 && tmem != 0u) { atomicExch(P.err, ERR_ALIGN + 10); __trap(); }   // a 512-column allocation starts at 0
+  if (warp < kEpiWarps && P.net.accumulate_only) {   // all MMAs accumulate: start from a zero accumulator
     uint32_t z[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) z[j] = 0u;
@@ -166,13 +160,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const int q = warp & 3, hcol = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const bool acc_only = P.prog->accumulate_only != 0;
+    const bool acc_only = P.net.accumulate_only != 0;
     uint32_t gl = 0;
     float sigma_val = 0.f;
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       const long long m = tile * kTileM + row;
       for (int li = 0; li < n_layers; ++li, ++gl) {
-        const LayerProg L = s_layers[li];
+        const LayerProg& L = P.net.layers[li];
         const int NC = L.n_out >> 6;
         const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
         const int heads = L.kind == KIND_SIGMA ? 1 : (L.kind == KIND_RGB ? 3 : (L.kind == KIND_OUT4 ? 4 : 0));
@@ -291,10 +285,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   } else if (warp < kProdWarp) {
     // =============================================================== front-end warps: next tile's encodings
     const int r = (warp - kFeWarp0) * 32 + lane;
-    const int Lx = P.prog->L_xyz, Ld = P.prog->L_dir, ix = P.prog->inc_xyz, id = P.prog->inc_dir;
-    const int has_dir = P.prog->dim_dir > 0;
-    const float* fx = P.prog->freq_xyz;
-    const float* fd = P.prog->freq_dir;
+    const int Lx = P.net.L_xyz, Ld = P.net.L_dir, ix = P.net.inc_xyz, id = P.net.inc_dir;
+    const int has_dir = P.net.dim_dir > 0;
+    const float* fx = P.net.freq_xyz;
+    const float* fd = P.net.freq_dir;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
@@ -345,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   } else {
     // =============================================================== MMA issuers (4 converged warps)
     const int w = warp - kMmaWarp0;
-    const uint32_t acc_only = P.prog->accumulate_only ? 1u : 0u;
+    const uint32_t acc_only = P.net.accumulate_only ? 1u : 0u;
     const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
     int slot = 0;
     uint32_t ph = 0, gl = 0, it = 0, gblock = 0;
@@ -356,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       ptx::tc_fence_after();
       const uint32_t pe_base = sbase + P.off_pe + buf * kPeBuf;
       for (int li = 0; li < n_layers; ++li, ++gl) {
-        const LayerProg L = s_layers[li];
+        const LayerProg& L = P.net.layers[li];
         const uint32_t none_d = (uint32_t)L.none_d >> (4 * w), none_k = (uint32_t)L.none_k >> (4 * w);
         int waited = -1;
         // Passing group g means the previous layer's chunk g is drained and its K-block g written; it is also the
@@ -370,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           }
         };
         for (int b = L.blk_begin; b < L.blk_end; ++b) {
-          const BlockProg B = s_blocks[b];
+          const BlockProg& B = P.net.blocks[b];
           if ((int)(B.flags >> 4) == w) {
             const long long tr0 = P.trace ? clock64() : 0;
             pass_group((int)B.group);
@@ -387,20 +381,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             const long long tr2 = P.trace ? clock64() : 0;
             ptx::tc_fence_after();
             const uint32_t wst = sbase + (uint32_t)slot * kStageBytes;
-            const uint32_t d_t = tmem + (uint32_t)B.nc * 64u;
-            for (int pass = 0; pass < ((P.dbg & 1) ? 0 : n_passes); ++pass) {
-              const bool a_lo = (pass == 1), w_lo = (pass == 2);
-              const uint64_t bdesc = ptx::make_kmajor_sw128_desc(wst + (w_lo ? (uint32_t)kHalfStage : 0u));
+            const uint32_t d_t = (uint32_t)B.nc * 64u;            // TMEM base is 0 (checked at start-up)
+            if (!(P.dbg & 1)) {
+              const uint64_t b_hi = ptx::make_kmajor_sw128_desc(wst), b_lo = ptx::make_kmajor_sw128_desc(wst + (uint32_t)kHalfStage);
+              const uint32_t acc_first = acc_only | (B.first ? 0u : 1u);
               if (B.src == SRC_ACT) {
-                const uint32_t a_t = tmem + (a_lo ? kColAlo : kColAhi) + (uint32_t)B.kb * 32u;
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-                  ptx::mma_ts_elect(d_t, a_t + 8u * s, bdesc + 2u * s, idesc, acc_only | !(B.first && pass == 0 && s == 0));
+                const uint32_t a_hi = kColAhi + (uint32_t)B.kb * 32u, a_lo = kColAlo + (uint32_t)B.kb * 32u;
+                if (n_passes == 3) ptx::mma_block_ts3(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first);
+                else ptx::mma_block_ts1(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first);
               } else {
-                const uint64_t adesc = ptx::make_kmajor_sw128_desc(pe_base + (B.src == SRC_PE_DIR ? 2 * kPeTile : 0u) +
-                                                                   (a_lo ? kPeTile : 0u));
-                for (int s = 0; s < (int)B.ksteps; ++s)
-                  ptx::mma_ss_elect(d_t, adesc + 2u * s, bdesc + 2u * s, idesc, acc_only | !(B.first && pass == 0 && s == 0));
+                const uint32_t pe_t = pe_base + (B.src == SRC_PE_DIR ? 2 * kPeTile : 0u);
+                const uint64_t a_hi = ptx::make_kmajor_sw128_desc(pe_t), a_lo = ptx::make_kmajor_sw128_desc(pe_t + kPeTile);
+                if (n_passes == 3) ptx::mma_block_ss3(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first, (uint32_t)B.ksteps);
+                else ptx::mma_block_ss1(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first, (uint32_t)B.ksteps);
               }
             }
             ptx::tc_commit_elect(bars + kBarWEmpty + 8 * slot);
@@ -430,7 +423,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   if (in.M <= 0) return 0;
   const NetProgram& hp = sigma_only ? net.sigma : net.full;
   TcParams P{};
-  P.prog = sigma_only ? net.d_sigma : net.d_full;
+  P.net = hp;
   P.wpack = sigma_only ? net.d_wpack_sigma : net.d_wpack_full;
   P.bias = net.d_bias;
   P.head = net.d_head;
@@ -454,7 +447,6 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   NM_CUDA(cudaGetDevice(&dev));
   NM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const uint32_t fixed = 2 * kPeBuf + align_up(hp.n_bias * 4, 16) + align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16) +
-                         align_up(hp.n_layers * sizeof(LayerProg), 16) + align_up(hp.n_blocks * sizeof(BlockProg), 16) +
                          (128 + 512) * 4 + kBarBytes;
   int ns = ((int)max_smem - (int)fixed) / kStageBytes;
   if (ns > kMaxStages) ns = kMaxStages;
@@ -465,8 +457,6 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.off_pe = off; off += 2 * kPeBuf;
   P.off_bias = off; off += align_up(hp.n_bias * 4, 16);
   P.off_head = off; off += align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16);
-  P.off_layers = off; off += align_up(hp.n_layers * sizeof(LayerProg), 16);
-  P.off_blocks = off; off += align_up(hp.n_blocks * sizeof(BlockProg), 16);
   P.off_red = off; off += (128 + 512) * 4;
   P.off_bars = off; off += kBarBytes;
   NM_CHECK((int)off <= max_smem, "shared-memory layout overflow");

@@ -100,6 +100,107 @@ __device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One schedule block (64x64, K=64) as ONE asm statement: a single elect, operands converted to uniform registers once,
+// descriptor increments in PTX.  Issuing the 12 (exact) / 4 (fast) MMAs one statement at a time costs ~85 cycles each
+// (five R2UR + elect per MMA); fused they approach the 32-cycle execution time of an N=64 MMA.
+// Order (exact): a_hi*b_hi, a_lo*b_hi, a_hi*b_lo; the first MMA overwrites when acc_first == 0.
+__device__ __forceinline__ void mma_block_ts3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                              uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pacc, pt;\n\t.reg .b32 a;\n\t.reg .b64 b;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pacc, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %5, pacc;\n\t"
+      "add.u32 a, %1, 8;\n\tadd.u64 b, %3, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %1, 16;\n\tadd.u64 b, %3, 4;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %1, 24;\n\tadd.u64 b, %3, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, pt;\n\t"
+      "add.u32 a, %2, 8;\n\tadd.u64 b, %3, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %2, 16;\n\tadd.u64 b, %3, 4;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %2, 24;\n\tadd.u64 b, %3, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %4, %5, pt;\n\t"
+      "add.u32 a, %1, 8;\n\tadd.u64 b, %4, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %1, 16;\n\tadd.u64 b, %4, 4;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %1, 24;\n\tadd.u64 b, %4, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+__device__ __forceinline__ void mma_block_ts1(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                              uint32_t idesc, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pacc, pt;\n\t.reg .b32 a;\n\t.reg .b64 b;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pacc, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %5, pacc;\n\t"
+      "add.u32 a, %1, 8;\n\tadd.u64 b, %3, 2;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %1, 16;\n\tadd.u64 b, %3, 4;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "add.u32 a, %1, 24;\n\tadd.u64 b, %3, 6;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [a], b, %5, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "r"(a_hi), "r"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_first)
+      : "memory");
+}
+// same for an encoding block (A from shared memory), ksteps (1..4) K=16 steps per pass
+__device__ __forceinline__ void mma_block_ss3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                              uint32_t idesc, uint32_t acc_first, uint32_t ksteps) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pk, pacc, pt;\n\t.reg .b64 a, b;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pacc, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "setp.gt.u32 pk, %7, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 0;\n\tadd.u64 b, %3, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pacc;\n\t"
+      "setp.gt.u32 pk, %7, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 2;\n\tadd.u64 b, %3, 2;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 4;\n\tadd.u64 b, %3, 4;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 6;\n\tadd.u64 b, %3, 6;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %2, 0;\n\tadd.u64 b, %3, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %2, 2;\n\tadd.u64 b, %3, 2;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %2, 4;\n\tadd.u64 b, %3, 4;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %2, 6;\n\tadd.u64 b, %3, 6;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 0;\n\tadd.u64 b, %4, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 2;\n\tadd.u64 b, %4, 2;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 4;\n\tadd.u64 b, %4, 4;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 6;\n\tadd.u64 b, %4, 6;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_first), "r"(ksteps)
+      : "memory");
+}
+__device__ __forceinline__ void mma_block_ss1(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                              uint32_t idesc, uint32_t acc_first, uint32_t ksteps) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pk, pacc, pt;\n\t.reg .b64 a, b;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pacc, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "setp.gt.u32 pk, %7, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 0;\n\tadd.u64 b, %3, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pacc;\n\t"
+      "setp.gt.u32 pk, %7, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 2;\n\tadd.u64 b, %3, 2;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 4;\n\tadd.u64 b, %3, 4;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 6;\n\tadd.u64 b, %3, 6;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_first), "r"(ksteps)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
