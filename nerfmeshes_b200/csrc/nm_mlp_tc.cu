@@ -46,7 +46,8 @@ constexpr int kFeWarp0 = 8;
 constexpr int kProdWarp = 12;
 constexpr int kMmaWarp0 = 13;
 constexpr uint32_t kPeTile = 16384;      // 128 rows x 128 B
-constexpr uint32_t kPeBuf = 4 * kPeTile;  // xyz_hi, xyz_lo, dir_hi, dir_lo
+constexpr uint32_t kPeBuf = 2 * kPeTile;  // one xyz encoding buffer: hi, lo (double-buffered: needed at the START of a tile)
+constexpr uint32_t kPeTotal = 3 * kPeBuf; // + one single-buffered view-direction buffer (needed only by the LAST layer)
 constexpr uint32_t kColAhi = 256, kColAlo = 384;
 constexpr int kMaxStages = 8;
 
@@ -70,7 +71,8 @@ struct TcParams {
 
 // barrier slots (8 B each) relative to off_bars
 constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
-                   kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kLoadedCnt = 264, kBarBytes = 320;
+                   kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kLoadedCnt = 264, kBarDirFull = 272, kBarDirEmpty = 280,
+                   kBarBytes = 320;
 
 enum : int { ERR_ALIGN = 1, ERR_W_EMPTY = 2, ERR_W_FULL = 3, ERR_PE_FULL = 4, ERR_PE_EMPTY = 5, ERR_CHUNK = 6,
              ERR_DFULL = 7, ERR_KBFREE = 8 };
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     if (sbase & 1023u) { atomicExch(P.err, ERR_ALIGN); __trap(); }
     for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(bars + kBarWFull + 8 * i, 1); ptx::mbar_init(bars + kBarWEmpty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bars + kBarPeFull + 8 * i, 128); ptx::mbar_init(bars + kBarPeEmpty + 8 * i, kIssuers); }
+    ptx::mbar_init(bars + kBarDirFull, 128);
+    ptx::mbar_init(bars + kBarDirEmpty, kIssuers);
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(bars + kBarChunk + 8 * i, 4);
       ptx::mbar_init(bars + kBarDFull + 8 * i, kIssuers);
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   }
   {
     uint4* z = reinterpret_cast<uint4*>(smem + P.off_pe);
-    for (int i = threadIdx.x; i < (int)(2 * kPeBuf / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (int)(kPeTotal / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) s_bias[i] = P.bias[i];
     for (int i = threadIdx.x; i < P.net.n_head; i += kThreads) s_head[i] = P.head[i];
   }
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // =============================================================== front-end warps: next tile's encodings
     const int r = (warp - kFeWarp0) * 32 + lane;
     const int Lx = P.net.L_xyz, Ld = P.net.L_dir, ix = P.net.inc_xyz, id = P.net.inc_dir;
-    const int has_dir = P.net.dim_dir > 0;
+    const int has_dir = P.net.uses_dir;
     const float* fx = P.net.freq_xyz;
     const float* fd = P.net.freq_dir;
     uint32_t it = 0;
@@ -306,9 +310,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         *reinterpret_cast<uint16_t*>(hi_tile + kPeTile + off) = f16_bits_sat(a - f16_bits_to_float(h));
       };
       positional_encoding(p, Lx, ix, fx, [&](int j, float val) { emit_to(tb, j, val); });
-      if (has_dir) positional_encoding(d, Ld, id, fd, [&](int j, float val) { emit_to(tb + 2 * kPeTile, j, val); });
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bars + kBarPeFull + 8 * buf);
+      if (has_dir) {   // the view-direction tile is free once the previous tile's last layer has read it
+        ptx::mbar_wait(bars + kBarDirEmpty, (it & 1) ^ 1, P.err, ERR_PE_EMPTY);
+        positional_encoding(d, Ld, id, fd, [&](int j, float val) { emit_to(smem + P.off_pe + 2 * kPeBuf, j, val); });
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(bars + kBarDirFull);
+      }
     }
   } else if (warp == kProdWarp) {
     // =============================================================== weight producer
@@ -349,6 +358,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
       ptx::tc_fence_after();
       const uint32_t pe_base = sbase + P.off_pe + buf * kPeBuf;
+      const uint32_t dir_base = sbase + P.off_pe + 2 * kPeBuf;
+      bool dir_waited = false;
       for (int li = 0; li < n_layers; ++li, ++gl) {
         const LayerProg& L = P.net.layers[li];
         const uint32_t none_d = (uint32_t)L.none_d >> (4 * w), none_k = (uint32_t)L.none_k >> (4 * w);
@@ -390,7 +401,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 if (n_passes == 3) ptx::mma_block_ts3(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first);
                 else ptx::mma_block_ts1(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first);
               } else {
-                const uint32_t pe_t = pe_base + (B.src == SRC_PE_DIR ? 2 * kPeTile : 0u);
+                if (B.src == SRC_PE_DIR && !dir_waited) {
+                  ptx::mbar_wait(bars + kBarDirFull, it & 1, P.err, ERR_PE_FULL);
+                  ptx::tc_fence_after();
+                  dir_waited = true;
+                }
+                const uint32_t pe_t = (B.src == SRC_PE_DIR) ? dir_base : pe_base;
                 const uint64_t a_hi = ptx::make_kmajor_sw128_desc(pe_t), a_lo = ptx::make_kmajor_sw128_desc(pe_t + kPeTile);
                 if (n_passes == 3) ptx::mma_block_ss3(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first, (uint32_t)B.ksteps);
                 else ptx::mma_block_ss1(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first, (uint32_t)B.ksteps);
@@ -407,6 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         pass_group(3);
       }
       ptx::tc_commit_elect(bars + kBarPeEmpty + 8 * buf);
+      ptx::tc_commit_elect(bars + kBarDirEmpty);
     }
   }
 
@@ -446,7 +463,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   int dev = 0, max_smem = 0;
   NM_CUDA(cudaGetDevice(&dev));
   NM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const uint32_t fixed = 2 * kPeBuf + align_up(hp.n_bias * 4, 16) + align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16) +
+  const uint32_t fixed = kPeTotal + align_up(hp.n_bias * 4, 16) + align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16) +
                          (128 + 512) * 4 + kBarBytes;
   int ns = ((int)max_smem - (int)fixed) / kStageBytes;
   if (ns > kMaxStages) ns = kMaxStages;
@@ -454,7 +471,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   NM_CHECK(ns >= 2, "network too large for the shared-memory budget (%u B fixed, %d B available)", fixed, max_smem);
   P.num_stages = ns;
   uint32_t off = (uint32_t)ns * kStageBytes;
-  P.off_pe = off; off += 2 * kPeBuf;
+  P.off_pe = off; off += kPeTotal;
   P.off_bias = off; off += align_up(hp.n_bias * 4, 16);
   P.off_head = off; off += align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16);
   P.off_red = off; off += (128 + 512) * 4;

@@ -122,6 +122,7 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
     }
   }
   p->n_layers = nl; p->n_bias = bias; p->n_head = head;
+  for (int i = 0; i < nl; ++i) if (p->layers[i].pe_src == SRC_PE_DIR) p->uses_dir = 1;
 
   // tensor-core schedule.  Block (k,n) needs epilogue chunks 0..max(k,n) of the previous layer: chunk k supplies
   // activation K-block k, chunk n frees accumulator chunk n.  Within a group the column part (all blocks into the

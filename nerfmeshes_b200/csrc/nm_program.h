@@ -62,6 +62,7 @@ struct NetProgram {
   int32_t dim_xyz, dim_dir;      // true PE widths
   int32_t L_xyz, L_dir, inc_xyz, inc_dir;
   int32_t n_bias, n_head;        // floats
+  int32_t uses_dir;              // some layer of THIS program reads the view-direction encoding
   int32_t accumulate_only;       // 1: blocks of a chunk come from several issuers (no order): always accumulate, epilogue re-zeroes
   float freq_xyz[kMaxFreq];
   float freq_dir[kMaxFreq];

@@ -54,7 +54,7 @@ class BlockProg(C.Structure):
 
 class NetProgram(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layers", "n_blocks", "hidden", "dim_xyz", "dim_dir", "L_xyz", "L_dir", "inc_xyz",
-                                         "inc_dir", "n_bias", "n_head", "accumulate_only")] + \
+                                         "inc_dir", "n_bias", "n_head", "uses_dir", "accumulate_only")] + \
                [("freq_xyz", C.c_float * 16), ("freq_dir", C.c_float * 16), ("layers", LayerProg * 24), ("blocks", BlockProg * 256)]
 
 

@@ -39,6 +39,8 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
     chunk = [Bar(f"chunk_ready{i}", 1) for i in range(4)]       # one arrival per epilogue set (4 warps act together)
     d_full = [Bar(f"d_full{i}", 4) for i in range(4)]
     kb_free = [Bar(f"kb_free{i}", 4) for i in range(4)]
+    dir_full, dir_empty = Bar("dir_full", 1), Bar("dir_empty", 4)
+    uses_dir = any(L[i].pe_src == 2 for i in range(len(L)))
     waiting = {}
     armed = [0]
     errors = []
@@ -66,6 +68,10 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
             if t >= 2:
                 yield from wait("frontend", pe_empty[buf], t // 2 - 1)
             pe_full[buf].arrive()
+            if uses_dir:
+                if t >= 1:
+                    yield from wait("frontend", dir_empty, t - 1)
+                dir_full.arrive()
 
     def issuer(w):
         me = f"issuer{w}"
@@ -92,6 +98,8 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
                     slot, rnd = g % NS, g // NS
                     if (B.flags >> 4) == w:
                         yield from pass_group(B.group)
+                        if B.src == 2:
+                            yield from wait(me, dir_full, t)
                         while armed_counter and armed[0] <= g:
                             waiting[me] = f"armed counter > {g}"
                             yield
@@ -107,6 +115,7 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
                 yield from pass_group(3)
                 gl += 1
             pe_empty[buf].arrive()
+            dir_empty.arrive()
 
     def epilogue(s):
         me = f"epi_set{s}"
@@ -127,16 +136,16 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
     while alive:
         progressed = False
         for name in list(alive):
-            before = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free),
-                      tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free))
+            before = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]),
+                      tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]))
             try:
                 next(alive[name])
             except StopIteration:
                 del alive[name]
                 progressed = True
                 continue
-            after = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free),
-                     tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free))
+            after = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]),
+                     tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]))
             progressed |= before != after
         steps += 1
         if not progressed:
