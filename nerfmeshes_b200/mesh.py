@@ -55,3 +55,51 @@ def extract_geometry(model, device, args):
     # division by a python scalar multiplies by the reciprocal, which differs in the last bit)
     vertices = args.limit * (verts.cpu() / (args.res / 2.0) - 1.0)    # keeps the reference's res/2 scale (:90)
     return vertices, faces.cpu(), normals.cpu(), density.cpu().numpy()
+
+
+def export_obj(vertices, triangles, diffuse, normals, filename):
+    """src/nerf/nerf_helpers.py:86-111, byte-identical text: `v x y z [r g b]`, `vn x y z`, `f i//i j//j k//k` (1-based).
+    The reference formats every float32 (torch or numpy) through python's format(): the value widened to double, shortest
+    round-trip repr.  Same text here, built in one pass and written with a single writelines()."""
+    def rows(a):
+        if isinstance(a, torch.Tensor):
+            a = a.detach().cpu()
+            if a.dtype.is_floating_point:
+                return [[repr(x) for x in r] for r in a.double().tolist()]
+            return [[str(x) for x in r] for r in a.tolist()]
+        a = np.asarray(a)
+        if a.dtype.kind == "f":                      # "{}".format(np.float32) widens to a python float first
+            return [[repr(x) for x in r] for r in a.astype(np.float64).tolist()]
+        return [[str(x) for x in r] for r in a.tolist()]
+
+    v, n, d = rows(vertices), rows(normals), rows(diffuse) if len(diffuse) else []
+    out = []
+    for i, r in enumerate(v):
+        out.append("v " + " ".join(r) + (" " + " ".join(d[i]) if len(d) > i else "") + "\n")
+    out.extend("vn " + " ".join(r) + "\n" for r in n)
+    tri = triangles.detach().cpu().numpy() if isinstance(triangles, torch.Tensor) else np.asarray(triangles)
+    out.extend("f" + "".join(f" {i + 1}//{i + 1}" for i in r) + "\n" for r in tri.tolist())
+    with open(filename, "w") as fh:
+        fh.writelines(out)
+
+
+def mesh_appearance(model, vertices, normals, args):
+    """The appearance pass of export_marching_cubes (src/mesh_nerf.py:160-192): per-vertex colour, either the raw network
+    colour at the vertex (no_view_dependence) or a short ray cast along -normal through model.query — one batched call
+    on the device instead of the reference's batchify loop."""
+    targets, directions = vertices, -normals
+    if getattr(args, "no_view_dependence", False):
+        return model.sample_points(targets.cuda(), directions.cuda())[..., :3].cpu().numpy()
+    ray_bounds = torch.tensor([0.0, args.view_disparity_max_bound], dtype=directions.dtype)
+    ray_origins = targets - args.view_disparity * directions
+    return model.query((ray_origins.cuda(), directions.cuda(), ray_bounds)).rgb_map.cpu().numpy()
+
+
+def export_marching_cubes(model, args, cfg=None, device="cuda"):
+    """src/mesh_nerf.py:131-201 without the cache / super-sampling branches: geometry -> appearance -> OBJ."""
+    import os
+    vertices, triangles, normals, density = extract_geometry(model, device, args)
+    diffuse = mesh_appearance(model, vertices, normals, args)
+    path = os.path.join(args.save_dir, args.mesh_name)
+    export_obj(vertices, triangles, diffuse, normals, path)
+    return path

@@ -240,3 +240,12 @@ def test_lightning_checkpoint_reader():
     assert m.cfg.nerf.train.num_coarse == 64 and m.cfg.experiment.model == "NeRFModel"
     b = nm.BuFFModel.load_from_checkpoint(p.format("buff-synthetic-lego"))
     assert torch.equal(b.tree.voxels, load_npz("weights_lego_buff.npz")["voxels"])
+
+
+def test_export_obj_matches_reference_text(tmp_path):
+    """OBJ writer (src/nerf/nerf_helpers.py:86-111): byte-identical to the file the reference's own writer produced
+    (tests/golden/golden_mesh.obj, generated by tests/golden/make_golden.py-style import of the reference)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "golden_mesh_inputs.npz"))
+    out = tmp_path / "m.obj"
+    nm.mesh.export_obj(torch.from_numpy(z["v"]), torch.from_numpy(z["f"]), z["d"], torch.from_numpy(z["n"]), str(out))
+    assert out.read_text() == open(os.path.join(ROOT, "tests", "golden", "golden_mesh.obj")).read()
