@@ -114,3 +114,32 @@ def test_extract_geometry_on_lego_grid():
     assert np.array_equal(tris.numpy(), f)
     np.testing.assert_array_equal(verts.numpy(), (1.2 * (torch.from_numpy(v) / (A.res / 2.0) - 1.0)).numpy())
     assert verts.shape[0] > 1000
+
+
+@pytest.mark.gpu
+def test_export_marching_cubes_writes_coloured_obj(tmp_path):
+    """mesh_nerf.export_marching_cubes (geometry -> view-dependent appearance by ray casting along -normal -> OBJ)."""
+    import nerfmeshes_b200 as nm
+    from conftest import load_npz
+    from test_gpu_parity import LEGO_CFG
+    model = nm.NeRFModel.from_npz(LEGO_CFG, load_npz("weights_lego_nerf.npz")).eval()
+
+    class A:
+        limit, res, iso_level = 1.2, 36, 32.0
+        no_view_dependence, view_disparity, view_disparity_max_bound = False, 1e-2, 4e0
+        save_dir, mesh_name = str(tmp_path), "mesh.obj"
+    path = nm.mesh.export_marching_cubes(model, A)
+    lines = open(path).read().splitlines()
+    v = [l for l in lines if l.startswith("v ")]
+    vn = [l for l in lines if l.startswith("vn ")]
+    f = [l for l in lines if l.startswith("f ")]
+    assert len(v) == len(vn) > 500 and len(f) > 1000
+    cols = np.array([[float(x) for x in l.split()[4:7]] for l in v])
+    assert cols.shape[1] == 3 and cols.min() >= 0.0 and cols.max() <= 1.0 + 1e-6 and cols.std() > 0.01
+    idx = np.array([[int(t.split("//")[0]) for t in l.split()[1:]] for l in f])
+    assert idx.min() == 1 and idx.max() == len(v)
+    # the no-view-dependence branch samples the network directly at the vertices
+    A.no_view_dependence = True
+    verts, tris, normals, _ = nm.extract_geometry(model, "cuda", A)
+    d = nm.mesh.mesh_appearance(model, verts, normals, A)
+    assert d.shape == (verts.shape[0], 3)
