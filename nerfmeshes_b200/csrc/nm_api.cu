@@ -2,6 +2,7 @@
 // of the hot path — the body of NeRFModel.forward / BuFFModel.forward (src/models/model_nerf.py:37-78,
 // model_buff.py:34-69) and extract_radiance (src/mesh_nerf.py:27-53) as stream-ordered kernel sequences.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -62,7 +63,11 @@ struct NmHandle_t {
 
 namespace {
 
-constexpr long long kChunkRays = 1ll << 20;
+// rays per internal chunk (bounds the per-sample workspace: 20 B x 192 samples x 1 Mi rays = 4 GB); NM_CHUNK_RAYS overrides (tests)
+long long chunk_rays() {
+  static long long v = [] { const char* e = getenv("NM_CHUNK_RAYS"); long long x = e ? atoll(e) : 0; return x > 0 ? x : (1ll << 20); }();
+  return v;
+}
 
 int bind_device(NmHandle h) {
   NM_CHECK(h != nullptr, "null handle");
@@ -215,9 +220,10 @@ int render_rays_impl(NmHandle h, const float* origins, int o_stride, const float
   NM_CHECK(near_dev || nf_host, "no near/far bounds given");
   NM_CHECK(h->s_table.p != nullptr, "sampler tables missing");
   const int S = out_samples(h, flags);
-  for (long long r0 = 0; r0 < R; r0 += kChunkRays) {
+  const long long kChunk = chunk_rays();
+  for (long long r0 = 0; r0 < R; r0 += kChunk) {
     RayBatch rb{};
-    rb.R = (R - r0 < kChunkRays) ? R - r0 : kChunkRays;
+    rb.R = (R - r0 < kChunk) ? R - r0 : kChunk;
     rb.origins = origins + (long long)o_stride * r0; rb.o_stride = o_stride; rb.dirs = dirs + 3 * r0;
     if (nf_host) { rb.nf[0] = nf_host[0]; rb.nf[1] = nf_host[1]; }
     rb.near_dev = near_dev ? near_dev + r0 : nullptr; rb.far_dev = far_dev ? far_dev + r0 : nullptr;

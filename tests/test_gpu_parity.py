@@ -270,3 +270,48 @@ def test_grid_sigma_and_iso(lego_model):
     mn, mx, sd = lego_model._engine().volume_stats(sig)
     s = sig.cpu().numpy()
     assert mn == s.min() and mx == s.max() and abs(sd - s.std()) <= 1e-4 * s.std()
+
+
+# ----------------------------------------------------------------------------------------------------- full size
+def test_full_size_image_properties(lego_model):
+    """BASELINE.json configs[1] at full size (800x800, 64+128): size-independent properties of the whole image plus an
+    end-to-end oracle comparison on a random subset of its rays."""
+    g = load_npz("golden_lego_nerf.npz")
+    H = W = 800
+    f = float(g["focal"])
+    eng = lego_model._engine()
+    o1 = eng.render_image(g["pose"], H, W, f, 2.0, 6.0, want=["rgb", "acc", "disp", "depth_raw", "t_vals", "weights"])
+    o2 = eng.render_image(g["pose"], H, W, f, 2.0, 6.0, want=["rgb"])
+    assert torch.equal(o1["rgb"], o2["rgb"])                                        # run-to-run deterministic
+    assert bool(torch.isfinite(o1["rgb"]).all()) and float(o1["rgb"].min()) >= 0.0 and float(o1["rgb"].max()) <= 1.0 + 1e-5
+    assert float(o1["acc"].max()) <= 1.0 + 1e-5 and float(o1["acc"].min()) >= 0.0
+    t = o1["t_vals"]
+    assert bool((t[:, 1:] >= t[:, :-1]).all()) and float(t.min()) >= 2.0 and float(t.max()) <= 6.0    # sorted, inside [near, far]
+    assert float((o1["weights"].sum(-1) - o1["acc"]).abs().max()) <= 2e-5           # acc is the sum of the weights
+    ids = torch.randint(0, H * W, (1024,), generator=torch.Generator().manual_seed(4))
+    orig, dirs = O.get_ray_bundle(H, W, f, g["pose"])
+    z = load_npz("weights_lego_nerf.npz")
+    from conftest import net_weights
+    bc, bf, _, _ = O.nerf_forward(net_weights(z, "coarse"), net_weights(z, "fine"), NET, NET, O.RenderCfg(), orig,
+                                  dirs.reshape(-1, 3)[ids], torch.tensor(2.0), torch.tensor(6.0), u=z["sample_pdf_u"])
+    err = (o1["rgb"].cpu()[ids] - bf.rgb_map).abs().flatten()
+    assert float(err.max()) <= 6e-4 and float(err.quantile(0.99)) <= 1e-4, (float(err.max()), float(err.quantile(0.99)))
+
+
+def test_internal_chunking_is_invisible(lego_model):
+    """nm_render_rays splits very large batches internally; the split must not change a single bit."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+            "import nerfmeshes_b200 as nm; from conftest import load_npz; from test_gpu_parity import LEGO_CFG;"
+            "g = load_npz('golden_lego_nerf.npz'); m = nm.NeRFModel.from_npz(LEGO_CFG, load_npz('weights_lego_nerf.npz')).eval();"
+            "o = m._engine().render_image(g['pose'], 50, 50, 70.0, 2.0, 6.0, want=['rgb', 'disp']);"
+            "torch.save({k: v.cpu() for k, v in o.items()}, sys.argv[1])")
+    from conftest import ROOT
+    outs = []
+    for chunk, name in (("0", "a.pt"), ("700", "b.pt")):
+        path = os.path.join("/tmp", f"nm_chunk_{name}")
+        subprocess.run([sys.executable, "-c", code % (ROOT, ROOT), path], check=True, env=dict(os.environ, NM_CHUNK_RAYS=chunk), timeout=300)
+        outs.append(torch.load(path))
+    assert torch.equal(outs[0]["rgb"], outs[1]["rgb"]) and torch.equal(outs[0]["disp"], outs[1]["disp"])
