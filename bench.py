@@ -258,6 +258,10 @@ def main():
         if dist is not None:
             dist.destroy_process_group()
         return
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_mlp_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("mean_bytes_per_launch")       # ncu dram read+write per MLP launch, same workload
     rays = H * W * a.steps * world
     peak_tf, _, peak_src = measured_peaks()
     achieved_tf = (mlp_pts * FLOP_PER_POINT / (mlp_ms * 1e-3)) / 1e12 if mlp_ms > 0 else None
@@ -274,7 +278,9 @@ def main():
                  "sigma_sweep_ms": grid_ms, "marching_cubes_ms": mc_ms, "n_vertices": int(n_mesh[0]), "n_triangles": int(n_mesh[1]),
                  "sweep_tflops": RES ** 3 * 982528 / (grid_ms * 1e-3) / 1e12},
         "roofline": {"bound": "tensor", "kernel": "mlp_tc_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
+                     "traffic_note": "DRAM bytes per launch (ncu); algorithmic 20 B/point = 1.64 GB per launch on average: no re-reads",
+                     "peak_source": peak_src,
                      "algorithmic_flop_per_point": FLOP_PER_POINT, "points_per_step": mlp_pts // max(a.steps, 1),
                      "launches_per_step": mlp_n // max(a.steps, 1), "kernel_ms_per_step": mlp_ms / max(a.steps, 1),
                      "note": "exact mode issues 3 MMAs per product: tensor-pipe work is 3x the algorithmic FLOPs"},
