@@ -27,3 +27,38 @@ def test_reference_mesh_script_runs_on_the_overlay(tmp_path):
         assert os.path.exists(tmp_path / "mesh.obj")
     else:
         assert r.returncode != 0 and "needs a CUDA device" in out, out[-2000:]
+
+
+@pytest.mark.gpu
+def test_overlay_modules_serve_the_mesh_script_call_sequence(tmp_path):
+    """On the GPU box the reference tree is absent, so replay the call sequence of its mesh script (mesh_nerf.py:27-53,
+    68-92, 160-201: batchify -> model.sample_points -> .cpu(); skimage.measure.marching_cubes on a numpy volume;
+    model.query on per-ray origins with CPU bounds; export_obj) against the overlay's modules."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    try:
+        import models as ov_models
+        from nerf.nerf_helpers import batchify, export_obj
+        from skimage import measure
+        from conftest import load_npz
+        from test_gpu_parity import LEGO_CFG
+        model = ov_models.NeRFModel.from_npz(LEGO_CFG, load_npz("weights_lego_nerf.npz")).eval().to("cuda")
+        res, limit = 28, 1.2
+        tiles = [torch.linspace(-limit, limit, res)] * 3
+        samples = torch.stack(torch.meshgrid(*tiles, indexing="ij"), -1).view(-1, 3).float()
+        rad = [model.sample_points(s, s).cpu() for (s,) in batchify(samples, batch_size=1024, device="cuda", progress=False)]
+        radiance = torch.cat(rad, 0).view(res, res, res, 4).contiguous().numpy()
+        verts, faces, normals, _ = measure.marching_cubes(radiance[..., 3], 32.0)
+        vertices = limit * (torch.from_numpy(np.ascontiguousarray(verts)) / (res / 2.0) - 1.0)
+        directions = -torch.from_numpy(np.ascontiguousarray(normals))
+        origins = vertices - 1e-2 * directions
+        diffuse = []
+        for (o, d) in batchify(origins, directions, batch_size=1024, device="cuda", progress=False):
+            diffuse.append(model.query((o, d, torch.tensor([0.0, 4.0]))).rgb_map.cpu())
+        diffuse = torch.cat(diffuse).numpy()
+        export_obj(vertices, torch.from_numpy(np.ascontiguousarray(faces)), diffuse, -directions, str(tmp_path / "m.obj"))
+        assert diffuse.shape == (verts.shape[0], 3) and verts.shape[0] > 300 and (tmp_path / "m.obj").stat().st_size > 10000
+    finally:
+        sys.path.remove(os.path.join(ROOT, "compat"))
+        for m in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "nerf" or k.startswith("nerf.") or k.startswith("skimage")]:
+            del sys.modules[m]
