@@ -87,14 +87,17 @@ __device__ __forceinline__ float f16_bits_to_float(uint16_t h) {
   asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
   return f;
 }
+// Event log of CTA 0 (NM_TC_TRACE).  Six writers (4 issuers, 2 epilogue sets) own disjoint regions and keep their own
+// cursor, so a record is five fire-and-forget global stores — no atomics, negligible perturbation.
+constexpr int kTraceRegion = 10000;
 __device__ __forceinline__ void trace_rec(const TcParams& P, unsigned kind, unsigned id, unsigned idx, unsigned gl, long long t0,
-                                          long long t1, long long t2, long long t3) {
-  if (!P.trace || blockIdx.x != 0) return;
-  const unsigned long long slot = atomicAdd(P.trace, 1ull);
-  if (slot >= 60000ull) return;
-  unsigned long long* r = P.trace + 1 + slot * 5;
+                                          long long t1, long long t2, long long t3, unsigned& cursor) {
+  if (!P.trace || blockIdx.x != 0 || cursor >= (unsigned)kTraceRegion) return;
+  const unsigned region = (kind == 1 ? 0u : 4u) + id;
+  unsigned long long* r = P.trace + 1 + ((unsigned long long)region * kTraceRegion + cursor) * 5;
   r[0] = ((unsigned long long)kind << 48) | ((unsigned long long)id << 40) | ((unsigned long long)idx << 24) | gl;
   r[1] = (unsigned long long)t0; r[2] = (unsigned long long)t1; r[3] = (unsigned long long)t2; r[4] = (unsigned long long)t3;
+  ++cursor;
 }
 __device__ __forceinline__ uint32_t swz_off(int r, int c) {
   return (uint32_t)r * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool acc_only = P.net.accumulate_only != 0;
     uint32_t gl = 0;
+    unsigned trace_cursor = 0;
     float sigma_val = 0.f;
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       const long long m = tile * kTileM + row;
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bars + kBarChunk + 8 * n);
-          if (P.trace && (warp & 3) == 0 && lane == 0) trace_rec(P, 2, hcol, n, gl, tr0, tr1, tr2, clock64());
+          if (P.trace && (warp & 3) == 0 && lane == 0) trace_rec(P, 2, hcol, n, gl, tr0, tr1, tr2, clock64(), trace_cursor);
         }
         if (heads) {
           // the two chunk sets of a row live in warps w and w+4: combine their partial dot products through smem
@@ -351,12 +355,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const uint32_t acc_only = P.net.accumulate_only ? 1u : 0u;
     const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
     int slot = 0;
-    uint32_t ph = 0, gl = 0, it = 0, gblock = 0;
+    uint32_t ph = 0, gl = 0, it = 0, cur_pos = 0;
+    unsigned trace_cursor = 0;
     const uint32_t cnt_addr = bars + kLoadedCnt;
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
       ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
       ptx::tc_fence_after();
+      const uint32_t base_pos = it * (uint32_t)n_blocks;
       const uint32_t pe_base = sbase + P.off_pe + buf * kPeBuf;
       const uint32_t dir_base = sbase + P.off_pe + 2 * kPeBuf;
       bool dir_waited = false;
@@ -374,19 +380,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             if ((none_k >> waited) & 1u) ptx::tc_commit_elect(bars + kBarKbFree + 8 * waited);
           }
         };
-        for (int b = L.blk_begin; b < L.blk_end; ++b) {
-          const BlockProg& B = P.net.blocks[b];
-          if ((int)(B.flags >> 4) == w) {
+        // walk this issuer's own blocks of the layer (first_blk, then BlockProg.next): no scan over other issuers' blocks
+        const uint32_t fb = ((uint32_t)L.first_blk >> (8 * w)) & 0xFFu;
+        if (fb != 0xFFu) {
+          int b = L.blk_begin + (int)fb;
+          while (true) {
+            const BlockProg& B = P.net.blocks[b];
+            const uint32_t gpos = base_pos + (uint32_t)b;          // schedule position since kernel start = ring position
+            slot += (int)(gpos - cur_pos);
+            cur_pos = gpos;
+            while (slot >= NS) { slot -= NS; ph ^= 1; }
             const long long tr0 = P.trace ? clock64() : 0;
             pass_group((int)B.group);
             const long long tr1 = P.trace ? clock64() : 0;
             {   // the producer must have armed this stage for THIS round before its parity means anything
               uint32_t c;
-              long long t0 = clock64();
-              do {
-                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(c) : "r"(cnt_addr) : "memory");
-                if (c <= gblock && clock64() - t0 > 4000000000LL) { atomicExch(P.err, ERR_W_FULL + 100); __trap(); }
-              } while (c <= gblock);
+              asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(c) : "r"(cnt_addr) : "memory");
+              if (c <= gpos) {
+                const long long t0 = clock64();
+                do {
+                  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(c) : "r"(cnt_addr) : "memory");
+                  if (c <= gpos && clock64() - t0 > 4000000000LL) { atomicExch(P.err, ERR_W_FULL + 100); __trap(); }
+                } while (c <= gpos);
+              }
             }
             ptx::mbar_wait(bars + kBarWFull + 8 * slot, ph, P.err, ERR_W_FULL);
             const long long tr2 = P.trace ? clock64() : 0;
@@ -415,10 +431,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             ptx::tc_commit_elect(bars + kBarWEmpty + 8 * slot);
             if (B.flags & 1) ptx::tc_commit_elect(bars + kBarDFull + 8 * B.nc);
             if (B.flags & 2) ptx::tc_commit_elect(bars + kBarKbFree + 8 * B.kb);
-            if (P.trace && lane == 0) trace_rec(P, 1, w, b, gl, tr0, tr1, tr2, clock64());
+            if (P.trace && lane == 0) trace_rec(P, 1, w, b, gl, tr0, tr1, tr2, clock64(), trace_cursor);
+            if (!B.next) break;
+            b += (int)B.next;
           }
-          ++gblock;
-          if (++slot == NS) { slot = 0; ph ^= 1; }
         }
         pass_group(3);
       }
@@ -485,7 +501,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   }
   long long grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   const char* trace_path = getenv("NM_TC_TRACE");
-  const size_t trace_words = 1 + 60000 * 5;
+  const size_t trace_words = 1 + 6 * (size_t)kTraceRegion * 5;
   if (trace_path) {
     NM_CUDA(cudaMalloc(&P.trace, trace_words * 8));
     NM_CUDA(cudaMemset(P.trace, 0, trace_words * 8));

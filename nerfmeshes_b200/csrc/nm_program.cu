@@ -69,7 +69,7 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
   memset(p, 0, sizeof(*p));
   const int h = d.hidden_size;
   NM_CHECK(h == 128 || h == 256, "hidden_size %d unsupported (128 or 256)", h);
-  NM_CHECK(d.num_layers >= 1 && d.num_layers <= 16, "num_layers %d unsupported", d.num_layers);
+  NM_CHECK(d.num_layers >= 1 && d.num_layers + 2 <= kMaxLayers, "num_layers %d unsupported", d.num_layers);
   NM_CHECK(d.skip_step >= 1, "skip_step must be >= 1");
   NM_CHECK(d.num_encoding_fn_xyz >= 0 && d.num_encoding_fn_xyz <= 10, "num_encoding_fn_xyz must be in [0,10]");
   NM_CHECK(d.num_encoding_fn_dir >= 0 && d.num_encoding_fn_dir <= 10, "num_encoding_fn_dir must be in [0,10]");
@@ -172,6 +172,17 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
     for (int b = L.blk_begin; b < L.blk_end; ++b) {
       const int issuer = policy == 0 ? (b & (kIssuers - 1)) : p->blocks[b].nc;
       p->blocks[b].flags = (uint8_t)(issuer << 4);
+    }
+    L.first_blk = -1;   // 0xFFFFFFFF
+    for (int w = 0; w < kIssuers; ++w) {
+      int prev = -1;
+      for (int b = L.blk_begin; b < L.blk_end; ++b) {
+        if ((p->blocks[b].flags >> 4) != w) continue;
+        if (prev < 0) L.first_blk = (L.first_blk & ~(0xFF << (8 * w))) | ((b - L.blk_begin) << (8 * w));
+        else p->blocks[prev].next = (uint8_t)(b - prev);
+        p->blocks[b].next = 0;
+        prev = b;
+      }
     }
     for (int w = 0; w < kIssuers; ++w) {
       int ld[4] = {-1, -1, -1, -1}, lk[4] = {-1, -1, -1, -1};

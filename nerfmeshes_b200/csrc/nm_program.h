@@ -6,8 +6,8 @@
 
 namespace nm {
 
-constexpr int kMaxLayers = 24;
-constexpr int kMaxBlocks = 256;
+constexpr int kMaxLayers = 16;   // NetProgram travels as a kernel parameter (constant bank): keep it under 4 KB
+constexpr int kMaxBlocks = 200;
 constexpr int kMaxFreq = 16;
 
 // tensor-core tiling constants
@@ -40,6 +40,7 @@ struct LayerProg {
   // tensor-core kernel, 4 issuing warps: bit (issuer*4 + i) set when that issuer has
   // no block into accumulator chunk i (none_d) / no block reading activation K-block i (none_k) in this layer
   int32_t none_d, none_k;
+  int32_t first_blk;  // byte w = offset from blk_begin of issuer w's first block in this layer, 0xFF = none
 };
 
 // One (K-block, N-chunk) step of the tensor-core schedule == one 16 KB weight stage.
@@ -49,10 +50,11 @@ struct BlockProg {
   uint8_t nc;      // N-chunk: accumulator columns nc*64..
   uint8_t ksteps;  // 1..4 MMAs of K=16
   uint8_t group;   // needs epilogue chunks 0..group of the previous layer done
-  uint8_t first;   // first block into this accumulator chunk in schedule order (bookkeeping / CPU replay)
-  uint8_t last;    // last block into this accumulator chunk in schedule order
+  uint8_t first;   // first block into this accumulator chunk in schedule order (the first MMA overwrites)
+  uint8_t last;    // last block into this accumulator chunk in schedule order (bookkeeping / CPU replay)
   uint8_t flags;   // bit0: its issuer's last block into chunk nc; bit1: its issuer's last block reading K-block kb;
-                   // bits 4-5: issuer warp
+                   // bits 2-3: unused; bits 4-5: issuer warp
+  uint8_t next;    // distance (in schedule blocks) to the same issuer's next block in this layer, 0 = none
 };
 
 struct NetProgram {

@@ -45,17 +45,17 @@ def test_fails_loudly_without_gpu():
 # ------------------------------------------------------------------------------------------ program + packing
 class LayerProg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_out", "k_act", "pe_src", "k_pe", "relu", "kind", "is_final", "bias_off",
-                                         "head_off", "blk_begin", "blk_end", "wt_off", "none_d", "none_k")]
+                                         "head_off", "blk_begin", "blk_end", "wt_off", "none_d", "none_k", "first_blk")]
 
 
 class BlockProg(C.Structure):
-    _fields_ = [(n, C.c_uint8) for n in ("src", "kb", "nc", "ksteps", "group", "first", "last", "flags")]
+    _fields_ = [(n, C.c_uint8) for n in ("src", "kb", "nc", "ksteps", "group", "first", "last", "flags", "next")]
 
 
 class NetProgram(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_layers", "n_blocks", "hidden", "dim_xyz", "dim_dir", "L_xyz", "L_dir", "inc_xyz",
                                          "inc_dir", "n_bias", "n_head", "uses_dir", "accumulate_only")] + \
-               [("freq_xyz", C.c_float * 16), ("freq_dir", C.c_float * 16), ("layers", LayerProg * 24), ("blocks", BlockProg * 256)]
+               [("freq_xyz", C.c_float * 16), ("freq_dir", C.c_float * 16), ("layers", LayerProg * 16), ("blocks", BlockProg * 200)]
 
 
 def debug_pack(cfg: O.NetCfg, sd, sigma_only=False):
@@ -166,6 +166,13 @@ def test_schedule_and_packing_reproduce_each_linear_layer(arch, sigma_only):
         # per-issuer bookkeeping: for every issuer w and index i exactly one of {a flagged block, the none bit}
         for w in range(4):
             mine = [b for b in range(Lp.blk_begin, Lp.blk_end) if (prog.blocks[b].flags >> 4) == w]
+            # the issuer's private walk through the layer: first_blk, then `next` deltas, visits exactly its blocks in order
+            fb = (Lp.first_blk >> (8 * w)) & 0xFF
+            walk, b = [], (Lp.blk_begin + fb if fb != 0xFF else None)
+            while b is not None:
+                walk.append(b)
+                b = b + prog.blocks[b].next if prog.blocks[b].next else None
+            assert walk == mine
             for i in range(4):
                 fd = [b for b in mine if prog.blocks[b].nc == i and prog.blocks[b].flags & 1]
                 fk = [b for b in mine if prog.blocks[b].src == 0 and prog.blocks[b].kb == i and prog.blocks[b].flags & 2]

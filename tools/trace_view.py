@@ -3,8 +3,9 @@ import sys
 import numpy as np
 
 raw = np.fromfile(sys.argv[1], dtype=np.uint64)
-n = int(min(raw[0], 60000))
-rec = raw[1:1 + n * 5].reshape(n, 5)
+rec = raw[1:].reshape(-1, 5)
+rec = rec[rec[:, 0] != 0]
+n = rec.shape[0]
 hdr = rec[:, 0]
 kind, rid, idx, gl = (hdr >> 48) & 0xFFFF, (hdr >> 40) & 0xFF, (hdr >> 24) & 0xFFFF, hdr & 0xFFFFFF
 t = rec[:, 1:].astype(np.int64)
