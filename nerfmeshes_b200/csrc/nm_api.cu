@@ -45,7 +45,7 @@ struct NmHandle_t {
   Buf s_table, u_table, voxels;
   int V = 0;
   // workspace
-  Buf t_c, raw_c, w_c, t_f, raw_f, t_u, dirs, origins, lin[3], small, stage_in[3], stage_out[12], mc_ws;
+  Buf t_c, raw_c, w_c, t_f, raw_f, t_u, dirs, origins, lin[3], small, stage_in[3], stage_out[12];
   int lin_n[3] = {0, 0, 0};
   int* d_err = nullptr;       // [0] tcgen05 watchdog code, [1] aabb hit-list overflow (device alias of h_err)
   int* h_err = nullptr;       // mapped pinned host memory: still readable after a device-side trap
@@ -232,12 +232,7 @@ int render_rays_impl(NmHandle h, const float* origins, int o_stride, const float
   return 0;
 }
 
-// copy every non-null field of a device-side NmRenderOut to the host-side one
-struct OutStage {
-  NmRenderOut dev{};
-  std::vector<std::pair<float**, size_t>> dummy;
-};
-
+// host-buffer calls: a device-side NmRenderOut whose non-null fields mirror the caller's host block
 int stage_outputs(NmHandle h, const NmRenderOut& host, long long R, int S, int Nc, NmRenderOut* dev, size_t sizes[12]) {
   float* const* hp = reinterpret_cast<float* const*>(&host);
   float** dp = reinterpret_cast<float**>(dev);
@@ -284,20 +279,24 @@ int nm_create(int device, const NmNetDesc* coarse, const NmNetDesc* fine, const 
   NM_CUDA(cudaSetDevice(device));
   NmHandle h = new NmHandle_t();
   h->device = device;
-  cudaDeviceProp p;
-  NM_CUDA(cudaGetDeviceProperties(&p, device));
-  h->num_sms = p.multiProcessorCount;
   h->desc[0] = *coarse;
   h->has_fine = fine != nullptr;
   if (fine) h->desc[1] = *fine;
-  NM_CUDA(cudaHostAlloc(&h->h_err, 2 * sizeof(int), cudaHostAllocMapped));
-  h->h_err[0] = h->h_err[1] = 0;
-  NM_CUDA(cudaHostGetDevicePointer(&h->d_err, h->h_err, 0));
-  NM_CUDA(cudaMalloc(&h->d_stats, 4 * sizeof(double)));
-  NM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  auto init = [&]() -> int {
+    cudaDeviceProp p;
+    NM_CUDA(cudaGetDeviceProperties(&p, device));
+    h->num_sms = p.multiProcessorCount;
+    NM_CUDA(cudaHostAlloc(&h->h_err, 2 * sizeof(int), cudaHostAllocMapped));
+    h->h_err[0] = h->h_err[1] = 0;
+    NM_CUDA(cudaHostGetDevicePointer(&h->d_err, h->h_err, 0));
+    NM_CUDA(cudaMalloc(&h->d_stats, 4 * sizeof(double)));
+    NM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    if (int e = nm_set_render_cfg(h, cfg)) return e;
+    return nm_set_tables(h, nullptr, nullptr);
+  };
+  if (int e = init()) { nm_destroy(h); *out = nullptr; return e; }
   *out = h;
-  if (int e = nm_set_render_cfg(h, cfg)) { nm_destroy(h); *out = nullptr; return e; }
-  return nm_set_tables(h, nullptr, nullptr);
+  return 0;
 }
 
 int nm_destroy(NmHandle h) {
@@ -306,12 +305,13 @@ int nm_destroy(NmHandle h) {
   cudaDeviceSynchronize();
   free_network(&h->nets[0]); free_network(&h->nets[1]);
   Buf* bufs[] = {&h->s_table, &h->u_table, &h->voxels, &h->t_c, &h->raw_c, &h->w_c, &h->t_f, &h->raw_f, &h->t_u,
-                 &h->dirs, &h->origins, &h->lin[0], &h->lin[1], &h->lin[2], &h->small, &h->mc_ws};
+                 &h->dirs, &h->origins, &h->lin[0], &h->lin[1], &h->lin[2], &h->small};
   for (Buf* b : bufs) b->release();
   for (Buf& b : h->stage_in) b.release();
   for (Buf& b : h->stage_out) b.release();
   if (h->mc_ws_ptr) cudaFree(h->mc_ws_ptr);
-  cudaFreeHost(h->h_err); cudaFree(h->d_stats);
+  if (h->h_err) cudaFreeHost(h->h_err);
+  cudaFree(h->d_stats);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

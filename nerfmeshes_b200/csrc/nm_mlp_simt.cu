@@ -134,11 +134,7 @@ int launch_mlp_simt(const NetDev& net, bool sigma_only, const MlpInput& in, floa
   P.out = out;
   P.out_sigma_only = sigma_only ? 1 : 0;
   const size_t smem = (size_t)(2 * 256 * kPts + 2 * 64 * kPts + kPts) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    NM_CUDA(cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  NM_CUDA(cudaFuncSetAttribute(mlp_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per current device
   const long long grid = (in.M + kPts - 1) / kPts;
   NM_CHECK(grid < (1ll << 31), "too many points for one launch");
   mlp_simt_kernel<<<(unsigned)grid, kThreads, smem, st>>>(P);

@@ -494,10 +494,10 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.off_bars = off; off += kBarBytes;
   NM_CHECK((int)off <= max_smem, "shared-memory layout overflow");
 
-  static int configured_dev = -1;
-  if (configured_dev != dev) {
+  static thread_local unsigned configured_devs = 0;        // per-device opt-in to the large dynamic shared memory window
+  if (!(configured_devs & (1u << (dev & 31)))) {
     NM_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    configured_dev = dev;
+    configured_devs |= 1u << (dev & 31);
   }
   long long grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   const char* trace_path = getenv("NM_TC_TRACE");
