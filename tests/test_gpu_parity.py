@@ -315,3 +315,63 @@ def test_internal_chunking_is_invisible(lego_model):
         subprocess.run([sys.executable, "-c", code % (ROOT, ROOT), path], check=True, env=dict(os.environ, NM_CHUNK_RAYS=chunk), timeout=300)
         outs.append(torch.load(path))
     assert torch.equal(outs[0]["rgb"], outs[1]["rgb"]) and torch.equal(outs[0]["disp"], outs[1]["disp"])
+
+
+# ----------------------------------------------------------------------------------------------------- other configs
+def _cfg(net_c, net_f, **kw):
+    cfg = {"dataset.near": 2.0, "dataset.far": 6.0, "dataset.white_background": kw.get("white", False),
+           "models.coarse_type": "FlexibleNeRFModel", "models.fine_type": "FlexibleNeRFModel", "models.use_fine": net_f is not None,
+           **{f"models.coarse.{k}": v for k, v in net_c.__dict__.items()},
+           **({f"models.fine.{k}": v for k, v in net_f.__dict__.items()} if net_f is not None else {})}
+    for mode in ("train", "validation"):
+        cfg.update({f"nerf.{mode}.num_coarse": kw.get("nc", 64), f"nerf.{mode}.num_fine": kw.get("nf", 128),
+                    f"nerf.{mode}.perturb": False, f"nerf.{mode}.lindisp": kw.get("lindisp", False),
+                    f"nerf.{mode}.radiance_field_noise_std": 0.0})
+    return cfg
+
+
+def test_tiny_config_coarse_only():
+    """BASELINE.json configs[0] (`tiny`: 64x64, coarse-only 4-layer 128-wide MLP, 32 samples, L_xyz=6) authored in the live
+    schema (the shipped config/tiny.yaml is stale), random weights, full image vs the oracle."""
+    import nerfmeshes_b200 as nm
+    net = O.NetCfg(num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6, num_encoding_fn_dir=4)
+    sd = O.init_weights(net, 8239)
+    model = nm.NeRFModel(_cfg(net, None, nc=32, nf=0)).eval()
+    model.model_coarse.load_state_dict(sd, strict=False)
+    H = W = 64
+    f = 64 * 1111.111 / 800
+    pose = O.pose_spherical(30.0, -30.0, 4.0)
+    out = model._engine().render_image(pose, H, W, f, 2.0, 6.0, want=["rgb", "acc", "disp", "t_vals"])
+    o, d = O.get_ray_bundle(H, W, f, pose)
+    bc, bf, t_c, _ = O.nerf_forward(sd, None, net, None, O.RenderCfg(num_coarse=32, num_fine=0), o, d.reshape(-1, 3),
+                                    torch.tensor(2.0), torch.tensor(6.0))
+    assert bf is None and torch.equal(out["t_vals"].cpu(), t_c)
+    close(out["rgb"], bc.rgb_map, 2e-5, name="tiny rgb")
+    close(out["acc"], bc.acc_map, 2e-5, name="tiny acc")
+    q = model.query((o.cuda(), d.reshape(-1, 3).cuda(), torch.tensor([2.0, 6.0])))        # coarse bundle when there is no fine net
+    assert torch.equal(q.rgb_map, out["rgb"])
+
+
+def test_sampler_and_compositor_options():
+    """lindisp sampling, per-ray near/far (modules.py:158-169), white background (modules.py:111-112), other sample counts."""
+    import nerfmeshes_b200 as nm
+    net = O.NetCfg(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)
+    sdc, sdf = O.init_weights(net, 3), O.init_weights(net, 4)
+    g = torch.Generator().manual_seed(9)
+    R = 333
+    o = torch.randn(R, 3, generator=g) * 0.3
+    d = torch.randn(R, 3, generator=g)
+    near, far = torch.rand(R, generator=g) + 0.5, torch.rand(R, generator=g) + 3.0
+    for kw in (dict(lindisp=True, white=True, nc=48, nf=80), dict(lindisp=False, white=False, nc=16, nf=33)):
+        model = nm.NeRFModel(_cfg(net, net, **kw)).eval()
+        model.model_coarse.load_state_dict(sdc, strict=False)
+        model.model_fine.load_state_dict(sdf, strict=False)
+        rc = O.RenderCfg(num_coarse=kw["nc"], num_fine=kw["nf"], lindisp=kw["lindisp"], white_background=kw["white"])
+        bc, bf, t_c, t_f = O.nerf_forward(sdc, sdf, net, net, rc, o, d, near, far)
+        coarse, fine = model.forward((o.cuda(), d.cuda(), (near.cuda(), far.cuda())))
+        close(coarse.rgb_map, bc.rgb_map, 2e-5, name=f"coarse rgb {kw}")
+        tv = model._engine().render_rays(o.cuda(), d.cuda(), near.cuda(), far.cuda(), want=["t_vals"])["t_vals"].cpu()
+        assert float((tv - t_f).abs().flatten().quantile(0.99)) <= 1e-5
+        err = (fine.rgb_map.cpu() - bf.rgb_map).abs().flatten()
+        assert float(err.max()) <= 6e-4 and float(err.quantile(0.99)) <= 1e-4, (kw, float(err.max()))
+        close(fine.acc_map, bf.acc_map, 6e-4, name="acc")
