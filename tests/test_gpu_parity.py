@@ -375,3 +375,23 @@ def test_sampler_and_compositor_options():
         err = (fine.rgb_map.cpu() - bf.rgb_map).abs().flatten()
         assert float(err.max()) <= 6e-4 and float(err.quantile(0.99)) <= 1e-4, (kw, float(err.max()))
         close(fine.acc_map, bf.acc_map, 6e-4, name="acc")
+
+
+def test_eval_loop_device_resident(lego_model, tmp_path):
+    """eval_nerf.py's image loop (src/eval_nerf.py:50-105) as one fused call per pose: images, disparities, MSE/PSNR."""
+    import numpy as np
+    from PIL import Image
+    from nerfmeshes_b200.eval import eval_poses, cast_to_pil_image
+    poses = [O.pose_spherical(a, -30.0, 4.0) for a in (30.0, 120.0)]
+    H = W = 72
+    f = 100.0
+    ref = eval_poses(lego_model, poses, H, W, f, 2.0, 6.0)
+    noisy = [r + 0.01 for r in ref["rgb"]]
+    res = eval_poses(lego_model, poses, H, W, f, 2.0, 6.0, targets=noisy, save_dir=str(tmp_path), save_disparity=True)
+    assert all(abs(m - 1e-4) < 1e-6 for m in res["mse"]) and all(abs(p - 40.0) < 0.05 for p in res["psnr"])
+    img = np.array(Image.open(tmp_path / "images" / "0001.png"))
+    assert np.array_equal(img, cast_to_pil_image(res["rgb"][1])) and img.std() > 5
+    assert (tmp_path / "disparity" / "0000.png").exists()
+    o, d = O.get_ray_bundle(H, W, f, poses[0])                   # and it is the same image model.query produces
+    q = lego_model.query((o.cuda(), d.reshape(-1, 3).cuda(), torch.tensor([2.0, 6.0])))
+    close(q.rgb_map.view(H, W, 3), res["rgb"][0], 2e-4, name="eval vs query")
