@@ -162,6 +162,28 @@ int nm_render_image_host(NmHandle h, const float* pose_host, int H, int W, float
 int nm_point_mlp_host(NmHandle h, int which, const float* pts_host, const float* dirs_host, int64_t M,
                       float* out_host, int sigma_only);
 
+/* ---- training --------------------------------------------------------------------------
+ * Replaces `loss.backward()` of NeRFModel.training_step / BuFFModel.training_step (src/models/model_nerf.py:88-151,
+ * model_buff.py) for the parameters of both FlexibleNeRFModels: gradients flow from the bundles' rgb_map through
+ * VolumeRenderer (src/nerf/modules.py:67-121) and the network (src/nerf/models.py:60-80); SamplePDF is detached
+ * (modules.py:201).  The call re-runs the forward for these rays (same flags + seed => same samples and noise) and
+ * ACCUMULATES dL/dtheta into the handle's gradient buffers (fp32, atomics: summation order is not reproducible).
+ *   nm_backward_rays : d_rgb_dev (R,3) = dL/d rgb_map of the main bundle (fine, or the only one);
+ *                      d_coarse_rgb_dev (R,3) or NULL = dL/d coarse rgb_map (two-network NeRF only).
+ *   nm_loss_backward : the reference's loss itself, mse(coarse.rgb_map, target) + mse(fine.rgb_map, target)
+ *                      (mean over R*3); loss_dev (2 floats, device, or NULL) += {coarse-or-only term, fine term}.
+ *   nm_get_grad      : copies the gradient of one state-dict tensor (SURVEY A.1 names, reference (out,in) layout)
+ *                      into out_dev.
+ * Loss terms other than rgb_map (depth, acc, weights) carry no gradient here; the reference has none. */
+int nm_zero_grad(NmHandle h, void* stream);
+int nm_backward_rays(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                     const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
+                     const float* d_rgb_dev, const float* d_coarse_rgb_dev, void* stream);
+int nm_loss_backward(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                     const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
+                     const float* target_rgb_dev, float* loss_dev, void* stream);
+int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t numel, void* stream);
+
 /* ---- host-only debugging aid (no CUDA): the layer program + tensor-core weight stream nm_load_weights would
  * upload, for CPU tests of the schedule / swizzle logic.  program_out receives the internal NetProgram struct
  * (nerfmeshes_b200/csrc/nm_program.h). */

@@ -56,6 +56,10 @@ _SIGNATURES = {
     "nm_query_host": (C.c_int, [_P, _P, _I, _P, _L, _P, _I, C.c_uint64, C.POINTER(NmRenderOut)]),
     "nm_render_image_host": (C.c_int, [_P, _P, _I, _I, _F, _I, _I, _I, _P, _I, C.c_uint64, C.POINTER(NmRenderOut)]),
     "nm_point_mlp_host": (C.c_int, [_P, _I, _P, _P, _L, _P, _I]),
+    "nm_zero_grad": (C.c_int, [_P, _P]),
+    "nm_backward_rays": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _I, C.c_uint64, _P, _P, _P]),
+    "nm_loss_backward": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _I, C.c_uint64, _P, _P, _P]),
+    "nm_get_grad": (C.c_int, [_P, _I, C.c_char_p, _P, _L, _P]),
     "nm_debug_pack": (C.c_int, [C.POINTER(NmNetDesc), _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64), _I, _P,
                                C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nm_kernel_flags": (C.c_int, [_P, C.POINTER(C.c_int32)]),

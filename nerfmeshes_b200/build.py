@@ -23,6 +23,7 @@ SOURCES = {
     "nm_mlp_simt.cu": [],
     "nm_render.cu": ["-fmad=false"],
     "nm_mc.cu": ["-fmad=false"],
+    "nm_train.cu": [],
     "nm_api.cu": [],
 }
 

@@ -59,6 +59,9 @@ struct NmHandle_t {
   int64_t mlp_points = 0, mlp_launches = 0;
   size_t mc_ws_bytes = 0;
   void* mc_ws_ptr = nullptr;
+  // training (nm_train.cu): gradient accumulators per network + scratch
+  Buf g_wt[2], g_bias[2], g_head[2], train_ws, dout, trans, tr_rgb[2], tr_drgb[2];
+  bool grads_ready = false;
 };
 
 namespace {
@@ -253,6 +256,105 @@ int copy_outputs(const NmRenderOut& host, const NmRenderOut& dev, const size_t s
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- training backward
+int ensure_grads(NmHandle h, cudaStream_t st, bool zero) {
+  for (int w = 0; w < 2; ++w) {
+    const NetDev& net = h->nets[w];
+    if (!net.loaded) continue;
+    const size_t nb[3] = {net.n_wt * 4, (size_t)net.full.n_bias * 4, (size_t)(net.full.n_head > 0 ? net.full.n_head : 1) * 4};
+    Buf* bufs[3] = {&h->g_wt[w], &h->g_bias[w], &h->g_head[w]};
+    for (int i = 0; i < 3; ++i) {
+      const bool fresh = bufs[i]->p == nullptr || bufs[i]->cap < nb[i];
+      if (int e = bufs[i]->ensure(nb[i])) return e;
+      if (fresh || zero) NM_CUDA(cudaMemsetAsync(bufs[i]->p, 0, bufs[i]->cap, st));
+    }
+  }
+  h->grads_ready = true;
+  return 0;
+}
+
+// One chunk of rays: forward (fills the per-sample workspaces), then for each bundle that carries a gradient the
+// compositor adjoint and the network backward over sub-chunks of points.
+int train_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const float* d_rgb, const float* d_rgb_coarse,
+                const float* target, long long R_total, float* loss_dev, cudaStream_t st) {
+  const NmRenderCfg& c = h->cfg;
+  const long long R = rb.R;
+  const bool buff = flags & NM_FLAG_BUFF;
+  const bool two = h->has_fine && !buff && c.num_fine > 0;
+  const int Nc = c.num_coarse, S = Nc + (two ? c.num_fine : 0);
+  NmRenderOut o{};
+  if (int e = h->tr_rgb[0].ensure((size_t)R * 12)) return e;
+  o.rgb = h->tr_rgb[0].as<float>();
+  if (two) { if (int e = h->tr_rgb[1].ensure((size_t)R * 12)) return e; o.coarse_rgb = h->tr_rgb[1].as<float>(); }
+  if (int e = render_chunk(h, rb, flags, seed, o, st)) return e;
+  if (target) {
+    for (int i = 0; i < (two ? 2 : 1); ++i) {
+      if (int e = h->tr_drgb[i].ensure((size_t)R * 12)) return e;
+      // loss_dev[0] = coarse (or only) bundle, loss_dev[1] = fine bundle — the two terms of model_nerf.py:118-126
+      float* slot = loss_dev ? loss_dev + ((two && i == 0) ? 1 : 0) : nullptr;
+      if (int e = launch_mse_grad(h->tr_rgb[i].as<float>(), target, 3 * R, 3 * R_total, h->tr_drgb[i].as<float>(), slot, st, &h->launches)) return e;
+    }
+    d_rgb = h->tr_drgb[0].as<float>();
+    d_rgb_coarse = two ? h->tr_drgb[1].as<float>() : nullptr;
+  }
+  struct Pass { int which; const float* raw; const float* t; int s; const float* g; };
+  Pass passes[2];
+  int np = 0;
+  if (two) {
+    if (d_rgb) passes[np++] = {NM_NET_FINE, h->raw_f.as<float>(), h->t_f.as<float>(), S, d_rgb};
+    if (d_rgb_coarse) passes[np++] = {NM_NET_COARSE, h->raw_c.as<float>(), h->t_c.as<float>(), Nc, d_rgb_coarse};
+  } else if (d_rgb) {
+    passes[np++] = {NM_NET_COARSE, h->raw_c.as<float>(), buff ? h->t_u.as<float>() : h->t_c.as<float>(), Nc, d_rgb};
+  }
+  for (int pi = 0; pi < np; ++pi) {
+    const Pass& P = passes[pi];
+    const NetDev& net = h->nets[P.which];
+    if (int e = h->dout.ensure((size_t)R * P.s * 16)) return e;
+    if (int e = h->trans.ensure((size_t)R * P.s * 4)) return e;
+    if (int e = launch_composite_backward(P.raw, P.t, rb.dirs, P.g, R, P.s, c.noise_std, seed ^ 0x5bd1e995u,
+                                          c.white_background, h->trans.as<float>(), h->dout.as<float>(), st, &h->launches)) return e;
+    const size_t per_point = train_ws_floats_per_point(net.full);
+    long long rays_sub = 65536 / P.s;
+    if (rays_sub < 1) rays_sub = 1;
+    if (int e = h->train_ws.ensure(per_point * (size_t)(rays_sub * P.s) * 4)) return e;
+    NetGrads g{h->g_wt[P.which].as<float>(), h->g_bias[P.which].as<float>(), h->g_head[P.which].as<float>()};
+    for (long long r0 = 0; r0 < R; r0 += rays_sub) {
+      const long long n = (R - r0 < rays_sub) ? R - r0 : rays_sub;
+      MlpInput in{};
+      in.mode = IN_RAYS; in.dirs = rb.dirs + 3 * r0; in.ray_o = rb.origins + (long long)rb.o_stride * r0;
+      in.o_stride = rb.o_stride; in.t = P.t + r0 * P.s; in.S = P.s; in.M = n * P.s;
+      if (int e = mlp_backward(net, in, h->dout.as<float>() + r0 * P.s * 4, h->train_ws.as<float>(), &g, h->num_sms, st, &h->launches)) return e;
+    }
+  }
+  return 0;
+}
+
+int train_impl(NmHandle h, const float* origins, int o_stride, const float* dirs, long long R, const float* nf_host,
+               const float* near_dev, const float* far_dev, int flags, uint64_t seed, const float* d_rgb,
+               const float* d_rgb_coarse, const float* target, float* loss_dev, cudaStream_t st) {
+  NM_CHECK(o_stride == 0 || o_stride == 3, "o_stride must be 0 or 3");
+  NM_CHECK(dirs && origins, "null ray pointers");
+  NM_CHECK((near_dev == nullptr) == (far_dev == nullptr), "near_dev / far_dev must be given together");
+  NM_CHECK(near_dev || nf_host, "no near/far bounds given");
+  NM_CHECK(!(flags & NM_FLAG_TEACHER_T), "NM_FLAG_TEACHER_T is not supported by the backward pass");
+  NM_CHECK(target || d_rgb || d_rgb_coarse, "no gradient source (target or d_rgb)");
+  NM_CHECK(h->s_table.p != nullptr, "sampler tables missing");
+  if (!h->grads_ready) if (int e = ensure_grads(h, st, true)) return e;
+  if (int e = ensure_grads(h, st, false)) return e;
+  const long long kChunk = chunk_rays();
+  for (long long r0 = 0; r0 < R; r0 += kChunk) {
+    RayBatch rb{};
+    rb.R = (R - r0 < kChunk) ? R - r0 : kChunk;
+    rb.origins = origins + (long long)o_stride * r0; rb.o_stride = o_stride; rb.dirs = dirs + 3 * r0;
+    if (nf_host) { rb.nf[0] = nf_host[0]; rb.nf[1] = nf_host[1]; }
+    rb.near_dev = near_dev ? near_dev + r0 : nullptr; rb.far_dev = far_dev ? far_dev + r0 : nullptr;
+    if (int e = train_chunk(h, rb, flags, seed + (uint64_t)r0, d_rgb ? d_rgb + 3 * r0 : nullptr,
+                            d_rgb_coarse ? d_rgb_coarse + 3 * r0 : nullptr, target ? target + 3 * r0 : nullptr, R,
+                            loss_dev, st)) return e;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -309,6 +411,8 @@ int nm_destroy(NmHandle h) {
   for (Buf* b : bufs) b->release();
   for (Buf& b : h->stage_in) b.release();
   for (Buf& b : h->stage_out) b.release();
+  for (int i = 0; i < 2; ++i) { h->g_wt[i].release(); h->g_bias[i].release(); h->g_head[i].release(); h->tr_rgb[i].release(); h->tr_drgb[i].release(); }
+  h->train_ws.release(); h->dout.release(); h->trans.release();
   if (h->mc_ws_ptr) cudaFree(h->mc_ws_ptr);
   if (h->h_err) cudaFreeHost(h->h_err);
   cudaFree(h->d_stats);
@@ -413,6 +517,60 @@ int nm_render_image(NmHandle h, const float* pose_host, int H, int W, float foca
   }
   return render_rays_impl(h, origins, o_stride, h->dirs.as<float>(), R, near_far_host, nullptr, nullptr, flags, seed,
                           *out_dev, st);
+}
+
+// ---------------------------------------------------------------------------------------------- training entry points
+int nm_zero_grad(NmHandle h, void* stream) {
+  if (int e = bind_device(h)) return e;
+  return ensure_grads(h, (cudaStream_t)stream, true);
+}
+
+int nm_backward_rays(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                     const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
+                     const float* d_rgb_dev, const float* d_coarse_rgb_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  return train_impl(h, origins_dev, o_stride, dirs_dev, R, near_far_host, near_dev, far_dev, flags, seed, d_rgb_dev,
+                    d_coarse_rgb_dev, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int nm_loss_backward(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                     const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
+                     const float* target_rgb_dev, float* loss_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(target_rgb_dev, "null target");
+  return train_impl(h, origins_dev, o_stride, dirs_dev, R, near_far_host, near_dev, far_dev, flags, seed, nullptr, nullptr,
+                    target_rgb_dev, loss_dev, (cudaStream_t)stream);
+}
+
+int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t numel, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(which == NM_NET_COARSE || (which == NM_NET_FINE && h->has_fine), "network slot %d not present", which);
+  NM_CHECK(name && out_dev, "null argument");
+  const NetDev& net = h->nets[which];
+  NM_CHECK(net.loaded && h->grads_ready && h->g_wt[which].p, "no gradients accumulated for network %d", which);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < net.full.n_layers; ++l) {
+    const LayerProg& L = net.full.layers[l];
+    const int K = L.k_act + L.k_pe, N = L.n_out;
+    const int heads = L.kind == KIND_SIGMA ? 1 : (L.kind == KIND_RGB ? 3 : (L.kind == KIND_OUT4 ? 4 : 0));
+    const std::string* nm4 = &net.names[4 * l];
+    if (nm4[0] == name) {
+      NM_CHECK(numel == (int64_t)K * N, "'%s' has %lld elements, expected %lld", name, (long long)numel, (long long)K * N);
+      return launch_transpose_out(h->g_wt[which].as<float>() + L.wt_off, K, N, out_dev, st, &h->launches);
+    }
+    const float* src = nullptr;
+    int64_t n = 0;
+    if (nm4[1] == name) { src = h->g_bias[which].as<float>() + L.bias_off; n = N; }
+    else if (heads && nm4[2] == name) { src = h->g_head[which].as<float>() + L.head_off; n = (int64_t)heads * N; }
+    else if (heads && nm4[3] == name) { src = h->g_head[which].as<float>() + L.head_off + heads * N; n = heads; }
+    if (src) {
+      NM_CHECK(numel == n, "'%s' has %lld elements, expected %lld", name, (long long)numel, (long long)n);
+      NM_CUDA(cudaMemcpyAsync(out_dev, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
+  }
+  NM_CHECK(false, "no parameter named '%s'", name);
+  return -1;
 }
 
 int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, const float* lin2_host, int n0, int n1,

@@ -42,6 +42,15 @@ struct NetDev {
   float* d_bias = nullptr;
   float* d_head = nullptr;
   float* d_wt = nullptr;             // transposed fp32 weights (CUDA-core kernel)
+  size_t n_wt = 0;                   // floats in d_wt
+  std::vector<std::string> names;    // per layer of `full`: weight, bias, head weight, head bias ("" if none)
+};
+
+// Gradient accumulators of one network, laid out like NetDev.d_wt / d_bias / d_head (nm_train.cu).
+struct NetGrads {
+  float* wt = nullptr;
+  float* bias = nullptr;
+  float* head = nullptr;
 };
 
 // Inputs of one fused-MLP launch (three front-end modes).
@@ -114,6 +123,16 @@ int launch_aabb(const float* voxels, int V, const float* origins, int o_stride, 
                 int* d_overflow, cudaStream_t st, int64_t* launches);
 int launch_volume_stats(const float* vol, long long n, double* d_scratch, float* out_host, cudaStream_t st,
                         int64_t* launches);
+// training backward (nm_train.cu)
+size_t train_ws_floats_per_point(const NetProgram& full);
+int mlp_backward(const NetDev& net, const MlpInput& in, const float* dout, float* ws, NetGrads* g, int num_sms,
+                 cudaStream_t st, int64_t* launches);
+int launch_composite_backward(const float* raw, const float* t, const float* dirs, const float* d_rgb, long long R, int S,
+                              float noise_std, uint64_t seed, int white_bg, float* scratch, float* dout,
+                              cudaStream_t st, int64_t* launches);
+int launch_mse_grad(const float* rgb, const float* target, long long n, long long count, float* d_rgb, float* loss,
+                    cudaStream_t st, int64_t* launches);
+int launch_transpose_out(const float* gt, int K, int N, float* out, cudaStream_t st, int64_t* launches);
 int mc_count(const float* vol, int nx, int ny, int nz, float iso, void** ws, size_t* ws_bytes, int64_t* counts_host,
              cudaStream_t st, int64_t* launches);
 int mc_emit(const float* vol, int nx, int ny, int nz, float iso, float x_off, void* ws, float* verts, float* normals,

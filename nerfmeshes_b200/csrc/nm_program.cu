@@ -295,6 +295,8 @@ int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net) {
 
   free_network(net);
   net->desc = d; net->full = full; net->sigma = sig;
+  net->n_wt = wt.size();
+  for (const LayerNames& n : nf) { net->names.push_back(n.w); net->names.push_back(n.b); net->names.push_back(n.head_w); net->names.push_back(n.head_b); }
   NM_CUDA(cudaMalloc(&net->d_full, sizeof(NetProgram)));
   NM_CUDA(cudaMalloc(&net->d_sigma, sizeof(NetProgram)));
   NM_CUDA(cudaMalloc(&net->d_wpack_full, pk_full.size()));

@@ -1,0 +1,567 @@
+// Training backward of the fused path: dL/dθ of both FlexibleNeRFModels given dL/d rgb_map of the
+// coarse and fine bundles — what `loss.backward()` produces for NeRFModel.training_step (src/models/model_nerf.py:88-151)
+// through VolumeRenderer (src/nerf/modules.py:67-121), the network (src/nerf/models.py:60-80) and nothing else
+// (SamplePDF is detached, modules.py:201; sample positions do not depend on θ).
+//
+// Round-1 shape of this row: correctness first.  The forward of a training step runs on the tcgen05 kernel
+// (nm_mlp_tc.cu); the backward here recomputes the activations layer by layer in plain fp32 FMA arithmetic on the
+// CUDA cores (the reference trains in fp32, TF32 off), keeps them in HBM for one sub-chunk of points, and walks the
+// layers back with three tiled SGEMM shapes:
+//     forward     Y  = act([X | PE] Wt + b)              sgemm<NN>
+//     data grad   dX = (dZ W) (+ dsigma w_alpha) * relu'  sgemm<NT>  (W = Wt^T, so B is read transposed)
+//     weight grad dWt += [X | PE]^T dZ                    sgemm_tn   (split over points, fp32 atomics)
+// Gradients accumulate into flat buffers with the layouts of NetDev.d_wt / d_bias / d_head; nm_get_grad returns
+// them in the reference's (out,in) layout.  A tcgen05 version of these GEMMs is the next step for this row.
+#include <math_constants.h>
+
+#include "nm_common.h"
+#include "nm_frontend.cuh"
+
+namespace nm {
+namespace {
+
+constexpr int kPeLd = 64;   // padded row length of the encoding buffers
+
+// ------------------------------------------------------------------------------------------------ encodings
+__global__ void encode_kernel(const __grid_constant__ MlpInput in, const NetProgram* __restrict__ prog,
+                              float* __restrict__ pe_x, float* __restrict__ pe_d) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= in.M) return;
+  const NetProgram& G = *prog;
+  float p[3], d[3];
+  fetch_point(in, m, p, d);
+  float* px = pe_x + m * kPeLd;
+  for (int j = G.dim_xyz; j < kPeLd; ++j) px[j] = 0.f;
+  positional_encoding(p, G.L_xyz, G.inc_xyz, G.freq_xyz, [&](int j, float v) { px[j] = v; });
+  if (G.dim_dir > 0) {
+    float* pd = pe_d + m * kPeLd;
+    for (int j = G.dim_dir; j < kPeLd; ++j) pd[j] = 0.f;
+    positional_encoding(d, G.L_dir, G.inc_dir, G.freq_dir, [&](int j, float v) { pd[j] = v; });
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SGEMM  C = A * op(B)
+// A (M,K) row-major.  BT=false: B (K,N) row-major;  BT=true: B (N,K) row-major (C = A B^T).
+// CTA tile 128 x (16*TN), 256 threads, 8 x TN micro-tile, BK = 16, register prefetch of the next K tile.
+struct GemmEpi {
+  int accumulate;          // C += (else C =)
+  const float* bias;       // + bias[n]
+  int relu;                // max(.,0)
+  const float* r1_vec;     // + r1_vec[m * r1_stride] * r1_w[n]
+  int r1_stride;
+  const float* r1_w;
+  const float* mask;       // * (mask[m*ldmask + n] > 0)
+  int ldmask;
+};
+
+template <int TN, bool BT>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                    int ldb, float* __restrict__ C, int ldc, int M, int N, int K,
+                                                    const GemmEpi epi) {
+  constexpr int BM = 128, BN = 16 * TN, BK = 16;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  // global -> register staging
+  float4 ra[2];
+  float4 rb[BN / 64 > 0 ? BN / 64 : 1];
+  constexpr int NB4 = BN / 64;                      // float4 per thread for the B tile (BK*BN/4/256)
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                   // A tile: 128 rows x 4 float4
+      const int f = tid + i * 256, r = f >> 2, kq = (f & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < M && k0 + kq < K) {
+        v = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k0 + kq);
+        if (k0 + kq + 1 >= K) v.y = 0.f;
+        if (k0 + kq + 2 >= K) v.z = 0.f;
+        if (k0 + kq + 3 >= K) v.w = 0.f;
+      }
+      ra[i] = v;
+    }
+    if (!BT) {
+#pragma unroll
+      for (int i = 0; i < NB4; ++i) {               // B tile (K,N): 16 rows x BN/4 float4
+        const int f = tid + i * 256, r = f / (BN / 4), c4 = (f % (BN / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + r < K && n0 + c4 < N) v = *reinterpret_cast<const float4*>(B + (size_t)(k0 + r) * ldb + n0 + c4);
+        rb[i] = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NB4; ++i) {               // B tile (N,K): BN rows x 4 float4
+        const int f = tid + i * 256, r = f >> 2, kq = (f & 3) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + r < N && k0 + kq < K) {
+          v = *reinterpret_cast<const float4*>(B + (size_t)(n0 + r) * ldb + k0 + kq);
+          if (k0 + kq + 1 >= K) v.y = 0.f;
+          if (k0 + kq + 2 >= K) v.z = 0.f;
+          if (k0 + kq + 3 >= K) v.w = 0.f;
+        }
+        rb[i] = v;
+      }
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * 256, r = f >> 2, kq = (f & 3) * 4;
+      As[kq + 0][r] = ra[i].x; As[kq + 1][r] = ra[i].y; As[kq + 2][r] = ra[i].z; As[kq + 3][r] = ra[i].w;
+    }
+    if (!BT) {
+#pragma unroll
+      for (int i = 0; i < NB4; ++i) {
+        const int f = tid + i * 256, r = f / (BN / 4), c4 = (f % (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[r][c4]) = rb[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NB4; ++i) {
+        const int f = tid + i * 256, r = f >> 2, kq = (f & 3) * 4;
+        Bs[kq + 0][r] = rb[i].x; Bs[kq + 1][r] = rb[i].y; Bs[kq + 2][r] = rb[i].z; Bs[kq + 3][r] = rb[i].w;
+      }
+    }
+  };
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    store_tiles();
+    __syncthreads();
+    if (k0 + BK < K) load_tiles(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[TN];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][(j >> 2) * 64 + tx * 4]);
+        b[j] = bv.x; b[j + 1] = bv.y; b[j + 2] = bv.z; b[j + 3] = bv.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+    const float r1 = epi.r1_vec ? epi.r1_vec[(size_t)m * epi.r1_stride] : 0.f;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (n >= N) continue;
+      float v = acc[i][j];
+      float* c = C + (size_t)m * ldc + n;
+      if (epi.accumulate) v += *c;
+      if (epi.bias) v += epi.bias[n];
+      if (epi.r1_vec) v = fmaf(r1, epi.r1_w[n], v);
+      if (epi.relu) v = fmaxf(v, 0.f);
+      if (epi.mask && !(epi.mask[(size_t)m * epi.ldmask + n] > 0.f)) v = 0.f;
+      *c = v;
+    }
+  }
+}
+
+template <bool BT>
+int sgemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K, const GemmEpi& epi,
+          cudaStream_t st, int64_t* launches) {
+  if (M <= 0 || N <= 0) return 0;
+  if (N % 128 == 0) {
+    dim3 grid((M + 127) / 128, N / 128);
+    sgemm_kernel<8, BT><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, epi);
+  } else {
+    dim3 grid((M + 127) / 128, (N + 63) / 64);
+    sgemm_kernel<4, BT><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, epi);
+  }
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ dWt += A^T B
+// A (P,K) row-major, B (P,N) row-major, G (K,N) row-major (ldg).  CTA tile 128(k) x 128(n), split over P.
+__global__ void __launch_bounds__(256) sgemm_tn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                       int ldb, float* __restrict__ G, int ldg, int P, int K, int N,
+                                                       int p_per_split) {
+  constexpr int BT_ = 128, BP = 16;
+  __shared__ __align__(16) float As[BP][BT_];
+  __shared__ __align__(16) float Bs[BP][BT_];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k0 = blockIdx.x * BT_, n0 = blockIdx.y * BT_;
+  const int p_begin = blockIdx.z * p_per_split;
+  const int p_end = min(P, p_begin + p_per_split);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 ra[2], rb[2];
+  auto load = [&](int p0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * 256, r = f >> 5, c4 = (f & 31) * 4;      // 16 rows x 32 float4
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if (p0 + r < p_end) {
+        if (k0 + c4 < K) {
+          va = *reinterpret_cast<const float4*>(A + (size_t)(p0 + r) * lda + k0 + c4);
+          if (k0 + c4 + 1 >= K) va.y = 0.f;
+          if (k0 + c4 + 2 >= K) va.z = 0.f;
+          if (k0 + c4 + 3 >= K) va.w = 0.f;
+        }
+        if (n0 + c4 < N) vb = *reinterpret_cast<const float4*>(B + (size_t)(p0 + r) * ldb + n0 + c4);
+      }
+      ra[i] = va; rb[i] = vb;
+    }
+  };
+  load(p_begin);
+  for (int p0 = p_begin; p0 < p_end; p0 += BP) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * 256, r = f >> 5, c4 = (f & 31) * 4;
+      *reinterpret_cast<float4*>(&As[r][c4]) = ra[i];
+      *reinterpret_cast<float4*>(&Bs[r][c4]) = rb[i];
+    }
+    __syncthreads();
+    if (p0 + BP < p_end) load(p0 + BP);
+#pragma unroll
+    for (int p = 0; p < BP; ++p) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[p][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[p][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[p][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[p][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + ty * 8 + i;
+    if (k >= K) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (n < N) atomicAdd(G + (size_t)k * ldg + n, acc[i][j]);
+    }
+  }
+}
+
+int sgemm_tn(const float* A, int lda, const float* B, int ldb, float* G, int ldg, int P, int K, int N, int num_sms,
+             cudaStream_t st, int64_t* launches) {
+  if (P <= 0 || K <= 0 || N <= 0) return 0;
+  const int tiles = ((K + 127) / 128) * ((N + 127) / 128);
+  int splits = (4 * num_sms + tiles - 1) / tiles;
+  const int max_splits = (P + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int per = (P + splits - 1) / splits;
+  per = (per + 15) & ~15;
+  splits = (P + per - 1) / per;
+  dim3 grid((K + 127) / 128, (N + 127) / 128, splits);
+  sgemm_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, G, ldg, P, K, N, per);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+// bias gradient: g[n] += sum_p Z[p][n]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z, int ldz, int P, int N,
+                                                     float* __restrict__ g, int p_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int p0 = blockIdx.y * p_per_block, p1 = min(P, p0 + p_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int p = p0 + ty; p < p1; p += 8) s += Z[(size_t)p * ldz + n];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += red[i][tx];
+    atomicAdd(g + n, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ heads
+// The (heads x N) linear heads evaluated in the forward epilogue (fc_alpha / fc_rgb / fc_out, src/nerf/models.py:70-80).
+// dout: (P,4) = [d rgb_raw(3), d sigma].  col0: first dout column this head consumes.
+// Accumulates g_head (weight rows then bias, the layout of NetDev.d_head) and, if dX != nullptr, writes
+// dX[p][k] = relu'(act[p][k]) * sum_h dout[p][col0+h] * W[h][k].
+__global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ dout, int col0, int heads,
+                                                            const float* __restrict__ act, int N, int P,
+                                                            const float* __restrict__ hw, float* __restrict__ g_head,
+                                                            float* __restrict__ dX, int relu_mask, int p_per_block) {
+  const int k = threadIdx.x;
+  const int p0 = blockIdx.x * p_per_block, p1 = min(P, p0 + p_per_block);
+  float w[4] = {0.f, 0.f, 0.f, 0.f}, gw[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < N)
+    for (int h = 0; h < heads; ++h) w[h] = hw[h * N + k];
+  for (int p = p0; p < p1; ++p) {
+    const float4 d4 = *reinterpret_cast<const float4*>(dout + (size_t)p * 4);
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    if (k < N) {
+      const float a = act[(size_t)p * N + k];
+      float dx = 0.f;
+      for (int h = 0; h < heads; ++h) {
+        const float g = dd[col0 + h];
+        gw[h] = fmaf(g, a, gw[h]);
+        dx = fmaf(g, w[h], dx);
+      }
+      if (dX) dX[(size_t)p * N + k] = (relu_mask && !(a > 0.f)) ? 0.f : dx;
+    }
+    if (k == 0)
+      for (int h = 0; h < heads; ++h) gb[h] += dd[col0 + h];
+  }
+  if (k < N)
+    for (int h = 0; h < heads; ++h) atomicAdd(g_head + h * N + k, gw[h]);
+  if (k == 0)
+    for (int h = 0; h < heads; ++h) atomicAdd(g_head + heads * N + h, gb[h]);
+}
+
+// ------------------------------------------------------------------------------------------------ compositor adjoint
+// VolumeRenderer.forward (src/nerf/modules.py:67-121) differentiated w.r.t. the raw network outputs, for a loss that
+// reads rgb_map only (model_nerf.py:118-126).  raw = (sigmoid rgb, raw sigma) as the forward kernels store it.
+// Same arithmetic / noise stream as composite_kernel (nm_render.cu).  One thread per ray; T_i goes through `scratch`.
+__device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+__device__ __forceinline__ float randn(uint64_t seed, uint64_t idx) {
+  const float a = fmaxf(u01(seed, 2 * idx), 1e-7f), b = u01(seed, 2 * idx + 1);
+  return sqrtf(-2.f * logf(a)) * cospif(2.f * b);
+}
+
+struct CompositeBwdArgs {
+  const float* raw;   // (R,S,4)
+  const float* t;     // (R,S)
+  const float* dirs;  // (R,3)
+  const float* d_rgb; // (R,3)
+  long long R;
+  int S;
+  float noise_std;
+  uint64_t seed;
+  int white_bg;
+  float* scratch;     // (R,S) transmittance
+  float* dout;        // (R,S,4)
+};
+
+__global__ void composite_backward_kernel(const __grid_constant__ CompositeBwdArgs a) {
+  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= a.R) return;
+  const int S = a.S;
+  const float4* raw = reinterpret_cast<const float4*>(a.raw) + ray * S;
+  const float* t = a.t + ray * S;
+  float* Ts = a.scratch + ray * S;
+  float4* dout = reinterpret_cast<float4*>(a.dout) + ray * S;
+  const float dx = a.dirs[3 * ray], dy = a.dirs[3 * ray + 1], dz = a.dirs[3 * ray + 2];
+  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float gr = a.d_rgb[3 * ray], gg = a.d_rgb[3 * ray + 1], gb = a.d_rgb[3 * ray + 2];
+  const float gbg = a.white_bg ? (gr + gg + gb) : 0.f;
+  auto sample = [&](int i, float* dist, float* pre) {
+    *dist = ((i + 1 < S) ? (t[i + 1] - t[i]) : 1e10f) * nrm;
+    float sg = raw[i].w;
+    if (a.noise_std > 0.f) sg = sg + randn(a.seed, (uint64_t)(ray * S + i)) * a.noise_std;
+    *pre = sg;
+  };
+  float T = 1.0f;
+  for (int i = 0; i < S; ++i) {
+    float dist, pre;
+    sample(i, &dist, &pre);
+    const float alpha = 1.0f - expf(-fmaxf(pre, 0.f) * dist);
+    Ts[i] = T;
+    T = T * (1.0f - alpha + 1e-10f);
+  }
+  float suffix = 0.f;                       // sum_{j>i} G_j w_j
+  for (int i = S - 1; i >= 0; --i) {
+    float dist, pre;
+    sample(i, &dist, &pre);
+    const float4 q = raw[i];
+    const float sg = fmaxf(pre, 0.f);
+    const float e = expf(-sg * dist);
+    const float alpha = 1.0f - e;
+    const float Ti = Ts[i];
+    const float w = alpha * Ti;
+    const float G = (gr * q.x + gg * q.y + gb * q.z) - gbg;          // dL/dw_i
+    const float dalpha = G * Ti - suffix / (1.0f - alpha + 1e-10f);
+    suffix = suffix + G * w;
+    float4 o;
+    o.x = gr * w * q.x * (1.0f - q.x);                               // through the sigmoid
+    o.y = gg * w * q.y * (1.0f - q.y);
+    o.z = gb * w * q.z * (1.0f - q.z);
+    o.w = (pre > 0.f) ? dalpha * dist * e : 0.f;                     // relu, alpha = 1 - exp(-sigma dist)
+    if (!isfinite(o.w)) o.w = 0.f;                                   // dist = 1e10 on the last sample: 1e10 * 0
+    dout[i] = o;
+  }
+}
+
+// MSE loss (torch.nn.functional.mse_loss, mean over R_total*3 elements) and its gradient w.r.t. rgb_map
+__global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ target, long long n,
+                                float inv_count, float* __restrict__ d_rgb, float* __restrict__ loss) {
+  __shared__ float red[256];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float sq = 0.f;
+  if (i < n) {
+    const float d = rgb[i] - target[i];
+    d_rgb[i] = 2.0f * d * inv_count;
+    sq = d * d * inv_count;
+  }
+  red[threadIdx.x] = sq;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, red[0]);
+}
+
+__global__ void transpose_out_kernel(const float* __restrict__ gt, int K, int N, float* __restrict__ out) {  // gt (K,N) -> out (N,K)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * N) return;
+  const int n = i / K, k = i % K;
+  out[i] = gt[(size_t)k * N + n];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+size_t train_ws_floats_per_point(const NetProgram& G) {
+  size_t f = 2 * kPeLd + 2 * (size_t)G.hidden;
+  for (int l = 0; l < G.n_layers; ++l) f += G.layers[l].n_out;
+  return f;
+}
+
+int launch_composite_backward(const float* raw, const float* t, const float* dirs, const float* d_rgb, long long R, int S,
+                              float noise_std, uint64_t seed, int white_bg, float* scratch, float* dout,
+                              cudaStream_t st, int64_t* launches) {
+  if (R <= 0) return 0;
+  CompositeBwdArgs a{raw, t, dirs, d_rgb, R, S, noise_std, seed, white_bg, scratch, dout};
+  composite_backward_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(a);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_mse_grad(const float* rgb, const float* target, long long n, long long count, float* d_rgb, float* loss,
+                    cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return 0;
+  mse_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rgb, target, n, 1.0f / (float)count, d_rgb, loss);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_transpose_out(const float* gt, int K, int N, float* out, cudaStream_t st, int64_t* launches) {
+  transpose_out_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(gt, K, N, out);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+// Backward of one network over P = in.M points.  dout (P,4).  ws: train_ws_floats_per_point(full) * P floats.
+int mlp_backward(const NetDev& net, const MlpInput& in, const float* dout, float* ws, NetGrads* g, int num_sms,
+                 cudaStream_t st, int64_t* launches) {
+  const NetProgram& G = net.full;
+  const int P = (int)in.M;
+  if (P <= 0) return 0;
+  const int h = G.hidden;
+  float* pe_x = ws;
+  float* pe_d = pe_x + (size_t)P * kPeLd;
+  float* dbuf[2] = {pe_d + (size_t)P * kPeLd, pe_d + (size_t)P * kPeLd + (size_t)P * h};
+  float* act[kMaxLayers];
+  {
+    float* p = dbuf[1] + (size_t)P * h;
+    for (int l = 0; l < G.n_layers; ++l) { act[l] = p; p += (size_t)P * G.layers[l].n_out; }
+  }
+  encode_kernel<<<(P + 127) / 128, 128, 0, st>>>(in, net.d_full, pe_x, pe_d);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+
+  auto pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? pe_x : pe_d; };
+  // forward recompute
+  for (int l = 0; l < G.n_layers; ++l) {
+    const LayerProg& L = G.layers[l];
+    const float* Wt = net.d_wt + L.wt_off;
+    GemmEpi fin{};
+    fin.bias = net.d_bias + L.bias_off; fin.relu = L.relu;
+    if (L.k_act > 0) {
+      GemmEpi e = L.pe_src ? GemmEpi{} : fin;
+      if (int rc = sgemm<false>(act[l - 1], G.layers[l - 1].n_out, Wt, L.n_out, act[l], L.n_out, P, L.n_out, L.k_act, e, st, launches)) return rc;
+    }
+    if (L.pe_src) {
+      fin.accumulate = L.k_act > 0 ? 1 : 0;
+      if (int rc = sgemm<false>(pe_of(L), kPeLd, Wt + (size_t)L.k_act * L.n_out, L.n_out, act[l], L.n_out, P, L.n_out, L.k_pe, fin, st, launches)) return rc;
+    }
+  }
+  // backward
+  int cur = 0;
+  const int p_per_block = (P + 2 * num_sms - 1) / (2 * num_sms);
+  const int hb_blocks = (P + p_per_block - 1) / p_per_block;
+  for (int l = G.n_layers - 1; l >= 0; --l) {
+    const LayerProg& L = G.layers[l];
+    const int N = L.n_out;
+    float* dZ = dbuf[cur];
+    if (L.kind == KIND_RGB || L.kind == KIND_OUT4) {
+      NM_CHECK(l == G.n_layers - 1, "rgb head must be the last layer");
+      const int heads = L.kind == KIND_RGB ? 3 : 4;
+      head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 0, heads, act[l], N, P, net.d_head + L.head_off,
+                                                     g->head + L.head_off, dZ, L.relu, p_per_block);
+      NM_CUDA(cudaGetLastError());
+      if (launches) ++*launches;
+    } else if (L.kind == KIND_SIGMA) {
+      // weight/bias gradient of fc_alpha; its contribution to dZ was added by the fc_feat data-grad epilogue
+      head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 3, 1, act[l], N, P, net.d_head + L.head_off,
+                                                     g->head + L.head_off, nullptr, 0, p_per_block);
+      NM_CUDA(cudaGetLastError());
+      if (launches) ++*launches;
+    }
+    // weight / bias gradients of this layer
+    float* gWt = g->wt + L.wt_off;
+    if (L.k_act > 0)
+      if (int rc = sgemm_tn(act[l - 1], G.layers[l - 1].n_out, dZ, N, gWt, N, P, L.k_act, N, num_sms, st, launches)) return rc;
+    if (L.pe_src)
+      if (int rc = sgemm_tn(pe_of(L), kPeLd, dZ, N, gWt + (size_t)L.k_act * N, N, P, L.k_pe, N, num_sms, st, launches)) return rc;
+    {
+      const int ppb = (P + 63) / 64;
+      dim3 grid((N + 31) / 32, (P + ppb - 1) / ppb);
+      colsum_kernel<<<grid, 256, 0, st>>>(dZ, N, P, N, g->bias + L.bias_off, ppb);
+      NM_CUDA(cudaGetLastError());
+      if (launches) ++*launches;
+    }
+    // data gradient into the previous layer's pre-activation
+    if (l > 0) {
+      const LayerProg& Lp = G.layers[l - 1];
+      NM_CHECK(L.k_act == Lp.n_out, "layer chain mismatch");
+      GemmEpi e{};
+      if (Lp.kind == KIND_SIGMA) { e.r1_vec = dout + 3; e.r1_stride = 4; e.r1_w = net.d_head + Lp.head_off; }
+      if (Lp.relu) { e.mask = act[l - 1]; e.ldmask = Lp.n_out; }
+      // dX (P,k_act) = dZ (P,N) * W[:, :k_act];  W[n][k] = Wt[k][n]  ->  B = Wt rows 0..k_act-1 viewed (k_act, N), transposed
+      if (int rc = sgemm<true>(dZ, N, net.d_wt + L.wt_off, N, dbuf[cur ^ 1], L.k_act, P, L.k_act, N, e, st, launches)) return rc;
+      cur ^= 1;
+    }
+  }
+  return 0;
+}
+
+}  // namespace nm

@@ -206,6 +206,56 @@ class Engine:
                                             _ptr(far_d), flags, seed, C.byref(block), self._stream()))
         return outs
 
+    # ------------------------------------------------------------------ training
+    def _ray_args(self, origins, dirs, near, far):
+        d = _f32c(torch.as_tensor(dirs))
+        if not d.is_cuda:
+            raise L.NmError("the backward pass takes CUDA tensors")
+        R = d.shape[0]
+        o = _f32c(origins, d.device)
+        if o.numel() == 3:
+            o, o_stride = o.reshape(3), 0
+        else:
+            assert o.shape == (R, 3), "origins must be (3,), (1,3) or (R,3)"
+            o_stride = 3
+        per_ray = isinstance(near, torch.Tensor) and near.dim() > 0 and near.numel() == R and R > 1
+        if per_ray:
+            return o, o_stride, d, R, None, _f32c(near, d.device), _f32c(far, d.device)
+        return o, o_stride, d, R, (C.c_float * 2)(float(near), float(far)), None, None
+
+    def zero_grad(self):
+        L.check(self.lib.nm_zero_grad(self._h, self._stream()))
+
+    def backward_rays(self, origins, dirs, near, far, d_rgb, d_coarse_rgb=None, *, training=True, buff=False, seed=0):
+        """Accumulate dL/dtheta given dL/d rgb_map of the main (and optionally the coarse) bundle; the forward is
+        re-run inside with the same flags and seed (same samples, same noise)."""
+        o, o_stride, d, R, nf, near_d, far_d = self._ray_args(origins, dirs, near, far)
+        g = None if d_rgb is None else _f32c(d_rgb, d.device)
+        gc = None if d_coarse_rgb is None else _f32c(d_coarse_rgb, d.device)
+        assert (g is None or g.shape == (R, 3)) and (gc is None or gc.shape == (R, 3))
+        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        if R:
+            L.check(self.lib.nm_backward_rays(self._h, _ptr(o), o_stride, _ptr(d), R, nf, _ptr(near_d), _ptr(far_d), flags,
+                                              seed, _ptr(g), _ptr(gc), self._stream()))
+
+    def loss_backward(self, origins, dirs, near, far, target_rgb, *, training=True, buff=False, seed=0):
+        """The reference's training loss and its backward in one call: returns a (2,) device tensor
+        [mse(coarse-or-only rgb_map, target), mse(fine rgb_map, target)] (src/models/model_nerf.py:118-126)."""
+        o, o_stride, d, R, nf, near_d, far_d = self._ray_args(origins, dirs, near, far)
+        tgt = _f32c(target_rgb, d.device)
+        assert tgt.shape == (R, 3)
+        loss = torch.zeros(2, dtype=torch.float32, device=d.device)
+        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        if R:
+            L.check(self.lib.nm_loss_backward(self._h, _ptr(o), o_stride, _ptr(d), R, nf, _ptr(near_d), _ptr(far_d), flags,
+                                              seed, _ptr(tgt), _ptr(loss), self._stream()))
+        return loss
+
+    def get_grad(self, which: int, name: str, like: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(like.shape, dtype=torch.float32, device=self.device)
+        L.check(self.lib.nm_get_grad(self._h, which, name.encode(), _ptr(out), out.numel(), self._stream()))
+        return out
+
     def render_image(self, pose, H, W, focal, near, far, *, ndc=False, rows=None, training=False, buff=False, seed=0,
                      want=None, to_host=False, host_out=None) -> Dict[str, torch.Tensor]:
         """Rays generated on the device from a 3x4 / 4x4 camera-to-world pose (get_ray_bundle [+ ndc_rays])."""

@@ -108,6 +108,31 @@ def _cfg_get(node, path, default=None):
     return node
 
 
+class _RenderGrad(torch.autograd.Function):
+    """Connects the bundles' rgb maps to the networks' parameters: backward() runs nm_backward_rays (the fused
+    forward is re-run with the same flags + seed, then the compositor adjoint and the layer-wise backward) and hands
+    autograd one gradient per parameter — what loss.backward() yields in the reference (model_nerf.py:88-151)."""
+
+    @staticmethod
+    def forward(ctx, model, rays, seed, buff, training, rgb, coarse_rgb, *params):
+        ctx.model, ctx.rays, ctx.seed, ctx.buff, ctx.training = model, rays, seed, buff, training
+        ctx.has_coarse = coarse_rgb is not None
+        if coarse_rgb is None:
+            return rgb.clone()
+        return rgb.clone(), coarse_rgb.clone()
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_coarse=None):
+        model = ctx.model
+        eng = model._engine()
+        o, d, near, far = ctx.rays
+        eng.zero_grad()
+        eng.backward_rays(o, d, near, far, g_rgb, g_coarse if ctx.has_coarse else None, training=ctx.training,
+                          buff=ctx.buff, seed=ctx.seed)
+        grads = [eng.get_grad(which, name, p) for which, name, p in model._named_net_params()]
+        return (None,) * 7 + tuple(grads)
+
+
 class BaseModel(torch.nn.Module):
     """Shared part of NeRFModel / BuFFModel (src/models/model_base.py:17-73), minus the Lightning trainer hooks."""
 
@@ -169,6 +194,34 @@ class BaseModel(torch.nn.Module):
 
     def _after_engine_created(self):
         pass
+
+    def _named_net_params(self):
+        """[(slot, state-dict key without prefix, parameter)] in a fixed order."""
+        out = []
+        for which, net in enumerate(self._nets()):
+            if net is not None:
+                out += [(which, name, p) for name, p in net.named_parameters()]
+        return out
+
+    def _pick_seed(self, seed):
+        """Explicit seed wins; otherwise a fresh stream per training call (the reference draws new torch.rand
+        jitter / noise every forward), and 0 in eval mode where nothing is random."""
+        if seed is not None:
+            return int(seed)
+        if not self.training:
+            return 0
+        self._seed_counter = getattr(self, "_seed_counter", 0) + 1
+        return (torch.initial_seed() * 1000003 + self._seed_counter) & 0x7FFFFFFFFFFFFFFF
+
+    def _attach_grad(self, rays, seed, buff, rgb, coarse_rgb=None):
+        """Make rgb maps differentiable w.r.t. the network parameters when autograd is recording."""
+        named = self._named_net_params()
+        if not (torch.is_grad_enabled() and any(p.requires_grad for _, _, p in named)):
+            return rgb, coarse_rgb
+        if not rgb.is_cuda:
+            raise L.NmError("training needs CUDA ray tensors (the backward pass has no host-buffer variant)")
+        res = _RenderGrad.apply(self, rays, seed, buff, self.training, rgb, coarse_rgb, *[p for _, _, p in named])
+        return (res, None) if coarse_rgb is None else res
 
     def _mode_cfg(self):
         return self.cfg.nerf.train if self.training else self.cfg.nerf.validation
@@ -258,13 +311,17 @@ class NeRFModel(BaseModel):
     def _after_engine_created(self):
         self._eng.set_tables(self.sampler.point_intervals[0], self.sample_pdf.u if self.model_fine is not None else None)
 
-    def forward(self, x, seed=0):
+    def forward(self, x, seed=None):
         ray_origins, ray_directions, near, far = self._unpack(x)
         eng = self._engine()
+        seed = self._pick_seed(seed)
         want = ["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights"]
         if self.model_fine is not None:
             want += ["coarse_rgb", "coarse_acc", "coarse_disp", "coarse_weights"]
         o = eng.render_rays(ray_origins, ray_directions, near, far, training=self.training, seed=seed, want=want)
+        o["rgb"], crgb = self._attach_grad((ray_origins, ray_directions, near, far), seed, False, o["rgb"], o.get("coarse_rgb"))
+        if crgb is not None:
+            o["coarse_rgb"] = crgb
         main = OutputBundle(o["rgb"], o["depth"], o["weights"], o["mask_weights"], o["acc"], o["disp"], o["depth_raw"])
         if self.model_fine is None:
             return main, None
@@ -336,8 +393,9 @@ class BuFFModel(BaseModel):
     def _after_engine_created(self):
         self._eng.set_tables(self.sampler.point_intervals[0], None)
 
-    def forward(self, x, seed=0):
+    def forward(self, x, seed=None):
         ray_origins, ray_directions, near, far = self._unpack(x)
+        seed = self._pick_seed(seed)
         if torch.as_tensor(ray_origins).dim() < 2:
             raise IndexError("BuFFModel needs ray origins of shape (1,3) or (R,3) (src/nerf/tree.py:231)")
         eng = self._engine()
@@ -346,6 +404,7 @@ class BuFFModel(BaseModel):
             self._tree_id = id(self.tree.voxels)
         o = eng.render_rays(ray_origins, ray_directions, near, far, training=self.training, buff=True, seed=seed,
                             want=["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights", "t_vals"])
+        o["rgb"], _ = self._attach_grad((ray_origins, ray_directions, near, far), seed, True, o["rgb"])
         b = OutputBundle(o["rgb"], o["depth"], o["weights"], o["mask_weights"], o["acc"], o["disp"], o["depth_raw"])
         b.t_vals = o["t_vals"]
         return b

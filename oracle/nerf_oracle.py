@@ -309,7 +309,7 @@ def sample_pdf_forward(t_coarse, weights, num_fine, perturb=False, u=None, gener
     if u is None:
         u = torch.linspace(0.0, 1.0, steps=num_fine)
     mids = 0.5 * (t_coarse[..., 1:] + t_coarse[..., :-1])
-    z = sample_pdf(mids, weights[..., 1:-1], u, det=(perturb == 0.0), generator=generator)
+    z = sample_pdf(mids, weights[..., 1:-1], u, det=(perturb == 0.0), generator=generator).detach()   # modules.py:201
     out, _ = torch.sort(torch.cat((t_coarse, z), dim=-1), dim=-1)
     return out
 

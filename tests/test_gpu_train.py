@@ -1,0 +1,205 @@
+"""Training backward against torch autograd on the CPU oracle: dL/dθ of
+mse(coarse.rgb_map, target) + mse(fine.rgb_map, target) (src/models/model_nerf.py:88-151), both networks.
+
+Tolerances (floating point; the reference trains in fp32):
+  * random-init networks (smooth): every parameter tensor within 5e-3 * max|grad_ref|.  Measured on a B200: 1e-5..1e-6
+    for most tensors, up to 1.5e-3 for the sigma head and the first layers — relu-gate flips of the few samples whose
+    raw sigma is within fp32 noise of 0 (random init puts sigma around 0) between the two forwards
+  * trained lego checkpoint (sigma up to 4.6e3, saturated alphas, fine samples re-derived on device): relative L2 error
+    <= 2e-2 per tensor and cosine >= 0.999 — the forward's own end-to-end difference (test_gpu_parity.py header) moves
+    individual fine samples, which a sharp trained field amplifies
+  * losses: 1e-5 relative
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_npz
+from oracle import nerf_oracle as O
+from test_gpu_parity import LEGO_CFG, BUFF_CFG, _cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _leafs(sd):
+    return {k: (v.clone().float().requires_grad_(True) if k.endswith((".weight", ".bias")) else v.clone()) for k, v in sd.items()}
+
+
+def oracle_grads(sdc, sdf, net_c, net_f, rc, o, d, near, far, target):
+    sdc, sdf = _leafs(sdc), (_leafs(sdf) if sdf is not None else None)
+    bc, bf, _, _ = O.nerf_forward(sdc, sdf, net_c, net_f, rc, o, d, near, far)
+    lc = torch.nn.functional.mse_loss(bc.rgb_map, target)
+    lf = torch.nn.functional.mse_loss(bf.rgb_map, target) if bf is not None else None
+    (lc + (lf if lf is not None else 0.0)).backward()
+    gc = {k: v.grad for k, v in sdc.items() if v.requires_grad}
+    gf = {k: v.grad for k, v in sdf.items() if v.requires_grad} if sdf is not None else None
+    return lc.item(), (lf.item() if lf is not None else None), gc, gf
+
+
+def model_grads(model, o, d, bounds, target, seed=0):
+    model.zero_grad(set_to_none=True)
+    coarse, fine = model.forward((o, d, bounds), seed=seed)
+    lc = torch.nn.functional.mse_loss(coarse.rgb_map, target)
+    lf = torch.nn.functional.mse_loss(fine.rgb_map, target) if fine is not None else None
+    (lc + (lf if lf is not None else 0.0)).backward()
+    nets = model._nets()
+    gc = {k: p.grad.cpu() for k, p in nets[0].named_parameters()}
+    gf = {k: p.grad.cpu() for k, p in nets[1].named_parameters()} if len(nets) > 1 and nets[1] is not None else None
+    return lc.item(), (lf.item() if lf is not None else None), gc, gf
+
+
+def compare(got, ref, rel_max=None, rel_l2=None, cos=None, name=""):
+    assert set(got) == set(ref), (sorted(got), sorted(ref))
+    worst, bad, table = 0.0, [], []
+    for k in ref:
+        a, b = got[k].double().flatten(), ref[k].double().flatten()
+        assert a.shape == b.shape, (name, k, a.shape, b.shape)
+        scale = float(b.abs().max())
+        err = float((a - b).abs().max())
+        e2 = float((a - b).norm() / b.norm().clamp_min(1e-30))
+        c = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        table.append(f"  {k:24s} max|ref| {scale:.3e}  max err {err:.3e}  rel L2 {e2:.3e}  cos {c:.6f}")
+        worst = max(worst, err / max(scale, 1e-30))
+        ok = bool(torch.isfinite(a).all())
+        ok &= rel_max is None or err <= rel_max * scale + 1e-10
+        ok &= rel_l2 is None or e2 <= rel_l2
+        ok &= cos is None or c >= cos or scale == 0.0
+        if not ok:
+            bad.append(k)
+    assert not bad, f"{name}: {len(bad)} tensors outside tolerance {bad}\n" + "\n".join(table)
+    return worst
+
+
+@pytest.mark.parametrize("case", ["nerf256", "tiny_coarse_only", "no_viewdirs_skip2"])
+def test_backward_matches_autograd_random_init(case):
+    import nerfmeshes_b200 as nm
+    if case == "nerf256":
+        net_c = net_f = O.NetCfg()
+        kw = dict(nc=24, nf=40, white=True)
+    elif case == "tiny_coarse_only":
+        net_c, net_f = O.NetCfg(num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6, num_encoding_fn_dir=4), None
+        kw = dict(nc=32, nf=0, lindisp=True)
+    else:
+        net_c = net_f = O.NetCfg(num_layers=6, hidden_size=256, skip_step=2, num_encoding_fn_xyz=8, use_viewdirs=False)
+        kw = dict(nc=16, nf=17)
+    sdc = O.init_weights(net_c, 11)
+    sdf = O.init_weights(net_f, 12) if net_f is not None else None
+    model = nm.NeRFModel(_cfg(net_c, net_f, **kw)).cuda().eval()          # eval: no jitter / noise -> deterministic samples
+    model.model_coarse.load_state_dict(sdc, strict=False)
+    if sdf is not None:
+        model.model_fine.load_state_dict(sdf, strict=False)
+    g = torch.Generator().manual_seed(5)
+    R = 301
+    o = torch.randn(R, 3, generator=g) * 0.3
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1) * (0.7 + torch.rand(R, 1, generator=g))
+    target = torch.rand(R, 3, generator=g)
+    near, far = torch.tensor(0.5), torch.tensor(3.5)
+    rc = O.RenderCfg(num_coarse=kw["nc"], num_fine=kw["nf"], lindisp=kw.get("lindisp", False), white_background=kw.get("white", False))
+    lc_ref, lf_ref, gc_ref, gf_ref = oracle_grads(sdc, sdf, net_c, net_f, rc, o, d, near, far, target)
+    lc, lf, gc, gf = model_grads(model, o.cuda(), d.cuda(), (near, far), target.cuda())
+    assert abs(lc - lc_ref) <= 1e-5 * abs(lc_ref) and (lf_ref is None or abs(lf - lf_ref) <= 1e-5 * abs(lf_ref))
+    w = compare(gc, gc_ref, rel_max=5e-3, name=f"{case} coarse")
+    if gf_ref is not None:
+        w = max(w, compare(gf, gf_ref, rel_max=5e-3, name=f"{case} fine"))
+    print(f"{case}: worst max-err / max|ref| = {w:.2e}")
+
+
+def test_backward_matches_autograd_lego_checkpoint():
+    import nerfmeshes_b200 as nm
+    z = load_npz("weights_lego_nerf.npz")
+    g = load_npz("golden_lego_nerf.npz")
+    model = nm.NeRFModel.from_npz(LEGO_CFG, z).cuda().eval()
+    sdc = {k[len("coarse."):]: torch.as_tensor(v) for k, v in z.items() if k.startswith("coarse.")}
+    sdf = {k[len("fine."):]: torch.as_tensor(v) for k, v in z.items() if k.startswith("fine.")}
+    R = 96
+    o, d = torch.as_tensor(g["origin"]), torch.as_tensor(g["dirs"])[:R]
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(1))
+    near, far = float(g["bounds"][0]), float(g["bounds"][1])
+    rc = O.RenderCfg()
+    lc_ref, lf_ref, gc_ref, gf_ref = oracle_grads(sdc, sdf, O.NetCfg(), O.NetCfg(), rc, o, d, torch.tensor(near), torch.tensor(far), target)
+    lc, lf, gc, gf = model_grads(model, o.cuda(), d.cuda(), torch.tensor([near, far]), target.cuda())
+    assert abs(lc - lc_ref) <= 1e-4 * abs(lc_ref) and abs(lf - lf_ref) <= 1e-4 * abs(lf_ref)
+    compare(gc, gc_ref, rel_l2=2e-2, cos=0.999, name="lego coarse")
+    compare(gf, gf_ref, rel_l2=2e-2, cos=0.999, name="lego fine")
+
+
+def test_fused_loss_backward_equals_autograd_path_and_accumulates():
+    """nm_loss_backward (loss + backward in one call) == the autograd.Function path, in TRAINING mode with jitter and
+    sigma noise (same seed -> same random stream); a second call without nm_zero_grad doubles the buffers."""
+    import nerfmeshes_b200 as nm
+    net = O.NetCfg(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)
+    cfg = _cfg(net, net, nc=20, nf=28)
+    cfg.update({"nerf.train.perturb": True, "nerf.train.radiance_field_noise_std": 0.3})
+    model = nm.NeRFModel(cfg).cuda().train()
+    model.model_coarse.load_state_dict(O.init_weights(net, 1), strict=False)
+    model.model_fine.load_state_dict(O.init_weights(net, 2), strict=False)
+    g = torch.Generator().manual_seed(2)
+    R = 777
+    o = (torch.randn(3, generator=g) * 0.2).cuda()
+    d = torch.randn(R, 3, generator=g).cuda()
+    target = torch.rand(R, 3, generator=g).cuda()
+    lc, lf, gc, gf = model_grads(model, o, d, (torch.tensor(0.5), torch.tensor(3.0)), target, seed=1234)
+    eng = model._engine()
+    eng.zero_grad()
+    loss = eng.loss_backward(o, d, 0.5, 3.0, target, training=True, seed=1234)
+    assert abs(float(loss[0]) - lc) <= 1e-6 * abs(lc) + 1e-9 and abs(float(loss[1]) - lf) <= 1e-6 * abs(lf) + 1e-9
+    fused_c = {k: eng.get_grad(0, k, p).cpu() for k, p in model.model_coarse.named_parameters()}
+    fused_f = {k: eng.get_grad(1, k, p).cpu() for k, p in model.model_fine.named_parameters()}
+    compare(fused_c, gc, rel_max=1e-5, name="fused coarse")
+    compare(fused_f, gf, rel_max=1e-5, name="fused fine")
+    eng.loss_backward(o, d, 0.5, 3.0, target, training=True, seed=1234)            # accumulate
+    twice = {k: eng.get_grad(1, k, p).cpu() for k, p in model.model_fine.named_parameters()}
+    compare(twice, {k: 2 * v for k, v in gf.items()}, rel_max=1e-5, name="accumulated")
+    # a different seed draws different jitter / noise
+    lc2, _, gc2, _ = model_grads(model, o, d, (torch.tensor(0.5), torch.tensor(3.0)), target, seed=99)
+    assert lc2 != lc and not torch.equal(gc2["layer1.weight"], gc["layer1.weight"])
+
+
+def test_buff_backward_matches_autograd():
+    import nerfmeshes_b200 as nm
+    z = load_npz("weights_lego_buff.npz")
+    g = load_npz("golden_lego_buff.npz")
+    model = nm.BuFFModel.from_npz(BUFF_CFG, z).cuda().eval()
+    sd = _leafs({k[len("coarse."):]: torch.as_tensor(v) for k, v in z.items() if k.startswith("coarse.")})
+    R = 48
+    o, d = torch.as_tensor(g["origin"])[None], torch.as_tensor(g["dirs"])[:R]
+    target = torch.rand(R, 3, generator=torch.Generator().manual_seed(3))
+    near, far = float(g["bounds"][0]), float(g["bounds"][1])
+    rc = O.RenderCfg(num_coarse=192, num_fine=0)
+    b, _, _ = O.buff_forward(sd, O.NetCfg(), rc, torch.as_tensor(z["voxels"]).float(), o, d, torch.tensor(near), torch.tensor(far))
+    loss_ref = torch.nn.functional.mse_loss(b.rgb_map, target)
+    loss_ref.backward()
+    ref = {k: v.grad for k, v in sd.items() if v.requires_grad}
+    model.zero_grad(set_to_none=True)
+    out = model.forward((o.cuda(), d.cuda(), torch.tensor([near, far])))
+    loss = torch.nn.functional.mse_loss(out.rgb_map, target.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * loss_ref.item()
+    got = {k: p.grad.cpu() for k, p in model.model.named_parameters()}
+    compare(got, ref, rel_l2=2e-2, cos=0.999, name="buff")
+
+
+def test_training_loop_reduces_loss():
+    """The reference's optimiser loop (Adam, model_base.py:150-177) on top of the fused forward/backward: fitting a
+    constant-colour target must drive the loss down, which exercises weight re-upload after every step."""
+    import nerfmeshes_b200 as nm
+    torch.manual_seed(0)
+    net = O.NetCfg(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)
+    cfg = _cfg(net, net, nc=24, nf=24)
+    cfg.update({"nerf.train.perturb": True, "nerf.train.radiance_field_noise_std": 0.1})
+    model = nm.NeRFModel(cfg).cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3)
+    g = torch.Generator().manual_seed(4)
+    R = 1024
+    o = torch.tensor([0.0, 0.0, 0.0]).cuda()
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).cuda()
+    target = torch.tensor([0.8, 0.3, 0.1]).expand(R, 3).contiguous().cuda()
+    losses = []
+    for step in range(40):
+        opt.zero_grad(set_to_none=True)
+        coarse, fine = model.forward((o, d, (torch.tensor(0.5), torch.tensor(3.0))))
+        loss = torch.nn.functional.mse_loss(coarse.rgb_map, target) + torch.nn.functional.mse_loss(fine.rgb_map, target)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert np.isfinite(losses).all() and losses[-1] < 0.25 * losses[0], losses[::8]
