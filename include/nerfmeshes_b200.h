@@ -106,6 +106,10 @@ int nm_set_render_cfg(NmHandle h, const NmRenderCfg* cfg);
  * ...); tensors_host[i] points at numel[i] fp32 values in the reference (out,in) row-major layout. */
 int nm_load_weights(NmHandle h, int which, int n_tensors, const char* const* names,
                     const float* const* tensors_host, const int64_t* numel);
+/* Same, with the tensors already in device memory (fp32, contiguous): transposes / packs on the device, stream-ordered,
+ * no host round trip — the per-step weight refresh of a training loop whose optimiser updates CUDA parameters. */
+int nm_load_weights_dev(NmHandle h, int which, int n_tensors, const char* const* names,
+                        const float* const* tensors_dev, const int64_t* numel, void* stream);
 /* Sampler tables: coarse s = torch.linspace(0,1,num_coarse) (src/nerf/modules.py:154) and the SamplePDF buffer
  * u = torch.linspace(0,1,num_fine) (modules.py:193).  Host pointers; NULL = recompute i/(n-1) in fp32. */
 int nm_set_tables(NmHandle h, const float* coarse_s_host, const float* fine_u_host);
@@ -183,6 +187,13 @@ int nm_loss_backward(NmHandle h, const float* origins_dev, int o_stride, const f
                      const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
                      const float* target_rgb_dev, float* loss_dev, void* stream);
 int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t numel, void* stream);
+
+/* Test hook for the tensor-core GEMM of the backward pass (nm_gemm_tc.cu): D (M,N) = A (M,K) B (N,K)^T from fp32
+ * row-major device arrays through the bf16 hi/lo operand packs.  a_cols / b_cols: that operand is given transposed
+ * ((K,M) / (K,N)) and packed along its rows (the weight-gradient operands); k_split: feed K as two segments;
+ * fp16: fp16 halves instead of bf16; atomic: D += with K split over CTAs. */
+int nm_debug_gemm(NmHandle h, const float* a_dev, const float* b_dev, int M, int N, int K, int a_cols, int b_cols,
+                  int k_split, int n_passes, int fp16, int atomic, float* d_dev, void* stream);
 
 /* ---- host-only debugging aid (no CUDA): the layer program + tensor-core weight stream nm_load_weights would
  * upload, for CPU tests of the schedule / swizzle logic.  program_out receives the internal NetProgram struct

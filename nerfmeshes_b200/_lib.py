@@ -43,6 +43,7 @@ _SIGNATURES = {
     "nm_destroy": (C.c_int, [_P]),
     "nm_set_render_cfg": (C.c_int, [_P, C.POINTER(NmRenderCfg)]),
     "nm_load_weights": (C.c_int, [_P, _I, _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "nm_load_weights_dev": (C.c_int, [_P, _I, _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64), _P]),
     "nm_set_tables": (C.c_int, [_P, _P, _P]),
     "nm_set_tree": (C.c_int, [_P, _P, C.c_int32]),
     "nm_point_mlp": (C.c_int, [_P, _I, _P, _P, _L, _P, _I, _P]),
@@ -60,6 +61,7 @@ _SIGNATURES = {
     "nm_backward_rays": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _I, C.c_uint64, _P, _P, _P]),
     "nm_loss_backward": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _I, C.c_uint64, _P, _P, _P]),
     "nm_get_grad": (C.c_int, [_P, _I, C.c_char_p, _P, _L, _P]),
+    "nm_debug_gemm": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "nm_debug_pack": (C.c_int, [C.POINTER(NmNetDesc), _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64), _I, _P,
                                C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nm_kernel_flags": (C.c_int, [_P, C.POINTER(C.c_int32)]),

@@ -24,6 +24,7 @@ SOURCES = {
     "nm_render.cu": ["-fmad=false"],
     "nm_mc.cu": ["-fmad=false"],
     "nm_train.cu": [],
+    "nm_gemm_tc.cu": [],
     "nm_api.cu": [],
 }
 

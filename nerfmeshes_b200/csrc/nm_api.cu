@@ -308,22 +308,26 @@ int train_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const 
   }
   for (int pi = 0; pi < np; ++pi) {
     const Pass& P = passes[pi];
-    const NetDev& net = h->nets[P.which];
+    NetDev& net = h->nets[P.which];
     if (int e = h->dout.ensure((size_t)R * P.s * 16)) return e;
     if (int e = h->trans.ensure((size_t)R * P.s * 4)) return e;
     if (int e = launch_composite_backward(P.raw, P.t, rb.dirs, P.g, R, P.s, c.noise_std, seed ^ 0x5bd1e995u,
                                           c.white_background, h->trans.as<float>(), h->dout.as<float>(), st, &h->launches)) return e;
-    const size_t per_point = train_ws_floats_per_point(net.full);
-    long long rays_sub = 65536 / P.s;
+    // sub-chunks of ~4 waves of 128-point row blocks (148 SMs): bounds the activation workspace (~16 KB per point)
+    const bool use_tc = c.precision != NM_PREC_FP32;
+    long long rays_sub = ((long long)h->num_sms * 128 * 4) / P.s;
     if (rays_sub < 1) rays_sub = 1;
-    if (int e = h->train_ws.ensure(per_point * (size_t)(rays_sub * P.s) * 4)) return e;
+    if (rays_sub > R) rays_sub = R;
+    if (int e = h->train_ws.ensure(train_ws_bytes(net.full, rays_sub * P.s, use_tc) + 1024)) return e;
+    float* ws = reinterpret_cast<float*>(((uintptr_t)h->train_ws.p + 1023) & ~(uintptr_t)1023);
     NetGrads g{h->g_wt[P.which].as<float>(), h->g_bias[P.which].as<float>(), h->g_head[P.which].as<float>()};
+    TrainMode mode{use_tc ? 1 : 0, c.precision == NM_PREC_FAST ? 1 : 3, h->d_err};
     for (long long r0 = 0; r0 < R; r0 += rays_sub) {
       const long long n = (R - r0 < rays_sub) ? R - r0 : rays_sub;
       MlpInput in{};
       in.mode = IN_RAYS; in.dirs = rb.dirs + 3 * r0; in.ray_o = rb.origins + (long long)rb.o_stride * r0;
       in.o_stride = rb.o_stride; in.t = P.t + r0 * P.s; in.S = P.s; in.M = n * P.s;
-      if (int e = mlp_backward(net, in, h->dout.as<float>() + r0 * P.s * 4, h->train_ws.as<float>(), &g, h->num_sms, st, &h->launches)) return e;
+      if (int e = mlp_backward(h->nets[P.which], in, h->dout.as<float>() + r0 * P.s * 4, ws, &g, h->num_sms, mode, st, &h->launches)) return e;
     }
   }
   return 0;
@@ -443,6 +447,15 @@ int nm_load_weights(NmHandle h, int which, int n_tensors, const char* const* nam
   return pack_network(h->desc[which], src, &h->nets[which]);
 }
 
+int nm_load_weights_dev(NmHandle h, int which, int n_tensors, const char* const* names, const float* const* tensors_dev,
+                        const int64_t* numel, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(which == NM_NET_COARSE || (which == NM_NET_FINE && h->has_fine), "network slot %d not present", which);
+  WeightSource src;
+  src.n = n_tensors; src.names = names; src.ptrs = tensors_dev; src.numel = numel;
+  return load_network_dev(h->desc[which], src, &h->nets[which], (cudaStream_t)stream, &h->launches);
+}
+
 int nm_set_tables(NmHandle h, const float* coarse_s_host, const float* fine_u_host) {
   if (int e = bind_device(h)) return e;
   std::vector<float> tmp;
@@ -556,7 +569,8 @@ int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t
     const std::string* nm4 = &net.names[4 * l];
     if (nm4[0] == name) {
       NM_CHECK(numel == (int64_t)K * N, "'%s' has %lld elements, expected %lld", name, (long long)numel, (long long)K * N);
-      return launch_transpose_out(h->g_wt[which].as<float>() + L.wt_off, K, N, out_dev, st, &h->launches);
+      NM_CUDA(cudaMemcpyAsync(out_dev, h->g_wt[which].as<float>() + L.wt_off, (size_t)K * N * 4, cudaMemcpyDeviceToDevice, st));
+      return 0;
     }
     const float* src = nullptr;
     int64_t n = 0;
@@ -571,6 +585,17 @@ int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t
   }
   NM_CHECK(false, "no parameter named '%s'", name);
   return -1;
+}
+
+int nm_debug_gemm(NmHandle h, const float* a_dev, const float* b_dev, int M, int N, int K, int a_cols, int b_cols,
+                  int k_split, int n_passes, int fp16, int atomic, float* d_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(a_dev && b_dev && d_dev && M > 0 && N > 0 && K > 0, "bad arguments");
+  const size_t need = 3 * ((size_t)((M > N ? M : N) + 127) / 128 * ((K + 63) / 64) * 32768 + 1024) + 1024;
+  if (int e = h->train_ws.ensure(need)) return e;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)h->train_ws.p + 1023) & ~(uintptr_t)1023);
+  return debug_tc_gemm(a_dev, b_dev, M, N, K, a_cols, b_cols, k_split, n_passes, fp16, atomic, d_dev, ws, need - 1024, h->num_sms,
+                       h->d_err, (cudaStream_t)stream, &h->launches);
 }
 
 int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, const float* lin2_host, int n0, int n1,

@@ -42,13 +42,20 @@ struct NetDev {
   float* d_bias = nullptr;
   float* d_head = nullptr;
   float* d_wt = nullptr;             // transposed fp32 weights (CUDA-core kernel)
+  float* d_w = nullptr;              // the same weights in the reference's (out,in) layout, same per-layer offsets
   size_t n_wt = 0;                   // floats in d_wt
+  // training backward on the tensor cores (nm_gemm_tc.cu): bf16 hi/lo operand packs of W (forward) and W^T (data
+  // gradient) per layer, rebuilt lazily after every weight load
+  uint8_t* d_tcw = nullptr;
+  size_t tcw_bytes = 0;
+  size_t tcw_fwd_off[kMaxLayers] = {}, tcw_bwd_off[kMaxLayers] = {};
+  bool tcw_valid = false;
   std::vector<std::string> names;    // per layer of `full`: weight, bias, head weight, head bias ("" if none)
 };
 
-// Gradient accumulators of one network, laid out like NetDev.d_wt / d_bias / d_head (nm_train.cu).
+// Gradient accumulators of one network, laid out like NetDev.d_w / d_bias / d_head (nm_train.cu).
 struct NetGrads {
-  float* wt = nullptr;
+  float* w = nullptr;
   float* bias = nullptr;
   float* head = nullptr;
 };
@@ -81,6 +88,7 @@ struct WeightSource {
   const float* find(const std::string& name, int64_t expect) const;
 };
 int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net);
+int load_network_dev(const NmNetDesc& d, const WeightSource& src_device, NetDev* net, cudaStream_t st, int64_t* launches);
 void free_network(NetDev* net);
 int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, NetProgram* prog, uint8_t* out, size_t cap,
                size_t* need);
@@ -124,15 +132,18 @@ int launch_aabb(const float* voxels, int V, const float* origins, int o_stride, 
 int launch_volume_stats(const float* vol, long long n, double* d_scratch, float* out_host, cudaStream_t st,
                         int64_t* launches);
 // training backward (nm_train.cu)
-size_t train_ws_floats_per_point(const NetProgram& full);
-int mlp_backward(const NetDev& net, const MlpInput& in, const float* dout, float* ws, NetGrads* g, int num_sms,
-                 cudaStream_t st, int64_t* launches);
+size_t train_ws_bytes(const NetProgram& full, long long points, bool use_tc);
+struct TrainMode { int use_tc; int n_passes; int* d_err; };
+int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws, NetGrads* g, int num_sms,
+                 const TrainMode& mode, cudaStream_t st, int64_t* launches);
+int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_cols, int b_cols, int k_split, int n_passes,
+                  int fp16, int atomic, float* D, uint8_t* scratch, size_t scratch_bytes, int num_sms, int* d_err, cudaStream_t st,
+                  int64_t* launches);
 int launch_composite_backward(const float* raw, const float* t, const float* dirs, const float* d_rgb, long long R, int S,
                               float noise_std, uint64_t seed, int white_bg, float* scratch, float* dout,
                               cudaStream_t st, int64_t* launches);
 int launch_mse_grad(const float* rgb, const float* target, long long n, long long count, float* d_rgb, float* loss,
                     cudaStream_t st, int64_t* launches);
-int launch_transpose_out(const float* gt, int K, int N, float* out, cudaStream_t st, int64_t* launches);
 int mc_count(const float* vol, int nx, int ny, int nz, float iso, void** ws, size_t* ws_bytes, int64_t* counts_host,
              cudaStream_t st, int64_t* launches);
 int mc_emit(const float* vol, int nx, int ny, int nz, float iso, float x_off, void* ws, float* verts, float* normals,

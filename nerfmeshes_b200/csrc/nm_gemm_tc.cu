@@ -1,0 +1,313 @@
+// tcgen05 GEMM for the training backward (nm_train.cu): D (M,N) = A (M,K) * B (N,K)^T with both operands given as
+// pre-packed bf16 hi/lo "ptiles" and fp32 accumulation in TMEM.  fp32 accuracy class comes from the same operand
+// split the forward kernel uses (x = hi + lo, three MMAs per product: hi*hi + lo*hi + hi*lo), with bf16 instead of
+// fp16 halves because gradients span fp32's exponent range (16 significand bits per operand, ~2^-16 per product).
+//
+// ptile = one (128 operand rows) x (64 K) block: [hi | lo], each 16 KB, K-major, 128-byte swizzled — the shared-memory
+// image tcgen05.mma reads, so a ptile moves global -> shared with ONE 32 KB cp.async.bulk.  A pack is ptiles ordered
+// [row block][K block].  Packs are produced by pack_rows_kernel (K along the source's columns) and
+// pack_cols_kernel (K along the source's rows: the A^T / B^T operands of the weight gradient).
+//
+// Kernel: one CTA per 128 x (128*NB) output tile, optional split over K (weight gradient: K = points).  6 warps:
+// warps 0-3 epilogue (TMEM lanes 32*warp..), warp 4 producer (bulk copies into a ring of K-block stages), warp 5 MMA
+// issuer.  Barriers: full[s] (tx bytes), empty[s] (tcgen05.commit), acc (tcgen05.commit after the last K block).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "nm_common.h"
+#include "nm_gemm.h"
+#include "nm_ptx.cuh"
+
+namespace nm {
+namespace {
+
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kIdescF16 = ptx::make_idesc_f16(128, 128);                              // A, B = fp16
+constexpr uint32_t kIdescBf16 = kIdescF16 | (1u << 7) | (1u << 10);                        // A, B = bf16
+
+template <int NB>
+__global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NS = (NB == 2) ? 2 : 3;
+  constexpr uint32_t STAGE = kPtileBytes * (1 + NB);
+  // barriers + the TMEM base live behind the stages so that the dynamic window keeps its 1024-byte alignment
+  const uint32_t sbase = ptx::smem_u32(smem);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + 6u * kPtileBytes;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + 6u * kPtileBytes + 64);
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (NS + s); };
+  const uint32_t acc_bar = bar0 + 8u * (2 * NS);
+
+  const int rb = blockIdx.x;                 // A row block
+  const int cb0 = blockIdx.y * NB;           // first B row block of this CTA
+  int nbv = P.n_rb_b - cb0;                  // valid B row blocks
+  if (nbv > NB) nbv = NB;
+  // K blocks of this CTA: segment 0 restricted to the split's range, then segment 1
+  int k0 = 0, k1 = P.seg[0].nkb;
+  if (P.kb_per_split > 0) { k0 = blockIdx.z * P.kb_per_split; k1 = min(P.seg[0].nkb, k0 + P.kb_per_split); }
+  const int n0 = k1 - k0;
+  const int nk = n0 + (P.nseg > 1 ? P.seg[1].nkb : 0);
+
+  if (threadIdx.x == 0) {
+    if (sbase & 1023u) { if (P.err) atomicExch(P.err, 90); __trap(); }
+    for (int s = 0; s < NS; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
+    ptx::mbar_init(acc_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(bar0 + 64u, 128 * NB);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % NS;
+        if (it >= NS) ptx::mbar_wait(empty(s), (uint32_t)((it / NS - 1) & 1), P.err, 91);
+        const int sg = it < n0 ? 0 : 1;
+        const int kb = it < n0 ? k0 + it : it - n0;
+        const TcSeg& S = P.seg[sg];
+        const uint32_t dst = sbase + (uint32_t)s * STAGE;
+        if (P.dbg & 2) { ptx::mbar_arrive(full(s)); continue; }
+        ptx::mbar_expect_tx(full(s), kPtileBytes * (uint32_t)(1 + nbv));
+        ptx::bulk_g2s(dst, S.a + ((size_t)rb * S.a_kbt + kb) * kPtileBytes, kPtileBytes, full(s));
+        for (int j = 0; j < nbv; ++j)
+          ptx::bulk_g2s(dst + kPtileBytes * (uint32_t)(1 + j), S.b + ((size_t)(cb0 + j) * S.b_kbt + kb) * kPtileBytes,
+                        kPtileBytes, full(s));
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer (whole warp converged; one lane issues)
+    const uint32_t idesc = P.fp16 ? kIdescF16 : kIdescBf16;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % NS;
+      ptx::mbar_wait(full(s), (uint32_t)((it / NS) & 1), P.err, 92);
+      ptx::tc_fence_after();
+      const uint32_t a = sbase + (uint32_t)s * STAGE;
+      const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a), a_lo = ptx::make_kmajor_sw128_desc(a + kPtileHalf);
+      for (int j = 0; j < ((P.dbg & 1) ? 0 : nbv); ++j) {
+        const uint32_t b = a + kPtileBytes * (uint32_t)(1 + j);
+        const uint64_t b_hi = ptx::make_kmajor_sw128_desc(b), b_lo = ptx::make_kmajor_sw128_desc(b + kPtileHalf);
+        if (P.n_passes == 3) ptx::mma_block_ss3(tmem + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, it > 0 ? 1u : 0u, 4u);
+        else ptx::mma_block_ss1(tmem + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, it > 0 ? 1u : 0u, 4u);
+      }
+      ptx::tc_commit_elect(empty(s));
+    }
+    ptx::tc_commit_elect(acc_bar);
+  } else {
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> shared -> global
+    // A thread owns one accumulator row (TMEM lane); each 32x32 block is transposed through the (now idle) stage
+    // memory so that every global access of the warp is one contiguous 128-byte row segment.
+    ptx::mbar_wait(acc_bar, 0u, P.err, 93);
+    ptx::tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch (float4 aligned)
+    const int row0 = rb * 128 + warp * 32;
+    const int sub = lane >> 3, q4 = (lane & 7) * 4;                       // a lane stores 4 columns of rows sub, sub+4, ...
+    const GemmEpi& E = P.epi;
+    for (int j = 0; j < nbv; ++j) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        NM_TMEM_LD32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 * j + c0), r);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[lane * 36 + i] = __uint_as_float(r[i]);
+        __syncwarp();
+        const int n = (cb0 + j) * 128 + c0 + q4;
+        if (n < P.N && !(P.dbg & 4)) {
+          if (P.atomic) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + sub, m = row0 + rr;
+              const float4 v = *reinterpret_cast<const float4*>(&stg[rr * 36 + q4]);
+              if (m < P.M) {
+                float* dp = P.D + (size_t)m * P.ldd + n;
+                atomicAdd(dp, v.x);
+                if (n + 1 < P.N) atomicAdd(dp + 1, v.y);
+                if (n + 2 < P.N) atomicAdd(dp + 2, v.z);
+                if (n + 3 < P.N) atomicAdd(dp + 3, v.w);
+              }
+            }
+          } else {
+            // data-path outputs: N is a multiple of 64, rows are 16-byte aligned
+            float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), w1 = bias;
+            if (E.bias) bias = *reinterpret_cast<const float4*>(E.bias + n);
+            if (E.r1_vec) w1 = *reinterpret_cast<const float4*>(E.r1_w + n);
+            float4 v[8], mk[8];
+            float r1[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + sub, m = min(row0 + rr, P.M - 1);
+              v[it] = *reinterpret_cast<const float4*>(&stg[rr * 36 + q4]);
+              mk[it] = E.mask ? *reinterpret_cast<const float4*>(E.mask + (size_t)m * E.ldmask + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+              r1[it] = E.r1_vec ? E.r1_vec[(size_t)m * E.r1_stride] : 0.f;
+              if (E.accumulate) {
+                const float4 c = *reinterpret_cast<const float4*>(P.D + (size_t)m * P.ldd + n);
+                v[it].x += c.x; v[it].y += c.y; v[it].z += c.z; v[it].w += c.w;
+              }
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + sub, m = row0 + rr;
+              float4 o = v[it];
+              o.x = fmaf(r1[it], w1.x, o.x + bias.x); o.y = fmaf(r1[it], w1.y, o.y + bias.y);
+              o.z = fmaf(r1[it], w1.z, o.z + bias.z); o.w = fmaf(r1[it], w1.w, o.w + bias.w);
+              if (E.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (!(mk[it].x > 0.f)) o.x = 0.f;
+              if (!(mk[it].y > 0.f)) o.y = 0.f;
+              if (!(mk[it].z > 0.f)) o.z = 0.f;
+              if (!(mk[it].w > 0.f)) o.w = 0.f;
+              if (m < P.M) *reinterpret_cast<float4*>(P.D + (size_t)m * P.ldd + n) = o;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) ptx::tmem_dealloc(tmem, 128 * NB);
+}
+
+// ------------------------------------------------------------------------------------------------ packers
+// x = hi + lo in two 16-bit floats: bf16 (8+8 significand bits, fp32's exponent range: gradients) or fp16 (11+11
+// bits, |x| < 65504: activations, encodings and weights of the forward recompute, like the forward kernel)
+__device__ __forceinline__ void split16(float x, int fp16, uint16_t* hi, uint16_t* lo) {
+  if (fp16) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    *hi = __half_as_ushort(h); *lo = __half_as_ushort(l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    *hi = __bfloat16_as_ushort(h); *lo = __bfloat16_as_ushort(l);
+  }
+}
+
+// K along the source's columns: operand row r = source row, K index c = source column (c < C valid, zero beyond).
+// grid (K blocks, row blocks); 256 threads: thread -> (row = tid/2, 32 columns).
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ src, int ld, int R, int C,
+                                                        uint8_t* __restrict__ out, int kbt, int fp16) {
+  const int kb = blockIdx.x, rb = blockIdx.y;
+  uint8_t* tile = out + ((size_t)rb * kbt + kb) * kPtileBytes;
+  const int r = threadIdx.x >> 1, ch0 = (threadIdx.x & 1) * 4;       // 4 chunks of 8 columns
+  const int row = rb * 128 + r;
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c8 = ch0 + q;                                          // 8-column chunk index within the K block
+    const int col = kb * 64 + c8 * 8;
+    float v[8];
+    if (vec && row < R && col + 8 <= C) {
+      const float4 x0 = *reinterpret_cast<const float4*>(src + (size_t)row * ld + col);
+      const float4 x1 = *reinterpret_cast<const float4*>(src + (size_t)row * ld + col + 4);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (row < R && col + i < C) ? src[(size_t)row * ld + col + i] : 0.f;
+    }
+    __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split16(v[i], fp16, &hi[i], &lo[i]);
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// K along the source's rows (points): operand row r = source column f (f < F valid), K index = source row p (p < P).
+// grid (K blocks over points, row blocks over features); the 64 x 128 fp32 source block goes through shared memory.
+__global__ void __launch_bounds__(256) pack_cols_kernel(const float* __restrict__ src, int ld, int P, int F,
+                                                        uint8_t* __restrict__ out, int kbt, int fp16) {
+  __shared__ float t[64][129];
+  const int kb = blockIdx.x, rb = blockIdx.y;
+  uint8_t* tile = out + ((size_t)rb * kbt + kb) * kPtileBytes;
+  for (int e = threadIdx.x; e < 64 * 128; e += 256) {
+    const int p = e >> 7, f = e & 127;
+    const int gp = kb * 64 + p, gf = rb * 128 + f;
+    t[p][f] = (gp < P && gf < F) ? src[(size_t)gp * ld + gf] : 0.f;
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 1, ch0 = (threadIdx.x & 1) * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c8 = ch0 + q;
+    __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split16(t[c8 * 8 + i][r], fp16, &hi[i], &lo[i]);
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+}  // namespace
+
+size_t pack_bytes(int rows, int k) { return (size_t)((rows + 127) / 128) * ((k + 63) / 64) * kPtileBytes; }
+
+int launch_pack_rows(const float* src, int ld, int R, int C, uint8_t* out, int fp16, cudaStream_t st, int64_t* launches) {
+  if (R <= 0 || C <= 0) return 0;
+  dim3 grid((C + 63) / 64, (R + 127) / 128);
+  pack_rows_kernel<<<grid, 256, 0, st>>>(src, ld, R, C, out, (C + 63) / 64, fp16);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int fp16, cudaStream_t st, int64_t* launches) {
+  if (P <= 0 || F <= 0) return 0;
+  dim3 grid((P + 63) / 64, (F + 127) / 128);
+  pack_cols_kernel<<<grid, 256, 0, st>>>(src, ld, P, F, out, (P + 63) / 64, fp16);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_tc_gemm(TcGemmParams P, int num_sms, cudaStream_t st, int64_t* launches) {
+  if (P.M <= 0 || P.N <= 0) return 0;
+  NM_CHECK(P.nseg >= 1 && P.nseg <= 2 && P.seg[0].nkb > 0, "bad K segments");
+  const int n_rb_a = (P.M + 127) / 128;
+  P.n_rb_b = (P.N + 127) / 128;
+  const int NB = P.n_rb_b >= 2 ? 2 : 1;
+  const int col_groups = (P.n_rb_b + NB - 1) / NB;
+  int splits = 1;
+  P.kb_per_split = 0;
+  if (P.atomic) {
+    NM_CHECK(P.nseg == 1, "split-K takes one K segment");
+    const int tiles = n_rb_a * col_groups;
+    splits = (2 * num_sms + tiles - 1) / tiles;
+    const int max_splits = (P.seg[0].nkb + 7) / 8;              // at least 8 K blocks (512 points) per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    P.kb_per_split = (P.seg[0].nkb + splits - 1) / splits;
+    splits = (P.seg[0].nkb + P.kb_per_split - 1) / P.kb_per_split;
+  }
+  static const int dbg_env = [] { const char* e = getenv("NM_GEMM_DBG"); return e ? atoi(e) : 0; }();
+  P.dbg = dbg_env;
+  static thread_local unsigned configured = 0;
+  int dev = 0;
+  NM_CUDA(cudaGetDevice(&dev));
+  const size_t smem = 6 * (size_t)kPtileBytes + 128;            // NB=2: 2 stages x 96 KB; NB=1: 3 stages x 64 KB; + barriers
+  if (!(configured & (1u << (dev & 31)))) {
+    NM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured |= 1u << (dev & 31);
+  }
+  dim3 grid(n_rb_a, col_groups, splits);
+  if (NB == 2) tc_gemm_kernel<2><<<grid, kGemmThreads, smem, st>>>(P);
+  else tc_gemm_kernel<1><<<grid, kGemmThreads, smem, st>>>(P);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+}  // namespace nm

@@ -257,7 +257,7 @@ int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, Net
 
 void free_network(NetDev* net) {
   cudaFree(net->d_full); cudaFree(net->d_sigma); cudaFree(net->d_wpack_full); cudaFree(net->d_wpack_sigma);
-  cudaFree(net->d_bias); cudaFree(net->d_head); cudaFree(net->d_wt);
+  cudaFree(net->d_bias); cudaFree(net->d_head); cudaFree(net->d_wt); cudaFree(net->d_w); cudaFree(net->d_tcw);
   *net = NetDev{};
 }
 
@@ -270,7 +270,7 @@ int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net) {
   std::vector<float> bias(full.n_bias), head(full.n_head > 0 ? full.n_head : 1);
   size_t wt_total = 0;
   for (int li = 0; li < full.n_layers; ++li) wt_total += (size_t)(full.layers[li].k_act + full.layers[li].k_pe) * full.layers[li].n_out;
-  std::vector<float> wt(wt_total);
+  std::vector<float> wt(wt_total), w_rm(wt_total);
   for (int li = 0; li < full.n_layers; ++li) {
     const LayerProg& L = full.layers[li];
     const int K = L.k_act + L.k_pe;
@@ -278,6 +278,7 @@ int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net) {
     const float* Bv = src.find(nf[li].b, L.n_out);
     if (!W || !Bv) return -1;
     memcpy(&bias[L.bias_off], Bv, sizeof(float) * L.n_out);
+    memcpy(&w_rm[L.wt_off], W, sizeof(float) * (size_t)L.n_out * K);
     for (int k = 0; k < K; ++k)
       for (int n = 0; n < L.n_out; ++n) wt[L.wt_off + (size_t)k * L.n_out + n] = W[(size_t)n * K + k];
     if (!nf[li].head_w.empty()) {
@@ -304,6 +305,8 @@ int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net) {
   NM_CUDA(cudaMalloc(&net->d_bias, bias.size() * sizeof(float)));
   NM_CUDA(cudaMalloc(&net->d_head, head.size() * sizeof(float)));
   NM_CUDA(cudaMalloc(&net->d_wt, wt.size() * sizeof(float)));
+  NM_CUDA(cudaMalloc(&net->d_w, wt.size() * sizeof(float)));
+  NM_CUDA(cudaMemcpy(net->d_w, w_rm.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
   NM_CUDA(cudaMemcpy(net->d_full, &full, sizeof(NetProgram), cudaMemcpyHostToDevice));
   NM_CUDA(cudaMemcpy(net->d_sigma, &sig, sizeof(NetProgram), cudaMemcpyHostToDevice));
   NM_CUDA(cudaMemcpy(net->d_wpack_full, pk_full.data(), pk_full.size(), cudaMemcpyHostToDevice));
@@ -311,6 +314,104 @@ int pack_network(const NmNetDesc& d, const WeightSource& src, NetDev* net) {
   NM_CUDA(cudaMemcpy(net->d_bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
   NM_CUDA(cudaMemcpy(net->d_head, head.data(), head.size() * sizeof(float), cudaMemcpyHostToDevice));
   NM_CUDA(cudaMemcpy(net->d_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+  net->loaded = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device-side load
+// The same packing with the state dict already in device memory (training: the optimiser updates CUDA parameters
+// every step, so the host round trip of pack_network would dominate the step).
+namespace {
+
+__global__ void transpose_in_kernel(const float* __restrict__ W, int N, int K, float* __restrict__ Wt) {  // (N,K) -> (K,N)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int k = i / N, n = i % N;
+  Wt[i] = W[(size_t)n * K + k];
+}
+
+__device__ __forceinline__ uint32_t swz_off_dev(int r, int c) {
+  return (uint32_t)r * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+}
+
+// one CTA per 16 KB stage of the schedule (pack_stream above, on the device)
+__global__ void __launch_bounds__(256) pack_stream_kernel(const NetProgram* __restrict__ prog, const float* __restrict__ w_rm,
+                                                          uint8_t* __restrict__ out) {
+  const NetProgram& P = *prog;
+  const int b = blockIdx.x;
+  int li = 0;
+  while (li + 1 < P.n_layers && b >= P.layers[li].blk_end) ++li;
+  const LayerProg& L = P.layers[li];
+  const BlockProg B = P.blocks[b];
+  const int K = L.k_act + L.k_pe;
+  const float* W = w_rm + L.wt_off;
+  uint8_t* st = out + (size_t)b * kStageBytes;
+  for (int e = threadIdx.x; e < kChunk * kChunk; e += blockDim.x) {
+    const int r = e >> 6, c = e & 63;
+    const int n = B.nc * kChunk + r;
+    int kcol;
+    if (B.src == SRC_ACT) kcol = B.kb * kChunk + c;
+    else kcol = (c < L.k_pe) ? L.k_act + c : -1;
+    const float w = (kcol >= 0) ? W[(size_t)n * K + kcol] : 0.f;
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn(w - __half2float(hi));
+    *reinterpret_cast<__half*>(st + swz_off_dev(r, c)) = hi;
+    *reinterpret_cast<__half*>(st + kHalfStage + swz_off_dev(r, c)) = lo;
+  }
+}
+
+}  // namespace
+
+int load_network_dev(const NmNetDesc& d, const WeightSource& src, NetDev* net, cudaStream_t st, int64_t* launches) {
+  std::vector<LayerNames> nf, ns;
+  NetProgram full, sig;
+  if (int e = build_one(d, false, &full, &nf)) return e;
+  if (int e = build_one(d, true, &sig, &ns)) return e;
+  size_t wt_total = 0;
+  for (int li = 0; li < full.n_layers; ++li) wt_total += (size_t)(full.layers[li].k_act + full.layers[li].k_pe) * full.layers[li].n_out;
+  const bool same = net->loaded && memcmp(&net->desc, &d, sizeof(d)) == 0 && net->n_wt == wt_total;
+  if (!same) {
+    free_network(net);
+    net->desc = d; net->full = full; net->sigma = sig; net->n_wt = wt_total;
+    for (const LayerNames& n : nf) { net->names.push_back(n.w); net->names.push_back(n.b); net->names.push_back(n.head_w); net->names.push_back(n.head_b); }
+    NM_CUDA(cudaMalloc(&net->d_full, sizeof(NetProgram)));
+    NM_CUDA(cudaMalloc(&net->d_sigma, sizeof(NetProgram)));
+    NM_CUDA(cudaMalloc(&net->d_wpack_full, (size_t)full.n_blocks * kStageBytes));
+    NM_CUDA(cudaMalloc(&net->d_wpack_sigma, (size_t)sig.n_blocks * kStageBytes));
+    NM_CUDA(cudaMalloc(&net->d_bias, (size_t)full.n_bias * sizeof(float)));
+    NM_CUDA(cudaMalloc(&net->d_head, (size_t)(full.n_head > 0 ? full.n_head : 1) * sizeof(float)));
+    NM_CUDA(cudaMalloc(&net->d_wt, wt_total * sizeof(float)));
+    NM_CUDA(cudaMalloc(&net->d_w, wt_total * sizeof(float)));
+    NM_CUDA(cudaMemcpy(net->d_full, &full, sizeof(NetProgram), cudaMemcpyHostToDevice));
+    NM_CUDA(cudaMemcpy(net->d_sigma, &sig, sizeof(NetProgram), cudaMemcpyHostToDevice));
+    NM_CUDA(cudaMemset(net->d_head, 0, (size_t)(full.n_head > 0 ? full.n_head : 1) * sizeof(float)));
+  }
+  for (int li = 0; li < full.n_layers; ++li) {
+    const LayerProg& L = full.layers[li];
+    const int K = L.k_act + L.k_pe, N = L.n_out;
+    const float* W = src.find(nf[li].w, (int64_t)N * K);
+    const float* Bv = src.find(nf[li].b, N);
+    if (!W || !Bv) return -1;
+    NM_CUDA(cudaMemcpyAsync(net->d_w + L.wt_off, W, sizeof(float) * (size_t)N * K, cudaMemcpyDeviceToDevice, st));
+    NM_CUDA(cudaMemcpyAsync(net->d_bias + L.bias_off, Bv, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    transpose_in_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(W, N, K, net->d_wt + L.wt_off);
+    NM_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    if (!nf[li].head_w.empty()) {
+      const int rows = L.kind == KIND_SIGMA ? 1 : (L.kind == KIND_RGB ? 3 : 4);
+      const float* HW = src.find(nf[li].head_w, (int64_t)rows * N);
+      const float* HB = src.find(nf[li].head_b, rows);
+      if (!HW || !HB) return -1;
+      NM_CUDA(cudaMemcpyAsync(net->d_head + L.head_off, HW, sizeof(float) * rows * N, cudaMemcpyDeviceToDevice, st));
+      NM_CUDA(cudaMemcpyAsync(net->d_head + L.head_off + rows * N, HB, sizeof(float) * rows, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  pack_stream_kernel<<<full.n_blocks, 256, 0, st>>>(net->d_full, net->d_w, net->d_wpack_full);
+  NM_CUDA(cudaGetLastError());
+  pack_stream_kernel<<<sig.n_blocks, 256, 0, st>>>(net->d_sigma, net->d_w, net->d_wpack_sigma);
+  NM_CUDA(cudaGetLastError());
+  if (launches) *launches += 2;
+  net->tcw_valid = false;
   net->loaded = true;
   return 0;
 }

@@ -14,8 +14,11 @@
 // them in the reference's (out,in) layout.  A tcgen05 version of these GEMMs is the next step for this row.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "nm_common.h"
 #include "nm_frontend.cuh"
+#include "nm_gemm.h"
 
 namespace nm {
 namespace {
@@ -43,16 +46,6 @@ __global__ void encode_kernel(const __grid_constant__ MlpInput in, const NetProg
 // ------------------------------------------------------------------------------------------------ SGEMM  C = A * op(B)
 // A (M,K) row-major.  BT=false: B (K,N) row-major;  BT=true: B (N,K) row-major (C = A B^T).
 // CTA tile 128 x (16*TN), 256 threads, 8 x TN micro-tile, BK = 16, register prefetch of the next K tile.
-struct GemmEpi {
-  int accumulate;          // C += (else C =)
-  const float* bias;       // + bias[n]
-  int relu;                // max(.,0)
-  const float* r1_vec;     // + r1_vec[m * r1_stride] * r1_w[n]
-  int r1_stride;
-  const float* r1_w;
-  const float* mask;       // * (mask[m*ldmask + n] > 0)
-  int ldmask;
-};
 
 template <int TN, bool BT>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
@@ -436,21 +429,73 @@ __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __re
   if (threadIdx.x == 0 && loss) atomicAdd(loss, red[0]);
 }
 
-__global__ void transpose_out_kernel(const float* __restrict__ gt, int K, int N, float* __restrict__ out) {  // gt (K,N) -> out (N,K)
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K * N) return;
-  const int n = i / K, k = i % K;
-  out[i] = gt[(size_t)k * N + n];
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+namespace {
+
+constexpr size_t kAlign = 1024;
+size_t up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+// workspace carving for one sub-chunk of P points (all regions 1 KB aligned; ptile packs need it)
+struct TrainWs {
+  float *pe_x, *pe_d, *dbuf[2], *act[kMaxLayers];
+  uint8_t *pk_a, *pk_pex, *pk_ped, *pkt_a, *pkt_b, *pkt_pex, *pkt_ped;
+  size_t bytes;
+};
+TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
+  TrainWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += up(bytes); return p; };
+  const int h = G.hidden;
+  w.pe_x = (float*)take((size_t)P * kPeLd * 4);
+  w.pe_d = (float*)take((size_t)P * kPeLd * 4);
+  w.dbuf[0] = (float*)take((size_t)P * h * 4);
+  w.dbuf[1] = (float*)take((size_t)P * h * 4);
+  for (int l = 0; l < G.n_layers; ++l) w.act[l] = (float*)take((size_t)P * G.layers[l].n_out * 4);
+  if (use_tc) {
+    w.pk_a = take(pack_bytes((int)P, h));
+    w.pk_pex = take(pack_bytes((int)P, kPeLd));
+    w.pk_ped = take(pack_bytes((int)P, kPeLd));
+    w.pkt_a = take(pack_bytes(h, (int)P));
+    w.pkt_b = take(pack_bytes(h, (int)P));
+    w.pkt_pex = take(pack_bytes(kPeLd, (int)P));
+    w.pkt_ped = take(pack_bytes(kPeLd, (int)P));
+  }
+  w.bytes = off;
+  return w;
+}
+
+// bf16 hi/lo packs of W (rows = out features, K = in features) and of W^T restricted to the activation inputs
+// (rows = in features, K = out features) for every layer
+int build_weight_packs(NetDev& net, cudaStream_t st, int64_t* launches) {
+  const NetProgram& G = net.full;
+  size_t total = 0;
+  for (int l = 0; l < G.n_layers; ++l) {
+    const LayerProg& L = G.layers[l];
+    net.tcw_fwd_off[l] = total; total += pack_bytes(L.n_out, L.k_act + L.k_pe);
+    net.tcw_bwd_off[l] = total; total += L.k_act > 0 ? pack_bytes(L.k_act, L.n_out) : 0;
+  }
+  if (net.tcw_bytes < total) {
+    cudaFree(net.d_tcw);
+    net.d_tcw = nullptr; net.tcw_bytes = 0;
+    NM_CUDA(cudaMalloc(&net.d_tcw, total));
+    net.tcw_bytes = total;
+  }
+  for (int l = 0; l < G.n_layers; ++l) {
+    const LayerProg& L = G.layers[l];
+    const int K = L.k_act + L.k_pe;
+    if (int e = launch_pack_rows(net.d_w + L.wt_off, K, L.n_out, K, net.d_tcw + net.tcw_fwd_off[l], 1, st, launches)) return e;
+    if (L.k_act > 0)
+      if (int e = launch_pack_rows(net.d_wt + L.wt_off, L.n_out, L.k_act, L.n_out, net.d_tcw + net.tcw_bwd_off[l], 0, st, launches)) return e;
+  }
+  net.tcw_valid = true;
+  return 0;
 }
 
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------ host side
-size_t train_ws_floats_per_point(const NetProgram& G) {
-  size_t f = 2 * kPeLd + 2 * (size_t)G.hidden;
-  for (int l = 0; l < G.n_layers; ++l) f += G.layers[l].n_out;
-  return f;
-}
+size_t train_ws_bytes(const NetProgram& G, long long points, bool use_tc) { return carve(G, points, use_tc, nullptr).bytes; }
 
 int launch_composite_backward(const float* raw, const float* t, const float* dirs, const float* d_rgb, long long R, int S,
                               float noise_std, uint64_t seed, int white_bg, float* scratch, float* dout,
@@ -472,76 +517,112 @@ int launch_mse_grad(const float* rgb, const float* target, long long n, long lon
   return 0;
 }
 
-int launch_transpose_out(const float* gt, int K, int N, float* out, cudaStream_t st, int64_t* launches) {
-  transpose_out_kernel<<<(K * N + 255) / 256, 256, 0, st>>>(gt, K, N, out);
-  NM_CUDA(cudaGetLastError());
-  if (launches) ++*launches;
-  return 0;
-}
-
-// Backward of one network over P = in.M points.  dout (P,4).  ws: train_ws_floats_per_point(full) * P floats.
-int mlp_backward(const NetDev& net, const MlpInput& in, const float* dout, float* ws, NetGrads* g, int num_sms,
-                 cudaStream_t st, int64_t* launches) {
+// Backward of one network over P = in.M points.  dout (P,4).  ws: train_ws_bytes(full, P, use_tc) bytes, 1 KB aligned.
+// Weight gradients accumulate in the reference's (out,in) layout at the offsets of NetDev.d_w.
+int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_base, NetGrads* g, int num_sms,
+                 const TrainMode& mode, cudaStream_t st, int64_t* launches) {
   const NetProgram& G = net.full;
   const int P = (int)in.M;
   if (P <= 0) return 0;
-  const int h = G.hidden;
-  float* pe_x = ws;
-  float* pe_d = pe_x + (size_t)P * kPeLd;
-  float* dbuf[2] = {pe_d + (size_t)P * kPeLd, pe_d + (size_t)P * kPeLd + (size_t)P * h};
-  float* act[kMaxLayers];
-  {
-    float* p = dbuf[1] + (size_t)P * h;
-    for (int l = 0; l < G.n_layers; ++l) { act[l] = p; p += (size_t)P * G.layers[l].n_out; }
-  }
-  encode_kernel<<<(P + 127) / 128, 128, 0, st>>>(in, net.d_full, pe_x, pe_d);
+  const bool tc = mode.use_tc != 0;
+  TrainWs W = carve(G, P, tc, reinterpret_cast<uint8_t*>(ws_base));
+  if (tc && !net.tcw_valid)
+    if (int e = build_weight_packs(net, st, launches)) return e;
+  const int kbtP = (P + 63) / 64;
+
+  encode_kernel<<<(P + 127) / 128, 128, 0, st>>>(in, net.d_full, W.pe_x, W.pe_d);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
-
-  auto pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? pe_x : pe_d; };
-  // forward recompute
-  for (int l = 0; l < G.n_layers; ++l) {
-    const LayerProg& L = G.layers[l];
-    const float* Wt = net.d_wt + L.wt_off;
-    GemmEpi fin{};
-    fin.bias = net.d_bias + L.bias_off; fin.relu = L.relu;
-    if (L.k_act > 0) {
-      GemmEpi e = L.pe_src ? GemmEpi{} : fin;
-      if (int rc = sgemm<false>(act[l - 1], G.layers[l - 1].n_out, Wt, L.n_out, act[l], L.n_out, P, L.n_out, L.k_act, e, st, launches)) return rc;
-    }
-    if (L.pe_src) {
-      fin.accumulate = L.k_act > 0 ? 1 : 0;
-      if (int rc = sgemm<false>(pe_of(L), kPeLd, Wt + (size_t)L.k_act * L.n_out, L.n_out, act[l], L.n_out, P, L.n_out, L.k_pe, fin, st, launches)) return rc;
+  if (tc) {
+    if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
+    if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, 0, st, launches)) return e;
+    if (G.dim_dir > 0) {
+      if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
+      if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, 0, st, launches)) return e;
     }
   }
-  // backward
+  auto pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? W.pe_x : W.pe_d; };
+  auto pk_pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? W.pk_pex : W.pk_ped; };
+  auto pkt_pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? W.pkt_pex : W.pkt_ped; };
+  auto tc_base = [&]() { TcGemmParams T{}; T.n_passes = mode.n_passes; T.err = mode.d_err; return T; };
+
+  // ---- forward recompute: act[l] = act_l([act[l-1] | PE] W^T + b)
+  for (int l = 0; l < G.n_layers; ++l) {
+    const LayerProg& L = G.layers[l];
+    const int N = L.n_out, Kt = L.k_act + L.k_pe;
+    GemmEpi fin{};
+    fin.bias = net.d_bias + L.bias_off; fin.relu = L.relu;
+    if (tc) {
+      TcGemmParams T = tc_base();
+      const uint8_t* wp = net.d_tcw + net.tcw_fwd_off[l];
+      const int kbtW = (Kt + 63) / 64;
+      int ns = 0;
+      if (L.k_act > 0) {
+        if (int e = launch_pack_rows(W.act[l - 1], G.layers[l - 1].n_out, P, L.k_act, W.pk_a, 1, st, launches)) return e;
+        T.seg[ns++] = TcSeg{W.pk_a, L.k_act / 64, wp, kbtW, L.k_act / 64};
+      }
+      if (L.pe_src) T.seg[ns++] = TcSeg{pk_pe_of(L), 1, wp + (size_t)(L.k_act / 64) * kPtileBytes, kbtW, 1};
+      T.nseg = ns; T.D = W.act[l]; T.ldd = N; T.M = P; T.N = N; T.epi = fin;
+      T.fp16 = 1;      // forward recompute in the forward kernel's precision class (relu masks must agree with it)
+      if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
+    } else {
+      const float* Wt = net.d_wt + L.wt_off;
+      if (L.k_act > 0) {
+        GemmEpi e0 = L.pe_src ? GemmEpi{} : fin;
+        if (int rc = sgemm<false>(W.act[l - 1], G.layers[l - 1].n_out, Wt, N, W.act[l], N, P, N, L.k_act, e0, st, launches)) return rc;
+      }
+      if (L.pe_src) {
+        fin.accumulate = L.k_act > 0 ? 1 : 0;
+        if (int rc = sgemm<false>(pe_of(L), kPeLd, Wt + (size_t)L.k_act * N, N, W.act[l], N, P, N, L.k_pe, fin, st, launches)) return rc;
+      }
+    }
+  }
+
+  // ---- backward
   int cur = 0;
   const int p_per_block = (P + 2 * num_sms - 1) / (2 * num_sms);
   const int hb_blocks = (P + p_per_block - 1) / p_per_block;
   for (int l = G.n_layers - 1; l >= 0; --l) {
     const LayerProg& L = G.layers[l];
-    const int N = L.n_out;
-    float* dZ = dbuf[cur];
+    const int N = L.n_out, Kt = L.k_act + L.k_pe;
+    float* dZ = W.dbuf[cur];
     if (L.kind == KIND_RGB || L.kind == KIND_OUT4) {
       NM_CHECK(l == G.n_layers - 1, "rgb head must be the last layer");
       const int heads = L.kind == KIND_RGB ? 3 : 4;
-      head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 0, heads, act[l], N, P, net.d_head + L.head_off,
+      head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 0, heads, W.act[l], N, P, net.d_head + L.head_off,
                                                      g->head + L.head_off, dZ, L.relu, p_per_block);
       NM_CUDA(cudaGetLastError());
       if (launches) ++*launches;
     } else if (L.kind == KIND_SIGMA) {
       // weight/bias gradient of fc_alpha; its contribution to dZ was added by the fc_feat data-grad epilogue
-      head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 3, 1, act[l], N, P, net.d_head + L.head_off,
+      head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 3, 1, W.act[l], N, P, net.d_head + L.head_off,
                                                      g->head + L.head_off, nullptr, 0, p_per_block);
       NM_CUDA(cudaGetLastError());
       if (launches) ++*launches;
     }
-    // weight / bias gradients of this layer
-    float* gWt = g->wt + L.wt_off;
-    if (L.k_act > 0)
-      if (int rc = sgemm_tn(act[l - 1], G.layers[l - 1].n_out, dZ, N, gWt, N, P, L.k_act, N, num_sms, st, launches)) return rc;
-    if (L.pe_src)
-      if (int rc = sgemm_tn(pe_of(L), kPeLd, dZ, N, gWt + (size_t)L.k_act * N, N, P, L.k_pe, N, num_sms, st, launches)) return rc;
+    // weight gradient dW (N, Kt) += dZ^T [act[l-1] | PE], bias gradient
+    float* gW = g->w + L.wt_off;
+    if (tc) {
+      if (int e = launch_pack_cols(dZ, N, P, N, W.pkt_a, 0, st, launches)) return e;
+      TcGemmParams T = tc_base();
+      T.nseg = 1; T.atomic = 1; T.ldd = Kt; T.M = N;
+      if (L.k_act > 0) {
+        if (int e = launch_pack_cols(W.act[l - 1], G.layers[l - 1].n_out, P, L.k_act, W.pkt_b, 0, st, launches)) return e;
+        T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_b, kbtP, kbtP};
+        T.D = gW; T.N = L.k_act;
+        if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
+      }
+      if (L.pe_src) {
+        T.seg[0] = TcSeg{W.pkt_a, kbtP, pkt_pe_of(L), kbtP, kbtP};
+        T.D = gW + L.k_act; T.N = L.k_pe;
+        if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
+      }
+    } else {
+      if (L.k_act > 0)
+        if (int rc = sgemm_tn(dZ, N, W.act[l - 1], G.layers[l - 1].n_out, gW, Kt, P, N, L.k_act, num_sms, st, launches)) return rc;
+      if (L.pe_src)
+        if (int rc = sgemm_tn(dZ, N, pe_of(L), kPeLd, gW + L.k_act, Kt, P, N, L.k_pe, num_sms, st, launches)) return rc;
+    }
     {
       const int ppb = (P + 63) / 64;
       dim3 grid((N + 31) / 32, (P + ppb - 1) / ppb);
@@ -549,18 +630,62 @@ int mlp_backward(const NetDev& net, const MlpInput& in, const float* dout, float
       NM_CUDA(cudaGetLastError());
       if (launches) ++*launches;
     }
-    // data gradient into the previous layer's pre-activation
+    // data gradient into the previous layer's pre-activation: dX (P,k_act) = dZ (P,N) W[:, :k_act]
     if (l > 0) {
       const LayerProg& Lp = G.layers[l - 1];
       NM_CHECK(L.k_act == Lp.n_out, "layer chain mismatch");
       GemmEpi e{};
       if (Lp.kind == KIND_SIGMA) { e.r1_vec = dout + 3; e.r1_stride = 4; e.r1_w = net.d_head + Lp.head_off; }
-      if (Lp.relu) { e.mask = act[l - 1]; e.ldmask = Lp.n_out; }
-      // dX (P,k_act) = dZ (P,N) * W[:, :k_act];  W[n][k] = Wt[k][n]  ->  B = Wt rows 0..k_act-1 viewed (k_act, N), transposed
-      if (int rc = sgemm<true>(dZ, N, net.d_wt + L.wt_off, N, dbuf[cur ^ 1], L.k_act, P, L.k_act, N, e, st, launches)) return rc;
+      if (Lp.relu) { e.mask = W.act[l - 1]; e.ldmask = Lp.n_out; }
+      if (tc) {
+        if (int rc = launch_pack_rows(dZ, N, P, N, W.pk_a, 0, st, launches)) return rc;
+        TcGemmParams T = tc_base();
+        const int kb = (N + 63) / 64;
+        T.nseg = 1; T.seg[0] = TcSeg{W.pk_a, kb, net.d_tcw + net.tcw_bwd_off[l], kb, kb};
+        T.D = W.dbuf[cur ^ 1]; T.ldd = L.k_act; T.M = P; T.N = L.k_act; T.epi = e;
+        if (int rc = launch_tc_gemm(T, num_sms, st, launches)) return rc;
+      } else {
+        // W[n][k] = Wt[k][n]  ->  B = Wt rows 0..k_act-1 viewed (k_act, N), read transposed
+        if (int rc = sgemm<true>(dZ, N, net.d_wt + L.wt_off, N, W.dbuf[cur ^ 1], L.k_act, P, L.k_act, N, e, st, launches)) return rc;
+      }
       cur ^= 1;
     }
   }
+  return 0;
+}
+
+// standalone entry for tests of the tensor-core GEMM: D (M,N) = A (M,K) B (N,K)^T from fp32 row-major device
+// arrays.  a_cols / b_cols != 0: the operand is given transposed ((K,M) / (K,N) row-major) and packed with
+// pack_cols.  k_split > 0 (multiple of 64, row-packed operands only): the K range is fed as two segments.
+int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_cols, int b_cols, int k_split, int n_passes,
+                  int fp16, int atomic, float* D, uint8_t* scratch, size_t scratch_bytes, int num_sms, int* d_err, cudaStream_t st,
+                  int64_t* launches) {
+  const size_t need = up(pack_bytes(M, K)) + up(pack_bytes(N, K)) + (k_split > 0 ? up(pack_bytes(M, K)) : 0);
+  NM_CHECK(scratch_bytes >= need, "scratch too small: need %zu bytes", need);
+  uint8_t* pa = scratch;
+  uint8_t* pb = pa + up(pack_bytes(M, K));
+  uint8_t* pa2 = pb + up(pack_bytes(N, K));
+  TcGemmParams T{};
+  T.n_passes = n_passes; T.fp16 = fp16; T.err = d_err; T.atomic = atomic; T.D = D; T.ldd = N; T.M = M; T.N = N;
+  const int kbt = (K + 63) / 64;
+  if (int e = b_cols ? launch_pack_cols(B, N, K, N, pb, fp16, st, launches) : launch_pack_rows(B, K, N, K, pb, fp16, st, launches)) return e;
+  if (k_split > 0) {
+    NM_CHECK(!a_cols && !b_cols && k_split % 64 == 0 && k_split < K && !atomic, "bad k_split");
+    if (int e = launch_pack_rows(A, K, M, k_split, pa, fp16, st, launches)) return e;
+    if (int e = launch_pack_rows(A + k_split, K, M, K - k_split, pa2, fp16, st, launches)) return e;
+    const int kb0 = k_split / 64, kb1 = kbt - kb0;
+    T.nseg = 2;
+    T.seg[0] = TcSeg{pa, kb0, pb, kbt, kb0};
+    T.seg[1] = TcSeg{pa2, kb1, pb + (size_t)kb0 * kPtileBytes, kbt, kb1};
+  } else {
+    if (int e = a_cols ? launch_pack_cols(A, M, K, M, pa, fp16, st, launches) : launch_pack_rows(A, K, M, K, pa, fp16, st, launches)) return e;
+    T.nseg = 1;
+    T.seg[0] = TcSeg{pa, kbt, pb, kbt, kbt};
+  }
+  int repeat = 1;
+  if (const char* e = getenv("NM_GEMM_REPEAT")) repeat = atoi(e) > 0 ? atoi(e) : 1;     // timing aid (tools/gemm_bench.py)
+  for (int i = 0; i < repeat; ++i)
+    if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
   return 0;
 }
 

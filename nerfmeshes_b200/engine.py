@@ -95,19 +95,28 @@ class Engine:
         L.check(self.lib.nm_set_render_cfg(self._h, C.byref(cfg)))
 
     def load_weights(self, which: int, state: Dict[str, torch.Tensor]):
-        """state: reference state-dict keys without the model prefix -> tensors (any device)."""
+        """state: reference state-dict keys without the model prefix -> tensors.  CUDA tensors on this engine's
+        device are packed on the device (nm_load_weights_dev); anything else goes through the host path."""
+        items = [(k, v) for k, v in state.items() if "frequency_bands" not in k]
+        on_dev = all(v.is_cuda and v.device == self.device for _, v in items)
         names, ptrs, numel, keep = [], [], [], []
-        for k, v in state.items():
-            if "frequency_bands" in k:
-                continue
-            a = np.ascontiguousarray(v.detach().cpu().numpy().astype(np.float32, copy=False))
+        for k, v in items:
+            if on_dev:
+                a = v.detach().to(torch.float32).contiguous()
+                ptrs.append(a.data_ptr())
+                numel.append(a.numel())
+            else:
+                a = np.ascontiguousarray(v.detach().cpu().numpy().astype(np.float32, copy=False))
+                ptrs.append(a.ctypes.data)
+                numel.append(a.size)
             keep.append(a)
             names.append(k.encode())
-            ptrs.append(a.ctypes.data)
-            numel.append(a.size)
         n = len(names)
-        L.check(self.lib.nm_load_weights(self._h, which, n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs),
-                                         (C.c_int64 * n)(*numel)))
+        args = (self._h, which, n, (C.c_char_p * n)(*names), (C.c_void_p * n)(*ptrs), (C.c_int64 * n)(*numel))
+        if on_dev:
+            L.check(self.lib.nm_load_weights_dev(*args, self._stream()))
+        else:
+            L.check(self.lib.nm_load_weights(*args))
 
     def set_tables(self, coarse_s: Optional[torch.Tensor] = None, fine_u: Optional[torch.Tensor] = None):
         s = None if coarse_s is None else np.ascontiguousarray(coarse_s.detach().cpu().numpy(), dtype=np.float32)
@@ -255,6 +264,17 @@ class Engine:
         out = torch.empty(like.shape, dtype=torch.float32, device=self.device)
         L.check(self.lib.nm_get_grad(self._h, which, name.encode(), _ptr(out), out.numel(), self._stream()))
         return out
+
+    def debug_gemm(self, a, b, *, a_cols=False, b_cols=False, k_split=0, n_passes=3, fp16=False, atomic=False, out=None):
+        """Test hook (nm_debug_gemm): D = A B^T on the backward pass's tensor-core GEMM.  a: (M,K) or (K,M) if a_cols;
+        b: (N,K) or (K,N) if b_cols."""
+        a, b = _f32c(a, self.device), _f32c(b, self.device)
+        M, K = (a.shape[1], a.shape[0]) if a_cols else a.shape
+        N = b.shape[1] if b_cols else b.shape[0]
+        d = out if out is not None else torch.zeros((M, N), dtype=torch.float32, device=self.device)
+        L.check(self.lib.nm_debug_gemm(self._h, _ptr(a), _ptr(b), M, N, K, int(a_cols), int(b_cols), k_split, n_passes,
+                                       int(fp16), int(atomic), _ptr(d), self._stream()))
+        return d
 
     def render_image(self, pose, H, W, focal, near, far, *, ndc=False, rows=None, training=False, buff=False, seed=0,
                      want=None, to_host=False, host_out=None) -> Dict[str, torch.Tensor]:

@@ -2,9 +2,16 @@
 mse(coarse.rgb_map, target) + mse(fine.rgb_map, target) (src/models/model_nerf.py:88-151), both networks.
 
 Tolerances (floating point; the reference trains in fp32):
-  * random-init networks (smooth): every parameter tensor within 5e-3 * max|grad_ref|.  Measured on a B200: 1e-5..1e-6
-    for most tensors, up to 1.5e-3 for the sigma head and the first layers — relu-gate flips of the few samples whose
-    raw sigma is within fp32 noise of 0 (random init puts sigma around 0) between the two forwards
+  * random-init networks with the sigma bias lifted to +0.6 (random init puts raw sigma around 0, where the relu gate of
+    individual samples is decided by fp32 noise): every parameter tensor within 6e-3 relative L2 (and no entry further
+    than 3e-2 * max|grad_ref|).
+    What sets this floor is not GEMM rounding but relu-gate flips: a hidden unit whose pre-activation is within the
+    forward's rounding error of 0 is gated differently by two implementations, which moves that (point, unit) gradient
+    entry by 100 %; with a fraction f of such entries the relative L2 difference is ~sqrt(f).  Measured on a B200: plain
+    fp32 FMAs (NM_PREC_FP32) 7e-5 at the first layer, the tensor-core path with the forward recompute in fp16 hi/lo
+    halves (22 bits, the forward kernel's class) 1.8e-3 (coarse) / 3.6e-3 (fine net, 64 samples) there and ~1e-4 in the
+    upper layers; a bf16 hi/lo recompute
+    (16 bits) gave 6e-3, which is why the recompute uses fp16 halves
   * trained lego checkpoint (sigma up to 4.6e3, saturated alphas, fine samples re-derived on device): relative L2 error
     <= 2e-2 per tensor and cosine >= 0.999 — the forward's own end-to-end difference (test_gpu_parity.py header) moves
     individual fine samples, which a sharp trained field amplifies
@@ -84,6 +91,12 @@ def test_backward_matches_autograd_random_init(case):
         kw = dict(nc=16, nf=17)
     sdc = O.init_weights(net_c, 11)
     sdf = O.init_weights(net_f, 12) if net_f is not None else None
+    for sd in (sdc, sdf):        # random init puts raw sigma around 0, where the relu gate (sigma > 0) of individual
+        if sd is not None:       # samples is decided by fp32 noise; lift it clear of 0 (closed gates: lego test below)
+            if "fc_alpha.bias" in sd:
+                sd["fc_alpha.bias"] = sd["fc_alpha.bias"] + 0.6
+            else:
+                sd["fc_out.bias"] = sd["fc_out.bias"] + torch.tensor([0.0, 0.0, 0.0, 0.6])
     model = nm.NeRFModel(_cfg(net_c, net_f, **kw)).cuda().eval()          # eval: no jitter / noise -> deterministic samples
     model.model_coarse.load_state_dict(sdc, strict=False)
     if sdf is not None:
@@ -98,9 +111,9 @@ def test_backward_matches_autograd_random_init(case):
     lc_ref, lf_ref, gc_ref, gf_ref = oracle_grads(sdc, sdf, net_c, net_f, rc, o, d, near, far, target)
     lc, lf, gc, gf = model_grads(model, o.cuda(), d.cuda(), (near, far), target.cuda())
     assert abs(lc - lc_ref) <= 1e-5 * abs(lc_ref) and (lf_ref is None or abs(lf - lf_ref) <= 1e-5 * abs(lf_ref))
-    w = compare(gc, gc_ref, rel_max=5e-3, name=f"{case} coarse")
+    w = compare(gc, gc_ref, rel_max=3e-2, rel_l2=6e-3, name=f"{case} coarse")
     if gf_ref is not None:
-        w = max(w, compare(gf, gf_ref, rel_max=5e-3, name=f"{case} fine"))
+        w = max(w, compare(gf, gf_ref, rel_max=3e-2, rel_l2=6e-3, name=f"{case} fine"))
     print(f"{case}: worst max-err / max|ref| = {w:.2e}")
 
 
@@ -203,3 +216,84 @@ def test_training_loop_reduces_loss():
         opt.step()
         losses.append(loss.item())
     assert np.isfinite(losses).all() and losses[-1] < 0.25 * losses[0], losses[::8]
+
+
+def test_device_side_weight_load_is_bit_identical():
+    """nm_load_weights_dev (transpose + fp16 hi/lo stage packing on the device) == the host packer."""
+    import nerfmeshes_b200 as nm
+    z = load_npz("weights_lego_nerf.npz")
+    g = load_npz("golden_lego_nerf.npz")
+    rays = (torch.as_tensor(g["origin"]).cuda(), torch.as_tensor(g["dirs"]).cuda(), torch.as_tensor(g["bounds"]))
+    model = nm.NeRFModel.from_npz(LEGO_CFG, z).eval()               # CPU parameters -> host path
+    with torch.no_grad():
+        a = model.query(rays)
+        pts = torch.rand(1000, 3).cuda() * 2 - 1
+        pa = model.sample_points(pts, pts)
+        model.cuda()                                                # CUDA parameters -> device path
+        b = model.query(rays)
+        pb = model.sample_points(pts, pts)
+    assert torch.equal(a.rgb_map, b.rgb_map) and torch.equal(a.depth_map, b.depth_map) and torch.equal(pa, pb)
+    close = float((b.rgb_map.cpu() - torch.as_tensor(g["fine_rgb"])).abs().max())
+    assert close < 1e-4, close
+
+
+@pytest.mark.parametrize("shape", [
+    dict(M=300, N=256, K=319, k_split=256),          # forward of the skip layer: [activations | encoding]
+    dict(M=1000, N=128, K=64),
+    dict(M=77, N=64, K=283, k_split=256),            # tiny net's direction layer
+    dict(M=5000, N=256, K=128),                      # data gradient shape
+    dict(M=256, N=63, K=5000, cols=True),            # weight gradient (encoding part): K = points, split + atomics
+    dict(M=128, N=256, K=70001, cols=True),
+])
+def test_tc_gemm_matches_fp64(shape):
+    """The backward's tcgen05 GEMM (operand split x = hi + lo, 3 MMAs per product) against an fp64 product.  Errors are
+    measured against the random-walk scale s = sqrt((A*A)(B*B)^T): bf16 halves (16 significand bits per operand) must stay
+    within 1e-4*s (expected ~2^-17 per term; measured 2-3e-5*s), fp16 halves (22 bits) within 2e-5*s (measured 3e-6*s at K=128,
+    1e-5*s at K=70001 where fp32 accumulation shows), and
+    the one-pass variant (bf16's 8 bits) must be at least 30x worse than the three-pass one — i.e. the two correction
+    passes really contribute."""
+    import nerfmeshes_b200 as nm
+    eng = nm.Engine(O.NetCfg().__dict__, None, nm.RenderSettings())
+    M, N, K = shape["M"], shape["N"], shape["K"]
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g) * torch.logspace(-2, 1, K)[None, :]        # wide dynamic range along K
+    b = torch.randn(N, K, generator=g)
+    ref = a.double() @ b.double().T
+    scale = ((a.double() ** 2) @ (b.double() ** 2).T).sqrt()
+    cols = shape.get("cols", False)
+    A = a.T.contiguous().cuda() if cols else a.cuda()
+    B = b.T.contiguous().cuda() if cols else b.cuda()
+    kw = dict(a_cols=cols, b_cols=cols, k_split=shape.get("k_split", 0), atomic=cols)
+    worst = {}
+    for name, opts in (("bf16x3", dict(n_passes=3)), ("bf16x1", dict(n_passes=1)), ("fp16x3", dict(n_passes=3, fp16=True))):
+        d = eng.debug_gemm(A, B, **kw, **opts)
+        worst[name] = float(((d.cpu().double() - ref).abs() / scale).max())
+    assert worst["bf16x3"] <= 1e-4 and worst["fp16x3"] <= 2e-5 and worst["bf16x1"] >= 30 * worst["bf16x3"], (shape, worst)
+    if cols:                                                                       # atomic: a second call accumulates
+        d1 = eng.debug_gemm(A, B, **kw, n_passes=3)
+        d2 = eng.debug_gemm(A, B, **kw, n_passes=3, out=d1.clone())
+        assert float(((d2.cpu().double() - 2 * ref).abs() / scale).max()) <= 2e-4
+
+
+def test_backward_tensor_core_vs_cuda_core_yardstick():
+    """The same backward with the GEMMs on the tensor cores (default) and in plain fp32 FMAs (NM_PREC_FP32)."""
+    import nerfmeshes_b200 as nm
+    from nerfmeshes_b200 import _lib as L
+    net = O.NetCfg()
+    model = nm.NeRFModel(_cfg(net, net, nc=32, nf=32)).cuda().train()
+    sdc, sdf = O.init_weights(net, 21), O.init_weights(net, 22)
+    sdc["fc_alpha.bias"] = sdc["fc_alpha.bias"] + 0.6
+    sdf["fc_alpha.bias"] = sdf["fc_alpha.bias"] + 0.6
+    model.model_coarse.load_state_dict(sdc, strict=False)
+    model.model_fine.load_state_dict(sdf, strict=False)
+    g = torch.Generator().manual_seed(8)
+    R = 1500
+    o = (torch.randn(3, generator=g) * 0.2).cuda()
+    d = torch.randn(R, 3, generator=g).cuda()
+    target = torch.rand(R, 3, generator=g).cuda()
+    bounds = (torch.tensor(0.5), torch.tensor(3.0))
+    _, _, gc, gf = model_grads(model, o, d, bounds, target, seed=5)
+    model.precision = L.PREC_FP32
+    _, _, gc32, gf32 = model_grads(model, o, d, bounds, target, seed=5)
+    compare(gc, gc32, rel_max=3e-2, rel_l2=6e-3, name="tc vs fp32 coarse")
+    compare(gf, gf32, rel_max=3e-2, rel_l2=6e-3, name="tc vs fp32 fine")
