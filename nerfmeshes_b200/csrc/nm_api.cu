@@ -261,7 +261,8 @@ int ensure_grads(NmHandle h, cudaStream_t st, bool zero) {
   for (int w = 0; w < 2; ++w) {
     const NetDev& net = h->nets[w];
     if (!net.loaded) continue;
-    const size_t nb[3] = {net.n_wt * 4, (size_t)net.full.n_bias * 4, (size_t)(net.full.n_head > 0 ? net.full.n_head : 1) * 4};
+    size_t go[kMaxLayers]; int gl[kMaxLayers];
+    const size_t nb[3] = {grad_layout(net.full, go, gl) * 4, (size_t)net.full.n_bias * 4, (size_t)(net.full.n_head > 0 ? net.full.n_head : 1) * 4};
     Buf* bufs[3] = {&h->g_wt[w], &h->g_bias[w], &h->g_head[w]};
     for (int i = 0; i < 3; ++i) {
       const bool fresh = bufs[i]->p == nullptr || bufs[i]->cap < nb[i];
@@ -313,9 +314,10 @@ int train_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const 
     if (int e = h->trans.ensure((size_t)R * P.s * 4)) return e;
     if (int e = launch_composite_backward(P.raw, P.t, rb.dirs, P.g, R, P.s, c.noise_std, seed ^ 0x5bd1e995u,
                                           c.white_background, h->trans.as<float>(), h->dout.as<float>(), st, &h->launches)) return e;
-    // sub-chunks of ~4 waves of 128-point row blocks (148 SMs): bounds the activation workspace (~16 KB per point)
+    // sub-chunks of `waves` full waves of 128-point row blocks (148 SMs): bounds the activation workspace (~17 KB per point)
     const bool use_tc = c.precision != NM_PREC_FP32;
-    long long rays_sub = ((long long)h->num_sms * 128 * 4) / P.s;
+    static const int waves = [] { const char* e = getenv("NM_TRAIN_WAVES"); int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+    long long rays_sub = ((long long)h->num_sms * 128 * waves) / P.s;
     if (rays_sub < 1) rays_sub = 1;
     if (rays_sub > R) rays_sub = R;
     if (int e = h->train_ws.ensure(train_ws_bytes(net.full, rays_sub * P.s, use_tc) + 1024)) return e;
@@ -569,7 +571,10 @@ int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t
     const std::string* nm4 = &net.names[4 * l];
     if (nm4[0] == name) {
       NM_CHECK(numel == (int64_t)K * N, "'%s' has %lld elements, expected %lld", name, (long long)numel, (long long)K * N);
-      NM_CUDA(cudaMemcpyAsync(out_dev, h->g_wt[which].as<float>() + L.wt_off, (size_t)K * N * 4, cudaMemcpyDeviceToDevice, st));
+      size_t go[kMaxLayers]; int gl[kMaxLayers];
+      grad_layout(net.full, go, gl);
+      NM_CUDA(cudaMemcpy2DAsync(out_dev, (size_t)K * 4, h->g_wt[which].as<float>() + go[l], (size_t)gl[l] * 4, (size_t)K * 4, N,
+                                cudaMemcpyDeviceToDevice, st));
       return 0;
     }
     const float* src = nullptr;

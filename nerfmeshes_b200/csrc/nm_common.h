@@ -53,7 +53,20 @@ struct NetDev {
   std::vector<std::string> names;    // per layer of `full`: weight, bias, head weight, head bias ("" if none)
 };
 
-// Gradient accumulators of one network, laid out like NetDev.d_w / d_bias / d_head (nm_train.cu).
+// Weight-gradient buffer layout: per layer (n_out, ld) row-major in the reference's (out,in) orientation, ld = in
+// features rounded up to 4 floats so that rows stay 16-byte aligned (vector atomics).  Returns the total float count.
+inline size_t grad_layout(const NetProgram& G, size_t off[kMaxLayers], int ld[kMaxLayers]) {
+  size_t total = 0;
+  for (int l = 0; l < G.n_layers; ++l) {
+    const int K = G.layers[l].k_act + G.layers[l].k_pe;
+    ld[l] = (K + 3) & ~3;
+    off[l] = total;
+    total += (size_t)G.layers[l].n_out * ld[l];
+  }
+  return total;
+}
+
+// Gradient accumulators of one network: weights per grad_layout(), biases / heads like NetDev.d_bias / d_head.
 struct NetGrads {
   float* w = nullptr;
   float* bias = nullptr;

@@ -37,6 +37,10 @@ struct TcGemmParams {
   int ldd, M, N;
   int atomic;              // D += via atomicAdd, K split over CTAs (weight gradients); the epilogue fields are ignored
   GemmEpi epi;
+  float* colsum;           // optional: colsum[n] += sum_m D[m][n] (bias gradient of the layer whose dZ this GEMM produces)
+  uint8_t* pack_out;       // optional: the epilogue also writes D as the row pack ([row block][K block = column / 64]) the
+  int pack_kbt;            //   next GEMM of the chain consumes as its A operand (saves a pack_rows pass over D)
+  int pack_fp16;
   int* err;                // watchdog code (mapped host memory) or nullptr
   int n_rb_b, kb_per_split;   // filled by launch_tc_gemm
   int dbg;                 // NM_GEMM_DBG experiments: 1 skip MMAs, 2 skip operand loads, 4 skip epilogue stores

@@ -23,9 +23,23 @@
 namespace nm {
 namespace {
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warps 0-7 epilogue (two column halves), 8 producer, 9 MMA issuer
 constexpr uint32_t kIdescF16 = ptx::make_idesc_f16(128, 128);                              // A, B = fp16
 constexpr uint32_t kIdescBf16 = kIdescF16 | (1u << 7) | (1u << 10);                        // A, B = bf16
+
+// x = hi + lo in two 16-bit floats: bf16 (8+8 significand bits, fp32's exponent range: gradients) or fp16 (11+11
+// bits, |x| < 65504: activations, encodings and weights of the forward recompute, like the forward kernel)
+__device__ __forceinline__ void split16(float x, int fp16, uint16_t* hi, uint16_t* lo) {
+  if (fp16) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    *hi = __half_as_ushort(h); *lo = __half_as_ushort(l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    *hi = __bfloat16_as_ushort(h); *lo = __bfloat16_as_ushort(l);
+  }
+}
 
 template <int NB>
 __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams P) {
@@ -57,7 +71,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
     ptx::mbar_init(acc_bar, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tmem_alloc(bar0 + 64u, 128 * NB);
     ptx::tmem_relinquish();
   }
@@ -66,7 +80,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
   ptx::tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------------------------------------ producer
     if (lane == 0) {
       for (int it = 0; it < nk; ++it) {
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
                         kPtileBytes, full(s));
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer (whole warp converged; one lane issues)
     const uint32_t idesc = P.fp16 ? kIdescF16 : kIdescBf16;
     for (int it = 0; it < nk; ++it) {
@@ -109,14 +123,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
     ptx::mbar_wait(acc_bar, 0u, P.err, 93);
     ptx::tc_fence_after();
     float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch (float4 aligned)
-    const int row0 = rb * 128 + warp * 32;
+    const int lg = warp & 3, half = warp >> 2;                            // TMEM lane group; column half of the CTA tile
+    const int row0 = rb * 128 + lg * 32;
     const int sub = lane >> 3, q4 = (lane & 7) * 4;                       // a lane stores 4 columns of rows sub, sub+4, ...
     const GemmEpi& E = P.epi;
-    for (int j = 0; j < nbv; ++j) {
+    const bool vec_atomic = (P.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(P.D) & 15) == 0;
+    // 128*NB accumulator columns: this warp's half is blocks [half*2*NB, (half+1)*2*NB) of 32 columns
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int blk = half * 2 * NB; blk < (half + 1) * 2 * NB; ++blk) {
+      const int j = blk >> 2, c0 = (blk & 3) * 32;
+      if (j < nbv) {
         uint32_t r[32];
-        NM_TMEM_LD32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(128 * j + c0), r);
+        NM_TMEM_LD32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 * j + c0), r);
         ptx::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg[lane * 36 + i] = __uint_as_float(r[i]);
@@ -130,10 +148,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
               const float4 v = *reinterpret_cast<const float4*>(&stg[rr * 36 + q4]);
               if (m < P.M) {
                 float* dp = P.D + (size_t)m * P.ldd + n;
-                atomicAdd(dp, v.x);
-                if (n + 1 < P.N) atomicAdd(dp + 1, v.y);
-                if (n + 2 < P.N) atomicAdd(dp + 2, v.z);
-                if (n + 3 < P.N) atomicAdd(dp + 3, v.w);
+                if (vec_atomic && n + 3 < P.N) {
+                  atomicAdd(reinterpret_cast<float4*>(dp), v);      // one 16-byte reduction instead of four
+                } else {
+                  atomicAdd(dp, v.x);
+                  if (n + 1 < P.N) atomicAdd(dp + 1, v.y);
+                  if (n + 2 < P.N) atomicAdd(dp + 2, v.z);
+                  if (n + 3 < P.N) atomicAdd(dp + 3, v.w);
+                }
               }
             }
           } else {
@@ -141,7 +163,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), w1 = bias;
             if (E.bias) bias = *reinterpret_cast<const float4*>(E.bias + n);
             if (E.r1_vec) w1 = *reinterpret_cast<const float4*>(E.r1_w + n);
-            float4 v[8], mk[8];
+            float4 v[8], mk[8], cs = make_float4(0.f, 0.f, 0.f, 0.f);
             float r1[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -165,7 +187,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
               if (!(mk[it].y > 0.f)) o.y = 0.f;
               if (!(mk[it].z > 0.f)) o.z = 0.f;
               if (!(mk[it].w > 0.f)) o.w = 0.f;
-              if (m < P.M) *reinterpret_cast<float4*>(P.D + (size_t)m * P.ldd + n) = o;
+              if (m < P.M) {
+                *reinterpret_cast<float4*>(P.D + (size_t)m * P.ldd + n) = o;
+                cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+              }
+              if (P.pack_out) {
+                // even lanes gather their neighbour's 4 columns: 8 consecutive columns = one 16-byte chunk of the tile row
+                if (m >= P.M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float e0 = __shfl_down_sync(0xffffffffu, o.x, 1), e1 = __shfl_down_sync(0xffffffffu, o.y, 1);
+                const float e2 = __shfl_down_sync(0xffffffffu, o.z, 1), e3 = __shfl_down_sync(0xffffffffu, o.w, 1);
+                if (!(lane & 1)) {
+                  const float vals[8] = {o.x, o.y, o.z, o.w, e0, e1, e2, e3};
+                  __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) split16(vals[i], P.pack_fp16, &hi[i], &lo[i]);
+                  const int r = lg * 32 + rr, c8 = (n & 63) >> 3;
+                  uint8_t* tile = P.pack_out + ((size_t)rb * P.pack_kbt + (n >> 6)) * kPtileBytes;
+                  const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+                  *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
+                  *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+                }
+              }
+            }
+            if (P.colsum) {      // lanes l, l+8, l+16, l+24 hold the same 4 columns
+#pragma unroll
+              for (int d = 8; d <= 16; d <<= 1) {
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, d); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, d);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, d); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, d);
+              }
+              if (lane < 8) {
+                atomicAdd(P.colsum + n, cs.x); atomicAdd(P.colsum + n + 1, cs.y);
+                atomicAdd(P.colsum + n + 2, cs.z); atomicAdd(P.colsum + n + 3, cs.w);
+              }
             }
           }
         }
@@ -175,37 +228,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) ptx::tmem_dealloc(tmem, 128 * NB);
+  if (warp == 9) ptx::tmem_dealloc(tmem, 128 * NB);
 }
 
 // ------------------------------------------------------------------------------------------------ packers
-// x = hi + lo in two 16-bit floats: bf16 (8+8 significand bits, fp32's exponent range: gradients) or fp16 (11+11
-// bits, |x| < 65504: activations, encodings and weights of the forward recompute, like the forward kernel)
-__device__ __forceinline__ void split16(float x, int fp16, uint16_t* hi, uint16_t* lo) {
-  if (fp16) {
-    const __half h = __float2half_rn(x);
-    const __half l = __float2half_rn(x - __half2float(h));
-    *hi = __half_as_ushort(h); *lo = __half_as_ushort(l);
-  } else {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-    *hi = __bfloat16_as_ushort(h); *lo = __bfloat16_as_ushort(l);
-  }
-}
-
 // K along the source's columns: operand row r = source row, K index c = source column (c < C valid, zero beyond).
-// grid (K blocks, row blocks); 256 threads: thread -> (row = tid/2, 32 columns).
+// grid (K blocks, row blocks); 256 threads: 8 lanes cover one 128-byte tile row (8 chunks of 8 columns), a warp 4 rows,
+// so every global access is a whole line; 4 passes of 32 rows.
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ src, int ld, int R, int C,
                                                         uint8_t* __restrict__ out, int kbt, int fp16) {
   const int kb = blockIdx.x, rb = blockIdx.y;
   uint8_t* tile = out + ((size_t)rb * kbt + kb) * kPtileBytes;
-  const int r = threadIdx.x >> 1, ch0 = (threadIdx.x & 1) * 4;       // 4 chunks of 8 columns
-  const int row = rb * 128 + r;
+  const int c8 = threadIdx.x & 7;
+  const int col = kb * 64 + c8 * 8;
   const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int c8 = ch0 + q;                                          // 8-column chunk index within the K block
-    const int col = kb * 64 + c8 * 8;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 32 + (threadIdx.x >> 3);
+    const int row = rb * 128 + r;
     float v[8];
     if (vec && row < R && col + 8 <= C) {
       const float4 x0 = *reinterpret_cast<const float4*>(src + (size_t)row * ld + col);
@@ -231,16 +271,27 @@ __global__ void __launch_bounds__(256) pack_cols_kernel(const float* __restrict_
   __shared__ float t[64][129];
   const int kb = blockIdx.x, rb = blockIdx.y;
   uint8_t* tile = out + ((size_t)rb * kbt + kb) * kPtileBytes;
-  for (int e = threadIdx.x; e < 64 * 128; e += 256) {
-    const int p = e >> 7, f = e & 127;
-    const int gp = kb * 64 + p, gf = rb * 128 + f;
-    t[p][f] = (gp < P && gf < F) ? src[(size_t)gp * ld + gf] : 0.f;
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && rb * 128 + 128 <= F;
+  if (vec) {
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {           // 64 points x 32 float4
+      const int p = e >> 5, f4 = (e & 31) * 4;
+      const int gp = kb * 64 + p;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gp < P) x = *reinterpret_cast<const float4*>(src + (size_t)gp * ld + rb * 128 + f4);
+      t[p][f4] = x.x; t[p][f4 + 1] = x.y; t[p][f4 + 2] = x.z; t[p][f4 + 3] = x.w;
+    }
+  } else {
+    for (int e = threadIdx.x; e < 64 * 128; e += 256) {
+      const int p = e >> 7, f = e & 127;
+      const int gp = kb * 64 + p, gf = rb * 128 + f;
+      t[p][f] = (gp < P && gf < F) ? src[(size_t)gp * ld + gf] : 0.f;
+    }
   }
   __syncthreads();
-  const int r = threadIdx.x >> 1, ch0 = (threadIdx.x & 1) * 4;
+  const int c8 = threadIdx.x & 7;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int c8 = ch0 + q;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 32 + (threadIdx.x >> 3);
     __align__(16) uint16_t hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) split16(t[c8 * 8 + i][r], fp16, &hi[i], &lo[i]);
@@ -284,7 +335,7 @@ int launch_tc_gemm(TcGemmParams P, int num_sms, cudaStream_t st, int64_t* launch
   if (P.atomic) {
     NM_CHECK(P.nseg == 1, "split-K takes one K segment");
     const int tiles = n_rb_a * col_groups;
-    splits = (2 * num_sms + tiles - 1) / tiles;
+    splits = num_sms / tiles;                                  // one wave: every extra split costs a full atomic epilogue
     const int max_splits = (P.seg[0].nkb + 7) / 8;              // at least 8 K blocks (512 points) per split
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

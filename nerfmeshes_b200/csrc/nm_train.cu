@@ -302,28 +302,45 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z
 __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ dout, int col0, int heads,
                                                             const float* __restrict__ act, int N, int P,
                                                             const float* __restrict__ hw, float* __restrict__ g_head,
-                                                            float* __restrict__ dX, int relu_mask, int p_per_block) {
+                                                            float* __restrict__ dX, int relu_mask, int p_per_block,
+                                                            float* __restrict__ g_bias) {
   const int k = threadIdx.x;
   const int p0 = blockIdx.x * p_per_block, p1 = min(P, p0 + p_per_block);
   float w[4] = {0.f, 0.f, 0.f, 0.f}, gw[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
+  float dsum = 0.f;                                     // column sum of dX: the layer's bias gradient
   if (k < N)
     for (int h = 0; h < heads; ++h) w[h] = hw[h * N + k];
-  for (int p = p0; p < p1; ++p) {
-    const float4 d4 = *reinterpret_cast<const float4*>(dout + (size_t)p * 4);
-    const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-    if (k < N) {
-      const float a = act[(size_t)p * N + k];
-      float dx = 0.f;
-      for (int h = 0; h < heads; ++h) {
-        const float g = dd[col0 + h];
-        gw[h] = fmaf(g, a, gw[h]);
-        dx = fmaf(g, w[h], dx);
-      }
-      if (dX) dX[(size_t)p * N + k] = (relu_mask && !(a > 0.f)) ? 0.f : dx;
+  for (int pb = p0; pb < p1; pb += 4) {                 // 4 points per trip: independent loads in flight
+    float a4[4];
+    float4 d4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = min(pb + u, p1 - 1);
+      d4[u] = *reinterpret_cast<const float4*>(dout + (size_t)p * 4);
+      a4[u] = (k < N) ? act[(size_t)p * N + k] : 0.f;
     }
-    if (k == 0)
-      for (int h = 0; h < heads; ++h) gb[h] += dd[col0 + h];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = pb + u;
+      if (p >= p1) break;
+      const float dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+      if (k < N) {
+        const float a = a4[u];
+        float dx = 0.f;
+        for (int h = 0; h < heads; ++h) {
+          const float g = dd[col0 + h];
+          gw[h] = fmaf(g, a, gw[h]);
+          dx = fmaf(g, w[h], dx);
+        }
+        if (relu_mask && !(a > 0.f)) dx = 0.f;
+        if (dX) dX[(size_t)p * N + k] = dx;
+        dsum += dx;
+      }
+      if (k == 0)
+        for (int h = 0; h < heads; ++h) gb[h] += dd[col0 + h];
+    }
   }
+  if (k < N && g_bias && dX) atomicAdd(g_bias + k, dsum);
   if (k < N)
     for (int h = 0; h < heads; ++h) atomicAdd(g_head + h * N + k, gw[h]);
   if (k == 0)
@@ -440,7 +457,7 @@ size_t up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 // workspace carving for one sub-chunk of P points (all regions 1 KB aligned; ptile packs need it)
 struct TrainWs {
   float *pe_x, *pe_d, *dbuf[2], *act[kMaxLayers];
-  uint8_t *pk_a, *pk_pex, *pk_ped, *pkt_a, *pkt_b, *pkt_pex, *pkt_ped;
+  uint8_t *pk_a[2], *pk_pex, *pk_ped, *pkt_a, *pkt_b, *pkt_pex, *pkt_ped;
   size_t bytes;
 };
 TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
@@ -454,7 +471,8 @@ TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
   w.dbuf[1] = (float*)take((size_t)P * h * 4);
   for (int l = 0; l < G.n_layers; ++l) w.act[l] = (float*)take((size_t)P * G.layers[l].n_out * 4);
   if (use_tc) {
-    w.pk_a = take(pack_bytes((int)P, h));
+    w.pk_a[0] = take(pack_bytes((int)P, h));
+    w.pk_a[1] = take(pack_bytes((int)P, h));
     w.pk_pex = take(pack_bytes((int)P, kPeLd));
     w.pk_ped = take(pack_bytes((int)P, kPeLd));
     w.pkt_a = take(pack_bytes(h, (int)P));
@@ -557,13 +575,12 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       const uint8_t* wp = net.d_tcw + net.tcw_fwd_off[l];
       const int kbtW = (Kt + 63) / 64;
       int ns = 0;
-      if (L.k_act > 0) {
-        if (int e = launch_pack_rows(W.act[l - 1], G.layers[l - 1].n_out, P, L.k_act, W.pk_a, 1, st, launches)) return e;
-        T.seg[ns++] = TcSeg{W.pk_a, L.k_act / 64, wp, kbtW, L.k_act / 64};
-      }
+      if (L.k_act > 0)      // the previous layer's epilogue left its output here as an fp16 row pack
+        T.seg[ns++] = TcSeg{W.pk_a[l & 1], L.k_act / 64, wp, kbtW, L.k_act / 64};
       if (L.pe_src) T.seg[ns++] = TcSeg{pk_pe_of(L), 1, wp + (size_t)(L.k_act / 64) * kPtileBytes, kbtW, 1};
       T.nseg = ns; T.D = W.act[l]; T.ldd = N; T.M = P; T.N = N; T.epi = fin;
       T.fp16 = 1;      // forward recompute in the forward kernel's precision class (relu masks must agree with it)
+      if (l + 1 < G.n_layers) { T.pack_out = W.pk_a[(l + 1) & 1]; T.pack_kbt = N / 64; T.pack_fp16 = 1; }
       if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
     } else {
       const float* Wt = net.d_wt + L.wt_off;
@@ -579,33 +596,40 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   }
 
   // ---- backward
+  size_t gw_off[kMaxLayers];
+  int gw_ld[kMaxLayers];
+  grad_layout(G, gw_off, gw_ld);
   int cur = 0;
+  bool dz_packed = false;      // W.pk_a[cur] already holds the bf16 row pack of dbuf[cur]
+  bool bias_done = false;      // the kernel that produced dbuf[cur] already accumulated its column sums (bias gradient)
   const int p_per_block = (P + 2 * num_sms - 1) / (2 * num_sms);
   const int hb_blocks = (P + p_per_block - 1) / p_per_block;
   for (int l = G.n_layers - 1; l >= 0; --l) {
     const LayerProg& L = G.layers[l];
-    const int N = L.n_out, Kt = L.k_act + L.k_pe;
+    const int N = L.n_out;
     float* dZ = W.dbuf[cur];
     if (L.kind == KIND_RGB || L.kind == KIND_OUT4) {
       NM_CHECK(l == G.n_layers - 1, "rgb head must be the last layer");
       const int heads = L.kind == KIND_RGB ? 3 : 4;
       head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 0, heads, W.act[l], N, P, net.d_head + L.head_off,
-                                                     g->head + L.head_off, dZ, L.relu, p_per_block);
+                                                     g->head + L.head_off, dZ, L.relu, p_per_block, g->bias + L.bias_off);
+      bias_done = true;
       NM_CUDA(cudaGetLastError());
       if (launches) ++*launches;
     } else if (L.kind == KIND_SIGMA) {
       // weight/bias gradient of fc_alpha; its contribution to dZ was added by the fc_feat data-grad epilogue
       head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 3, 1, W.act[l], N, P, net.d_head + L.head_off,
-                                                     g->head + L.head_off, nullptr, 0, p_per_block);
+                                                     g->head + L.head_off, nullptr, 0, p_per_block, nullptr);
       NM_CUDA(cudaGetLastError());
       if (launches) ++*launches;
     }
     // weight gradient dW (N, Kt) += dZ^T [act[l-1] | PE], bias gradient
-    float* gW = g->w + L.wt_off;
+    float* gW = g->w + gw_off[l];
+    const int ldg = gw_ld[l];
     if (tc) {
       if (int e = launch_pack_cols(dZ, N, P, N, W.pkt_a, 0, st, launches)) return e;
       TcGemmParams T = tc_base();
-      T.nseg = 1; T.atomic = 1; T.ldd = Kt; T.M = N;
+      T.nseg = 1; T.atomic = 1; T.ldd = ldg; T.M = N;
       if (L.k_act > 0) {
         if (int e = launch_pack_cols(W.act[l - 1], G.layers[l - 1].n_out, P, L.k_act, W.pkt_b, 0, st, launches)) return e;
         T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_b, kbtP, kbtP};
@@ -619,11 +643,11 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       }
     } else {
       if (L.k_act > 0)
-        if (int rc = sgemm_tn(dZ, N, W.act[l - 1], G.layers[l - 1].n_out, gW, Kt, P, N, L.k_act, num_sms, st, launches)) return rc;
+        if (int rc = sgemm_tn(dZ, N, W.act[l - 1], G.layers[l - 1].n_out, gW, ldg, P, N, L.k_act, num_sms, st, launches)) return rc;
       if (L.pe_src)
-        if (int rc = sgemm_tn(dZ, N, pe_of(L), kPeLd, gW + L.k_act, Kt, P, N, L.k_pe, num_sms, st, launches)) return rc;
+        if (int rc = sgemm_tn(dZ, N, pe_of(L), kPeLd, gW + L.k_act, ldg, P, N, L.k_pe, num_sms, st, launches)) return rc;
     }
-    {
+    if (!bias_done) {
       const int ppb = (P + 63) / 64;
       dim3 grid((N + 31) / 32, (P + ppb - 1) / ppb);
       colsum_kernel<<<grid, 256, 0, st>>>(dZ, N, P, N, g->bias + L.bias_off, ppb);
@@ -638,15 +662,21 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       if (Lp.kind == KIND_SIGMA) { e.r1_vec = dout + 3; e.r1_stride = 4; e.r1_w = net.d_head + Lp.head_off; }
       if (Lp.relu) { e.mask = W.act[l - 1]; e.ldmask = Lp.n_out; }
       if (tc) {
-        if (int rc = launch_pack_rows(dZ, N, P, N, W.pk_a, 0, st, launches)) return rc;
+        // A = row pack of dZ: written by the previous data-gradient epilogue, or packed here at the head of the chain
+        if (!dz_packed)
+          if (int rc = launch_pack_rows(dZ, N, P, N, W.pk_a[cur], 0, st, launches)) return rc;
         TcGemmParams T = tc_base();
         const int kb = (N + 63) / 64;
-        T.nseg = 1; T.seg[0] = TcSeg{W.pk_a, kb, net.d_tcw + net.tcw_bwd_off[l], kb, kb};
+        T.nseg = 1; T.seg[0] = TcSeg{W.pk_a[cur], kb, net.d_tcw + net.tcw_bwd_off[l], kb, kb};
         T.D = W.dbuf[cur ^ 1]; T.ldd = L.k_act; T.M = P; T.N = L.k_act; T.epi = e;
+        if (l - 1 > 0) { T.pack_out = W.pk_a[cur ^ 1]; T.pack_kbt = L.k_act / 64; T.pack_fp16 = 0; dz_packed = true; }
+        T.colsum = g->bias + Lp.bias_off;
+        bias_done = true;
         if (int rc = launch_tc_gemm(T, num_sms, st, launches)) return rc;
       } else {
         // W[n][k] = Wt[k][n]  ->  B = Wt rows 0..k_act-1 viewed (k_act, N), read transposed
         if (int rc = sgemm<true>(dZ, N, net.d_wt + L.wt_off, N, W.dbuf[cur ^ 1], L.k_act, P, L.k_act, N, e, st, launches)) return rc;
+        bias_done = false;
       }
       cur ^= 1;
     }
