@@ -143,6 +143,28 @@ def cpu_reference_run(steps, warmup, chunk=2048):
             f"CPU, {cores} threads (fastest of a probe over thread counts; {avail} logical CPUs visible)", tot / steps * 1e3)
 
 
+def cpu_train_run(cores, rays=256, steps=2):
+    """The reference's training step on the CPU (oracle forward + torch autograd backward, model_nerf.py:88-151)."""
+    from oracle import nerf_oracle as O
+    z = load_npz("weights_lego_nerf.npz")
+    leaf = lambda d: {k: (v.clone().requires_grad_(True) if k.endswith((".weight", ".bias")) else v) for k, v in d.items()}
+    coarse = leaf({k[7:]: torch.as_tensor(v) for k, v in z.items() if k.startswith("coarse.")})
+    fine = leaf({k[5:]: torch.as_tensor(v) for k, v in z.items() if k.startswith("fine.")})
+    net, rc = O.NetCfg(), O.RenderCfg()
+    o, d = O.get_ray_bundle(H, W, float(FOCAL), poses120()[40])
+    d = d.reshape(-1, 3)[320000:320000 + rays]
+    tgt = torch.rand(rays, 3, generator=torch.Generator().manual_seed(0))
+    torch.set_num_threads(cores)
+    times = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        bc, bf, _, _ = O.nerf_forward(coarse, fine, net, net, rc, o, d, torch.tensor(NEAR), torch.tensor(FAR), u=torch.as_tensor(z["sample_pdf_u"]))
+        (torch.nn.functional.mse_loss(bc.rgb_map, tgt) + torch.nn.functional.mse_loss(bf.rgb_map, tgt)).backward()
+        if i:
+            times.append(time.perf_counter() - t0)
+    return rays * steps / sum(times), f"{steps} x {rays}-ray forward+backward steps of the same workload, torch autograd on {cores} CPU threads"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,11 +275,32 @@ def main():
     n_mesh = torch.tensor([mv.shape[0], mf.shape[0]], dtype=torch.float64, device="cuda")
     del sigma, mv, mf, mn
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, grid_ms, mc_ms], dtype=torch.float64, device="cuda")
+    # ---------------------------------------------------------------- secondary: one training step
+    # fused forward + mse(coarse)+mse(fine) + backward of both networks on TRAIN_RAYS centre-of-image rays per rank
+    TRAIN_RAYS, TRAIN_STEPS = 4096, 3
+    d_tr = d_h[320000:320000 + TRAIN_RAYS].cuda()
+    o_tr = o_h.cuda()
+    tgt = torch.rand(TRAIN_RAYS, 3, generator=torch.Generator().manual_seed(0)).cuda()
+    eng.zero_grad()
+    eng.loss_backward(o_tr, d_tr, NEAR, FAR, tgt, training=True, seed=0)          # warm-up (workspace allocation, weight packs)
+    barrier()
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l_tr0 = eng.launch_count()
+    t0e.record()
+    for i in range(TRAIN_STEPS):
+        eng.zero_grad()
+        loss = eng.loss_backward(o_tr, d_tr, NEAR, FAR, tgt, training=True, seed=1 + i)
+    t1e.record()
+    barrier()
+    train_ms = t0e.elapsed_time(t1e) / TRAIN_STEPS
+    train_launches = (eng.launch_count() - l_tr0) // TRAIN_STEPS
+    train_loss = [float(x) for x in loss]
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, grid_ms, mc_ms, train_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n_mesh, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, grid_ms, mc_ms = (float(x) for x in t)
+    dev_ms, e2e_ms, grid_ms, mc_ms, train_ms = (float(x) for x in t)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -281,6 +324,13 @@ def main():
                  "workload": "lego 512^3 sigma sweep (sigma-only trunk, 982,528 FLOP/voxel) + marching cubes iso=32, x-slabs across ranks",
                  "sigma_sweep_ms": grid_ms, "marching_cubes_ms": mc_ms, "n_vertices": int(n_mesh[0]), "n_triangles": int(n_mesh[1]),
                  "sweep_tflops": RES ** 3 * 982528 / (grid_ms * 1e-3) / 1e12},
+        "train": {"metric": "train-rays/sec", "value": TRAIN_RAYS * world / (train_ms * 1e-3), "unit": "rays/s",
+                  "rays_per_step_per_gpu": TRAIN_RAYS, "ms_per_step": train_ms, "launches_per_step": int(train_launches),
+                  "workload": "nm_loss_backward: fused forward + mse(coarse)+mse(fine) + backward of both 8x256 networks "
+                              "(64+192 samples per ray), gradients accumulated on device; no optimiser step",
+                  "loss": train_loss,
+                  "algorithmic_tflops": TRAIN_RAYS * (64 + 192) * FLOP_PER_POINT * 4 / (train_ms * 1e-3) / 1e12,
+                  "note": "4x forward FLOPs per step: forward, recompute, data gradient, weight gradient"},
         "roofline": {"bound": "tensor", "kernel": "mlp_tc_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved_tf / peak_tf) if achieved_tf else None, "traffic": traffic,
                      "traffic_note": "DRAM bytes per launch (ncu); algorithmic 20 B/point = 1.64 GB per launch on average: no re-reads",
@@ -292,6 +342,8 @@ def main():
     if not a.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_run(a.cpu_steps, 1)
         result["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+        tv, tsample = cpu_train_run(cores)
+        result["train"]["cpu_baseline"] = {"value": tv, "unit": "rays/s", "cores": cores, "kind": "port", "sample": tsample}
     print(json.dumps(result))
     if dist is not None:
         dist.destroy_process_group()

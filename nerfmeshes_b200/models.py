@@ -216,7 +216,8 @@ class BaseModel(torch.nn.Module):
     def _attach_grad(self, rays, seed, buff, rgb, coarse_rgb=None):
         """Make rgb maps differentiable w.r.t. the network parameters when autograd is recording."""
         named = self._named_net_params()
-        if not (torch.is_grad_enabled() and any(p.requires_grad for _, _, p in named)):
+        # training mode only: evaluation scripts call query() outside torch.no_grad() and expect plain tensors
+        if not (self.training and torch.is_grad_enabled() and any(p.requires_grad for _, _, p in named)):
             return rgb, coarse_rgb
         if not rgb.is_cuda:
             raise L.NmError("training needs CUDA ray tensors (the backward pass has no host-buffer variant)")

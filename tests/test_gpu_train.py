@@ -97,7 +97,7 @@ def test_backward_matches_autograd_random_init(case):
                 sd["fc_alpha.bias"] = sd["fc_alpha.bias"] + 0.6
             else:
                 sd["fc_out.bias"] = sd["fc_out.bias"] + torch.tensor([0.0, 0.0, 0.0, 0.6])
-    model = nm.NeRFModel(_cfg(net_c, net_f, **kw)).cuda().eval()          # eval: no jitter / noise -> deterministic samples
+    model = nm.NeRFModel(_cfg(net_c, net_f, **kw)).cuda().train()         # _cfg: no jitter / noise -> deterministic samples
     model.model_coarse.load_state_dict(sdc, strict=False)
     if sdf is not None:
         model.model_fine.load_state_dict(sdf, strict=False)
@@ -121,7 +121,7 @@ def test_backward_matches_autograd_lego_checkpoint():
     import nerfmeshes_b200 as nm
     z = load_npz("weights_lego_nerf.npz")
     g = load_npz("golden_lego_nerf.npz")
-    model = nm.NeRFModel.from_npz(LEGO_CFG, z).cuda().eval()
+    model = nm.NeRFModel.from_npz({**LEGO_CFG, "nerf.train.radiance_field_noise_std": 0.0}, z).cuda().train()
     sdc = {k[len("coarse."):]: torch.as_tensor(v) for k, v in z.items() if k.startswith("coarse.")}
     sdf = {k[len("fine."):]: torch.as_tensor(v) for k, v in z.items() if k.startswith("fine.")}
     R = 96
@@ -172,7 +172,7 @@ def test_buff_backward_matches_autograd():
     import nerfmeshes_b200 as nm
     z = load_npz("weights_lego_buff.npz")
     g = load_npz("golden_lego_buff.npz")
-    model = nm.BuFFModel.from_npz(BUFF_CFG, z).cuda().eval()
+    model = nm.BuFFModel.from_npz({**BUFF_CFG, "nerf.train.radiance_field_noise_std": 0.0}, z).cuda().train()
     sd = _leafs({k[len("coarse."):]: torch.as_tensor(v) for k, v in z.items() if k.startswith("coarse.")})
     R = 48
     o, d = torch.as_tensor(g["origin"])[None], torch.as_tensor(g["dirs"])[:R]
