@@ -42,7 +42,7 @@ struct TcGemmParams {
   int pack_kbt;            //   next GEMM of the chain consumes as its A operand (saves a pack_rows pass over D)
   int pack_fp16;
   int* err;                // watchdog code (mapped host memory) or nullptr
-  int n_rb_b, kb_per_split;   // filled by launch_tc_gemm
+  int n_rb_a, n_rb_b, col_groups, kb_per_split;   // filled by launch_tc_gemm
   int dbg;                 // NM_GEMM_DBG experiments: 1 skip MMAs, 2 skip operand loads, 4 skip epilogue stores
 };
 

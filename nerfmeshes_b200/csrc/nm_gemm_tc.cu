@@ -41,25 +41,35 @@ __device__ __forceinline__ void split16(float x, int fp16, uint16_t* hi, uint16_
   }
 }
 
+constexpr uint32_t kStgOff = 6u * kPtileBytes;                       // epilogue staging: 8 warps x 32 rows x 33 floats
+constexpr uint32_t kStgWarp = 32u * 33u * 4u;
+constexpr uint32_t kBarOff = kStgOff + 8u * kStgWarp;                // barriers + TMEM base behind the 1024-aligned stages
+constexpr uint32_t kGemmSmem = kBarOff + 128u;
+
+// Tiles of one CTA.  Data-path GEMMs are persistent: grid = min(tiles, SMs), tile t = blockIdx.x + i * gridDim.x walks
+// (row block, column group) pairs, and the accumulator is double-buffered in TMEM so that the epilogue of tile i
+// overlaps the main loop of tile i+1.  Split-K (weight gradient) launches one tile per CTA: (row block, column group,
+// K split) = blockIdx.
 template <int NB>
 __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NS = (NB == 2) ? 2 : 3;
   constexpr uint32_t STAGE = kPtileBytes * (1 + NB);
-  // barriers + the TMEM base live behind the stages so that the dynamic window keeps its 1024-byte alignment
   const uint32_t sbase = ptx::smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const uint32_t bar0 = sbase + 6u * kPtileBytes;
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + 6u * kPtileBytes + 64);
+  const uint32_t bar0 = sbase + kBarOff;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + kBarOff + 120);
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (NS + s); };
-  const uint32_t acc_bar = bar0 + 8u * (2 * NS);
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * NS + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * NS + 2 + b); };
 
-  const int rb = blockIdx.x;                 // A row block
-  const int cb0 = blockIdx.y * NB;           // first B row block of this CTA
-  int nbv = P.n_rb_b - cb0;                  // valid B row blocks
-  if (nbv > NB) nbv = NB;
-  // K blocks of this CTA: segment 0 restricted to the split's range, then segment 1
+  const bool pers = P.atomic == 0;
+  const int n_tiles = pers ? P.n_rb_a * P.col_groups : 1;
+  const int t_first = pers ? (int)blockIdx.x : 0, t_step = pers ? (int)gridDim.x : 1;
+  auto tile_rb = [&](int t) { return pers ? t / P.col_groups : (int)blockIdx.x; };
+  auto tile_cb0 = [&](int t) { return (pers ? t % P.col_groups : (int)blockIdx.y) * NB; };
+  // K blocks of a tile: segment 0 restricted to the split's range, then segment 1
   int k0 = 0, k1 = P.seg[0].nkb;
   if (P.kb_per_split > 0) { k0 = blockIdx.z * P.kb_per_split; k1 = min(P.seg[0].nkb, k0 + P.kb_per_split); }
   const int n0 = k1 - k0;
@@ -68,11 +78,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
   if (threadIdx.x == 0) {
     if (sbase & 1023u) { if (P.err) atomicExch(P.err, 90); __trap(); }
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
-    ptx::mbar_init(acc_bar, 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full(b), 1); ptx::mbar_init(acc_empty(b), 8); }
     ptx::fence_mbar_init();
   }
   if (warp == 9) {
-    ptx::tmem_alloc(bar0 + 64u, 128 * NB);
+    ptx::tmem_alloc(bar0 + 120u, 256 * NB);          // two accumulator buffers of 128*NB columns
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -83,61 +93,82 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
   if (warp == 8) {
     // ------------------------------------------------------------ producer
     if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % NS;
-        if (it >= NS) ptx::mbar_wait(empty(s), (uint32_t)((it / NS - 1) & 1), P.err, 91);
-        const int sg = it < n0 ? 0 : 1;
-        const int kb = it < n0 ? k0 + it : it - n0;
-        const TcSeg& S = P.seg[sg];
-        const uint32_t dst = sbase + (uint32_t)s * STAGE;
-        if (P.dbg & 2) { ptx::mbar_arrive(full(s)); continue; }
-        ptx::mbar_expect_tx(full(s), kPtileBytes * (uint32_t)(1 + nbv));
-        ptx::bulk_g2s(dst, S.a + ((size_t)rb * S.a_kbt + kb) * kPtileBytes, kPtileBytes, full(s));
-        for (int j = 0; j < nbv; ++j)
-          ptx::bulk_g2s(dst + kPtileBytes * (uint32_t)(1 + j), S.b + ((size_t)(cb0 + j) * S.b_kbt + kb) * kPtileBytes,
-                        kPtileBytes, full(s));
+      int it = 0;
+      for (int t = t_first; t < n_tiles; t += t_step) {
+        const int rb = tile_rb(t), cb0 = tile_cb0(t);
+        const int nbv = min(NB, P.n_rb_b - cb0);
+        for (int kk = 0; kk < nk; ++kk, ++it) {
+          const int s = it % NS;
+          if (it >= NS) ptx::mbar_wait(empty(s), (uint32_t)((it / NS - 1) & 1), P.err, 91);
+          const int sg = kk < n0 ? 0 : 1;
+          const int kb = kk < n0 ? k0 + kk : kk - n0;
+          const TcSeg& S = P.seg[sg];
+          const uint32_t dst = sbase + (uint32_t)s * STAGE;
+          if (P.dbg & 2) { ptx::mbar_arrive(full(s)); continue; }
+          ptx::mbar_expect_tx(full(s), kPtileBytes * (uint32_t)(1 + nbv));
+          ptx::bulk_g2s(dst, S.a + ((size_t)rb * S.a_kbt + kb) * kPtileBytes, kPtileBytes, full(s));
+          for (int j = 0; j < nbv; ++j)
+            ptx::bulk_g2s(dst + kPtileBytes * (uint32_t)(1 + j), S.b + ((size_t)(cb0 + j) * S.b_kbt + kb) * kPtileBytes,
+                          kPtileBytes, full(s));
+        }
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer (whole warp converged; one lane issues)
     const uint32_t idesc = P.fp16 ? kIdescF16 : kIdescBf16;
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % NS;
-      ptx::mbar_wait(full(s), (uint32_t)((it / NS) & 1), P.err, 92);
-      ptx::tc_fence_after();
-      const uint32_t a = sbase + (uint32_t)s * STAGE;
-      const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a), a_lo = ptx::make_kmajor_sw128_desc(a + kPtileHalf);
-      for (int j = 0; j < ((P.dbg & 1) ? 0 : nbv); ++j) {
-        const uint32_t b = a + kPtileBytes * (uint32_t)(1 + j);
-        const uint64_t b_hi = ptx::make_kmajor_sw128_desc(b), b_lo = ptx::make_kmajor_sw128_desc(b + kPtileHalf);
-        if (P.n_passes == 3) ptx::mma_block_ss3(tmem + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, it > 0 ? 1u : 0u, 4u);
-        else ptx::mma_block_ss1(tmem + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, it > 0 ? 1u : 0u, 4u);
+    int it = 0, i = 0;
+    for (int t = t_first; t < n_tiles; t += t_step, ++i) {
+      const int nbv = min(NB, P.n_rb_b - tile_cb0(t));
+      const int b = i & 1;
+      if (i >= 2) {                                   // the epilogue must have drained this accumulator buffer
+        ptx::mbar_wait(acc_empty(b), (uint32_t)(((i >> 1) - 1) & 1), P.err, 94);
+        ptx::tc_fence_after();
       }
-      ptx::tc_commit_elect(empty(s));
+      const uint32_t dacc = tmem + (uint32_t)(b * 128 * NB);
+      for (int kk = 0; kk < nk; ++kk, ++it) {
+        const int s = it % NS;
+        ptx::mbar_wait(full(s), (uint32_t)((it / NS) & 1), P.err, 92);
+        ptx::tc_fence_after();
+        const uint32_t a = sbase + (uint32_t)s * STAGE;
+        const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a), a_lo = ptx::make_kmajor_sw128_desc(a + kPtileHalf);
+        for (int j = 0; j < ((P.dbg & 1) ? 0 : nbv); ++j) {
+          const uint32_t bs = a + kPtileBytes * (uint32_t)(1 + j);
+          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(bs), b_lo = ptx::make_kmajor_sw128_desc(bs + kPtileHalf);
+          if (P.n_passes == 3) ptx::mma_block_ss3(dacc + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, kk > 0 ? 1u : 0u, 4u);
+          else ptx::mma_block_ss1(dacc + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, kk > 0 ? 1u : 0u, 4u);
+        }
+        ptx::tc_commit_elect(empty(s));
+      }
+      ptx::tc_commit_elect(acc_full(b));
     }
-    ptx::tc_commit_elect(acc_bar);
   } else {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> shared -> global
-    // A thread owns one accumulator row (TMEM lane); each 32x32 block is transposed through the (now idle) stage
-    // memory so that every global access of the warp is one contiguous 128-byte row segment.
-    ptx::mbar_wait(acc_bar, 0u, P.err, 93);
-    ptx::tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 36);      // 32 rows, 144-byte pitch (float4 aligned)
+    // A thread owns one accumulator row (TMEM lane); each 32x32 block is transposed through a per-warp staging tile
+    // so that every global access of the warp is made of contiguous 128-byte row segments.
+    float* stg = reinterpret_cast<float*>(smem + kStgOff + (uint32_t)warp * kStgWarp);     // 32 rows, pitch 33 floats
     const int lg = warp & 3, half = warp >> 2;                            // TMEM lane group; column half of the CTA tile
-    const int row0 = rb * 128 + lg * 32;
     const int sub = lane >> 3, q4 = (lane & 7) * 4;                       // a lane stores 4 columns of rows sub, sub+4, ...
     const GemmEpi& E = P.epi;
     const bool vec_atomic = (P.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(P.D) & 15) == 0;
+    int i = 0;
+    for (int t = t_first; t < n_tiles; t += t_step, ++i) {
+    const int rb = tile_rb(t), cb0 = tile_cb0(t);
+    const int nbv = min(NB, P.n_rb_b - cb0);
+    const int b = i & 1;
+    const uint32_t dacc = tmem + (uint32_t)(b * 128 * NB);
+    ptx::mbar_wait(acc_full(b), (uint32_t)((i >> 1) & 1), P.err, 93);
+    ptx::tc_fence_after();
+    const int row0 = rb * 128 + lg * 32;
     // 128*NB accumulator columns: this warp's half is blocks [half*2*NB, (half+1)*2*NB) of 32 columns
 #pragma unroll 1
     for (int blk = half * 2 * NB; blk < (half + 1) * 2 * NB; ++blk) {
       const int j = blk >> 2, c0 = (blk & 3) * 32;
       if (j < nbv) {
         uint32_t r[32];
-        NM_TMEM_LD32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 * j + c0), r);
+        NM_TMEM_LD32(dacc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 * j + c0), r);
         ptx::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * 36 + i] = __uint_as_float(r[i]);
+        for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(r[c]);
         __syncwarp();
         const int n = (cb0 + j) * 128 + c0 + q4;
         if (n < P.N && !(P.dbg & 4)) {
@@ -145,7 +176,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + sub, m = row0 + rr;
-              const float4 v = *reinterpret_cast<const float4*>(&stg[rr * 36 + q4]);
+              const float* sp = &stg[rr * 33 + q4];
+              const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
               if (m < P.M) {
                 float* dp = P.D + (size_t)m * P.ldd + n;
                 if (vec_atomic && n + 3 < P.N) {
@@ -168,7 +200,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + sub, m = min(row0 + rr, P.M - 1);
-              v[it] = *reinterpret_cast<const float4*>(&stg[rr * 36 + q4]);
+              { const float* sp = &stg[rr * 33 + q4]; v[it] = make_float4(sp[0], sp[1], sp[2], sp[3]); }
               mk[it] = E.mask ? *reinterpret_cast<const float4*>(E.mask + (size_t)m * E.ldmask + n) : make_float4(1.f, 1.f, 1.f, 1.f);
               r1[it] = E.r1_vec ? E.r1_vec[(size_t)m * E.r1_stride] : 0.f;
               if (E.accumulate) {
@@ -225,10 +257,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
         __syncwarp();
       }
     }
+    // all TMEM reads of this warp for tile i are complete (wait::ld above): hand the buffer back to the MMA warp
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(acc_empty(b));
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc(tmem, 128 * NB);
+  if (warp == 9) ptx::tmem_dealloc(tmem, 256 * NB);
 }
 
 // ------------------------------------------------------------------------------------------------ packers
@@ -347,13 +384,16 @@ int launch_tc_gemm(TcGemmParams P, int num_sms, cudaStream_t st, int64_t* launch
   static thread_local unsigned configured = 0;
   int dev = 0;
   NM_CUDA(cudaGetDevice(&dev));
-  const size_t smem = 6 * (size_t)kPtileBytes + 128;            // NB=2: 2 stages x 96 KB; NB=1: 3 stages x 64 KB; + barriers
+  const size_t smem = kGemmSmem;
   if (!(configured & (1u << (dev & 31)))) {
     NM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured |= 1u << (dev & 31);
   }
-  dim3 grid(n_rb_a, col_groups, splits);
+  P.n_rb_a = n_rb_a;
+  P.col_groups = col_groups;
+  const int tiles = n_rb_a * col_groups;
+  dim3 grid = P.atomic ? dim3(n_rb_a, col_groups, splits) : dim3(tiles < num_sms ? tiles : num_sms, 1, 1);
   if (NB == 2) tc_gemm_kernel<2><<<grid, kGemmThreads, smem, st>>>(P);
   else tc_gemm_kernel<1><<<grid, kGemmThreads, smem, st>>>(P);
   NM_CUDA(cudaGetLastError());

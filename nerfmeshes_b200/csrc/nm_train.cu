@@ -602,7 +602,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   int cur = 0;
   bool dz_packed = false;      // W.pk_a[cur] already holds the bf16 row pack of dbuf[cur]
   bool bias_done = false;      // the kernel that produced dbuf[cur] already accumulated its column sums (bias gradient)
-  const int p_per_block = (P + 2 * num_sms - 1) / (2 * num_sms);
+  const int p_per_block = (P + 8 * num_sms - 1) / (8 * num_sms);      // 8 CTAs per SM keep enough loads in flight
   const int hb_blocks = (P + p_per_block - 1) / p_per_block;
   for (int l = G.n_layers - 1; l >= 0; --l) {
     const LayerProg& L = G.layers[l];
