@@ -41,6 +41,9 @@ struct TcGemmParams {
   uint8_t* pack_out;       // optional: the epilogue also writes D as the row pack ([row block][K block = column / 64]) the
   int pack_kbt;            //   next GEMM of the chain consumes as its A operand (saves a pack_rows pass over D)
   int pack_fp16;
+  uint8_t* packT_out;      // optional: ... and as the bf16 pack with K along the rows (points): the A^T / B^T operand of the
+  int packT_kbt;           //   weight-gradient GEMMs ([column block of 128][K block = row / 64]); needs packT_kbt = 2 * row blocks
+  int skip_d;              // do not write the fp32 D at all (its only consumers read the packs)
   int* err;                // watchdog code (mapped host memory) or nullptr
   int n_rb_a, n_rb_b, col_groups, kb_per_split;   // filled by launch_tc_gemm
   int dbg;                 // NM_GEMM_DBG experiments: 1 skip MMAs, 2 skip operand loads, 4 skip epilogue stores
@@ -48,7 +51,7 @@ struct TcGemmParams {
 
 size_t pack_bytes(int rows, int k);
 int launch_pack_rows(const float* src, int ld, int R, int C, uint8_t* out, int fp16, cudaStream_t st, int64_t* launches);
-int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int fp16, cudaStream_t st, int64_t* launches);
+int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int kbt, int fp16, cudaStream_t st, int64_t* launches);
 int launch_tc_gemm(TcGemmParams P, int num_sms, cudaStream_t st, int64_t* launches);
 
 }  // namespace nm

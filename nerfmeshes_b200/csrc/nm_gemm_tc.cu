@@ -220,12 +220,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
               if (!(mk[it].z > 0.f)) o.z = 0.f;
               if (!(mk[it].w > 0.f)) o.w = 0.f;
               if (m < P.M) {
-                *reinterpret_cast<float4*>(P.D + (size_t)m * P.ldd + n) = o;
+                if (!P.skip_d) *reinterpret_cast<float4*>(P.D + (size_t)m * P.ldd + n) = o;
                 cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+              } else {
+                o = make_float4(0.f, 0.f, 0.f, 0.f);
               }
+              if (P.packT_out) { float* sp = &stg[rr * 33 + q4]; sp[0] = o.x; sp[1] = o.y; sp[2] = o.z; sp[3] = o.w; }
               if (P.pack_out) {
                 // even lanes gather their neighbour's 4 columns: 8 consecutive columns = one 16-byte chunk of the tile row
-                if (m >= P.M) o = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float e0 = __shfl_down_sync(0xffffffffu, o.x, 1), e1 = __shfl_down_sync(0xffffffffu, o.y, 1);
                 const float e2 = __shfl_down_sync(0xffffffffu, o.z, 1), e3 = __shfl_down_sync(0xffffffffu, o.w, 1);
                 if (!(lane & 1)) {
@@ -239,6 +241,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
                   *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
                   *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
                 }
+              }
+            }
+            if (P.packT_out) {   // the finished 32x32 block, transposed: lane = column (feature), 4 chunks of 8 rows (points)
+              __syncwarp();
+              const int nf = (cb0 + j) * 128 + c0 + lane;
+              const int row = nf & 127;
+              uint8_t* tile = P.packT_out + ((size_t)(nf >> 7) * P.packT_kbt + (rb * 2 + (lg >> 1))) * kPtileBytes;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split16(stg[(c * 8 + e) * 33 + lane], 0, &hi[e], &lo[e]);
+                const int c8 = (lg & 1) * 4 + c;
+                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
               }
             }
             if (P.colsum) {      // lanes l, l+8, l+16, l+24 hold the same 4 columns
@@ -351,10 +369,11 @@ int launch_pack_rows(const float* src, int ld, int R, int C, uint8_t* out, int f
   return 0;
 }
 
-int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int fp16, cudaStream_t st, int64_t* launches) {
+int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int kbt, int fp16, cudaStream_t st, int64_t* launches) {
   if (P <= 0 || F <= 0) return 0;
-  dim3 grid((P + 63) / 64, (F + 127) / 128);
-  pack_cols_kernel<<<grid, 256, 0, st>>>(src, ld, P, F, out, (P + 63) / 64, fp16);
+  if (kbt <= 0) kbt = (P + 63) / 64;                  // callers may ask for zero-filled K blocks beyond P
+  dim3 grid(kbt, (F + 127) / 128);
+  pack_cols_kernel<<<grid, 256, 0, st>>>(src, ld, P, F, out, kbt, fp16);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   return 0;

@@ -457,7 +457,7 @@ size_t up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 // workspace carving for one sub-chunk of P points (all regions 1 KB aligned; ptile packs need it)
 struct TrainWs {
   float *pe_x, *pe_d, *dbuf[2], *act[kMaxLayers];
-  uint8_t *pk_a[2], *pk_pex, *pk_ped, *pkt_a, *pkt_b, *pkt_pex, *pkt_ped;
+  uint8_t *pk_a[2], *pk_pex, *pk_ped, *pkt_a, *pkt_act[kMaxLayers], *pkt_pex, *pkt_ped;
   size_t bytes;
 };
 TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
@@ -475,10 +475,11 @@ TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
     w.pk_a[1] = take(pack_bytes((int)P, h));
     w.pk_pex = take(pack_bytes((int)P, kPeLd));
     w.pk_ped = take(pack_bytes((int)P, kPeLd));
-    w.pkt_a = take(pack_bytes(h, (int)P));
-    w.pkt_b = take(pack_bytes(h, (int)P));
-    w.pkt_pex = take(pack_bytes(kPeLd, (int)P));
-    w.pkt_ped = take(pack_bytes(kPeLd, (int)P));
+    const int P128 = (int)((P + 127) / 128) * 128;     // K blocks of the point-major packs come in pairs (one per 128-row tile)
+    w.pkt_a = take(pack_bytes(h, P128));
+    for (int l = 0; l + 1 < G.n_layers; ++l) w.pkt_act[l] = take(pack_bytes(G.layers[l].n_out, P128));
+    w.pkt_pex = take(pack_bytes(kPeLd, P128));
+    w.pkt_ped = take(pack_bytes(kPeLd, P128));
   }
   w.bytes = off;
   return w;
@@ -546,17 +547,17 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   TrainWs W = carve(G, P, tc, reinterpret_cast<uint8_t*>(ws_base));
   if (tc && !net.tcw_valid)
     if (int e = build_weight_packs(net, st, launches)) return e;
-  const int kbtP = (P + 63) / 64;
+  const int kbtP = 2 * ((P + 127) / 128);      // K blocks of the point-major packs (zero-filled beyond P)
 
   encode_kernel<<<(P + 127) / 128, 128, 0, st>>>(in, net.d_full, W.pe_x, W.pe_d);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   if (tc) {
     if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
-    if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, 0, st, launches)) return e;
+    if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, kbtP, 0, st, launches)) return e;
     if (G.dim_dir > 0) {
       if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
-      if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, 0, st, launches)) return e;
+      if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, kbtP, 0, st, launches)) return e;
     }
   }
   auto pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? W.pe_x : W.pe_d; };
@@ -580,7 +581,10 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       if (L.pe_src) T.seg[ns++] = TcSeg{pk_pe_of(L), 1, wp + (size_t)(L.k_act / 64) * kPtileBytes, kbtW, 1};
       T.nseg = ns; T.D = W.act[l]; T.ldd = N; T.M = P; T.N = N; T.epi = fin;
       T.fp16 = 1;      // forward recompute in the forward kernel's precision class (relu masks must agree with it)
-      if (l + 1 < G.n_layers) { T.pack_out = W.pk_a[(l + 1) & 1]; T.pack_kbt = N / 64; T.pack_fp16 = 1; }
+      if (l + 1 < G.n_layers) {      // the next layer's A operand, and the B^T operand of its weight gradient
+        T.pack_out = W.pk_a[(l + 1) & 1]; T.pack_kbt = N / 64; T.pack_fp16 = 1;
+        T.packT_out = W.pkt_act[l]; T.packT_kbt = kbtP;
+      }
       if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
     } else {
       const float* Wt = net.d_wt + L.wt_off;
@@ -601,6 +605,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   grad_layout(G, gw_off, gw_ld);
   int cur = 0;
   bool dz_packed = false;      // W.pk_a[cur] already holds the bf16 row pack of dbuf[cur]
+  bool dz_colpacked = false;   // W.pkt_a already holds the point-major bf16 pack of dbuf[cur]
   bool bias_done = false;      // the kernel that produced dbuf[cur] already accumulated its column sums (bias gradient)
   const int p_per_block = (P + 8 * num_sms - 1) / (8 * num_sms);      // 8 CTAs per SM keep enough loads in flight
   const int hb_blocks = (P + p_per_block - 1) / p_per_block;
@@ -627,12 +632,12 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
     float* gW = g->w + gw_off[l];
     const int ldg = gw_ld[l];
     if (tc) {
-      if (int e = launch_pack_cols(dZ, N, P, N, W.pkt_a, 0, st, launches)) return e;
+      if (!dz_colpacked)
+        if (int e = launch_pack_cols(dZ, N, P, N, W.pkt_a, kbtP, 0, st, launches)) return e;
       TcGemmParams T = tc_base();
       T.nseg = 1; T.atomic = 1; T.ldd = ldg; T.M = N;
       if (L.k_act > 0) {
-        if (int e = launch_pack_cols(W.act[l - 1], G.layers[l - 1].n_out, P, L.k_act, W.pkt_b, 0, st, launches)) return e;
-        T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_b, kbtP, kbtP};
+        T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_act[l - 1], kbtP, kbtP};
         T.D = gW; T.N = L.k_act;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
@@ -672,6 +677,8 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
         if (l - 1 > 0) { T.pack_out = W.pk_a[cur ^ 1]; T.pack_kbt = L.k_act / 64; T.pack_fp16 = 0; dz_packed = true; }
         T.colsum = g->bias + Lp.bias_off;
         bias_done = true;
+        T.packT_out = W.pkt_a; T.packT_kbt = kbtP; dz_colpacked = true;
+        T.skip_d = 1;      // dZ is consumed only through its two packs and the column sums
         if (int rc = launch_tc_gemm(T, num_sms, st, launches)) return rc;
       } else {
         // W[n][k] = Wt[k][n]  ->  B = Wt rows 0..k_act-1 viewed (k_act, N), read transposed
@@ -698,7 +705,7 @@ int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_col
   TcGemmParams T{};
   T.n_passes = n_passes; T.fp16 = fp16; T.err = d_err; T.atomic = atomic; T.D = D; T.ldd = N; T.M = M; T.N = N;
   const int kbt = (K + 63) / 64;
-  if (int e = b_cols ? launch_pack_cols(B, N, K, N, pb, fp16, st, launches) : launch_pack_rows(B, K, N, K, pb, fp16, st, launches)) return e;
+  if (int e = b_cols ? launch_pack_cols(B, N, K, N, pb, 0, fp16, st, launches) : launch_pack_rows(B, K, N, K, pb, fp16, st, launches)) return e;
   if (k_split > 0) {
     NM_CHECK(!a_cols && !b_cols && k_split % 64 == 0 && k_split < K && !atomic, "bad k_split");
     if (int e = launch_pack_rows(A, K, M, k_split, pa, fp16, st, launches)) return e;
@@ -708,7 +715,7 @@ int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_col
     T.seg[0] = TcSeg{pa, kb0, pb, kbt, kb0};
     T.seg[1] = TcSeg{pa2, kb1, pb + (size_t)kb0 * kPtileBytes, kbt, kb1};
   } else {
-    if (int e = a_cols ? launch_pack_cols(A, M, K, M, pa, fp16, st, launches) : launch_pack_rows(A, K, M, K, pa, fp16, st, launches)) return e;
+    if (int e = a_cols ? launch_pack_cols(A, M, K, M, pa, 0, fp16, st, launches) : launch_pack_rows(A, K, M, K, pa, fp16, st, launches)) return e;
     T.nseg = 1;
     T.seg[0] = TcSeg{pa, kbt, pb, kbt, kbt};
   }
