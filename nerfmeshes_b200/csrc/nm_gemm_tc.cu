@@ -195,13 +195,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), w1 = bias;
             if (E.bias) bias = *reinterpret_cast<const float4*>(E.bias + n);
             if (E.r1_vec) w1 = *reinterpret_cast<const float4*>(E.r1_w + n);
-            float4 v[8], mk[8], cs = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v[8], cs = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t mw[8];
             float r1[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int rr = it * 4 + sub, m = min(row0 + rr, P.M - 1);
               { const float* sp = &stg[rr * 33 + q4]; v[it] = make_float4(sp[0], sp[1], sp[2], sp[3]); }
-              mk[it] = E.mask ? *reinterpret_cast<const float4*>(E.mask + (size_t)m * E.ldmask + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+              mw[it] = P.bits_in ? (P.bits_in[(size_t)m * P.bits_ld + (n >> 5)] >> q4) : 0xfu;      // this lane's 4 mask bits
               r1[it] = E.r1_vec ? E.r1_vec[(size_t)m * E.r1_stride] : 0.f;
               if (E.accumulate) {
                 const float4 c = *reinterpret_cast<const float4*>(P.D + (size_t)m * P.ldd + n);
@@ -215,10 +216,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
               o.x = fmaf(r1[it], w1.x, o.x + bias.x); o.y = fmaf(r1[it], w1.y, o.y + bias.y);
               o.z = fmaf(r1[it], w1.z, o.z + bias.z); o.w = fmaf(r1[it], w1.w, o.w + bias.w);
               if (E.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              if (!(mk[it].x > 0.f)) o.x = 0.f;
-              if (!(mk[it].y > 0.f)) o.y = 0.f;
-              if (!(mk[it].z > 0.f)) o.z = 0.f;
-              if (!(mk[it].w > 0.f)) o.w = 0.f;
+              if (!(mw[it] & 1u)) o.x = 0.f;
+              if (!(mw[it] & 2u)) o.y = 0.f;
+              if (!(mw[it] & 4u)) o.z = 0.f;
+              if (!(mw[it] & 8u)) o.w = 0.f;
+              if (P.bits_out) {      // relu mask of this output row: 8 lanes x 4 bits -> one word
+                uint32_t bits = ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << q4;
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+                if (!(lane & 7) && m < P.M) P.bits_out[(size_t)m * P.bits_ld + (n >> 5)] = bits;
+              }
               if (m < P.M) {
                 if (!P.skip_d) *reinterpret_cast<float4*>(P.D + (size_t)m * P.ldd + n) = o;
                 cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
