@@ -41,9 +41,9 @@ struct TcGemmParams {
   uint8_t* pack_out;       // optional: the epilogue also writes D as the row pack ([row block][K block = column / 64]) the
   int pack_kbt;            //   next GEMM of the chain consumes as its A operand (saves a pack_rows pass over D)
   int pack_fp16;
-  uint32_t* bits_out;      // optional: relu mask of the output, one bit per element: word [m * bits_ld + n / 32] bit n % 32
-  const uint32_t* bits_in; // optional: zero the output where the bit is clear (relu' of the tensor the bits were taken from)
-  int bits_ld;             //   words per row (= N / 32)
+  uint16_t* bits_out;      // optional: relu mask of the output, one bit per element: halfword [m * bits_ld + n / 16] bit n % 16
+  const uint16_t* bits_in; // optional: zero the output where the bit is clear (relu' of the tensor the bits were taken from)
+  int bits_ld;             //   halfwords per row (= N / 16)
   uint8_t* packT_out;      // optional: ... and as the bf16 pack with K along the rows (points): the A^T / B^T operand of the
   int packT_kbt;           //   weight-gradient GEMMs ([column block of 128][K block = row / 64]); needs packT_kbt = 2 * row blocks
   int skip_d;              // do not write the fp32 D at all (its only consumers read the packs)

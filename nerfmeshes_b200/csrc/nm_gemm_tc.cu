@@ -23,7 +23,8 @@
 namespace nm {
 namespace {
 
-constexpr int kGemmThreads = 320;   // warps 0-7 epilogue (two column halves), 8 producer, 9 MMA issuer
+constexpr int kGemmThreads = 576;   // warps 0-15 epilogue (4 TMEM lane groups x 4 column quarters), 16 producer, 17 MMA issuer
+constexpr int kEpiWarps = 16, kProdWarp = 16, kMmaWarp = 17;
 constexpr uint32_t kIdescF16 = ptx::make_idesc_f16(128, 128);                              // A, B = fp16
 constexpr uint32_t kIdescBf16 = kIdescF16 | (1u << 7) | (1u << 10);                        // A, B = bf16
 
@@ -41,9 +42,9 @@ __device__ __forceinline__ void split16(float x, int fp16, uint16_t* hi, uint16_
   }
 }
 
-constexpr uint32_t kStgOff = 6u * kPtileBytes;                       // epilogue staging: 8 warps x 32 rows x 33 floats
-constexpr uint32_t kStgWarp = 32u * 33u * 4u;
-constexpr uint32_t kBarOff = kStgOff + 8u * kStgWarp;                // barriers + TMEM base behind the 1024-aligned stages
+constexpr uint32_t kStgOff = 6u * kPtileBytes;                       // epilogue staging: 16 warps x 32 rows x 17 floats
+constexpr uint32_t kStgWarp = 32u * 17u * 4u;
+constexpr uint32_t kBarOff = kStgOff + (uint32_t)kEpiWarps * kStgWarp;                // barriers + TMEM base behind the 1024-aligned stages
 constexpr uint32_t kGemmSmem = kBarOff + 128u;
 
 // Tiles of one CTA.  Data-path GEMMs are persistent: grid = min(tiles, SMs), tile t = blockIdx.x + i * gridDim.x walks
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
   if (threadIdx.x == 0) {
     if (sbase & 1023u) { if (P.err) atomicExch(P.err, 90); __trap(); }
     for (int s = 0; s < NS; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full(b), 1); ptx::mbar_init(acc_empty(b), 8); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full(b), 1); ptx::mbar_init(acc_empty(b), kEpiWarps); }
     ptx::fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     ptx::tmem_alloc(bar0 + 120u, 256 * NB);          // two accumulator buffers of 128*NB columns
     ptx::tmem_relinquish();
   }
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
   ptx::tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp == 8) {
+  if (warp == kProdWarp) {
     // ------------------------------------------------------------ producer
     if (lane == 0) {
       int it = 0;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer (whole warp converged; one lane issues)
     const uint32_t idesc = P.fp16 ? kIdescF16 : kIdescBf16;
     int it = 0, i = 0;
@@ -143,40 +144,41 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
     }
   } else {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> shared -> global
-    // A thread owns one accumulator row (TMEM lane); each 32x32 block is transposed through a per-warp staging tile
-    // so that every global access of the warp is made of contiguous 128-byte row segments.
-    float* stg = reinterpret_cast<float*>(smem + kStgOff + (uint32_t)warp * kStgWarp);     // 32 rows, pitch 33 floats
-    const int lg = warp & 3, half = warp >> 2;                            // TMEM lane group; column half of the CTA tile
-    const int sub = lane >> 3, q4 = (lane & 7) * 4;                       // a lane stores 4 columns of rows sub, sub+4, ...
+    // 16 warps: warp w reads TMEM lanes 32*(w%4).. (its 32 rows) and the column quarter w/4 of the CTA tile, in blocks of
+    // 32 rows x 16 columns.  A thread owns one accumulator row; each block is transposed through a per-warp staging tile
+    // so that global accesses are contiguous row segments: a lane then handles 4 columns of rows sub, sub+8, ...
+    // The epilogue is instruction-latency bound, hence many warps with short dependent chains rather than few wide ones.
+    float* stg = reinterpret_cast<float*>(smem + kStgOff + (uint32_t)warp * kStgWarp);     // 32 rows, pitch 17 floats
+    const int lg = warp & 3, quarter = warp >> 2;
+    const int sub = lane >> 2, q4 = (lane & 3) * 4;
     const GemmEpi& E = P.epi;
     const bool vec_atomic = (P.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(P.D) & 15) == 0;
     int i = 0;
     for (int t = t_first; t < n_tiles; t += t_step, ++i) {
-    const int rb = tile_rb(t), cb0 = tile_cb0(t);
-    const int nbv = min(NB, P.n_rb_b - cb0);
-    const int b = i & 1;
-    const uint32_t dacc = tmem + (uint32_t)(b * 128 * NB);
-    ptx::mbar_wait(acc_full(b), (uint32_t)((i >> 1) & 1), P.err, 93);
-    ptx::tc_fence_after();
-    const int row0 = rb * 128 + lg * 32;
-    // 128*NB accumulator columns: this warp's half is blocks [half*2*NB, (half+1)*2*NB) of 32 columns
+      const int rb = tile_rb(t), cb0 = tile_cb0(t);
+      const int nbv = min(NB, P.n_rb_b - cb0);
+      const int b = i & 1;
+      const uint32_t dacc = tmem + (uint32_t)(b * 128 * NB);
+      ptx::mbar_wait(acc_full(b), (uint32_t)((i >> 1) & 1), P.err, 93);
+      ptx::tc_fence_after();
+      const int row0 = rb * 128 + lg * 32;
 #pragma unroll 1
-    for (int blk = half * 2 * NB; blk < (half + 1) * 2 * NB; ++blk) {
-      const int j = blk >> 2, c0 = (blk & 3) * 32;
-      if (j < nbv) {
-        uint32_t r[32];
-        NM_TMEM_LD32(dacc + ((uint32_t)(lg * 32) << 16) + (uint32_t)(128 * j + c0), r);
+      for (int blk = quarter * 2 * NB; blk < (quarter + 1) * 2 * NB; ++blk) {
+        const int cbase = blk * 16, j = cbase >> 7, c0 = cbase & 127;
+        if (j >= nbv) continue;
+        uint32_t r[16];
+        NM_TMEM_LD16(dacc + ((uint32_t)(lg * 32) << 16) + (uint32_t)cbase, r);
         ptx::tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(r[c]);
+        for (int c = 0; c < 16; ++c) stg[lane * 17 + c] = __uint_as_float(r[c]);
         __syncwarp();
-        const int n = (cb0 + j) * 128 + c0 + q4;
+        const int n = (cb0 + j) * 128 + c0 + q4;                 // first of this lane's 4 global columns
         if (n < P.N && !(P.dbg & 4)) {
           if (P.atomic) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + sub, m = row0 + rr;
-              const float* sp = &stg[rr * 33 + q4];
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + sub, m = row0 + rr;
+              const float* sp = &stg[rr * 17 + q4];
               const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
               if (m < P.M) {
                 float* dp = P.D + (size_t)m * P.ldd + n;
@@ -195,14 +197,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
             float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), w1 = bias;
             if (E.bias) bias = *reinterpret_cast<const float4*>(E.bias + n);
             if (E.r1_vec) w1 = *reinterpret_cast<const float4*>(E.r1_w + n);
-            float4 v[8], cs = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t mw[8];
-            float r1[8];
+            float4 v[4], cs = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t mw[4];
+            float r1[4];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + sub, m = min(row0 + rr, P.M - 1);
-              { const float* sp = &stg[rr * 33 + q4]; v[it] = make_float4(sp[0], sp[1], sp[2], sp[3]); }
-              mw[it] = P.bits_in ? (P.bits_in[(size_t)m * P.bits_ld + (n >> 5)] >> q4) : 0xfu;      // this lane's 4 mask bits
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + sub, m = min(row0 + rr, P.M - 1);
+              const float* sp = &stg[rr * 17 + q4];
+              v[it] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+              mw[it] = P.bits_in ? ((uint32_t)P.bits_in[(size_t)m * P.bits_ld + (n >> 4)] >> q4) : 0xfu;   // this lane's 4 mask bits
               r1[it] = E.r1_vec ? E.r1_vec[(size_t)m * E.r1_stride] : 0.f;
               if (E.accumulate) {
                 const float4 c = *reinterpret_cast<const float4*>(P.D + (size_t)m * P.ldd + n);
@@ -210,8 +213,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
               }
             }
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + sub, m = row0 + rr;
+            for (int it = 0; it < 4; ++it) {
+              const int rr = it * 8 + sub, m = row0 + rr;
               float4 o = v[it];
               o.x = fmaf(r1[it], w1.x, o.x + bias.x); o.y = fmaf(r1[it], w1.y, o.y + bias.y);
               o.z = fmaf(r1[it], w1.z, o.z + bias.z); o.w = fmaf(r1[it], w1.w, o.w + bias.w);
@@ -220,12 +223,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
               if (!(mw[it] & 2u)) o.y = 0.f;
               if (!(mw[it] & 4u)) o.z = 0.f;
               if (!(mw[it] & 8u)) o.w = 0.f;
-              if (P.bits_out) {      // relu mask of this output row: 8 lanes x 4 bits -> one word
+              if (P.bits_out) {      // relu mask of this output row segment: 4 lanes x 4 bits -> one halfword
                 uint32_t bits = ((o.x > 0.f ? 1u : 0u) | (o.y > 0.f ? 2u : 0u) | (o.z > 0.f ? 4u : 0u) | (o.w > 0.f ? 8u : 0u)) << q4;
                 bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
                 bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-                bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
-                if (!(lane & 7) && m < P.M) P.bits_out[(size_t)m * P.bits_ld + (n >> 5)] = bits;
+                if (!(lane & 3) && m < P.M) P.bits_out[(size_t)m * P.bits_ld + (n >> 4)] = (uint16_t)bits;
               }
               if (m < P.M) {
                 if (!P.skip_d) *reinterpret_cast<float4*>(P.D + (size_t)m * P.ldd + n) = o;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
               } else {
                 o = make_float4(0.f, 0.f, 0.f, 0.f);
               }
-              if (P.packT_out) { float* sp = &stg[rr * 33 + q4]; sp[0] = o.x; sp[1] = o.y; sp[2] = o.z; sp[3] = o.w; }
+              if (P.packT_out) { float* sp = &stg[rr * 17 + q4]; sp[0] = o.x; sp[1] = o.y; sp[2] = o.z; sp[3] = o.w; }
               if (P.pack_out) {
                 // even lanes gather their neighbour's 4 columns: 8 consecutive columns = one 16-byte chunk of the tile row
                 const float e0 = __shfl_down_sync(0xffffffffu, o.x, 1), e1 = __shfl_down_sync(0xffffffffu, o.y, 1);
@@ -242,38 +244,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
                   const float vals[8] = {o.x, o.y, o.z, o.w, e0, e1, e2, e3};
                   __align__(16) uint16_t hi[8], lo[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) split16(vals[i], P.pack_fp16, &hi[i], &lo[i]);
-                  const int r = lg * 32 + rr, c8 = (n & 63) >> 3;
+                  for (int e = 0; e < 8; ++e) split16(vals[e], P.pack_fp16, &hi[e], &lo[e]);
+                  const int r_t = lg * 32 + rr, c8 = (n & 63) >> 3;
                   uint8_t* tile = P.pack_out + ((size_t)rb * P.pack_kbt + (n >> 6)) * kPtileBytes;
-                  const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+                  const uint32_t off = (uint32_t)r_t * 128u + (uint32_t)((c8 ^ (r_t & 7)) << 4);
                   *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
                   *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
                 }
               }
             }
-            if (P.packT_out) {   // the finished 32x32 block, transposed: lane = column (feature), 4 chunks of 8 rows (points)
+            if (P.packT_out) {   // the finished 32x16 block, transposed: lane = (column f, pair of 8-row chunks)
               __syncwarp();
-              const int nf = (cb0 + j) * 128 + c0 + lane;
+              const int f = lane & 15, ch0 = (lane >> 4) * 2;
+              const int nf = (cb0 + j) * 128 + c0 + f;
               const int row = nf & 127;
               uint8_t* tile = P.packT_out + ((size_t)(nf >> 7) * P.packT_kbt + (rb * 2 + (lg >> 1))) * kPtileBytes;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
+              for (int c = ch0; c < ch0 + 2; ++c) {
                 __align__(16) uint16_t hi[8], lo[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split16(stg[(c * 8 + e) * 33 + lane], 0, &hi[e], &lo[e]);
+                for (int e = 0; e < 8; ++e) split16(stg[(c * 8 + e) * 17 + f], 0, &hi[e], &lo[e]);
                 const int c8 = (lg & 1) * 4 + c;
                 const uint32_t off = (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4);
                 *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
                 *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
               }
             }
-            if (P.colsum) {      // lanes l, l+8, l+16, l+24 hold the same 4 columns
+            if (P.colsum) {      // lanes with equal lane%4 hold the same 4 columns
 #pragma unroll
-              for (int d = 8; d <= 16; d <<= 1) {
+              for (int d = 4; d <= 16; d <<= 1) {
                 cs.x += __shfl_xor_sync(0xffffffffu, cs.x, d); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, d);
                 cs.z += __shfl_xor_sync(0xffffffffu, cs.z, d); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, d);
               }
-              if (lane < 8) {
+              if (lane < 4) {
                 atomicAdd(P.colsum + n, cs.x); atomicAdd(P.colsum + n + 1, cs.y);
                 atomicAdd(P.colsum + n + 2, cs.z); atomicAdd(P.colsum + n + 3, cs.w);
               }
@@ -282,16 +285,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
         }
         __syncwarp();
       }
-    }
-    // all TMEM reads of this warp for tile i are complete (wait::ld above): hand the buffer back to the MMA warp
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(acc_empty(b));
+      // all TMEM reads of this warp for tile i are complete (wait::ld above): hand the buffer back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty(b));
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc(tmem, 256 * NB);
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem, 256 * NB);
 }
 
 // ------------------------------------------------------------------------------------------------ packers

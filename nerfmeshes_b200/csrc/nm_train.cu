@@ -458,7 +458,7 @@ size_t up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 struct TrainWs {
   float *pe_x, *pe_d, *dbuf[2], *act[kMaxLayers];
   uint8_t *pk_a[2], *pk_pex, *pk_ped, *pkt_a, *pkt_act[kMaxLayers], *pkt_pex, *pkt_ped;
-  uint32_t* bits[kMaxLayers];     // relu masks of the recomputed activations, 1 bit per element (tensor-core path)
+  uint16_t* bits[kMaxLayers];     // relu masks of the recomputed activations, 1 bit per element (tensor-core path)
   size_t bytes;
 };
 TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
@@ -481,7 +481,7 @@ TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
     for (int l = 0; l + 1 < G.n_layers; ++l) w.pkt_act[l] = take(pack_bytes(G.layers[l].n_out, P128));
     w.pkt_pex = take(pack_bytes(kPeLd, P128));
     w.pkt_ped = take(pack_bytes(kPeLd, P128));
-    for (int l = 0; l < G.n_layers; ++l) w.bits[l] = (uint32_t*)take((size_t)P * (G.layers[l].n_out / 32) * 4);
+    for (int l = 0; l < G.n_layers; ++l) w.bits[l] = (uint16_t*)take((size_t)P * (G.layers[l].n_out / 16) * 2);
   }
   w.bytes = off;
   return w;
@@ -587,7 +587,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
         T.pack_out = W.pk_a[(l + 1) & 1]; T.pack_kbt = N / 64; T.pack_fp16 = 1;
         T.packT_out = W.pkt_act[l]; T.packT_kbt = kbtP;
       }
-      if (L.relu) { T.bits_out = W.bits[l]; T.bits_ld = N / 32; }
+      if (L.relu) { T.bits_out = W.bits[l]; T.bits_ld = N / 16; }
       // fp32 activations are only read by the SIMT head kernels (trunk output for fc_alpha, last layer for fc_rgb / fc_out)
       T.skip_d = (L.kind == KIND_HIDDEN) ? 1 : 0;
       if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
@@ -679,7 +679,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
         const int kb = (N + 63) / 64;
         T.nseg = 1; T.seg[0] = TcSeg{W.pk_a[cur], kb, net.d_tcw + net.tcw_bwd_off[l], kb, kb};
         T.D = W.dbuf[cur ^ 1]; T.ldd = L.k_act; T.M = P; T.N = L.k_act; T.epi = e;
-        if (Lp.relu) { T.bits_in = W.bits[l - 1]; T.bits_ld = Lp.n_out / 32; }
+        if (Lp.relu) { T.bits_in = W.bits[l - 1]; T.bits_ld = Lp.n_out / 16; }
         if (l - 1 > 0) { T.pack_out = W.pk_a[cur ^ 1]; T.pack_kbt = L.k_act / 64; T.pack_fp16 = 0; dz_packed = true; }
         T.colsum = g->bias + Lp.bias_off;
         bias_done = true;
