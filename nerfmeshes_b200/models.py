@@ -394,15 +394,18 @@ class BuFFModel(BaseModel):
     def _after_engine_created(self):
         self._eng.set_tables(self.sampler.point_intervals[0], None)
 
+    def _sync_tree(self, eng):
+        if self._tree_id != id(self.tree.voxels):
+            eng.set_tree(self.tree.voxels)
+            self._tree_id = id(self.tree.voxels)
+
     def forward(self, x, seed=None):
         ray_origins, ray_directions, near, far = self._unpack(x)
         seed = self._pick_seed(seed)
         if torch.as_tensor(ray_origins).dim() < 2:
             raise IndexError("BuFFModel needs ray origins of shape (1,3) or (R,3) (src/nerf/tree.py:231)")
         eng = self._engine()
-        if self._tree_id != id(self.tree.voxels):
-            eng.set_tree(self.tree.voxels)
-            self._tree_id = id(self.tree.voxels)
+        self._sync_tree(eng)
         o = eng.render_rays(ray_origins, ray_directions, near, far, training=self.training, buff=True, seed=seed,
                             want=["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights", "t_vals"])
         o["rgb"], _ = self._attach_grad((ray_origins, ray_directions, near, far), seed, True, o["rgb"])

@@ -5,6 +5,8 @@ to the single-GPU image (no cross-shard arithmetic), the exchange is one all_gat
 Mesh: x-slabs of the density grid with one overlapping plane; per-slab marching cubes in global index coordinates; the
 exchange is an all_gather of the per-slab indexed meshes ("triangle soup", padded to the largest slab) plus three scalar
 all_reduces for the iso-level statistics (extract_iso_level, src/mesh_nerf.py:56-65).
+Training: data parallel over rays — every rank runs forward + backward on its own ray batch (no collective inside), then
+ONE all_reduce of the flattened gradients of both networks (595 k - 1.19 M floats, 4.8 MB) before the optimiser step.
 The collectives go through torch.distributed (NCCL on GPUs, gloo in the CPU tests); there is no data-path collective
 inside a shard's computation.
 """
@@ -75,6 +77,24 @@ def global_stats(local_min: float, local_max: float, local_sum: float, local_sum
     q = torch.tensor([local_sumsq_centered_fn(mean)], dtype=torch.float64, device=device)
     dist.all_reduce(q, op=dist.ReduceOp.SUM, group=group)
     return float(t[0]), float(-t[1]), math.sqrt(float(q[0]) / float(s[1]))
+
+
+def allreduce_gradients(params, group=None, average=True):
+    """Data-parallel training step, exchange part: one all_reduce over the flattened .grad of `params` (the parameters of
+    both FlexibleNeRFModels); the mean over ranks is what a single process would get from the concatenated ray batch
+    when every rank's loss is a mean over equally many rays (src/models/model_nerf.py:118-126)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return int(flat.numel())
 
 
 def render_image_sharded(model, pose, H, W, focal, near, far, *, ndc=False, want=("rgb", "depth", "acc", "disp"), group=None):

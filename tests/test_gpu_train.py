@@ -297,3 +297,37 @@ def test_backward_tensor_core_vs_cuda_core_yardstick():
     _, _, gc32, gf32 = model_grads(model, o, d, bounds, target, seed=5)
     compare(gc, gc32, rel_max=3e-2, rel_l2=6e-3, name="tc vs fp32 coarse")
     compare(gf, gf32, rel_max=3e-2, rel_l2=6e-3, name="tc vs fp32 fine")
+
+
+def test_fused_training_step_matches_autograd_route():
+    """nerfmeshes_b200.training_step (the reference's training_step body with manual batching, one fused call per chunk)
+    == forward/backward through autograd on the same chunks with the same seeds; log values like the reference."""
+    import nerfmeshes_b200 as nm
+    net = O.NetCfg(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)
+    cfg = _cfg(net, net, nc=16, nf=24)
+    cfg.update({"nerf.train.perturb": True, "nerf.train.radiance_field_noise_std": 0.2, "nerf.train.chunksize": 400})
+    model = nm.NeRFModel(cfg).cuda().train()
+    model.model_coarse.load_state_dict(O.init_weights(net, 5), strict=False)
+    model.model_fine.load_state_dict(O.init_weights(net, 6), strict=False)
+    g = torch.Generator().manual_seed(12)
+    R = 800
+    o = (torch.randn(3, generator=g) * 0.2).cuda()
+    d = torch.randn(R, 3, generator=g).cuda()
+    target = torch.rand(R, 3, generator=g).cuda()
+    bounds = (torch.tensor(0.5), torch.tensor(3.0))
+    model.zero_grad(set_to_none=True)
+    out = nm.training_step(model, (o, d, bounds), target, seed=77)
+    fused = {f"{w}.{k}": p.grad.clone().cpu() for w, k, p in model._named_net_params()}
+    model.zero_grad(set_to_none=True)
+    lc = lf = 0.0
+    for i in range(0, R, 400):
+        coarse, fine = model.forward((o, d[i:i + 400], bounds), seed=77 + i)
+        lc = lc + torch.nn.functional.mse_loss(coarse.rgb_map, target[i:i + 400])
+        lf = lf + torch.nn.functional.mse_loss(fine.rgb_map, target[i:i + 400])
+    lc, lf = lc / 2, lf / 2
+    (lc + lf).backward()
+    ref = {f"{w}.{k}": p.grad.cpu() for w, k, p in model._named_net_params()}
+    compare(fused, ref, rel_max=1e-5, name="fused training_step")
+    log = out["log"]
+    assert abs(log["train/coarse_loss"] - lc.item()) <= 1e-6 * lc.item() and abs(log["train/fine_loss"] - lf.item()) <= 1e-6 * lf.item()
+    assert abs(out["loss"] - (lc + lf).item()) <= 1e-6 * out["loss"] and abs(log["train/fine_psnr"] + 10 * np.log10(lf.item())) < 1e-4

@@ -54,6 +54,14 @@ def _worker(rank, world, port, q):
         mn, mx, sd = P.global_stats(float(own.min()), float(own.max()), float(own.double().sum()),
                                     lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), torch.device("cpu"))
         ok &= mn == float(vol.min()) and mx == float(vol.max()) and abs(sd - float(vol.double().std(unbiased=False))) < 1e-9
+        # data-parallel gradient exchange: mean over ranks, one flat all_reduce, parameters without a gradient skipped
+        ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(1))]
+        ps[0].grad = torch.full((3, 2), float(rank + 1))
+        ps[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+        n = P.allreduce_gradients(ps)
+        mean = sum(r + 1 for r in range(world)) / world
+        ok &= n == 11 and torch.equal(ps[0].grad, torch.full((3, 2), mean)) and ps[2].grad is None
+        ok &= torch.allclose(ps[1].grad, torch.arange(5, dtype=torch.float32) * mean)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

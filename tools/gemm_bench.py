@@ -5,12 +5,15 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import nerfmeshes_b200 as nm
-from oracle import nerf_oracle as O
+
+
+ARCH = dict(num_layers=8, hidden_size=256, skip_step=4, num_encoding_fn_xyz=10, num_encoding_fn_dir=4, include_input_xyz=True,
+            include_input_dir=True, log_sampling_xyz=True, log_sampling_dir=True, use_viewdirs=True)
 
 
 def run(M, N, K, cols, rep):
     os.environ["NM_GEMM_REPEAT"] = str(rep)
-    eng = nm.Engine(O.NetCfg().__dict__, None, nm.RenderSettings())
+    eng = nm.Engine(ARCH, None, nm.RenderSettings())
     a = torch.randn((K, M) if cols else (M, K), device="cuda")
     b = torch.randn((K, N) if cols else (N, K), device="cuda")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]

@@ -4,12 +4,13 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import nerfmeshes_b200 as nm
-from oracle import nerf_oracle as O
 
-NET = O.NetCfg()
+ARCH = dict(num_layers=8, hidden_size=256, skip_step=4, num_encoding_fn_xyz=10, num_encoding_fn_dir=4, include_input_xyz=True,
+            include_input_dir=True, log_sampling_xyz=True, log_sampling_dir=True, use_viewdirs=True)
+FLOP_PER_POINT = 1186816
 CFG = {"dataset.near": 2.0, "dataset.far": 6.0, "dataset.white_background": True,
        "models.coarse_type": "FlexibleNeRFModel", "models.fine_type": "FlexibleNeRFModel", "models.use_fine": True,
-       **{f"models.coarse.{k}": v for k, v in NET.__dict__.items()}, **{f"models.fine.{k}": v for k, v in NET.__dict__.items()}}
+       **{f"models.coarse.{k}": v for k, v in ARCH.items()}, **{f"models.fine.{k}": v for k, v in ARCH.items()}}
 for mode in ("train", "validation"):
     CFG.update({f"nerf.{mode}.num_coarse": 64, f"nerf.{mode}.num_fine": 128, f"nerf.{mode}.perturb": True,
                 f"nerf.{mode}.lindisp": False, f"nerf.{mode}.radiance_field_noise_std": 0.2})
@@ -46,7 +47,7 @@ def main():
         opt.step()
     t0 = time.time(); full = timeit(step, 5); wall = (time.time() - t0) / 6
     pts = R * (64 + 192)
-    flops = pts * NET.flops_per_point() * 3
+    flops = pts * FLOP_PER_POINT * 3
     print(f"R={R}: forward {fwd:.2f} ms | loss+backward (fwd re-run inside) {bwd:.2f} ms = {R / bwd * 1e3:,.0f} rays/s, "
           f"{flops / (bwd - fwd) / 1e9:.1f} TFLOP/s fp32 over the backward part | full autograd+Adam step {full:.2f} ms "
           f"(wall {wall * 1e3:.1f} ms) = {R / full * 1e3:,.0f} rays/s")
