@@ -155,6 +155,13 @@ int nm_marching_cubes_count(NmHandle h, const float* vol_dev, int nx, int ny, in
 int nm_marching_cubes_emit(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, float x_off,
                            float* verts_dev, float* normals_dev, int32_t* faces_dev, void* stream);
 
+/* Replaces export_obj (src/nerf/nerf_helpers.py:86-111): `v x y z [r g b]`, `vn x y z`, `f i//i j//j k//k` (1-based) with
+ * byte-identical number formatting (python repr of the float32 widened to double).  Host arrays, no GPU involved;
+ * diffuse may be NULL or shorter than the vertex list (vertices beyond it get no colour, like the reference's
+ * len(diffuse) > idx test). */
+int nm_export_obj(const char* path, const float* verts_host, int64_t n_verts, const int32_t* faces_host, int64_t n_faces,
+                  const float* diffuse_host, int64_t n_diffuse, const float* normals_host, int64_t n_normals);
+
 /* ---- hot path, host buffers (what a reference-side caller holding CPU tensors binds) ------------------ */
 /* model.query(ray_batch) with host tensors (src/eval_nerf.py:62-69): copies H2D, renders, copies D2H, syncs. */
 int nm_query_host(NmHandle h, const float* origins_host, int o_stride, const float* dirs_host, int64_t R,

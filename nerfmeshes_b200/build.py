@@ -25,6 +25,7 @@ SOURCES = {
     "nm_mc.cu": ["-fmad=false"],
     "nm_train.cu": [],
     "nm_gemm_tc.cu": [],
+    "nm_objwriter.cu": [],
     "nm_api.cu": [],
 }
 

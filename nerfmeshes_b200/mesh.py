@@ -4,6 +4,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import _lib as L
+
 
 def extract_radiance(model, args, device, nums, sigma_only=False, slab=None):
     """src/mesh_nerf.py:27-53.  Returns the (n0,n1,n2,4) numpy radiance grid like the reference, or — with
@@ -57,10 +59,8 @@ def extract_geometry(model, device, args):
     return vertices, faces.cpu(), normals.cpu(), density.cpu().numpy()
 
 
-def export_obj(vertices, triangles, diffuse, normals, filename):
-    """src/nerf/nerf_helpers.py:86-111, byte-identical text: `v x y z [r g b]`, `vn x y z`, `f i//i j//j k//k` (1-based).
-    The reference formats every float32 (torch or numpy) through python's format(): the value widened to double, shortest
-    round-trip repr.  Same text here, built in one pass and written with a single writelines()."""
+def _export_obj_python(vertices, triangles, diffuse, normals, filename):
+    """Pure-python formatter (any dtype); the native writer below must produce the same bytes."""
     def rows(a):
         if isinstance(a, torch.Tensor):
             a = a.detach().cpu()
@@ -81,6 +81,27 @@ def export_obj(vertices, triangles, diffuse, normals, filename):
     out.extend("f" + "".join(f" {i + 1}//{i + 1}" for i in r) + "\n" for r in tri.tolist())
     with open(filename, "w") as fh:
         fh.writelines(out)
+
+
+def export_obj(vertices, triangles, diffuse, normals, filename):
+    """src/nerf/nerf_helpers.py:86-111, byte-identical text: `v x y z [r g b]`, `vn x y z`, `f i//i j//j k//k` (1-based).
+    The reference formats every float32 (torch or numpy) through python's format(): the value widened to double, shortest
+    round-trip repr.  float32 inputs (what the mesh path produces) go through the library's native writer
+    (nm_export_obj: ~1 s per million vertices); anything else through the python formatter with the same output."""
+    def arr(a):
+        return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    v, n, t = arr(vertices), arr(normals), arr(triangles)
+    d = arr(diffuse) if len(diffuse) else np.zeros((0, 3), np.float32)
+    native = all(x.dtype == np.float32 and x.ndim == 2 and x.shape[1] == 3 for x in (v, n, d)) and t.dtype.kind in "iu" and \
+        t.ndim == 2 and t.shape[1] == 3 and (t.size == 0 or int(t.max()) < 2 ** 31 - 1)
+    if not native:
+        return _export_obj_python(vertices, triangles, diffuse, normals, filename)
+    import ctypes as C
+    v, n, d = np.ascontiguousarray(v), np.ascontiguousarray(n), np.ascontiguousarray(d)
+    t = np.ascontiguousarray(t, dtype=np.int32)
+    ptr = lambda a: C.c_void_p(a.ctypes.data) if a.size else None
+    L.check(L.load().nm_export_obj(str(filename).encode(), ptr(v), v.shape[0], ptr(t), t.shape[0], ptr(d), d.shape[0],
+                                   ptr(n), n.shape[0]))
 
 
 def mesh_appearance(model, vertices, normals, args):

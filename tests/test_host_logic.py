@@ -251,3 +251,26 @@ def test_export_obj_matches_reference_text(tmp_path):
     out = tmp_path / "m.obj"
     nm.mesh.export_obj(torch.from_numpy(z["v"]), torch.from_numpy(z["f"]), z["d"], torch.from_numpy(z["n"]), str(out))
     assert out.read_text() == open(os.path.join(ROOT, "tests", "golden", "golden_mesh.obj")).read()
+
+
+def test_native_obj_writer_is_byte_identical_to_python_formatting(tmp_path):
+    """nm_export_obj (csrc/nm_objwriter.cu) reproduces python's repr() of the float32 values widened to double — fixed /
+    scientific switch at 1e-4 and 1e16, two-digit exponents, -0.0, subnormals, inf / nan — and the reference's partial-colour
+    rule; compared with the pure-python formatter on adversarial values plus 20k random ones."""
+    rng = np.random.default_rng(7)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 0.1, 1e-4, 9.999e-5, 1e-5, 123456.789, 1e15, 9.9999999e15, 1e16, 1.5e22, 3.4028235e38,
+                        1.1754944e-38, 1e-45, 16777216.0, 0.30000001192092896, 2.5, 1e7, 1e-7, np.inf, -np.inf, np.nan],
+                       dtype=np.float32)
+    vals = np.concatenate([special, rng.standard_normal(20000).astype(np.float32) * np.float32(10.0) ** rng.integers(-12, 12, 20000).astype(np.float32)])
+    vals = vals[: (vals.size // 3) * 3].astype(np.float32)
+    v = vals.reshape(-1, 3)
+    n = np.ascontiguousarray(v[::-1])
+    d = np.abs(v[: v.shape[0] // 2])                          # fewer colours than vertices
+    f = rng.integers(0, v.shape[0], (5000, 3)).astype(np.int64)
+    a, b = tmp_path / "native.obj", tmp_path / "python.obj"
+    nm.mesh.export_obj(v, f, d, n, str(a))
+    nm.mesh._export_obj_python(v, f, d, n, str(b))
+    assert a.read_bytes() == b.read_bytes()
+    nm.mesh.export_obj(torch.from_numpy(v), torch.from_numpy(f), [], torch.from_numpy(n), str(a))     # no colours at all
+    nm.mesh._export_obj_python(v, f, [], n, str(b))
+    assert a.read_bytes() == b.read_bytes()
