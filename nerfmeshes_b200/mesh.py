@@ -116,10 +116,27 @@ def mesh_appearance(model, vertices, normals, args):
     return model.query((ray_origins.cuda(), directions.cuda(), ray_bounds)).rgb_map.cpu().numpy()
 
 
-def export_marching_cubes(model, args, cfg=None, device="cuda"):
-    """src/mesh_nerf.py:131-201 without the cache / super-sampling branches: geometry -> appearance -> OBJ."""
+def cached_geometry(args, build):
+    """The mesh cache of export_marching_cubes (src/mesh_nerf.py:141-158): a torch.save'd tuple
+    (vertices, triangles, normals, density) at save_dir/cache_name, loaded when --use-cached-mesh is set and the file
+    exists, (re)written when it was requested but missing or --override-cache-mesh is set.  `build()` produces the tuple."""
     import os
-    vertices, triangles, normals, density = extract_geometry(model, device, args)
+    use = bool(getattr(args, "use_cached_mesh", False))
+    name = getattr(args, "cache_name", None)
+    path = os.path.join(args.save_dir, name) if name else None
+    exists = bool(path) and os.path.exists(path)
+    if use and exists:
+        return tuple(torch.load(path, weights_only=False))
+    out = build()
+    if path and ((use and not exists) or getattr(args, "override_cache_mesh", False)):
+        torch.save(tuple(out), path)
+    return out
+
+
+def export_marching_cubes(model, args, cfg=None, device="cuda"):
+    """src/mesh_nerf.py:131-201 without the super-sampling branch (PyMCubes): geometry (or its cache) -> appearance -> OBJ."""
+    import os
+    vertices, triangles, normals, density = cached_geometry(args, lambda: extract_geometry(model, device, args))
     diffuse = mesh_appearance(model, vertices, normals, args)
     path = os.path.join(args.save_dir, args.mesh_name)
     export_obj(vertices, triangles, diffuse, normals, path)

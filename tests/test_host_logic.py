@@ -274,3 +274,26 @@ def test_native_obj_writer_is_byte_identical_to_python_formatting(tmp_path):
     nm.mesh.export_obj(torch.from_numpy(v), torch.from_numpy(f), [], torch.from_numpy(n), str(a))     # no colours at all
     nm.mesh._export_obj_python(v, f, [], n, str(b))
     assert a.read_bytes() == b.read_bytes()
+
+
+def test_mesh_cache_branch(tmp_path):
+    """export_marching_cubes' cache (src/mesh_nerf.py:141-158): load when requested and present, write when requested and
+    missing or when --override-cache-mesh is given, otherwise neither."""
+    class A:
+        save_dir, cache_name, use_cached_mesh, override_cache_mesh = str(tmp_path), "mesh_cache.pt", False, False
+    calls = []
+
+    def build():
+        calls.append(1)
+        return (torch.ones(4, 3) * len(calls), torch.zeros(2, 3, dtype=torch.int32), torch.ones(4, 3), np.zeros((2, 2, 2), np.float32))
+    cache = tmp_path / "mesh_cache.pt"
+    nm.mesh.cached_geometry(A, build)
+    assert len(calls) == 1 and not cache.exists()                       # not requested: built, nothing written
+    A.use_cached_mesh = True
+    v = nm.mesh.cached_geometry(A, build)[0]
+    assert len(calls) == 2 and cache.exists() and float(v[0, 0]) == 2   # requested but missing: built and saved
+    v = nm.mesh.cached_geometry(A, build)[0]
+    assert len(calls) == 2 and float(v[0, 0]) == 2                      # present: loaded, not rebuilt
+    A.use_cached_mesh, A.override_cache_mesh = False, True
+    nm.mesh.cached_geometry(A, build)
+    assert len(calls) == 3 and float(torch.load(cache, weights_only=False)[0][0, 0]) == 3     # override: rebuilt and rewritten
