@@ -195,6 +195,19 @@ int nm_loss_backward(NmHandle h, const float* origins_dev, int o_stride, const f
                      const float* target_rgb_dev, float* loss_dev, void* stream);
 int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t numel, void* stream);
 
+/* ---- BuFF tree maintenance ----------------------------------------------------------
+ * nm_ray_voxel_indices: the `indices` output of TreeSampling.batch_ray_voxel_intersect (src/nerf/tree.py:215-343,
+ *   deterministic branch) for cfg.num_coarse samples per ray: the voxel (row of the nm_set_tree list) every sample lies
+ *   in, int32 (R,S), -1 on rays that hit no voxel; z_out_dev (R,S) optionally receives the sample distances with the
+ *   uniform fallback on those rays (model_buff.py:52-53).
+ * nm_tree_integrate: TreeSampling.ray_batch_integration (tree.py:177-206) past its step gate: memm[v] +=
+ *   (sum of weights / sum of weight masks of the samples in v - memm[v]) / counter for every voxel that received a sample.
+ *   idx/weights/mask: n = R*S entries (whole batch, idx -1 skipped, or only the rows of rays that hit). */
+int nm_ray_voxel_indices(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                         const float* near_far_host, float* z_out_dev, int32_t* idx_out_dev, void* stream);
+int nm_tree_integrate(NmHandle h, const int32_t* idx_dev, const float* weights_dev, const float* mask_weights_dev, int64_t n,
+                      float* memm_dev, int32_t V, int32_t counter, void* stream);
+
 /* Test hook for the tensor-core GEMM of the backward pass (nm_gemm_tc.cu): D (M,N) = A (M,K) B (N,K)^T from fp32
  * row-major device arrays through the bf16 hi/lo operand packs.  a_cols / b_cols: that operand is given transposed
  * ((K,M) / (K,N)) and packed along its rows (the weight-gradient operands); k_split: feed K as two segments;

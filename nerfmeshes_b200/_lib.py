@@ -62,6 +62,8 @@ _SIGNATURES = {
     "nm_backward_rays": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _I, C.c_uint64, _P, _P, _P]),
     "nm_loss_backward": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _I, C.c_uint64, _P, _P, _P]),
     "nm_get_grad": (C.c_int, [_P, _I, C.c_char_p, _P, _L, _P]),
+    "nm_ray_voxel_indices": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _P]),
+    "nm_tree_integrate": (C.c_int, [_P, _P, _P, _P, _L, _P, C.c_int32, C.c_int32, _P]),
     "nm_debug_gemm": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "nm_debug_pack": (C.c_int, [C.POINTER(NmNetDesc), _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64), _I, _P,
                                C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),

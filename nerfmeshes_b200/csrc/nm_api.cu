@@ -176,7 +176,7 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
     if (int e = h->t_u.ensure((size_t)R * Nc * 4)) return e;
     float* z = h->t_u.as<float>();
     if (int e = launch_aabb(h->voxels.as<float>(), h->V, rb.origins, rb.o_stride, rb.dirs, R, rb.nf[0], rb.nf[1], Nc,
-                            h->s_table.as<float>(), t_c, z, h->d_err + 1, st, &h->launches)) return e;
+                            h->s_table.as<float>(), t_c, z, nullptr, h->d_err + 1, st, &h->launches)) return e;
     if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
     if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(z, Nc), h->raw_c.as<float>(), st)) return e;
     if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, z, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
@@ -601,6 +601,35 @@ int nm_debug_gemm(NmHandle h, const float* a_dev, const float* b_dev, int M, int
   uint8_t* ws = reinterpret_cast<uint8_t*>(((uintptr_t)h->train_ws.p + 1023) & ~(uintptr_t)1023);
   return debug_tc_gemm(a_dev, b_dev, M, N, K, a_cols, b_cols, k_split, n_passes, fp16, atomic, d_dev, ws, need - 1024, h->num_sms,
                        h->d_err, (cudaStream_t)stream, &h->launches);
+}
+
+// ---------------------------------------------------------------------------------------------- BuFF tree maintenance
+int nm_ray_voxel_indices(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                         const float* near_far_host, float* z_out_dev, int32_t* idx_out_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(origins_dev && dirs_dev && near_far_host && idx_out_dev, "null argument");
+  NM_CHECK(o_stride == 0 || o_stride == 3, "o_stride must be 0 or 3");
+  NM_CHECK(h->V > 0, "no voxel list (nm_set_tree)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = h->cfg.num_coarse;
+  float* t_u = nullptr;
+  if (z_out_dev) {     // rays without a hit fall back to the uniform samples (src/models/model_buff.py:53)
+    if (int e = h->t_c.ensure((size_t)R * S * 4)) return e;
+    t_u = h->t_c.as<float>();
+    if (int e = launch_stratified(h->s_table.as<float>(), S, R, near_far_host, nullptr, nullptr, h->cfg.lindisp, 0, 0, t_u, st,
+                                  &h->launches)) return e;
+  }
+  return launch_aabb(h->voxels.as<float>(), h->V, origins_dev, o_stride, dirs_dev, R, near_far_host[0], near_far_host[1], S,
+                     h->s_table.as<float>(), t_u, z_out_dev, idx_out_dev, h->d_err + 1, st, &h->launches);
+}
+
+int nm_tree_integrate(NmHandle h, const int32_t* idx_dev, const float* weights_dev, const float* mask_weights_dev, int64_t n,
+                      float* memm_dev, int32_t V, int32_t counter, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(idx_dev && weights_dev && mask_weights_dev && memm_dev && V > 0 && n >= 0, "bad arguments");
+  if (int e = h->small.ensure(sizeof(float) * 2 * (size_t)V + 64)) return e;
+  return launch_tree_integrate(idx_dev, weights_dev, mask_weights_dev, n, memm_dev, V, counter, h->small.as<float>(),
+                               (cudaStream_t)stream, &h->launches);
 }
 
 int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, const float* lin2_host, int n0, int n1,

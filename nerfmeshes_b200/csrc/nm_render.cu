@@ -209,7 +209,26 @@ __global__ void __launch_bounds__(kInvWarps * 32) invcdf_kernel(const float* __r
 constexpr int kMaxHits = 512;
 constexpr int kAabbWarps = 4;
 
-__device__ __forceinline__ void warp_bitonic_sort_pairs(float* key, float* val, int n_pow2, int lane) {
+__device__ __forceinline__ void warp_bitonic_sort_tagged(float* key, int* tag, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        const int p = i ^ j;
+        if (p > i) {
+          const float x = key[i], y = key[p];
+          const bool up = ((i & k) == 0);
+          if ((x > y) == up) {
+            key[i] = y; key[p] = x;
+            const int tx = tag[i]; tag[i] = tag[p]; tag[p] = tx;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__device__ __forceinline__ void warp_bitonic_sort_triples(float* key, float* val, int* tag, int n_pow2, int lane) {
   for (int k = 2; k <= n_pow2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = lane; i < n_pow2; i += 32) {
@@ -220,6 +239,7 @@ __device__ __forceinline__ void warp_bitonic_sort_pairs(float* key, float* val, 
           if ((x > y) == up) {
             key[i] = y; key[p] = x;
             const float vx = val[i]; val[i] = val[p]; val[p] = vx;
+            const int tx = tag[i]; tag[i] = tag[p]; tag[p] = tx;
           }
         }
       }
@@ -233,7 +253,9 @@ __global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __re
                                                               const float* __restrict__ dirs, long long R, float near,
                                                               float far, int S, const float* __restrict__ s_table,
                                                               const float* __restrict__ t_uniform,
-                                                              float* __restrict__ z_out, int* __restrict__ overflow) {
+                                                              float* __restrict__ z_out, int* __restrict__ idx_out,
+                                                              int* __restrict__ overflow) {
+  __shared__ int s_vox[kAabbWarps][kMaxHits];
   __shared__ float s_lo[kAabbWarps][kMaxHits];
   __shared__ float s_hi[kAabbWarps][kMaxHits];
   __shared__ float s_z[kAabbWarps][kMaxTotal];
@@ -245,6 +267,7 @@ __global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __re
   float* hi = s_hi[wid];
   float* z = s_z[wid];
   int* bucket = s_bucket[wid];
+  int* vox = s_vox[wid];
   float o[3], inv[3];
   bool neg[3];
 #pragma unroll
@@ -278,21 +301,24 @@ __global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __re
     const unsigned bal = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       const int pos = H + __popc(bal & ((1u << lane) - 1));
-      if (pos < kMaxHits) { lo[pos] = tmin; hi[pos] = tmax; }
+      if (pos < kMaxHits) { lo[pos] = tmin; hi[pos] = tmax; vox[pos] = v; }
     }
     H += __popc(bal);
   }
   if (H > kMaxHits) { if (lane == 0) atomicExch(overflow, 1); H = kMaxHits; }
   __syncwarp();
-  if (H == 0) {                                 // miss: uniform fallback samples
-    for (int k = lane; k < S; k += 32) z_out[ray * S + k] = t_uniform[ray * S + k];
+  if (H == 0) {                                 // miss: uniform fallback samples, no voxel
+    for (int k = lane; k < S; k += 32) {
+      if (z_out) z_out[ray * S + k] = t_uniform[ray * S + k];
+      if (idx_out) idx_out[ray * S + k] = -1;
+    }
     return;
   }
   int n2 = 1;
   while (n2 < H) n2 <<= 1;
-  for (int i = H + lane; i < n2; i += 32) { lo[i] = CUDART_INF_F; hi[i] = CUDART_INF_F; }
+  for (int i = H + lane; i < n2; i += 32) { lo[i] = CUDART_INF_F; hi[i] = CUDART_INF_F; vox[i] = -1; }
   __syncwarp();
-  warp_bitonic_sort_pairs(lo, hi, n2, lane);    // hits by entry distance
+  warp_bitonic_sort_triples(lo, hi, vox, n2, lane);   // hits by entry distance, voxel ids riding along
   // running sum of the interval lengths (torch.cumsum, sequential), kept in hi[]
   if (lane == 0) {
     float run = 0.f;
@@ -313,12 +339,54 @@ __global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __re
     while (a < b) { const int mid = (a + b) >> 1; if (bucket[mid] < bk) a = mid + 1; else b = mid; }
     z[k] = lo[bk] + (s_table[k] * total - s_table[a] * total);
   }
+  __syncwarp();
+  for (int k = lane; k < S; k += 32) bucket[k] = vox[bucket[k]];      // sample -> voxel id (tree.py:333-335)
   int m2 = 1;
   while (m2 < S) m2 <<= 1;
-  for (int i = S + lane; i < m2; i += 32) z[i] = CUDART_INF_F;
+  for (int i = S + lane; i < m2; i += 32) { z[i] = CUDART_INF_F; bucket[i] = -1; }
   __syncwarp();
-  warp_bitonic_sort(z, m2, lane);
-  for (int k = lane; k < S; k += 32) z_out[ray * S + k] = z[k];
+  warp_bitonic_sort_tagged(z, bucket, m2, lane);                      // (:338-341) ids follow their samples
+  for (int k = lane; k < S; k += 32) {
+    if (z_out) z_out[ray * S + k] = z[k];
+    if (idx_out) idx_out[ray * S + k] = bucket[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BuFF tree maintenance
+// TreeSampling.ray_batch_integration (src/nerf/tree.py:177-206): per-voxel sums of the sample weights / weight masks
+// that fell into it (idx < 0: ray without a hit, skipped), then memm[v] += (acc/freq - memm[v]) / counter where freq > 0.
+// The reference materialises two dense (R,V) matrices; here a block-level shared-memory histogram feeds fp32 atomics.
+__global__ void __launch_bounds__(256) tree_scatter_kernel(const int* __restrict__ idx, const float* __restrict__ w,
+                                                           const float* __restrict__ mw, long long n, int V, int use_smem,
+                                                           float* __restrict__ acc, float* __restrict__ freq) {
+  extern __shared__ float sh[];
+  float* a = use_smem ? sh : acc;
+  float* f = use_smem ? sh + V : freq;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < 2 * V; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int v = idx[i];
+    if (v >= 0 && v < V) {
+      atomicAdd(a + v, w[i]);
+      atomicAdd(f + v, mw[i]);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      if (sh[V + i] != 0.f || sh[i] != 0.f) { atomicAdd(acc + i, sh[i]); atomicAdd(freq + i, sh[V + i]); }
+    }
+  }
+}
+
+__global__ void tree_update_kernel(float* __restrict__ memm, const float* __restrict__ acc, const float* __restrict__ freq,
+                                   int V, float counter) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const float fr = freq[v];
+  if (fr > 0.f) memm[v] = memm[v] + (acc[v] / fr - memm[v]) / counter;
 }
 
 // ------------------------------------------------------------------------------------------------ a14
@@ -413,14 +481,33 @@ int launch_invcdf(const float* t_c, const float* w_c, const float* u_table, int 
 }
 
 int launch_aabb(const float* voxels, int V, const float* origins, int o_stride, const float* dirs, long long R,
-                     float near, float far, int S, const float* s_table, const float* t_uniform, float* z_out,
+                     float near, float far, int S, const float* s_table, const float* t_uniform, float* z_out, int* idx_out,
                      int* d_overflow, cudaStream_t st, int64_t* launches) {
   NM_CHECK(S <= kMaxTotal, "sample count %d exceeds the AABB sampler limit", S);
+  NM_CHECK(z_out == nullptr || t_uniform != nullptr, "z output needs the uniform fallback samples");
   if (R <= 0) return 0;
   aabb_kernel<<<(unsigned)((R + kAabbWarps - 1) / kAabbWarps), kAabbWarps * 32, 0, st>>>(
-      voxels, V, origins, o_stride, dirs, R, near, far, S, s_table, t_uniform, z_out, d_overflow);
+      voxels, V, origins, o_stride, dirs, R, near, far, S, s_table, t_uniform, z_out, idx_out, d_overflow);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
+  return 0;
+}
+
+int launch_tree_integrate(const int* idx, const float* w, const float* mw, long long n, float* memm, int V, int counter,
+                          float* scratch2v, cudaStream_t st, int64_t* launches) {
+  if (n <= 0 || V <= 0) return 0;
+  NM_CHECK(counter >= 1, "counter must be >= 1");
+  NM_CUDA(cudaMemsetAsync(scratch2v, 0, sizeof(float) * 2 * (size_t)V, st));
+  const int use_smem = V <= 6144;
+  long long blocks = (n + 256 * 16 - 1) / (256 * 16);
+  if (blocks > 1184) blocks = 1184;
+  if (blocks < 1) blocks = 1;
+  tree_scatter_kernel<<<(unsigned)blocks, 256, use_smem ? sizeof(float) * 2 * (size_t)V : 0, st>>>(idx, w, mw, n, V, use_smem,
+                                                                                                  scratch2v, scratch2v + V);
+  NM_CUDA(cudaGetLastError());
+  tree_update_kernel<<<(V + 255) / 256, 256, 0, st>>>(memm, scratch2v, scratch2v + V, V, (float)counter);
+  NM_CUDA(cudaGetLastError());
+  if (launches) *launches += 2;
   return 0;
 }
 

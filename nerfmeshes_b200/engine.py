@@ -265,6 +265,27 @@ class Engine:
         L.check(self.lib.nm_get_grad(self._h, which, name.encode(), _ptr(out), out.numel(), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ BuFF tree maintenance
+    def ray_voxel_indices(self, origins, dirs, near, far, want_z=False):
+        """(R,S) int32 voxel index of every AABB sample (-1 on rays without a hit) [, (R,S) sample distances]."""
+        o, o_stride, d, R, nf, near_d, far_d = self._ray_args(origins, dirs, near, far)
+        if nf is None:
+            raise L.NmError("the BuFF sampler takes scalar near/far")
+        S = self.settings.num_coarse
+        idx = torch.empty((R, S), dtype=torch.int32, device=d.device)
+        z = torch.empty((R, S), dtype=torch.float32, device=d.device) if want_z else None
+        if R:
+            L.check(self.lib.nm_ray_voxel_indices(self._h, _ptr(o), o_stride, _ptr(d), R, nf, _ptr(z), _ptr(idx), self._stream()))
+        return (idx, z) if want_z else idx
+
+    def tree_integrate(self, idx, weights, mask_weights, memm, counter):
+        """TreeSampling.ray_batch_integration on the device: updates `memm` (V,) in place."""
+        idx = idx.to(torch.int32).contiguous()
+        w, mw = _f32c(weights, idx.device), _f32c(mask_weights, idx.device)
+        assert memm.is_cuda and memm.dtype == torch.float32 and memm.is_contiguous() and w.numel() == idx.numel() == mw.numel()
+        L.check(self.lib.nm_tree_integrate(self._h, _ptr(idx), _ptr(w), _ptr(mw), idx.numel(), _ptr(memm), memm.numel(),
+                                           int(counter), self._stream()))
+
     def debug_gemm(self, a, b, *, a_cols=False, b_cols=False, k_split=0, n_passes=3, fp16=False, atomic=False, out=None):
         """Test hook (nm_debug_gemm): D = A B^T on the backward pass's tensor-core GEMM.  a: (M,K) or (K,M) if a_cols;
         b: (N,K) or (K,N) if b_cols."""

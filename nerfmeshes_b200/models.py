@@ -23,6 +23,7 @@ import torch
 
 from . import _lib as L
 from .cfgnode import CfgNode, flatten_dict, nest_dict
+from .tree import Node, TreeSampling
 from .engine import NET_KEYS, Engine, RenderSettings
 
 
@@ -268,7 +269,7 @@ class BaseModel(torch.nn.Module):
         if "sample_pdf_u" in weights and hasattr(model, "sample_pdf"):
             model.sample_pdf.u.copy_(torch.as_tensor(weights["sample_pdf_u"]))
         if "voxels" in weights and hasattr(model, "tree"):
-            model.tree.voxels = torch.as_tensor(weights["voxels"]).float()
+            model.tree.set_voxels(weights["voxels"])
         return model
 
 
@@ -335,35 +336,6 @@ class NeRFModel(BaseModel):
         return fine_bundle if fine_bundle is not None else coarse_bundle
 
 
-class Node:
-    """Unpickling target for the octree nodes stored in BuFF checkpoints (src/nerf/tree.py:4-36).  Only the flat
-    voxel tensor is used for inference; the node graph is kept as loaded so it can be re-serialised."""
-
-    def __init__(self, *a, **k):
-        pass
-
-
-class TreeSampling:
-    """Inference view of src/nerf/tree.py:39-358: holds `voxels` (V,2,3) and answers batch_ray_voxel_intersect."""
-
-    def __init__(self, config, device=None):
-        self.config = config
-        near, far = float(config.dataset.near), float(config.dataset.far)
-        mean = (near + far) / 2
-        # untrained default: the outer subdivision of the root box [near-mean, far-mean]^3 (tree.py:76-87)
-        n = int(_cfg_get(config, "tree.subdivision_outer_count", 1) or 1)
-        lo, size = near - mean, (far - near) / n
-        idx = torch.stack(torch.meshgrid(*([torch.arange(n)] * 3), indexing="ij"), -1).reshape(-1, 3).float()
-        self.voxels = torch.stack((lo + idx * size, lo + (idx + 1) * size), 1)
-        self.root, self.memm, self.counter = None, None, 1
-
-    def serialize(self):
-        return {"root": self.root, "voxels": self.voxels, "memm": self.memm, "counter": self.counter}
-
-    def deserialize(self, d):
-        self.root, self.voxels, self.memm, self.counter = d["root"], d["voxels"].float().cpu(), d["memm"], d["counter"]
-
-
 class BuFFModel(BaseModel):
     def __init__(self, cfg, *args, **kwargs):
         super().__init__(cfg, *args, **kwargs)
@@ -371,6 +343,7 @@ class BuFFModel(BaseModel):
         self.model = FlexibleNeRFModel(**m.coarse)
         self.model.bind(self, L.NET_COARSE)
         self.tree = TreeSampling(self.cfg)
+        self.global_step = 0                             # Lightning's step counter: gates the tree integration
         self.sampler = _Holder()
         self.sampler.count = int(self.cfg.nerf.train.num_coarse)
         self.sampler.point_intervals = torch.linspace(0.0, 1.0, self.sampler.count)[None, :]
@@ -395,6 +368,7 @@ class BuFFModel(BaseModel):
         self._eng.set_tables(self.sampler.point_intervals[0], None)
 
     def _sync_tree(self, eng):
+        self.tree.engine = eng
         if self._tree_id != id(self.tree.voxels):
             eng.set_tree(self.tree.voxels)
             self._tree_id = id(self.tree.voxels)
@@ -408,6 +382,12 @@ class BuFFModel(BaseModel):
         self._sync_tree(eng)
         o = eng.render_rays(ray_origins, ray_directions, near, far, training=self.training, buff=True, seed=seed,
                             want=["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights", "t_vals"])
+        if self.training and o["rgb"].is_cuda:
+            # accumulate the (detached) sample weights into the voxels (model_buff.py:65-66; tree.py:177-206)
+            step_gate = int(_cfg_get(self.cfg, "tree.step_size_integration_offset", 0) or 0)
+            if self.global_step >= step_gate:
+                idx = eng.ray_voxel_indices(ray_origins, ray_directions, near, far)
+                self.tree.ray_batch_integration(self.global_step, idx, o["weights"], o["mask_weights"])
         o["rgb"], _ = self._attach_grad((ray_origins, ray_directions, near, far), seed, True, o["rgb"])
         b = OutputBundle(o["rgb"], o["depth"], o["weights"], o["mask_weights"], o["acc"], o["disp"], o["depth_raw"])
         b.t_vals = o["t_vals"]

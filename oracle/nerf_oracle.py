@@ -318,7 +318,7 @@ def sample_pdf_forward(t_coarse, weights, num_fine, perturb=False, u=None, gener
 # a10: AABB-clipped sampling (BuFF)
 # --------------------------------------------------------------------------------------
 def batch_ray_voxel_intersect(voxels: torch.Tensor, origins: torch.Tensor, dirs: torch.Tensor, near, far,
-                              samples_count: int):
+                              samples_count: int, return_indices: bool = False, literal_sort: bool = False):
     """src/nerf/tree.py:215-343, deterministic branch (use_random_sampling False in every shipped config).
 
     voxels (V,2,3) [min,max]; origins (1,3) or (R,3); dirs (R,3).  Returns z (R,S) ascending and ray_mask (R,).
@@ -353,7 +353,7 @@ def batch_ray_voxel_intersect(voxels: torch.Tensor, origins: torch.Tensor, dirs:
     ray_mask = mask.sum(-1) > 0
     z = torch.zeros(R, samples_count)
     if ray_mask.sum() == 0:
-        return z, ray_mask
+        return (z, torch.ones(R, samples_count, dtype=torch.long), ray_mask) if return_indices else (z, ray_mask)
     # hits sorted by entry distance, compacted to the front (:299-308)
     order = tmin.sort(-1)
     tmin_s = order.values
@@ -367,8 +367,35 @@ def batch_ray_voxel_intersect(voxels: torch.Tensor, origins: torch.Tensor, dirs:
     bucket = torch.searchsorted(cums, s.contiguous())            # left (:321)
     first = torch.searchsorted(bucket, bucket, right=False)     # first sample of each bucket (:324)
     z = lo.gather(-1, bucket.clamp(max=V - 1)) + (s - s.gather(-1, first))    # (:327-330)
-    z, _ = z.sort(-1)                                             # (:338)
-    return z, ray_mask
+    z, perm = z.sort(-1)                                          # (:338)
+    if not return_indices:
+        return z, ray_mask
+    # voxel of every sample (:333-341): bucket -> position in the compacted hit list -> position in the entry-sorted
+    # list -> voxel id, then reordered like the samples.  Rows of rays without a hit are meaningless (callers index
+    # with ray_mask, src/models/model_buff.py:66).
+    # QUIRK: the reference compacts the hit INTERVALS by boolean indexing (entry order, :307) but maps buckets to voxels
+    # through the permutation of `mask.long().sort(descending=True)` (:305,:333), which torch does not promise to be
+    # stable — with the CPU build used for the goldens only 21 % of the samples end up attributed to the voxel that
+    # contains them.  literal_sort=True repeats that exact call (pins the oracle to the golden indices); the default
+    # is the stable permutation, i.e. every sample is attributed to the voxel whose interval produced it.
+    if literal_sort:
+        front = mask_s.long().sort(descending=True)
+    hit_pos = front.indices.gather(-1, bucket.clamp(max=V - 1))
+    vox = order.indices.gather(-1, hit_pos)
+    return z, vox.gather(-1, perm), ray_mask
+
+
+def ray_batch_integration(memm: torch.Tensor, counter: int, indices: torch.Tensor, weights: torch.Tensor,
+                          mask_weights: torch.Tensor):
+    """src/nerf/tree.py:177-206 past the step gate: per-voxel mean of the sample weights that fell into it, folded into the
+    running mean `memm` with 1/counter.  indices / weights / mask_weights are the rows of the rays that hit (…[mask])."""
+    V = memm.shape[0]
+    acc = torch.zeros(V).index_add_(0, indices.reshape(-1), weights.reshape(-1).float())
+    freq = torch.zeros(V).index_add_(0, indices.reshape(-1), mask_weights.reshape(-1).float())
+    m = freq > 0
+    out = memm.clone()
+    out[m] += (acc[m] / freq[m] - out[m]) / counter
+    return out, counter + 1
 
 
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,82 @@
+"""BuFF tree maintenance on the device: nm_ray_voxel_indices / nm_tree_integrate against the oracle and
+the reference-generated goldens, and the training-mode hook of BuFFModel.forward."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_npz
+from oracle import nerf_oracle as O
+from test_gpu_parity import BUFF_CFG
+
+pytestmark = pytest.mark.gpu
+G = dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_tree.npz")))
+
+
+@pytest.fixture(scope="module")
+def buff():
+    import nerfmeshes_b200 as nm
+    return nm.BuFFModel.from_npz(BUFF_CFG, load_npz("weights_lego_buff.npz")).cuda().eval()
+
+
+def test_voxel_indices_match_oracle_bit_exact(buff):
+    g = load_npz("golden_lego_buff.npz")
+    vox = load_npz("weights_lego_buff.npz")["voxels"].float()
+    near, far = float(g["bounds"][0]), float(g["bounds"][1])
+    eng = buff._engine()
+    buff._sync_tree(eng)
+    idx, z = eng.ray_voxel_indices(g["origin"][None].cuda(), g["dirs"].cuda(), near, far, want_z=True)
+    z_ref, idx_ref, mask = O.batch_ray_voxel_intersect(vox, g["origin"][None], g["dirs"], near, far, 192, return_indices=True)
+    idx, z = idx.cpu(), z.cpu()
+    assert torch.equal(z[mask], z_ref[mask]) and torch.equal(z, g["z"])            # placement incl. the uniform fallback rows
+    assert bool((idx[~mask] == -1).all()) and torch.equal(idx[mask], idx_ref[mask].int())
+
+
+def test_tree_integration_matches_reference(buff):
+    g = load_npz("golden_lego_buff.npz")
+    eng = buff._engine()
+    mask = torch.from_numpy(G["ray_mask"])
+    idx = torch.from_numpy(G["idx"]).clone()
+    idx[~mask] = -1                                                    # whole batch, misses flagged (the reference passes x[mask])
+    w, mw = g["out_weights"].cuda(), g["out_mask_weights"].cuda()
+    memm = torch.zeros(buff.tree.voxels.shape[0], device="cuda")
+    eng.tree_integrate(idx.cuda(), w, mw, memm, 1)
+    assert float((memm.cpu() - torch.from_numpy(G["memm1"])).abs().max()) < 1e-6
+    eng.tree_integrate(idx.cuda()[mask.cuda()], (w * 0.5)[mask.cuda()], mw[mask.cuda()], memm, 2)     # ...[mask] rows work too
+    assert float((memm.cpu() - torch.from_numpy(G["memm2"])).abs().max()) < 1e-6
+
+
+def test_training_forward_feeds_the_tree_and_consolidate_rebuilds_the_voxels():
+    import nerfmeshes_b200 as nm
+    g = load_npz("golden_lego_buff.npz")
+    cfg = {**BUFF_CFG, "nerf.train.radiance_field_noise_std": 0.0, "tree.step_size_integration_offset": 5, "tree.step_size_tree": 3,
+           "tree.eps": 1e-4, "tree.max_depth": 4, "tree.subdivision_inner_count": 2, "tree.max_voxel_count": 1536}
+    model = nm.BuFFModel.from_npz(cfg, load_npz("weights_lego_buff.npz")).cuda().train()
+    rays = (g["origin"][None].cuda(), g["dirs"].cuda(), g["bounds"])
+    model.global_step = 2
+    with torch.no_grad():
+        model.forward(rays)
+    assert model.tree.counter == 1                                      # before the offset: nothing accumulated
+    model.global_step = 5
+    with torch.no_grad():
+        out = model.forward(rays)
+        model.forward(rays)
+    assert model.tree.counter == 3 and model.tree.memm.is_cuda
+    hit = torch.from_numpy(G["ray_mask"])
+    vox = load_npz("weights_lego_buff.npz")["voxels"].float()
+    _, idx, _ = O.batch_ray_voxel_intersect(vox, g["origin"][None], g["dirs"], float(g["bounds"][0]), float(g["bounds"][1]), 192,
+                                            return_indices=True)
+    ref, c = torch.zeros(vox.shape[0]), 1
+    for _ in range(2):
+        ref, c = O.ray_batch_integration(ref, c, idx[hit], out.weights.cpu()[hit], out.mask_weights.cpu()[hit])
+    assert float((model.tree.memm.cpu() - ref).abs().max()) < 1e-5 and int((ref > 0).sum()) > 20
+    # graft a node graph onto the flat checkpoint voxels, then prune + subdivide and render with the new list
+    from nerfmeshes_b200.tree import Node
+    model.tree.root.children = [Node(model.tree.config, (b[0].clone(), b[1].clone()), 3) for b in vox]
+    n_before = vox.shape[0]
+    model.tree.consolidate()
+    assert model.tree.voxels.shape[0] != n_before and model.tree.counter == 1 and float(model.tree.memm.abs().sum()) == 0
+    with torch.no_grad():
+        out2 = model.forward(rays)
+    assert bool(torch.isfinite(out2.rgb_map).all())
