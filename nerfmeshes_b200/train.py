@@ -19,17 +19,33 @@ def mse2psnr(mse: float) -> float:
 
 
 def training_step(model, ray_batch, ray_targets, *, chunksize: Optional[int] = None, seed: Optional[int] = None,
-                  group=None, allreduce: bool = True):
+                  group=None, allreduce: bool = True, global_step: Optional[int] = None):
     """ray_batch = (ray_origins (3,) | (R,3), ray_directions (R,3), (near, far)); ray_targets (R,3).  All CUDA tensors.
-    Returns the reference's dict {"loss", "log": {"train/loss", "train/coarse_loss", "train/coarse_psnr", ...}} with python
-    floats; parameters' .grad hold d loss / d theta (averaged over ranks when torch.distributed is initialised)."""
+    Returns the reference's dict {"loss", "log": {...}} with python floats; parameters' .grad hold d loss / d theta
+    (averaged over ranks when torch.distributed is initialised).
+    NeRFModel: manual batching over `chunksize`, {"train/loss", "train/coarse_loss", "train/coarse_psnr", "train/fine_*"}
+    (model_nerf.py:88-151).  BuFFModel: one batch, {"train/loss", "train/psnr"}, the sample weights are integrated into the
+    voxel tree and the tree is consolidated when its schedule ticks (model_buff.py:75-110)."""
     if not model.training:
         raise RuntimeError("training_step needs model.train()")
+    if global_step is not None:
+        model.global_step = int(global_step)
+    named = model._named_net_params()
+    if type(model).__name__ == "BuFFModel":
+        # through forward(): it owns the tree-integration hook (model_buff.py:65-66); gradients via the autograd bridge
+        for _, _, p in named:
+            p.grad = None
+        out = model.forward(ray_batch, seed=seed)
+        loss = torch.nn.functional.mse_loss(out.rgb_map, ray_targets.to(out.rgb_map.device))
+        loss.backward()
+        if allreduce:
+            parallel.allreduce_gradients([p for _, _, p in named], group)
+        if model.tree.ticked(model.global_step):
+            model.tree.consolidate()
+        value = float(loss)
+        return {"loss": value, "log": {"train/loss": value, "train/psnr": mse2psnr(value)}}
     ray_origins, ray_directions, near, far = model._unpack(ray_batch)
     eng = model._engine()
-    buff = type(model).__name__ == "BuFFModel"
-    if buff:
-        model._sync_tree(eng)
     R = ray_directions.shape[0]
     chunk = int(chunksize or model.cfg.nerf.train.get("chunksize", R) or R)
     n_chunks = R / chunk                                         # the reference divides by this float (model_nerf.py:93)
@@ -40,9 +56,7 @@ def training_step(model, ray_batch, ray_targets, *, chunksize: Optional[int] = N
     for i in range(0, R, chunk):
         sl = slice(i, i + chunk)
         o = ray_origins[sl] if per_ray_o else ray_origins
-        loss += eng.loss_backward(o, ray_directions[sl], near, far, ray_targets[sl], training=True, buff=buff,
-                                  seed=base_seed + i)
-    named = model._named_net_params()
+        loss += eng.loss_backward(o, ray_directions[sl], near, far, ray_targets[sl], training=True, seed=base_seed + i)
     for which, name, p in named:
         g = eng.get_grad(which, name, p)
         p.grad = g.div_(n_chunks) if p.grad is None else p.grad.add_(g.div_(n_chunks))

@@ -80,3 +80,31 @@ def test_training_forward_feeds_the_tree_and_consolidate_rebuilds_the_voxels():
     with torch.no_grad():
         out2 = model.forward(rays)
     assert bool(torch.isfinite(out2.rgb_map).all())
+
+
+def test_buff_training_step_updates_weights_tree_and_schedule():
+    """nerfmeshes_b200.training_step on a BuFFModel (model_buff.py:75-110): loss + gradients, weight integration into the
+    tree on every step past the offset, consolidate() when the schedule ticks."""
+    import nerfmeshes_b200 as nm
+    from nerfmeshes_b200.tree import Node
+    g = load_npz("golden_lego_buff.npz")
+    z = load_npz("weights_lego_buff.npz")
+    cfg = {**BUFF_CFG, "nerf.train.radiance_field_noise_std": 0.0, "tree.step_size_integration_offset": 2, "tree.step_size_tree": 2,
+           "tree.eps": 1e-4, "tree.max_depth": 4, "tree.subdivision_inner_count": 2, "tree.max_voxel_count": 1536}
+    model = nm.BuFFModel.from_npz(cfg, z).cuda().train()
+    model.tree.root.children = [Node(model.tree.config, (b[0].clone(), b[1].clone()), 3) for b in z["voxels"].float()]
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    rays = (g["origin"][None].cuda(), g["dirs"].cuda(), g["bounds"])
+    target = torch.rand(g["dirs"].shape[0], 3, generator=torch.Generator().manual_seed(0)).cuda()
+    n0 = model.tree.voxels.shape[0]
+    sizes, losses = [], []
+    for step in range(5):
+        out = nm.training_step(model, rays, target, global_step=step)
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+        opt.step()
+        losses.append(out["loss"])
+        sizes.append((model.tree.voxels.shape[0], model.tree.counter))
+    # steps 0,1: before the offset; step 2,3 integrate; step 4 = offset + 2 ticks -> integrate then consolidate (counter back to 1)
+    assert sizes[0] == (n0, 1) and sizes[1] == (n0, 1) and sizes[2] == (n0, 2) and sizes[3] == (n0, 3)
+    assert sizes[4][1] == 1 and sizes[4][0] != n0
+    assert abs(out["log"]["train/psnr"] + 10 * np.log10(out["loss"])) < 1e-6 and np.isfinite(losses).all()
