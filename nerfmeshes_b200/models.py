@@ -254,7 +254,27 @@ class BaseModel(torch.nn.Module):
         if hasattr(model, "on_load_checkpoint"):
             model.on_load_checkpoint(ck)
         model.load_state_dict(ck["state_dict"], strict=False)
+        if hasattr(model, "global_step"):
+            model.global_step = int(ck.get("global_step", 0))
         return model
+
+    def save_checkpoint(self, path, global_step=None, optimizer=None, lr_scheduler=None):
+        """Write what load_from_checkpoint reads back, with the keys of a Lightning-0.9 checkpoint (SURVEY section 5
+        'Checkpoint / resume'): state_dict under the reference's parameter names, hyper_parameters (the flat config),
+        global_step, the on_save_checkpoint extras (BuFF: the voxel tree with its node graph, weights and counter), and
+        optionally the optimiser / scheduler states for resuming."""
+        ck = {"state_dict": {k: v.detach().cpu() for k, v in self.state_dict().items()},
+              "hyper_parameters": dict(self.hparams),
+              "global_step": int(getattr(self, "global_step", 0) if global_step is None else global_step),
+              "pytorch-lightning_version": "0.9.0"}
+        if optimizer is not None:
+            ck["optimizer_states"] = [optimizer.state_dict()]
+        if lr_scheduler is not None:
+            ck["lr_schedulers"] = [lr_scheduler.state_dict()]
+        if hasattr(self, "on_save_checkpoint"):
+            self.on_save_checkpoint(ck)
+        torch.save(ck, path)
+        return ck
 
     @classmethod
     def from_npz(cls, cfg, weights: dict):

@@ -297,3 +297,37 @@ def test_mesh_cache_branch(tmp_path):
     A.use_cached_mesh, A.override_cache_mesh = False, True
     nm.mesh.cached_geometry(A, build)
     assert len(calls) == 3 and float(torch.load(cache, weights_only=False)[0][0, 0]) == 3     # override: rebuilt and rewritten
+
+
+def test_checkpoint_roundtrip_with_tree(tmp_path):
+    """save_checkpoint -> load_from_checkpoint: parameters, hyper-parameters, step counter and the BuFF tree (node graph,
+    voxels, accumulated weights, counter) survive; the file has the reference's Lightning-0.9 top-level keys."""
+    cfg = {"experiment.model": "BuFFModel", "dataset.near": 2.0, "dataset.far": 6.0, "dataset.white_background": False,
+           "models.coarse_type": "FlexibleNeRFModel", "models.use_fine": False,
+           **{f"models.coarse.{k}": v for k, v in dict(num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6,
+                                                        num_encoding_fn_dir=4, include_input_xyz=True, include_input_dir=True,
+                                                        log_sampling_xyz=True, log_sampling_dir=True, use_viewdirs=True).items()},
+           "tree.subdivision_outer_count": 3, "tree.subdivision_inner_count": 2, "tree.max_depth": 3, "tree.eps": 0.3,
+           "tree.max_voxel_count": 60, "tree.step_size_integration_offset": 10, "tree.step_size_tree": 4}
+    for mode in ("train", "validation"):
+        cfg.update({f"nerf.{mode}.num_coarse": 32, f"nerf.{mode}.num_fine": 0, f"nerf.{mode}.perturb": False,
+                    f"nerf.{mode}.lindisp": False, f"nerf.{mode}.radiance_field_noise_std": 0.0})
+    m = nm.BuFFModel(cfg)
+    with torch.no_grad():
+        m.model.layer1.weight.add_(1.25)
+    m.tree.memm = torch.rand(m.tree.voxels.shape[0], generator=torch.Generator().manual_seed(1))
+    m.tree.consolidate()
+    m.tree.memm += 0.5
+    m.tree.counter = 7
+    m.global_step = 1234
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    ck = m.save_checkpoint(str(tmp_path / "m.ckpt"), optimizer=opt)
+    assert {"state_dict", "hyper_parameters", "global_step", "tree", "optimizer_states"} <= set(ck)
+    r = nm.BuFFModel.load_from_checkpoint(str(tmp_path / "m.ckpt"))
+    assert r.global_step == 1234 and r.tree.counter == 7
+    assert torch.equal(r.model.layer1.weight, m.model.layer1.weight) and torch.equal(r.tree.voxels, m.tree.voxels)
+    assert torch.equal(r.tree.memm, m.tree.memm) and len(r.tree.root.children) == len(m.tree.root.children)
+    assert r.cfg.tree.max_voxel_count == 60 and set(r.state_dict()) == set(m.state_dict())
+    r.tree.memm = torch.ones_like(r.tree.memm)
+    r.tree.consolidate()                                       # the restored node graph keeps subdividing
+    assert r.tree.voxels.shape[0] >= m.tree.voxels.shape[0]
