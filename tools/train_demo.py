@@ -26,7 +26,8 @@ for mode in ("train", "validation"):
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     R = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-    z = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights_lego_nerf.npz")).items()}
+    raw = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights_lego_nerf.npz"))
+    z = {k: torch.from_numpy(raw[k]) for k in raw.files if raw[k].dtype.kind in "fiub"}
     teacher = nm.NeRFModel.from_npz(CFG, z).cuda().eval()
     torch.manual_seed(0)
     student = nm.NeRFModel(CFG).cuda().train()
