@@ -1,7 +1,10 @@
 """End-to-end training on the fused path, without a dataset: a fresh two-network NeRF (8x256) is fitted to images rendered
 by the shipped lego checkpoint (re-packed in tests/golden/weights_lego_nerf.npz) — the reference's training loop
 (training_step -> Adam -> exponential LambdaLR, src/models/model_base.py:150-177) with every forward / backward on the
-library's kernels.  Prints the loss / PSNR curve and the throughput.      python tools/train_demo.py [steps] [rays]
+library's kernels.  Prints the loss / PSNR curve and the throughput.      python tools/train_demo.py [steps] [rays] [seed]
+As with the reference, an unlucky initialisation can leave one of the two networks in NeRF's "all-empty" local minimum for
+a while (the reference carries check_early_stopping for it, src/models/model_base.py:179-186); the gradients themselves are
+checked against torch autograd in tests/test_gpu_train.py and tools/train_diag.py.
 """
 import os
 import sys
@@ -20,7 +23,7 @@ CFG = {"dataset.near": 2.0, "dataset.far": 6.0, "dataset.white_background": Fals
        **{f"models.coarse.{k}": v for k, v in ARCH.items()}, **{f"models.fine.{k}": v for k, v in ARCH.items()}}
 for mode in ("train", "validation"):
     CFG.update({f"nerf.{mode}.num_coarse": 64, f"nerf.{mode}.num_fine": 128, f"nerf.{mode}.perturb": mode == "train",
-                f"nerf.{mode}.lindisp": False, f"nerf.{mode}.radiance_field_noise_std": 0.0})
+                f"nerf.{mode}.lindisp": False, f"nerf.{mode}.radiance_field_noise_std": 0.2 if mode == "train" else 0.0})
 
 
 def main():
@@ -29,7 +32,7 @@ def main():
     raw = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "weights_lego_nerf.npz"))
     z = {k: torch.from_numpy(raw[k]) for k in raw.files if raw[k].dtype.kind in "fiub"}
     teacher = nm.NeRFModel.from_npz(CFG, z).cuda().eval()
-    torch.manual_seed(0)
+    torch.manual_seed(int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     student = nm.NeRFModel(CFG).cuda().train()
     opt = torch.optim.Adam(student.parameters(), lr=5e-4)
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda s: 0.1 ** (s / 250000))
