@@ -1,16 +1,23 @@
 // tcgen05 GEMM for the training backward (nm_train.cu): D (M,N) = A (M,K) * B (N,K)^T with both operands given as
-// pre-packed bf16 hi/lo "ptiles" and fp32 accumulation in TMEM.  fp32 accuracy class comes from the same operand
-// split the forward kernel uses (x = hi + lo, three MMAs per product: hi*hi + lo*hi + hi*lo), with bf16 instead of
-// fp16 halves because gradients span fp32's exponent range (16 significand bits per operand, ~2^-16 per product).
+// pre-packed hi/lo "ptiles" and fp32 accumulation in TMEM.  fp32 accuracy class comes from the same operand split the
+// forward kernel uses (x = hi + lo, three MMAs per product: hi*hi + lo*hi + hi*lo).  Halves are bf16 for the gradient
+// GEMMs (gradients span fp32's exponent range; 16 significand bits per operand, ~2^-16 per product) and fp16 for the
+// forward recompute (22 bits, the forward kernel's class: its relu masks must agree with the forward's).
 //
 // ptile = one (128 operand rows) x (64 K) block: [hi | lo], each 16 KB, K-major, 128-byte swizzled — the shared-memory
 // image tcgen05.mma reads, so a ptile moves global -> shared with ONE 32 KB cp.async.bulk.  A pack is ptiles ordered
-// [row block][K block].  Packs are produced by pack_rows_kernel (K along the source's columns) and
-// pack_cols_kernel (K along the source's rows: the A^T / B^T operands of the weight gradient).
+// [row block][K block].  Packs are produced by pack_rows_kernel (K along the source's columns), pack_cols_kernel (K
+// along the source's rows: the A^T / B^T operands of the weight gradient) and, for everything inside the layer chain,
+// by this kernel's own epilogue.
 //
-// Kernel: one CTA per 128 x (128*NB) output tile, optional split over K (weight gradient: K = points).  6 warps:
-// warps 0-3 epilogue (TMEM lanes 32*warp..), warp 4 producer (bulk copies into a ring of K-block stages), warp 5 MMA
-// issuer.  Barriers: full[s] (tx bytes), empty[s] (tcgen05.commit), acc (tcgen05.commit after the last K block).
+// Kernel: 18 warps — 0-15 epilogue (TMEM lane group w%4, column quarter w/4, blocks of 32 rows x 16 columns), 16 producer
+// (bulk copies into a ring of K-block stages: 2 x 96 KB for 256-wide tiles, 3 x 64 KB for 128-wide), 17 MMA issuer.
+// Data-path GEMMs are persistent (grid = min(tiles, SMs)) with the accumulator double-buffered in TMEM, so the
+// epilogue of tile i overlaps the main loop of tile i+1; the weight gradient (K = points) splits K over one wave of
+// CTAs and reduces with vector atomics.  Barriers: full[s] (tx bytes), empty[s] (tcgen05.commit), acc_full[b]
+// (tcgen05.commit after a tile's last K block), acc_empty[b] (16 epilogue warps).  tests/test_gemm_protocol.py models
+// the protocol with one-bit parities.  The fused epilogue (bias/relu, rank-1 term, 1-bit masks in and out, row pack and
+// point-major pack of the output, bias-gradient column sums) is described in DESIGN.md section 4.4.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 

@@ -3,15 +3,18 @@
 // through VolumeRenderer (src/nerf/modules.py:67-121), the network (src/nerf/models.py:60-80) and nothing else
 // (SamplePDF is detached, modules.py:201; sample positions do not depend on θ).
 //
-// Round-1 shape of this row: correctness first.  The forward of a training step runs on the tcgen05 kernel
-// (nm_mlp_tc.cu); the backward here recomputes the activations layer by layer in plain fp32 FMA arithmetic on the
-// CUDA cores (the reference trains in fp32, TF32 off), keeps them in HBM for one sub-chunk of points, and walks the
-// layers back with three tiled SGEMM shapes:
-//     forward     Y  = act([X | PE] Wt + b)              sgemm<NN>
-//     data grad   dX = (dZ W) (+ dsigma w_alpha) * relu'  sgemm<NT>  (W = Wt^T, so B is read transposed)
-//     weight grad dWt += [X | PE]^T dZ                    sgemm_tn   (split over points, fp32 atomics)
-// Gradients accumulate into flat buffers with the layouts of NetDev.d_wt / d_bias / d_head; nm_get_grad returns
-// them in the reference's (out,in) layout.  A tcgen05 version of these GEMMs is the next step for this row.
+// The forward of a training step runs on the fused tcgen05 kernel (nm_mlp_tc.cu).  The backward recomputes the
+// activations layer by layer for one sub-chunk of points (kept in HBM as operand packs + 1-bit relu masks) and walks the
+// layers back with three GEMM shapes:
+//     forward     Y  = act([X | PE] W^T + b)
+//     data grad   dX = (dZ W) (+ dsigma w_alpha) * relu'
+//     weight grad dW += dZ^T [X | PE]                     (K = points: split over CTAs, fp32 atomics)
+// Default: all three on the tensor cores through tc_gemm_kernel (nm_gemm_tc.cu), whose epilogues hand the next GEMM its
+// operands.  NM_PREC_FP32: the same walk in plain fp32 FMAs on the CUDA cores (sgemm_kernel / sgemm_tn_kernel below; the
+// reference trains in fp32, TF32 off) — the numerical yard-stick the tensor-core path is tested against.
+// Small SIMT kernels around them: encodings, the 3-/4-row heads, the compositor adjoint, the MSE gradient.
+// Gradients accumulate in the reference's (out,in) orientation (rows padded to 4 floats, grad_layout()); nm_get_grad
+// returns them per state-dict tensor.
 #include <math_constants.h>
 
 #include <cstdlib>
