@@ -331,3 +331,24 @@ def test_checkpoint_roundtrip_with_tree(tmp_path):
     r.tree.memm = torch.ones_like(r.tree.memm)
     r.tree.consolidate()                                       # the restored node graph keeps subdividing
     assert r.tree.voxels.shape[0] >= m.tree.voxels.shape[0]
+
+
+def test_training_entry_points_fail_loudly_without_gpu():
+    """No CPU path for training either: the fused step needs the library's kernels."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nerfmeshes_b200.train import mse2psnr, training_step
+    assert abs(mse2psnr(0.01) - 20.0) < 1e-9 and abs(mse2psnr(0.0) - 50.0) < 1e-9
+    net = dict(num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6, num_encoding_fn_dir=4, include_input_xyz=True,
+               include_input_dir=True, log_sampling_xyz=True, log_sampling_dir=True, use_viewdirs=True)
+    cfg = {"dataset.near": 2.0, "dataset.far": 6.0, "dataset.white_background": False, "models.coarse_type": "FlexibleNeRFModel",
+           "models.use_fine": False, **{f"models.coarse.{k}": v for k, v in net.items()}}
+    for mode in ("train", "validation"):
+        cfg.update({f"nerf.{mode}.num_coarse": 16, f"nerf.{mode}.num_fine": 0, f"nerf.{mode}.perturb": False,
+                    f"nerf.{mode}.lindisp": False, f"nerf.{mode}.radiance_field_noise_std": 0.0})
+    m = nm.NeRFModel(cfg)
+    rays = (torch.zeros(3), torch.randn(8, 3), (2.0, 6.0))
+    with pytest.raises(RuntimeError):
+        training_step(m.eval(), rays, torch.rand(8, 3))               # eval mode
+    with pytest.raises(L.NmError):
+        training_step(m.train(), rays, torch.rand(8, 3))              # no CUDA device: the engine refuses to exist
