@@ -258,6 +258,25 @@ class BaseModel(torch.nn.Module):
             model.global_step = int(ck.get("global_step", 0))
         return model
 
+    # ------------------------------------------------------------------ optimiser (src/models/model_base.py:150-177)
+    def get_scheduler(self, optimizer):
+        """Exponential decay gamma ** (step / step_size) (model_base.py:150-158)."""
+        gamma = float(self.cfg.scheduler.options.gamma)
+        step_size = float(self.cfg.scheduler.options.step_size)
+        return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda step: gamma ** (step / step_size))
+
+    def configure_optimizers(self):
+        """getattr(torch.optim, cfg.optimizer.type)(parameters, lr=cfg.optimizer.lr) + a torch scheduler named by
+        cfg.scheduler.type, or the exponential LambdaLR above when torch has no scheduler of that name; returned in
+        Lightning's ([optimizer], [{'scheduler', 'interval': 'step', 'frequency': 1}]) shape (model_base.py:160-177)."""
+        optimizer = getattr(torch.optim, self.cfg.optimizer.type)(self.parameters(), lr=float(self.cfg.optimizer.lr))
+        stype = _cfg_get(self.cfg, "scheduler.type", "")
+        if stype and hasattr(torch.optim.lr_scheduler, stype):
+            scheduler = getattr(torch.optim.lr_scheduler, stype)(optimizer, **dict(self.cfg.scheduler.options))
+        else:
+            scheduler = self.get_scheduler(optimizer)
+        return [optimizer], [{"scheduler": scheduler, "interval": "step", "frequency": 1}]
+
     def save_checkpoint(self, path, global_step=None, optimizer=None, lr_scheduler=None):
         """Write what load_from_checkpoint reads back, with the keys of a Lightning-0.9 checkpoint (SURVEY section 5
         'Checkpoint / resume'): state_dict under the reference's parameter names, hyper_parameters (the flat config),

@@ -352,3 +352,29 @@ def test_training_entry_points_fail_loudly_without_gpu():
         training_step(m.eval(), rays, torch.rand(8, 3))               # eval mode
     with pytest.raises(L.NmError):
         training_step(m.train(), rays, torch.rand(8, 3))              # no CUDA device: the engine refuses to exist
+
+
+def test_configure_optimizers_matches_reference_schedule():
+    """model_base.py:150-177: Adam at cfg.optimizer.lr, exponential LambdaLR gamma ** (step / step_size) stepped per batch."""
+    net = dict(num_layers=4, hidden_size=128, skip_step=4, num_encoding_fn_xyz=6, num_encoding_fn_dir=4, include_input_xyz=True,
+               include_input_dir=True, log_sampling_xyz=True, log_sampling_dir=True, use_viewdirs=True)
+    cfg = {"dataset.near": 2.0, "dataset.far": 6.0, "dataset.white_background": False, "models.coarse_type": "FlexibleNeRFModel",
+           "models.use_fine": False, **{f"models.coarse.{k}": v for k, v in net.items()},
+           "optimizer.type": "Adam", "optimizer.lr": 5e-3, "scheduler.type": "ExponentialLR_custom",
+           "scheduler.options.gamma": 0.1, "scheduler.options.step_size": 250}
+    for mode in ("train", "validation"):
+        cfg.update({f"nerf.{mode}.num_coarse": 16, f"nerf.{mode}.num_fine": 0, f"nerf.{mode}.perturb": False,
+                    f"nerf.{mode}.lindisp": False, f"nerf.{mode}.radiance_field_noise_std": 0.0})
+    m = nm.NeRFModel(cfg)
+    (opt,), (sd,) = m.configure_optimizers()
+    assert isinstance(opt, torch.optim.Adam) and sd["interval"] == "step" and sd["frequency"] == 1
+    assert len(opt.param_groups[0]["params"]) == len(list(m.parameters()))
+    lrs = []
+    for _ in range(500):
+        opt.step()
+        sd["scheduler"].step()
+        lrs.append(opt.param_groups[0]["lr"])
+    assert abs(lrs[249] - 5e-3 * 0.1) < 1e-9 and abs(lrs[499] - 5e-3 * 0.01) < 1e-10
+    cfg2 = {**cfg, "scheduler.type": "StepLR", "scheduler.options.gamma": 0.5, "scheduler.options.step_size": 10}
+    (opt2,), (sd2,) = nm.NeRFModel(cfg2).configure_optimizers()
+    assert isinstance(sd2["scheduler"], torch.optim.lr_scheduler.StepLR)
