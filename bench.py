@@ -203,7 +203,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     model = nm.NeRFModel.from_npz(lego_cfg(), load_npz("weights_lego_nerf.npz")).eval()
     model.precision = {"exact": nm.PREC_EXACT, "fast": nm.PREC_FAST, "fp32": nm.PREC_FP32}[a.precision]
-    model._cuda_index = local
+    model.cuda(local)
     eng = model._engine()
     poses = poses120()
     my_pose = lambda i: poses[(i * world + rank) % len(poses)]

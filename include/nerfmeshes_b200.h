@@ -136,6 +136,10 @@ int nm_render_image(NmHandle h, const float* pose_host, int H, int W, float foca
  * when ndc (else the origin is pose[:,3]). */
 int nm_ray_bundle(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, float ndc_near, int row0,
                   int row1, float* origins_dev_or_null, float* dirs_dev, void* stream);
+/* ndc_rays(H, W, focal, near, rays_o, rays_d) on caller-supplied rays (src/nerf/nerf_helpers.py:280-307, called positionally
+ * by DataBundle.ndc, src/data/data_helpers.py:164-167): n rays, origins with o_stride 0 (one shared origin) or 3. */
+int nm_ndc_rays(NmHandle h, int H, int W, float focal, float near, const float* origins_dev, int o_stride,
+                const float* dirs_dev, int64_t n, float* origins_out_dev, float* dirs_out_dev, void* stream);
 /* extract_radiance (src/mesh_nerf.py:27-53) for grid planes [x0,x1): points from the three linspace tables
  * (host, lengths n0,n1,n2; pass torch.linspace values for bit-identical coordinates), dirs := positions.
  * sigma_dev (x1-x0,n1,n2) raw density; rgb_dev (x1-x0,n1,n2,3) or NULL (sigma-only fast path). */
@@ -225,6 +229,10 @@ int nm_debug_pack(const NmNetDesc* desc, int n_tensors, const char* const* names
 /* Device-side error flags, readable even after a kernel trapped: out2[0] = tcgen05 pipeline watchdog code (0 = ok),
  * out2[1] = AABB hit-list overflow. */
 int nm_kernel_flags(NmHandle h, int32_t* out2);
+/* Synchronises `stream`, then fails (<0, message in nm_last_error) if a kernel of this handle raised a device-side flag.
+ * The asynchronous device-pointer entry points report flags raised by EARLIER calls when they are entered; *_host calls
+ * check before they return. */
+int nm_check_flags(NmHandle h, void* stream);
 
 /* ---- introspection ---------------------------------------------------------------------------------- */
 /* number of kernels launched through this handle since creation (bench.py's gpu_launches). */

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "nm_debug_pack": (C.c_int, [C.POINTER(NmNetDesc), _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64), _I, _P,
                                C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nm_kernel_flags": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "nm_check_flags": (C.c_int, [_P, _P]),
+    "nm_ndc_rays": (C.c_int, [_P, _I, _I, _F, _F, _P, _I, _P, _L, _P, _P, _P]),
     "nm_launch_count": (C.c_int64, [_P]),
     "nm_set_timing": (C.c_int, [_P, _I]),
     "nm_mlp_time_ms": (C.c_double, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

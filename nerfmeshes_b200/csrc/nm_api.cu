@@ -72,10 +72,20 @@ long long chunk_rays() {
   return v;
 }
 
+int check_kernel_flags(NmHandle h);
+
 int bind_device(NmHandle h) {
   NM_CHECK(h != nullptr, "null handle");
   NM_CUDA(cudaSetDevice(h->device));
   return 0;
+}
+
+// device-pointer (asynchronous) entry points cannot wait for their own kernels; they report the device-side error flags
+// raised by EARLIER work on this handle (mapped host memory, no synchronisation) and callers that need the answer for
+// the current call use nm_check_flags(h, stream), which synchronises first.
+int bind_checked(NmHandle h) {
+  if (int e = bind_device(h)) return e;
+  return check_kernel_flags(h);
 }
 
 void linspace_host(int n, std::vector<float>* out) {  // torch.linspace(0,1,n) fp32 (ATen's two-sided formula)
@@ -94,7 +104,7 @@ int upload(Buf* b, const void* src, size_t bytes) {
 int check_kernel_flags(NmHandle h) {
   const volatile int* flags = h->h_err;
   NM_CHECK(flags[0] == 0, "tcgen05 pipeline watchdog fired (code %d)", flags[0]);
-  NM_CHECK(flags[1] == 0, "AABB sampler: more than 512 voxel hits on one ray");
+  NM_CHECK(flags[1] == 0, "AABB sampler: more than 512 voxel hits on one ray (samples / voxel indices of that ray are truncated)");
   return 0;
 }
 
@@ -125,6 +135,8 @@ int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* o
   return 0;
 }
 
+constexpr uint64_t kNoiseSaltMain = 0x5bd1e995ull, kNoiseSaltCoarse = 0x7f4a7c15a3c59ac3ull;
+
 struct RayBatch {
   const float* origins; int o_stride; const float* dirs; long long R;
   float nf[2]; const float* near_dev; const float* far_dev;
@@ -142,10 +154,11 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
   const bool training = flags & NM_FLAG_TRAINING;
   const int Nf = (h->has_fine && !buff) ? c.num_fine : 0;
   const int S = Nc + Nf;
+  // the coarse and the fine compositor draw independent sigma noise (two torch.randn calls in the reference): distinct salts
   auto composite = [&](const float* raw, const float* t, int s, float* rgb, float* depth, float* depth_raw, float* acc,
-                       float* disp, float* w, float* mw) {
+                       float* disp, float* w, float* mw, uint64_t salt = kNoiseSaltMain) {
     CompositeArgs a{};
-    a.raw = raw; a.t = t; a.dirs = rb.dirs; a.R = R; a.S = s; a.noise_std = c.noise_std; a.seed = seed ^ 0x5bd1e995u;
+    a.raw = raw; a.t = t; a.dirs = rb.dirs; a.R = R; a.S = s; a.noise_std = c.noise_std; a.seed = seed ^ salt;
     a.white_bg = c.white_background; a.training = training ? 1 : 0; a.thr = c.attenuation_threshold;
     a.rgb = rgb; a.depth = depth; a.depth_raw = depth_raw; a.acc = acc; a.disp = disp; a.weights = w; a.mask_weights = mw;
     return launch_composite(a, st, &h->launches);
@@ -190,7 +203,8 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
   }
   float* w_c = o.coarse_weights;
   if (!w_c) { if (int e = h->w_c.ensure((size_t)R * Nc * 4)) return e; w_c = h->w_c.as<float>(); }
-  if (int e = composite(h->raw_c.as<float>(), t_c, Nc, o.coarse_rgb, nullptr, nullptr, o.coarse_acc, o.coarse_disp, w_c, nullptr)) return e;
+  if (int e = composite(h->raw_c.as<float>(), t_c, Nc, o.coarse_rgb, nullptr, nullptr, o.coarse_acc, o.coarse_disp, w_c, nullptr,
+                        kNoiseSaltCoarse)) return e;
   // inverse-CDF resampling + merge (a8)
   float* t_f = o.t_vals;
   if (!t_f) { if (int e = h->t_f.ensure((size_t)R * S * 4)) return e; t_f = h->t_f.as<float>(); }
@@ -298,21 +312,21 @@ int train_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const 
     d_rgb = h->tr_drgb[0].as<float>();
     d_rgb_coarse = two ? h->tr_drgb[1].as<float>() : nullptr;
   }
-  struct Pass { int which; const float* raw; const float* t; int s; const float* g; };
+  struct Pass { int which; const float* raw; const float* t; int s; const float* g; uint64_t salt; };
   Pass passes[2];
   int np = 0;
   if (two) {
-    if (d_rgb) passes[np++] = {NM_NET_FINE, h->raw_f.as<float>(), h->t_f.as<float>(), S, d_rgb};
-    if (d_rgb_coarse) passes[np++] = {NM_NET_COARSE, h->raw_c.as<float>(), h->t_c.as<float>(), Nc, d_rgb_coarse};
+    if (d_rgb) passes[np++] = {NM_NET_FINE, h->raw_f.as<float>(), h->t_f.as<float>(), S, d_rgb, kNoiseSaltMain};
+    if (d_rgb_coarse) passes[np++] = {NM_NET_COARSE, h->raw_c.as<float>(), h->t_c.as<float>(), Nc, d_rgb_coarse, kNoiseSaltCoarse};
   } else if (d_rgb) {
-    passes[np++] = {NM_NET_COARSE, h->raw_c.as<float>(), buff ? h->t_u.as<float>() : h->t_c.as<float>(), Nc, d_rgb};
+    passes[np++] = {NM_NET_COARSE, h->raw_c.as<float>(), buff ? h->t_u.as<float>() : h->t_c.as<float>(), Nc, d_rgb, kNoiseSaltMain};
   }
   for (int pi = 0; pi < np; ++pi) {
     const Pass& P = passes[pi];
     NetDev& net = h->nets[P.which];
     if (int e = h->dout.ensure((size_t)R * P.s * 16)) return e;
     if (int e = h->trans.ensure((size_t)R * P.s * 4)) return e;
-    if (int e = launch_composite_backward(P.raw, P.t, rb.dirs, P.g, R, P.s, c.noise_std, seed ^ 0x5bd1e995u,
+    if (int e = launch_composite_backward(P.raw, P.t, rb.dirs, P.g, R, P.s, c.noise_std, seed ^ P.salt,
                                           c.white_background, h->trans.as<float>(), h->dout.as<float>(), st, &h->launches)) return e;
     // sub-chunks of `waves` full waves of 128-point row blocks (148 SMs): bounds the activation workspace (~17 KB per point)
     const bool use_tc = c.precision != NM_PREC_FP32;
@@ -480,7 +494,7 @@ int nm_set_tree(NmHandle h, const float* voxels_host, int32_t V) {
 
 int nm_point_mlp(NmHandle h, int which, const float* pts_dev, const float* dirs_dev, int64_t M, float* out_dev,
                  int sigma_only, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   NM_CHECK(which == NM_NET_COARSE || (which == NM_NET_FINE && h->has_fine), "network slot %d not present", which);
   NM_CHECK(pts_dev && out_dev && M >= 0, "bad arguments");
   MlpInput in{};
@@ -491,7 +505,7 @@ int nm_point_mlp(NmHandle h, int which, const float* pts_dev, const float* dirs_
 int nm_render_rays(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
                    const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
                    const NmRenderOut* out_dev, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   NM_CHECK(out_dev, "null output block");
   return render_rays_impl(h, origins_dev, o_stride, dirs_dev, R, near_far_host, near_dev, far_dev, flags, seed, *out_dev,
                           (cudaStream_t)stream);
@@ -511,7 +525,7 @@ int nm_ray_bundle(NmHandle h, const float* pose_host, int H, int W, float focal,
 
 int nm_render_image(NmHandle h, const float* pose_host, int H, int W, float focal, int ndc, int row0, int row1,
                     const float* near_far_host, int flags, uint64_t seed, const NmRenderOut* out_dev, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   NM_CHECK(out_dev && pose_host && near_far_host, "null argument");
   const long long R = (long long)(row1 - row0) * W;
   cudaStream_t st = (cudaStream_t)stream;
@@ -543,7 +557,7 @@ int nm_zero_grad(NmHandle h, void* stream) {
 int nm_backward_rays(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
                      const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
                      const float* d_rgb_dev, const float* d_coarse_rgb_dev, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   return train_impl(h, origins_dev, o_stride, dirs_dev, R, near_far_host, near_dev, far_dev, flags, seed, d_rgb_dev,
                     d_coarse_rgb_dev, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -551,7 +565,7 @@ int nm_backward_rays(NmHandle h, const float* origins_dev, int o_stride, const f
 int nm_loss_backward(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
                      const float* near_far_host, const float* near_dev, const float* far_dev, int flags, uint64_t seed,
                      const float* target_rgb_dev, float* loss_dev, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   NM_CHECK(target_rgb_dev, "null target");
   return train_impl(h, origins_dev, o_stride, dirs_dev, R, near_far_host, near_dev, far_dev, flags, seed, nullptr, nullptr,
                     target_rgb_dev, loss_dev, (cudaStream_t)stream);
@@ -606,7 +620,7 @@ int nm_debug_gemm(NmHandle h, const float* a_dev, const float* b_dev, int M, int
 // ---------------------------------------------------------------------------------------------- BuFF tree maintenance
 int nm_ray_voxel_indices(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
                          const float* near_far_host, float* z_out_dev, int32_t* idx_out_dev, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   NM_CHECK(origins_dev && dirs_dev && near_far_host && idx_out_dev, "null argument");
   NM_CHECK(o_stride == 0 || o_stride == 3, "o_stride must be 0 or 3");
   NM_CHECK(h->V > 0, "no voxel list (nm_set_tree)");
@@ -625,7 +639,7 @@ int nm_ray_voxel_indices(NmHandle h, const float* origins_dev, int o_stride, con
 
 int nm_tree_integrate(NmHandle h, const int32_t* idx_dev, const float* weights_dev, const float* mask_weights_dev, int64_t n,
                       float* memm_dev, int32_t V, int32_t counter, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   NM_CHECK(idx_dev && weights_dev && mask_weights_dev && memm_dev && V > 0 && n >= 0, "bad arguments");
   if (int e = h->small.ensure(sizeof(float) * 2 * (size_t)V + 64)) return e;
   return launch_tree_integrate(idx_dev, weights_dev, mask_weights_dev, n, memm_dev, V, counter, h->small.as<float>(),
@@ -634,7 +648,7 @@ int nm_tree_integrate(NmHandle h, const int32_t* idx_dev, const float* weights_d
 
 int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, const float* lin2_host, int n0, int n1,
                   int n2, int x0, int x1, float* sigma_dev, float* rgb_dev, void* stream) {
-  if (int e = bind_device(h)) return e;
+  if (int e = bind_checked(h)) return e;
   NM_CHECK(lin0_host && lin1_host && lin2_host && sigma_dev, "null argument");
   NM_CHECK(0 <= x0 && x0 <= x1 && x1 <= n0 && n1 > 0 && n2 > 0, "bad slab range");
   const int which = h->has_fine ? NM_NET_FINE : NM_NET_COARSE;     // BaseModel.get_model(): finest net
@@ -740,6 +754,21 @@ int nm_debug_pack(const NmNetDesc* desc, int n_tensors, const char* const* names
   WeightSource src;
   src.n = n_tensors; src.names = names; src.ptrs = tensors_host; src.numel = numel;
   return debug_pack(*desc, src, sigma_only != 0, reinterpret_cast<NetProgram*>(program_out), pack_out, pack_cap, pack_need);
+}
+
+int nm_check_flags(NmHandle h, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return check_kernel_flags(h);
+}
+
+int nm_ndc_rays(NmHandle h, int H, int W, float focal, float near, const float* origins_dev, int o_stride,
+                const float* dirs_dev, int64_t n, float* origins_out_dev, float* dirs_out_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(origins_dev && dirs_dev && origins_out_dev && dirs_out_dev && n >= 0, "bad arguments");
+  NM_CHECK(o_stride == 0 || o_stride == 3, "o_stride must be 0 or 3");
+  return launch_ndc(H, W, focal, near, origins_dev, o_stride, dirs_dev, n, origins_out_dev, dirs_out_dev, (cudaStream_t)stream,
+                    &h->launches);
 }
 
 int nm_kernel_flags(NmHandle h, int32_t* out2) {

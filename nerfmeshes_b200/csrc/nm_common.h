@@ -121,6 +121,8 @@ struct RayGenArgs {
   int row0, row1;
 };
 int launch_raygen(const RayGenArgs& a, float* origins_or_null, float* dirs, cudaStream_t st, int64_t* launches);
+int launch_ndc(int H, int W, float focal, float near, const float* origins, int o_stride, const float* dirs, long long n,
+               float* out_o, float* out_d, cudaStream_t st, int64_t* launches);
 int launch_stratified(const float* s_table, int Nc, long long R, const float* near_far2, const float* near_dev,
                       const float* far_dev, int lindisp, int perturb, uint64_t seed, float* t_out, cudaStream_t st,
                       int64_t* launches);

@@ -34,6 +34,29 @@ struct RayGenDev {
   int row0;
   long long n;
 };
+// ndc_rays body (src/nerf/nerf_helpers.py:283-305), op for op: shift the origin to the near plane, then project.
+__device__ __forceinline__ void ndc_warp(float near, float sx, float sy, float two_near, float o[3], float d[3]) {
+  const float t = -(near + o[2]) / d[2];
+  o[0] = o[0] + t * d[0]; o[1] = o[1] + t * d[1]; o[2] = o[2] + t * d[2];
+  const float o0 = sx * o[0] / o[2], o1 = sy * o[1] / o[2], o2 = 1.0f + two_near / o[2];
+  const float d0 = sx * (d[0] / d[2] - o[0] / o[2]);
+  const float d1 = sy * (d[1] / d[2] - o[1] / o[2]);
+  const float d2 = -two_near / o[2];
+  o[0] = o0; o[1] = o1; o[2] = o2;
+  d[0] = d0; d[1] = d1; d[2] = d2;
+}
+// ndc_rays on caller-supplied rays (the positional call of DataBundle.ndc, src/data/data_helpers.py:164-167).
+__global__ void ndc_kernel(float near, float sx, float sy, float two_near, const float* __restrict__ origins, int o_stride,
+                           const float* __restrict__ dirs, long long n, float* __restrict__ out_o, float* __restrict__ out_d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float o[3], d[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { o[j] = origins[(long long)o_stride * i + j]; d[j] = dirs[3 * i + j]; }
+  ndc_warp(near, sx, sy, two_near, o, d);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { out_o[3 * i + j] = o[j]; out_d[3 * i + j] = d[j]; }
+}
 __global__ void raygen_kernel(const __grid_constant__ RayGenDev a, float* __restrict__ origins, float* __restrict__ dirs) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
@@ -49,16 +72,7 @@ __global__ void raygen_kernel(const __grid_constant__ RayGenDev a, float* __rest
     d[j] = (x * a.pose[4 * j + 0] + y * a.pose[4 * j + 1]) + z * a.pose[4 * j + 2];
     o[j] = a.pose[4 * j + 3];
   }
-  if (a.ndc) {
-    const float t = -(a.ndc_near + o[2]) / d[2];
-    o[0] = o[0] + t * d[0]; o[1] = o[1] + t * d[1]; o[2] = o[2] + t * d[2];
-    const float o0 = a.sx * o[0] / o[2], o1 = a.sy * o[1] / o[2], o2 = 1.0f + a.two_near / o[2];
-    const float d0 = a.sx * (d[0] / d[2] - o[0] / o[2]);
-    const float d1 = a.sy * (d[1] / d[2] - o[1] / o[2]);
-    const float d2 = -a.two_near / o[2];
-    o[0] = o0; o[1] = o1; o[2] = o2;
-    d[0] = d0; d[1] = d1; d[2] = d2;
-  }
+  if (a.ndc) ndc_warp(a.ndc_near, a.sx, a.sy, a.two_near, o, d);
   dirs[3 * i + 0] = d[0]; dirs[3 * i + 1] = d[1]; dirs[3 * i + 2] = d[2];
   if (origins) { origins[3 * i + 0] = o[0]; origins[3 * i + 1] = o[1]; origins[3 * i + 2] = o[2]; }
 }
@@ -443,6 +457,18 @@ int launch_raygen(const RayGenArgs& a, float* origins, float* dirs, cudaStream_t
   d.n = (long long)(a.row1 - a.row0) * a.W;
   if (d.n <= 0) return 0;
   raygen_kernel<<<(unsigned)((d.n + 255) / 256), 256, 0, st>>>(d, origins, dirs);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  return 0;
+}
+
+int launch_ndc(int H, int W, float focal, float near, const float* origins, int o_stride, const float* dirs, long long n,
+               float* out_o, float* out_d, cudaStream_t st, int64_t* launches) {
+  if (n <= 0) return 0;
+  const float sx = (float)(-1.0 / ((double)W / (2.0 * (double)focal)));
+  const float sy = (float)(-1.0 / ((double)H / (2.0 * (double)focal)));
+  ndc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(near, sx, sy, (float)(2.0 * (double)near), origins, o_stride, dirs, n,
+                                                          out_o, out_d);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   return 0;

@@ -332,6 +332,27 @@ class Engine:
             origins = torch.from_numpy(p[:, 3].copy()).to(self.device)
         return origins, dirs
 
+    def ndc_rays(self, H, W, focal, near, rays_o, rays_d):
+        """ndc_rays(H, W, focal, near, rays_o, rays_d) on caller-supplied rays (src/nerf/nerf_helpers.py:280-307)."""
+        d = _f32c(rays_d, self.device)
+        shape = d.shape
+        d = d.reshape(-1, 3)
+        o = _f32c(rays_o, self.device)
+        if o.numel() == 3:
+            o, o_stride = o.reshape(3), 0
+        else:
+            o = o.expand(shape).reshape(-1, 3).contiguous()
+            o_stride = 3
+        oo, dd = torch.empty_like(d), torch.empty_like(d)
+        L.check(self.lib.nm_ndc_rays(self._h, int(H), int(W), float(focal), float(near), _ptr(o), o_stride, _ptr(d), d.shape[0],
+                                     _ptr(oo), _ptr(dd), self._stream()))
+        return oo.reshape(shape), dd.reshape(shape)
+
+    def check_flags(self):
+        """Synchronise the current stream and raise if a kernel of this handle flagged an error (AABB hit-list overflow,
+        tcgen05 watchdog)."""
+        L.check(self.lib.nm_check_flags(self._h, self._stream()))
+
     def grid_sigma(self, lins, x0=0, x1=None, with_rgb=False):
         """extract_radiance for planes [x0,x1): lins = three 1-D fp32 tensors (torch.linspace values)."""
         ls = [np.ascontiguousarray(torch.as_tensor(t).detach().cpu().numpy(), dtype=np.float32) for t in lins]

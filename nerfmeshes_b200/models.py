@@ -153,7 +153,7 @@ class BaseModel(torch.nn.Module):
         self.volume_renderer = vr
         self._eng: Optional[Engine] = None
         self._synced = {}
-        self._cuda_index = 0
+        self._cuda_index = None
 
     # ------------------------------------------------------------------ engine plumbing
     def _nets(self):
@@ -173,12 +173,29 @@ class BaseModel(torch.nn.Module):
                 self._cuda_index = torch.device(a).index
         return super().to(*args, **kwargs)
 
+    def _device_index(self) -> int:
+        """The CUDA device the parameters live on (so `torch.cuda.set_device(rank); model.cuda()` lands on `rank`);
+        CPU-resident parameters (host-buffer callers) fall back to an explicit cuda(i)/to('cuda:i'), then the current device."""
+        p = next(self.parameters(), None)
+        if p is not None and p.is_cuda:
+            return p.device.index if p.device.index is not None else torch.cuda.current_device()
+        if self._cuda_index is not None:
+            return self._cuda_index
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
     def _engine(self) -> Engine:
         nets = self._nets()
+        dev = self._device_index()
+        if self._eng is not None and self._eng.device.index != dev:
+            # the module moved to another GPU after its handle was created: rebuild there (packed weights, tables, tree)
+            self._eng.close()
+            self._eng, self._synced = None, {}
+            if hasattr(self, "_tree_version"):
+                self._tree_version = None
         if self._eng is None:
             coarse = nets[0].arch
             fine = nets[1].arch if len(nets) > 1 and nets[1] is not None else None
-            self._eng = Engine(coarse, fine, self._render_settings(), device=self._cuda_index)
+            self._eng = Engine(coarse, fine, self._render_settings(), device=dev)
             self._after_engine_created()
         for which, net in enumerate(nets):
             if net is None:
@@ -386,7 +403,7 @@ class BuFFModel(BaseModel):
         self.sampler = _Holder()
         self.sampler.count = int(self.cfg.nerf.train.num_coarse)
         self.sampler.point_intervals = torch.linspace(0.0, 1.0, self.sampler.count)[None, :]
-        self._tree_id = None
+        self._tree_version = None
 
     def _nets(self):
         return [self.model]
@@ -408,9 +425,10 @@ class BuFFModel(BaseModel):
 
     def _sync_tree(self, eng):
         self.tree.engine = eng
-        if self._tree_id != id(self.tree.voxels):
+        key = (self.tree.version, tuple(self.tree.voxels.shape))
+        if self._tree_version != key:
             eng.set_tree(self.tree.voxels)
-            self._tree_id = id(self.tree.voxels)
+            self._tree_version = key
 
     def forward(self, x, seed=None):
         ray_origins, ray_directions, near, far = self._unpack(x)
@@ -426,6 +444,7 @@ class BuFFModel(BaseModel):
             step_gate = int(_cfg_get(self.cfg, "tree.step_size_integration_offset", 0) or 0)
             if self.global_step >= step_gate:
                 idx = eng.ray_voxel_indices(ray_origins, ray_directions, near, far)
+                eng.check_flags()      # a truncated hit list (> 512 voxels on a ray) must not reach the tree statistics
                 self.tree.ray_batch_integration(self.global_step, idx, o["weights"], o["mask_weights"])
         o["rgb"], _ = self._attach_grad((ray_origins, ray_directions, near, far), seed, True, o["rgb"])
         b = OutputBundle(o["rgb"], o["depth"], o["weights"], o["mask_weights"], o["acc"], o["disp"], o["depth_raw"])

@@ -29,10 +29,16 @@ def get_ray_bundle(height: int, width: int, focal_length: float, tform_cam2world
 
 
 def ndc_rays(H, W, focal, near, rays_o=None, rays_d=None, tform_cam2world=None):
-    """src/nerf/nerf_helpers.py:280-307.  The fused entry point regenerates the pinhole rays from the pose (the
-    reference's only caller, src/data/data_helpers.py:164-167, feeds it get_ray_bundle's output)."""
+    """src/nerf/nerf_helpers.py:280-307.  Called like the reference — ndc_rays(H, W, focal, near, rays_o, rays_d), the
+    positional form of DataBundle.ndc (src/data/data_helpers.py:164-167) — the given rays are warped on the device and come
+    back on the device of `rays_d` (CPU tensors in, CPU tensors out).  With `tform_cam2world=` instead of rays, the pinhole
+    rays are generated and warped in one kernel (the fused fast path nm_render_image uses)."""
+    if rays_o is not None and rays_d is not None:
+        rays_d = torch.as_tensor(rays_d)
+        o, d = _engine().ndc_rays(H, W, float(focal), float(near), torch.as_tensor(rays_o), rays_d)
+        return (o, d) if rays_d.is_cuda else (o.cpu(), d.cpu())
     if tform_cam2world is None:
-        raise ValueError("ndc_rays on the fused path takes the camera pose (tform_cam2world=...)")
+        raise ValueError("ndc_rays needs (rays_o, rays_d) or tform_cam2world=")
     return _engine().ray_bundle(tform_cam2world, H, W, float(focal), ndc=True, ndc_near=float(near))
 
 

@@ -62,6 +62,7 @@ class TreeSampling:
         self.root = Node(config, bounds, 0)
         self.root.subdivide()
         self.voxels, self.memm, self.counter = None, None, 1
+        self.version = 0                       # bumped whenever `voxels` is replaced (BuFFModel re-uploads the list on change)
         self.engine = None                     # set by BuFFModel: the handle whose kernels run the integration
         self.consolidate()
 
@@ -70,6 +71,11 @@ class TreeSampling:
         self.voxels = torch.as_tensor(voxels).float().to(self.device)
         self.memm = torch.zeros(self.voxels.shape[0], device=self.device)
         self.counter = 1
+        self.version += 1
+
+    def touch(self):
+        """Call after editing `voxels` in place."""
+        self.version += 1
 
     # ------------------------------------------------------------------ schedule
     def ticked(self, step):
@@ -106,6 +112,7 @@ class TreeSampling:
         self.voxels = torch.stack([torch.stack(tuple(n.bounds), 0) for n in self.root.children], 0).to(self.device)
         self.memm = torch.zeros(self.voxels.shape[0], device=self.device)
         self.counter = 1
+        self.version = getattr(self, "version", 0) + 1
 
     # ------------------------------------------------------------------ per-step weight accumulation (tree.py:177-206)
     def ray_batch_integration(self, step, ray_voxel_indices, ray_batch_weights, ray_batch_weights_mask):
@@ -147,3 +154,4 @@ class TreeSampling:
         self.voxels = d["voxels"].float().to(self.device)
         self.memm = d["memm"].float().to(self.device) if d.get("memm") is not None else torch.zeros(self.voxels.shape[0], device=self.device)
         self.counter = d["counter"]
+        self.version = getattr(self, "version", 0) + 1
