@@ -155,12 +155,22 @@ class Engine:
         s = self.settings
         return s.num_coarse + (s.num_fine if (self.has_fine and not buff) else 0)
 
-    def _alloc_out(self, R, S, device, want, pin=False):
-        sizes = dict(rgb=(R, 3), depth=(R,), depth_raw=(R,), acc=(R,), disp=(R,), weights=(R, S), mask_weights=(R, S),
-                     t_vals=(R, S), coarse_rgb=(R, 3), coarse_acc=(R,), coarse_disp=(R,),
-                     coarse_weights=(R, self.settings.num_coarse))
+    def out_sizes(self, R, S):
+        return dict(rgb=(R, 3), depth=(R,), depth_raw=(R,), acc=(R,), disp=(R,), weights=(R, S), mask_weights=(R, S),
+                    t_vals=(R, S), coarse_rgb=(R, 3), coarse_acc=(R,), coarse_disp=(R,),
+                    coarse_weights=(R, self.settings.num_coarse))
+
+    def _alloc_out(self, R, S, device, want, pin=False, into=None):
+        """Output tensors + the NmRenderOut pointer block.  `into`: caller-owned contiguous fp32 tensors (e.g. views of
+        one gather buffer) used instead of fresh allocations."""
+        sizes = self.out_sizes(R, S)
         outs = {}
         for k in want:
+            if into is not None and k in into:
+                t = into[k]
+                assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == int(np.prod(sizes[k])) and t.device == device
+                outs[k] = t
+                continue
             t = torch.empty(sizes[k], dtype=torch.float32, device=device)
             if pin and device.type == "cpu":
                 t = t.pin_memory()
@@ -171,7 +181,7 @@ class Engine:
     DEFAULT_OUT = ("rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights")
 
     def render_rays(self, origins, dirs, near, far, *, training=False, buff=False, seed=0, want=None,
-                    teacher_t: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                    teacher_t: Optional[torch.Tensor] = None, out=None) -> Dict[str, torch.Tensor]:
         """NeRFModel.forward / BuFFModel.forward on a ray batch.  origins (3,), (1,3) or (R,3); dirs (R,3);
         near/far python floats / 0-dim tensors, or (R,) tensors (CUDA path only)."""
         want = tuple(want or self.DEFAULT_OUT)
@@ -201,7 +211,7 @@ class Engine:
         if teacher_t is not None:
             flags |= L.FLAG_TEACHER_T
             want = tuple(k for k in want if k != "t_vals")
-        outs, block = self._alloc_out(R, S, dev, want)
+        outs, block = self._alloc_out(R, S, dev, want, into=out)
         if teacher_t is not None:
             tt = _f32c(teacher_t, d.device)
             assert tt.shape == (R, S) and not host
@@ -298,7 +308,7 @@ class Engine:
         return d
 
     def render_image(self, pose, H, W, focal, near, far, *, ndc=False, rows=None, training=False, buff=False, seed=0,
-                     want=None, to_host=False, host_out=None) -> Dict[str, torch.Tensor]:
+                     want=None, to_host=False, host_out=None, out=None) -> Dict[str, torch.Tensor]:
         """Rays generated on the device from a 3x4 / 4x4 camera-to-world pose (get_ray_bundle [+ ndc_rays])."""
         want = tuple(want or ("rgb", "depth", "acc", "disp"))
         row0, row1 = rows if rows is not None else (0, H)
@@ -316,7 +326,7 @@ class Engine:
             L.check(self.lib.nm_render_image_host(self._h, p.ctypes.data, H, W, float(focal), int(ndc), row0, row1, nf,
                                                   flags, seed, C.byref(block)))
         else:
-            outs, block = self._alloc_out(R, S, self.device, want)
+            outs, block = self._alloc_out(R, S, self.device, want, into=out)
             L.check(self.lib.nm_render_image(self._h, p.ctypes.data, H, W, float(focal), int(ndc), row0, row1, nf, flags,
                                              seed, C.byref(block), self._stream()))
         return outs

@@ -97,31 +97,130 @@ def allreduce_gradients(params, group=None, average=True):
     return int(flat.numel())
 
 
-def render_image_sharded(model, pose, H, W, focal, near, far, *, ndc=False, want=("rgb", "depth", "acc", "disp"), group=None):
-    """eval_nerf.py's image loop on N GPUs: this rank renders its rows, then one all_gather assembles the image."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    r0, r1 = row_shard(H, rank, world)
-    local = model._engine().render_image(pose, H, W, focal, near, far, ndc=ndc, rows=(r0, r1), want=list(want))
-    return gather_rows(local, group)
+class RowExchange:
+    """The exchange step of a row-sharded image: one flat buffer per rank, laid out map after map
+    ([rgb | depth | acc | disp], every segment padded to the largest shard), which the render kernels fill through
+    `views`, and ONE `all_gather_into_tensor` (NCCL over NVLink) that leaves every full map on every rank."""
+    MAPS = ("rgb", "depth", "depth_raw", "acc", "disp", "coarse_rgb", "coarse_acc", "coarse_disp")
+
+    def __init__(self, device, H, W, want=("rgb", "depth", "acc", "disp"), group=None):
+        self.group, self.H, self.W, self.want = group, H, W, tuple(want)
+        assert all(k in self.MAPS for k in self.want), "only per-ray maps can be exchanged"
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.r0, self.r1 = row_shard(H, self.rank, self.world)
+        self.widths = {k: (3 if k.endswith("rgb") else 1) for k in self.want}
+        self.rmax = (H + self.world - 1) // self.world * W            # rays of the largest shard
+        C = sum(self.widths.values())
+        self.local = torch.empty(C * self.rmax, dtype=torch.float32, device=device)
+        self.full = torch.empty(self.world * C * self.rmax, dtype=torch.float32, device=device)
+        R, off = (self.r1 - self.r0) * W, 0
+        self.views = {}
+        for k in self.want:
+            w = self.widths[k]
+            self.views[k] = self.local[off:off + w * R].view((R, 3) if w == 3 else (R,))
+            off += w * self.rmax
+
+    def gather(self):
+        dist.all_gather_into_tensor(self.full, self.local, group=self.group)
+        full = self.full.view(self.world, -1)
+        out, off = {}, 0
+        n = self.H * self.W
+        for k in self.want:
+            w = self.widths[k]
+            if self.H % self.world == 0:
+                seg = full[:, off:off + w * self.rmax].reshape((n, 3) if w == 3 else (n,))
+            else:
+                spans = [row_shard(self.H, r, self.world) for r in range(self.world)]
+                parts = [full[r, off:off + w * (b - a) * self.W] for r, (a, b) in enumerate(spans)]
+                seg = torch.cat(parts).view((n, 3) if w == 3 else (n,))
+            out[k] = seg
+            off += w * self.rmax
+        return out
 
 
-def extract_geometry_sharded(model, args, group=None):
+_EXCHANGES = {}
+
+
+def row_exchange(device, H, W, want, group=None) -> RowExchange:
+    key = (str(device), H, W, tuple(want), id(group))
+    if key not in _EXCHANGES:
+        _EXCHANGES.clear()
+        _EXCHANGES[key] = RowExchange(device, H, W, want, group)
+    return _EXCHANGES[key]
+
+
+def render_image_sharded(model, pose, H, W, focal, near, far, *, ndc=False, buff=False, want=("rgb", "depth", "acc", "disp"),
+                         group=None, seed=0):
+    """eval_nerf.py's image loop on N GPUs: this rank renders image rows [r0, r1) — rays generated on the device
+    from the pose, kernels writing straight into this rank's segment of the exchange buffer — then ONE all_gather assembles
+    every output map on every rank.  No arithmetic crosses a shard boundary, so the assembled maps are bit-identical to
+    the single-GPU image."""
+    eng = model._engine()
+    if buff:
+        model._sync_tree(eng)
+    ex = row_exchange(eng.device, H, W, want, group)
+    eng.render_image(pose, H, W, focal, near, far, ndc=ndc, rows=(ex.r0, ex.r1), buff=buff, seed=seed, want=list(ex.want),
+                     out=ex.views)
+    return ex.gather()
+
+
+def _rank_world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class _StageTimer:
+    """CUDA-event stage timing on the current stream (filled into a caller-supplied dict as `<stage>_ms`)."""
+
+    def __init__(self, sink):
+        self.sink, self.marks = sink, []
+
+    def mark(self, name=None):
+        if self.sink is None:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.marks.append((name, e))
+
+    def finish(self):
+        if self.sink is None:
+            return
+        torch.cuda.current_stream().synchronize()
+        for (_, a), (name, b) in zip(self.marks, self.marks[1:]):
+            self.sink[name + "_ms"] = self.sink.get(name + "_ms", 0.0) + a.elapsed_time(b)
+
+
+def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None):
     """mesh_nerf.extract_geometry on N GPUs: slab sigma sweep -> global iso statistics -> per-slab marching cubes ->
-    all_gather of the slab meshes.  Returns (vertices, triangles, normals) like the single-GPU function (vertices
-    rescaled to (-limit, limit)); the density grid stays sharded."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    all_gather of the slab meshes.  Returns (vertices, triangles, normals, iso) like the single-GPU function (vertices
+    rescaled to (-limit, limit)); the density grid stays sharded.  Works without a process group (one slab)."""
+    rank, world = _rank_world(group)
     eng = model._engine()
     res = args.res
+    tm = _StageTimer(timings)
     tiles = [torch.linspace(-args.limit, args.limit, res) for _ in range(3)]
     x0, x1 = slab_shard(res, rank, world)
+    tm.mark()
     sigma = eng.grid_sigma(tiles, x0, x1)
+    tm.mark("sweep")
     own = sigma if rank == world - 1 else sigma[:-1]          # the shared plane is counted once
-    mn, mx, _ = eng.volume_stats(own)
-    s = float(own.double().sum())
-    smin, smax, sstd = global_stats(mn, mx, s, lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), sigma.device, group)
     import numpy as np
+    if world > 1:
+        mn, mx, _ = eng.volume_stats(own)
+        s = float(own.double().sum())
+        smin, smax, sstd = global_stats(mn, mx, s, lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), sigma.device, group)
+    else:
+        smin, smax, sstd = eng.volume_stats(own)
     iso = min(max(args.iso_level, np.float32(smin) + np.float32(sstd)), np.float32(smax) - np.float32(sstd))
+    tm.mark("stats")
     v, f, n = eng.marching_cubes(sigma, float(iso), x_off=float(x0))
-    V, F, N = gather_mesh(v, f, n, group)
-    vertices = args.limit * (V.cpu() / (res / 2.0) - 1.0)
-    return vertices, F.cpu(), N.cpu(), float(iso)
+    tm.mark("mc")
+    if world > 1:
+        v, f, n = gather_mesh(v, f, n, group)
+    tm.mark("gather")
+    tm.finish()
+    if to_host:
+        v = args.limit * (v.cpu() / (res / 2.0) - 1.0)
+        return v, f.cpu(), n.cpu(), float(iso)
+    return v, f, n, float(iso)
