@@ -149,15 +149,27 @@ int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, co
  * {min, max, std}; synchronises. */
 int nm_volume_stats(NmHandle h, const float* vol_dev, int64_t n, float* out_host);
 
-/* skimage.measure.marching_cubes(volume, level) seam (src/mesh_nerf.py:79) on a device volume (nx,ny,nz) fp32:
- * classify -> scan -> emit.  Two-call protocol: nm_marching_cubes_count fills counts_host = {n_vertices,
- * n_triangles} (synchronises); nm_marching_cubes_emit writes verts (n_vertices,3) fp32 in index coordinates
- * (x offset x_off added, for slab sharding), normals (n_vertices,3), faces (n_triangles,3) int32.  Vertices are
- * unique per crossed grid edge (indexed mesh, like the Lewiner output). */
+/* skimage.measure.marching_cubes(volume, level) seam (src/mesh_nerf.py:79) on a device volume (nx,ny,nz) fp32, Lewiner-style
+ * topology resolution (face / interior tests, cell-centre vertices): sign bit-volume -> count -> scan -> emit.  Two-call
+ * protocol: nm_marching_cubes_count fills counts_host = {n_vertices, n_triangles} (synchronises);
+ * nm_marching_cubes_emit (same volume and iso) writes verts (n_vertices,3) fp32 in index coordinates (x_off, an integer,
+ * added to axis 0), normals (n_vertices,3), faces (n_triangles,3) int32.  Indexed mesh: one vertex per crossed grid edge
+ * plus the centre vertices, ordered by owning grid point. */
 int nm_marching_cubes_count(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso,
                             int64_t* counts_host, void* stream);
 int nm_marching_cubes_emit(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, float x_off,
                            float* verts_dev, float* normals_dev, int32_t* faces_dev, void* stream);
+/* The same for ONE SHARD of a grid split along axis 0 (mesh_nerf.py:27-92 on N GPUs): the buffer holds global
+ * planes [g_x0, g_x0+nb) of a grid with g_nx planes and the call owns the grid points of buffer planes [p_lo,p_hi): it
+ * emits their vertices and the triangles of their cells.  The buffer must also hold, where they exist globally, plane
+ * p_hi (cells of the last owned layer), p_hi+1 and p_lo-1 (gradient normals): halo planes, received from the neighbours or
+ * recomputed.  Face indices are v_base + local id, and ids of plane-p_hi vertices (owned by the next shard) continue the
+ * local numbering; with v_base = the exclusive scan of the shards' n_vertices, the concatenated shard outputs ARE the
+ * single-GPU arrays, bit for bit (no duplicate vertices, nothing to de-duplicate). */
+int nm_mc_count(NmHandle h, const float* vol_dev, int nb, int ny, int nz, float iso, int g_x0, int g_nx, int p_lo, int p_hi,
+                int64_t* counts_host, void* stream);
+int nm_mc_emit(NmHandle h, const float* vol_dev, int nb, int ny, int nz, float iso, int g_x0, int g_nx, int p_lo, int p_hi,
+               int64_t v_base, float* verts_dev, float* normals_dev, int32_t* faces_dev, void* stream);
 
 /* Replaces export_obj (src/nerf/nerf_helpers.py:86-111): `v x y z [r g b]`, `vn x y z`, `f i//i j//j k//k` (1-based) with
  * byte-identical number formatting (python repr of the float32 widened to double).  Host arrays, no GPU involved;

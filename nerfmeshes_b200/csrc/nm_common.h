@@ -161,9 +161,16 @@ int launch_composite_backward(const float* raw, const float* t, const float* dir
                               cudaStream_t st, int64_t* launches);
 int launch_mse_grad(const float* rgb, const float* target, long long n, long long count, float* d_rgb, float* loss,
                     cudaStream_t st, int64_t* launches);
-int mc_count(const float* vol, int nx, int ny, int nz, float iso, void** ws, size_t* ws_bytes, int64_t* counts_host,
-             cudaStream_t st, int64_t* launches);
-int mc_emit(const float* vol, int nx, int ny, int nz, float iso, float x_off, void* ws, float* verts, float* normals,
-            int32_t* faces, cudaStream_t st, int64_t* launches);
+// marching cubes (nm_mc.cu): one shard of a global grid — buffer planes [0,nb) are global planes [g_x0, g_x0+nb) of g_nx;
+// the call owns the points (vertices, cells) of buffer planes [p_lo,p_hi)
+struct McShard {
+  const float* vol;
+  int nb, ny, nz;
+  float iso;
+  int g_x0, g_nx, p_lo, p_hi;
+};
+int mc_count(const McShard& s, void** ws, size_t* ws_bytes, int64_t* counts_host, cudaStream_t st, int64_t* launches);
+int mc_emit(const McShard& s, void* ws, size_t ws_bytes, long long v_base, float* verts, float* normals, int32_t* faces,
+            cudaStream_t st, int64_t* launches);
 
 }  // namespace nm

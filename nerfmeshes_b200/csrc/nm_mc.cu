@@ -1,19 +1,33 @@
 // Marching cubes on a device-resident fp32 volume — the skimage.measure.marching_cubes(volume, level) seam of
-// src/mesh_nerf.py:79 (a15).  HBM-bound integer/byte work: classify -> scan -> emit, one pass over the 4*N-byte
-// volume per stage, everything else is byte-sized side arrays.
+// src/mesh_nerf.py:79 (a15), Lewiner-style (MC33) topology resolution.  HBM-bound byte / bit work:
 //
-// Output contract (mirrors the Lewiner output the reference consumes at mesh_nerf.py:79-90): an INDEXED mesh with one
-// vertex per crossed grid edge, vertices (V,3) fp32 in index coordinates (axis0, axis1, axis2), faces (F,3) int32,
-// normals (V,3) unit vectors pointing towards decreasing values (the reference shoots colouring rays along -normal).
-// Canonical order: vertices by owning grid point (flat index (i*ny + j)*nz + k), then axis; triangles by cell, then
-// table order — identical to oracle/mc_oracle.c, so the two can be compared array-for-array, bit-for-bit.
+//   1. mc_sign_kernel    ONE streaming pass over the 4*N-byte volume -> a sign BIT-volume (1 bit per grid point, N/8 bytes:
+//                        16.7 MB at 512^3, L2-resident).  This is the only pass that reads the whole volume.
+//   2. mc_count_kernel   one thread per 32-point word of a grid line: crossed edges (X, Y, Z) and active cells fall out of
+//                        XORs / shifts of four neighbouring sign words; only active cells (~1 %) are visited one by one, and
+//                        only topologically ambiguous ones read their 8 corner values (face tests, interior test).  Writes
+//                        per word: the X/Y/Z/C bit words, vertex + triangle counts; per block: the count sums.
+//   3. mc_scan_blocks / mc_scan_words   two-level exclusive scan of the counts (per-word vertex / triangle prefixes).
+//   4. mc_emit_vertices / mc_emit_triangles   one thread per word again; a vertex id anywhere in the grid is
+//                        prefix[word] + popcount(bits below) — no dense per-point id array.
 //
-// Parity status: scikit-image 0.17.2 (the reference's pinned dependency) is not installed anywhere we can run, and
-// the reference has no test at this seam: PARITY UNPINNED.  What is reproduced from the published
-// algorithm: one vertex per sign-crossing edge, placed at the 1/(FLT_EPSILON + |v - iso|)-weighted mean of the edge's
-// end points evaluated in double precision and stored as float32.  Lewiner's extra cell-centre vertices (some
-// ambiguous sub-cases) are not generated; triangulation is the 256-case table derived in tools/gen_mc_tables.py.
+// Output contract (mirrors the Lewiner output the reference consumes at mesh_nerf.py:79-90): an INDEXED mesh, one vertex
+// per crossed grid edge plus Lewiner's cell-centre vertices, vertices (V,3) fp32 in index coordinates (axis0, axis1, axis2),
+// faces (F,3) int32, normals (V,3) unit vectors pointing towards decreasing values.  Canonical order: vertices by owning
+// grid point (flat index (i*ny + j)*nz + k), then slot (axis-0/1/2 edge, centre); triangles by cell, then table order —
+// identical to oracle/mc_oracle.c, which derives everything procedurally (no shared table), so the two implementations
+// can be compared array for array, bit for bit.
+//
+// Sharding: the buffer holds global planes [g_x0, g_x0+nb); this call owns the points of buffer planes
+// [p_lo, p_hi).  Ids of the next plane's vertices (referenced by the last owned cell layer) continue this shard's
+// numbering, which is exactly what the next shard assigns from v_base + nv: concatenated shard outputs equal the
+// single-GPU arrays bit for bit, no duplicate vertices, no dedup pass.
+//
+// Parity status: scikit-image 0.17.2 is not installable here: PARITY UNPINNED.  What follows the published
+// algorithm and what cannot: oracle/mc_oracle.c header and DESIGN.md 4.3.  This TU is compiled with -fmad=false: the face /
+// interior tests and the vertex interpolation are evaluated in double with separate roundings, like the C oracle.
 #include <cfloat>
+#include <math_constants.h>
 
 #include "nm_common.h"
 #include "nm_mc_tables.h"
@@ -21,254 +35,485 @@
 namespace nm {
 namespace {
 
+struct L1Entry { unsigned short base; unsigned char nf, mu, lew_case; unsigned char faces[6]; };
+struct L2Entry { unsigned char itest, tif; unsigned short none, tunnel; };
+struct L3Entry { unsigned char ntri, uses_c; unsigned char idx[3 * NM_MC_MAX_TRI]; };
+
+__device__ const L1Entry g_l1[256] = NM_MC_L1;
+__device__ const L2Entry g_l2[NM_MC_N_L2] = NM_MC_L2;
+__device__ const L3Entry g_l3[NM_MC_N_L3] = NM_MC_L3;
 __constant__ unsigned char c_edge_lo[12] = NM_MC_EDGE_LO;
 __constant__ unsigned char c_edge_axis[12] = NM_MC_EDGE_AXIS;
-__constant__ unsigned char c_ntri[256] = NM_MC_NTRI;
-__constant__ unsigned char c_tri[256 * 15] = NM_MC_TRI;
+__constant__ unsigned char c_face_corners[6][4] = NM_MC_FACE_CORNERS;
+__constant__ unsigned char c_lew2my[8] = NM_MC_LEW2MY;
+__constant__ unsigned char c_itest_edge[12][8] = NM_MC_ITEST_EDGE;
 
-constexpr int kLineThreads = 128;
+constexpr int kBlock = 256;
+constexpr double kEps = (double)FLT_EPSILON;
 
-struct McWs {            // workspace header (device pointers into one allocation)
-  unsigned char* mask;   // per point: bit a set when the +axis-a edge owned by the point is crossed
-  unsigned char* cube;   // per point: 8-bit case of the cell whose low corner is the point (0 when not a cell)
-  unsigned int* vbase;   // per point: id of its first owned vertex
-  unsigned int* line_v;  // per (i,j) line: vertex count, then exclusive scan
-  unsigned int* line_t;  // per line: triangle count, then exclusive scan
-  unsigned long long* totals;  // [n_vertices, n_triangles]
-  int nx, ny, nz;
+struct McGrid {
+  const float* vol;
+  int nb, ny, nz, W;          // buffer planes, lines per plane, points per line, 32-bit words per line
+  int g_x0, g_nx;             // global index of buffer plane 0, planes of the global grid
+  int p_lo, p_hi, p_end;      // owned planes [p_lo,p_hi); [p_hi,p_end) = the shadow plane (ids only), 0 or 1 plane
+  float iso;
+  // workspace
+  unsigned* sign;             // [nb*ny*W]
+  uint4* bits;                // [(p_end-p_lo)*ny*W] X, Y, Z, C
+  unsigned* cnt;              // per word: vertices | triangles << 16
+  unsigned* vpre;             // per word: exclusive vertex prefix
+  unsigned* tpre;             // per word: exclusive triangle prefix
+  unsigned* blk;              // per block of kBlock words: {vertex sum, triangle sum} -> exclusive prefixes
+  unsigned long long* totals; // [n_vertices incl. shadow plane, n_triangles, n_vertices owned]
+  long long nwords;           // words of planes [p_lo,p_end)
+  long long nwords_own;       // words of planes [p_lo,p_hi)
 };
 
-__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* s_warp, unsigned* total) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned x = v;
+// ------------------------------------------------------------------------------------------------ 1. sign bit-volume
+__global__ void __launch_bounds__(kBlock) mc_sign_kernel(const float* __restrict__ vol, long long nlines, int nz, int W,
+                                                         float iso, unsigned* __restrict__ sign) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = nlines * W;
+  const long long warps = (long long)gridDim.x * (kBlock / 32);
+  long long word = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  constexpr int U = 8;
+  for (; word < nw; word += warps * U) {
+    float v[U];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) s_warp[wid] = x;
-  __syncthreads();
-  unsigned base = 0, tot = 0;
-  for (int w = 0; w < kLineThreads / 32; ++w) {
-    if (w < wid) base += s_warp[w];
-    tot += s_warp[w];
-  }
-  __syncthreads();
-  if (total) *total = tot;
-  return base + x - v;
-}
-
-// stage 1: classify.  One block per (i,j) line, threads stride over k (coalesced along the contiguous axis).
-__global__ void __launch_bounds__(kLineThreads) mc_classify(const float* __restrict__ vol, McWs ws, float iso) {
-  __shared__ unsigned s_warp[kLineThreads / 32];
-  const int nx = ws.nx, ny = ws.ny, nz = ws.nz;
-  const int line = blockIdx.x, i = line / ny, j = line % ny;
-  const size_t row = (size_t)line * nz;
-  const size_t sx = (size_t)ny * nz, sy = (size_t)nz;
-  unsigned nv = 0, nt = 0;
-  for (int k = threadIdx.x; k < nz; k += kLineThreads) {
-    const size_t p = row + k;
-    const bool in0 = vol[p] > iso;
-    const bool hx = i + 1 < nx, hy = j + 1 < ny, hz = k + 1 < nz;
-    unsigned m = 0;
-    if (hx && ((vol[p + sx] > iso) != in0)) m |= 1u;
-    if (hy && ((vol[p + sy] > iso) != in0)) m |= 2u;
-    if (hz && ((vol[p + 1] > iso) != in0)) m |= 4u;
-    unsigned cube = 0;
-    if (hx && hy && hz) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const size_t q = p + (c & 1) * sx + ((c >> 1) & 1) * sy + ((c >> 2) & 1);
-        cube |= (vol[q] > iso ? 1u : 0u) << c;
+    for (int u = 0; u < U; ++u) {
+      const long long wd = word + warps * u;
+      v[u] = -CUDART_INF_F;
+      if (wd < nw) {
+        const long long line = wd / W;
+        const int k = (int)(wd - line * W) * 32 + lane;
+        if (k < nz) v[u] = __ldcs(vol + line * nz + k);
       }
-      nt += c_ntri[cube];
     }
-    ws.mask[p] = (unsigned char)m;
-    ws.cube[p] = (unsigned char)cube;
-    nv += __popc(m);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long wd = word + warps * u;
+      const unsigned b = __ballot_sync(0xffffffffu, v[u] > iso);
+      if (lane == 0 && wd < nw) sign[wd] = b;
+    }
   }
-  unsigned tv, tt;
-  block_excl_scan(nv, s_warp, &tv);
-  block_excl_scan(nt, s_warp, &tt);
-  if (threadIdx.x == 0) { ws.line_v[line] = tv; ws.line_t[line] = tt; }
 }
 
-// stage 2: exclusive scan of the per-line counts (<= a few 1e5 entries: one block, serial over chunks).
-__global__ void __launch_bounds__(1024) mc_scan_lines(McWs ws, int nlines) {
+// ------------------------------------------------------------------------------------------------ cell resolution
+// test_face: are the MARKED corners joined across ambiguous face f?   (oracle/mc_oracle.c face_joined)
+__device__ __forceinline__ int face_joined(const double* val, int f, int mu_pos) {
+  const double A = val[c_face_corners[f][0]], B = val[c_face_corners[f][1]], C = val[c_face_corners[f][2]],
+               D = val[c_face_corners[f][3]];
+  const double X = A * C - B * D;
+  if (X > -kEps && X < kEps) return mu_pos;
+  return mu_pos ? (A * X >= 0.0) : (A * X <= 0.0);
+}
+
+// test_interior reduced to its indicator (oracle/mc_oracle.c interior_I)
+__device__ int interior_I(const double* val, int itest) {
+  double At, Bt, Ct, Dt;
+  if (itest == 1) {
+    const double v0 = val[c_lew2my[0]], v1 = val[c_lew2my[1]], v2 = val[c_lew2my[2]], v3 = val[c_lew2my[3]];
+    const double v4 = val[c_lew2my[4]], v5 = val[c_lew2my[5]], v6 = val[c_lew2my[6]], v7 = val[c_lew2my[7]];
+    const double a = (v4 - v0) * (v6 - v2) - (v7 - v3) * (v5 - v1);
+    const double b = v2 * (v4 - v0) + v0 * (v6 - v2) - v1 * (v7 - v3) - v3 * (v5 - v1);
+    const double t = -b / (2 * a + kEps);
+    if (t < 0 || t > 1) return 0;
+    At = v0 + (v4 - v0) * t; Bt = v3 + (v7 - v3) * t; Ct = v2 + (v6 - v2) * t; Dt = v1 + (v5 - v1) * t;
+  } else {
+    const unsigned char* r = c_itest_edge[itest - 2];
+    const double t = val[r[0]] / (val[r[0]] - val[r[1]]);
+    At = 0;
+    Bt = val[r[2]] + (val[r[3]] - val[r[2]]) * t;
+    Ct = val[r[4]] + (val[r[5]] - val[r[4]]) * t;
+    Dt = val[r[6]] + (val[r[7]] - val[r[6]]) * t;
+  }
+  const int test = (At >= 0 ? 1 : 0) | (Bt >= 0 ? 2 : 0) | (Ct >= 0 ? 4 : 0) | (Dt >= 0 ? 8 : 0);
+  switch (test) {
+    case 7: case 11: case 13: case 14: case 15: return 1;
+    case 5: return !(At * Ct - Bt * Dt < kEps);
+    case 10: return !(At * Ct - Bt * Dt >= kEps);
+    default: return 0;
+  }
+}
+
+// level-3 entry (triangulation) of the cell with sign mask m whose low corner is flat point index p
+__device__ __forceinline__ int resolve_cell(const McGrid& g, unsigned m, size_t p) {
+  const L1Entry e1 = g_l1[m];
+  L2Entry e2 = g_l2[e1.base];
+  if (e1.nf == 0 && e2.itest == 0) return e2.none;
+  double val[8];
+  const size_t sx = (size_t)g.ny * g.nz, sy = (size_t)g.nz;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) val[c] = (double)g.vol[p + (c & 1) * sx + ((c >> 1) & 1) * sy + ((c >> 2) & 1)] - (double)g.iso;
+  int J = 0;
+  for (int q = 0; q < e1.nf; ++q) J |= face_joined(val, e1.faces[q], e1.mu) << q;
+  e2 = g_l2[e1.base + J];
+  if (e2.itest == 0) return e2.none;
+  return interior_I(val, e2.itest) == e2.tif ? e2.tunnel : e2.none;
+}
+
+// the four sign words around word (i,j,w) and their k+1 shifts
+struct Nbhd {
+  unsigned s[4], sh[4];      // index di + 2*dj
+  unsigned X, Y, Z, active;
+};
+__device__ __forceinline__ Nbhd load_nbhd(const McGrid& g, int i, int j, int w) {
+  Nbhd n;
+  const bool has_i1 = g.g_x0 + i + 1 < g.g_nx, has_j1 = j + 1 < g.ny;
+  const int k0 = w * 32;
+  const unsigned validk = (g.nz - k0 >= 32) ? 0xffffffffu : ((1u << (g.nz - k0)) - 1u);
+  const unsigned validk1 = (g.nz - 1 - k0 >= 32) ? 0xffffffffu : (g.nz - 1 - k0 <= 0 ? 0u : ((1u << (g.nz - 1 - k0)) - 1u));
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int di = c & 1, dj = c >> 1;
+    const bool ok = (!di || has_i1) && (!dj || has_j1);
+    unsigned a = 0, an = 0;
+    if (ok) {
+      const size_t base = ((size_t)(i + di) * g.ny + (j + dj)) * g.W + w;
+      a = g.sign[base];
+      if (w + 1 < g.W) an = g.sign[base + 1];
+    }
+    n.s[c] = a;
+    n.sh[c] = (a >> 1) | (an << 31);
+  }
+  n.X = has_i1 ? ((n.s[0] ^ n.s[1]) & validk) : 0u;
+  n.Y = has_j1 ? ((n.s[0] ^ n.s[2]) & validk) : 0u;
+  n.Z = (n.s[0] ^ n.sh[0]) & validk1;
+  if (has_i1 && has_j1) {
+    const unsigned o = n.s[0] | n.s[1] | n.s[2] | n.s[3] | n.sh[0] | n.sh[1] | n.sh[2] | n.sh[3];
+    const unsigned a = n.s[0] & n.s[1] & n.s[2] & n.s[3] & n.sh[0] & n.sh[1] & n.sh[2] & n.sh[3];
+    n.active = (o & ~a) & validk1;
+  } else {
+    n.active = 0u;
+  }
+  return n;
+}
+__device__ __forceinline__ unsigned cell_mask(const Nbhd& n, int b) {   // corner c = di + 2 dj + 4 dk
+  return ((n.s[0] >> b) & 1u) | (((n.s[1] >> b) & 1u) << 1) | (((n.s[2] >> b) & 1u) << 2) | (((n.s[3] >> b) & 1u) << 3) |
+         (((n.sh[0] >> b) & 1u) << 4) | (((n.sh[1] >> b) & 1u) << 5) | (((n.sh[2] >> b) & 1u) << 6) | (((n.sh[3] >> b) & 1u) << 7);
+}
+
+__device__ __forceinline__ void word_coords(const McGrid& g, long long wl, int* i, int* j, int* w) {
+  const long long line = wl / g.W;
+  *w = (int)(wl - line * g.W);
+  *i = g.p_lo + (int)(line / g.ny);
+  *j = (int)(line % g.ny);
+}
+
+__device__ __forceinline__ unsigned block_sum(unsigned v, unsigned* s_warp) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+  __syncthreads();
+  unsigned t = 0;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; ++w) t += s_warp[w];
+  __syncthreads();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------ 2. count
+__global__ void __launch_bounds__(kBlock) mc_count_kernel(const McGrid g) {
+  __shared__ unsigned s_warp[kBlock / 32];
+  const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
+  unsigned vc = 0, tc = 0;
+  if (wl < g.nwords) {
+    int i, j, w;
+    word_coords(g, wl, &i, &j, &w);
+    const Nbhd n = load_nbhd(g, i, j, w);
+    unsigned C = 0;
+    const bool owned = i < g.p_hi;
+    unsigned act = n.active;
+    while (act) {
+      const int b = __ffs(act) - 1;
+      act &= act - 1;
+      const size_t p = ((size_t)i * g.ny + j) * g.nz + (size_t)w * 32 + b;
+      const L3Entry* e = &g_l3[resolve_cell(g, cell_mask(n, b), p)];
+      if (owned) tc += e->ntri;
+      C |= (unsigned)e->uses_c << b;
+    }
+    vc = __popc(n.X) + __popc(n.Y) + __popc(n.Z) + __popc(C);
+    g.bits[wl] = make_uint4(n.X, n.Y, n.Z, C);
+    g.cnt[wl] = vc | (tc << 16);
+  }
+  const unsigned sv = block_sum(vc, s_warp), stt = block_sum(tc, s_warp);
+  if (threadIdx.x == 0) { g.blk[2 * blockIdx.x] = sv; g.blk[2 * blockIdx.x + 1] = stt; }
+}
+
+// ------------------------------------------------------------------------------------------------ 3. scans
+// exclusive scan of the per-block sums (<= a few 1e4 entries: one block, each thread a contiguous chunk)
+__global__ void __launch_bounds__(1024) mc_scan_blocks(McGrid g, int nblocks) {
   __shared__ unsigned long long s_part[2][1024];
   const int t = threadIdx.x;
-  const int per = (nlines + 1023) / 1024;
-  const int lo = t * per, hi = min(nlines, lo + per);
-  unsigned long long sv = 0, st = 0;
-  for (int l = lo; l < hi; ++l) { sv += ws.line_v[l]; st += ws.line_t[l]; }
-  s_part[0][t] = sv; s_part[1][t] = st;
+  const int per = (nblocks + 1023) / 1024;
+  const int lo = t * per, hi = min(nblocks, lo + per);
+  unsigned long long sv = 0, stt = 0;
+  for (int l = lo; l < hi; ++l) { sv += g.blk[2 * l]; stt += g.blk[2 * l + 1]; }
+  s_part[0][t] = sv; s_part[1][t] = stt;
   __syncthreads();
-  if (t == 0) {
-    unsigned long long av = 0, at = 0;
-    for (int x = 0; x < 1024; ++x) {
-      const unsigned long long v = s_part[0][x], w = s_part[1][x];
-      s_part[0][x] = av; s_part[1][x] = at;
-      av += v; at += w;
-    }
-    ws.totals[0] = av; ws.totals[1] = at;
+  // Hillis-Steele inclusive scan over the 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned long long a = t >= o ? s_part[0][t - o] : 0, b = t >= o ? s_part[1][t - o] : 0;
+    __syncthreads();
+    s_part[0][t] += a; s_part[1][t] += b;
+    __syncthreads();
   }
-  __syncthreads();
-  unsigned long long av = s_part[0][t], at = s_part[1][t];
+  unsigned long long av = s_part[0][t] - sv, at = s_part[1][t] - stt;
+  if (t == 1023) { g.totals[0] = s_part[0][t]; g.totals[1] = s_part[1][t]; }
   for (int l = lo; l < hi; ++l) {
-    const unsigned v = ws.line_v[l], w = ws.line_t[l];
-    ws.line_v[l] = (unsigned)av; ws.line_t[l] = (unsigned)at;
+    const unsigned v = g.blk[2 * l], w = g.blk[2 * l + 1];
+    g.blk[2 * l] = (unsigned)av; g.blk[2 * l + 1] = (unsigned)at;
     av += v; at += w;
   }
 }
 
-__device__ __forceinline__ float grad_axis(const float* __restrict__ vol, size_t p, int c, int n, size_t stride) {
-  // central difference inside, one-sided on the boundary
-  if (c == 0) return vol[p + stride] - vol[p];
-  if (c == n - 1) return vol[p] - vol[p - stride];
-  return 0.5f * (vol[p + stride] - vol[p - stride]);
+__global__ void __launch_bounds__(kBlock) mc_scan_words(const McGrid g) {
+  __shared__ unsigned s_v[kBlock / 32], s_t[kBlock / 32];
+  const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const unsigned c = wl < g.nwords ? g.cnt[wl] : 0u;
+  const unsigned v = c & 0xffffu, t = c >> 16;
+  unsigned xv = v, xt = t;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned yv = __shfl_up_sync(0xffffffffu, xv, o), yt = __shfl_up_sync(0xffffffffu, xt, o);
+    if (lane >= o) { xv += yv; xt += yt; }
+  }
+  if (lane == 31) { s_v[wid] = xv; s_t[wid] = xt; }
+  __syncthreads();
+  unsigned bv = g.blk[2 * blockIdx.x], bt = g.blk[2 * blockIdx.x + 1];
+  for (int q = 0; q < wid; ++q) { bv += s_v[q]; bt += s_t[q]; }
+  if (wl < g.nwords) {
+    g.vpre[wl] = bv + xv - v;
+    g.tpre[wl] = bt + xt - t;
+    if (wl == g.nwords_own) g.totals[2] = bv + xv - v;            // first word of the shadow plane: owned vertex count
+  }
 }
 
-// stage 3: vertex ids + vertex / normal emission.
-__global__ void __launch_bounds__(kLineThreads) mc_emit_vertices(const float* __restrict__ vol, McWs ws, float iso, float x_off,
-                                                                float* __restrict__ verts, float* __restrict__ normals) {
-  __shared__ unsigned s_warp[kLineThreads / 32];
-  const int nx = ws.nx, ny = ws.ny, nz = ws.nz;
-  const int line = blockIdx.x, i = line / ny, j = line % ny;
-  const size_t row = (size_t)line * nz;
-  const size_t strides[3] = {(size_t)ny * nz, (size_t)nz, 1};
-  const int dims[3] = {nx, ny, nz};
-  // contiguous k-segments per thread so the canonical (k-ascending) order falls out of one block scan
-  const int per = (nz + kLineThreads - 1) / kLineThreads;
-  const int k0 = threadIdx.x * per, k1 = min(nz, k0 + per);
-  unsigned cnt = 0;
-  for (int k = k0; k < k1; ++k) cnt += __popc(ws.mask[row + k]);
-  unsigned id = ws.line_v[line] + block_excl_scan(cnt, s_warp, nullptr);
-  for (int k = k0; k < k1; ++k) {
-    const size_t p = row + k;
-    const unsigned m = ws.mask[p];
-    ws.vbase[p] = id;
-    if (!m) continue;
-    const int c0[3] = {i, j, k};
-    const float v0 = vol[p];
-    float g0[3];
+// ------------------------------------------------------------------------------------------------ 4. emission
+// central difference inside the GLOBAL grid, one-sided on its boundary (the halo planes are in the buffer)
+__device__ __forceinline__ void grid_grad(const McGrid& g, int i, int j, int k, float out[3]) {
+  const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
+  const size_t st[3] = {(size_t)g.ny * g.nz, (size_t)g.nz, 1};
+  const int gl[3] = {g.g_x0 + i, j, k}, n[3] = {g.g_nx, g.ny, g.nz};
 #pragma unroll
-    for (int a = 0; a < 3; ++a) g0[a] = grad_axis(vol, p, c0[a], dims[a], strides[a]);
+  for (int a = 0; a < 3; ++a) {
+    const bool lo = gl[a] > 0, hi = gl[a] + 1 < n[a];
+    if (lo && hi) out[a] = 0.5f * (g.vol[p + st[a]] - g.vol[p - st[a]]);
+    else if (hi) out[a] = g.vol[p + st[a]] - g.vol[p];
+    else if (lo) out[a] = g.vol[p] - g.vol[p - st[a]];
+    else out[a] = 0.f;
+  }
+}
+
+__device__ __forceinline__ void store_vertex(float* verts, float* normals, size_t id, const double pos[3], const double n[3]) {
+  const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  const double inv = len > 0.0 ? 1.0 / len : 0.0;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    verts[3 * id + b] = (float)pos[b];
+    if (normals) normals[3 * id + b] = (float)(n[b] * inv);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) mc_emit_vertices(const McGrid g, float* __restrict__ verts, float* __restrict__ normals) {
+  const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (wl >= g.nwords_own) return;
+  const uint4 B = g.bits[wl];
+  unsigned any = B.x | B.y | B.z | B.w;
+  if (!any) return;
+  int i, j, w;
+  word_coords(g, wl, &i, &j, &w);
+  size_t id = g.vpre[wl];
+  const size_t st[3] = {(size_t)g.ny * g.nz, (size_t)g.nz, 1};
+  const double iso = (double)g.iso;
+  while (any) {
+    const int b = __ffs(any) - 1;
+    any &= any - 1;
+    const int k = w * 32 + b;
+    const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
+    const double base[3] = {(double)(g.g_x0 + i), (double)j, (double)k};
+    const unsigned bitsel[3] = {(B.x >> b) & 1u, (B.y >> b) & 1u, (B.z >> b) & 1u};
+    float g0[3];
+    double w0 = 0.0;
+    if (bitsel[0] | bitsel[1] | bitsel[2]) {
+      grid_grad(g, i, j, k, g0);
+      w0 = 1.0 / (kEps + fabs((double)g.vol[p] - iso));
+    }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      if (!(m & (1u << a))) continue;
-      const size_t q = p + strides[a];
-      const float v1 = vol[q];
+      if (!bitsel[a]) continue;
       int c1[3] = {i, j, k};
       c1[a] += 1;
+      const double w1 = 1.0 / (kEps + fabs((double)g.vol[p + st[a]] - iso));
+      const double ff = w0 + w1;
+      double pos[3] = {base[0], base[1], base[2]};
+      pos[a] = base[a] + w1 / ff;                  // x + step * fx / ff with fx = 0*w0 + 1*w1 (scikit-image's form)
       float g1[3];
-#pragma unroll
-      for (int b = 0; b < 3; ++b) g1[b] = grad_axis(vol, q, c1[b], dims[b], strides[b]);
-      const double w0 = 1.0 / ((double)FLT_EPSILON + fabs((double)v0 - (double)iso));
-      const double w1 = 1.0 / ((double)FLT_EPSILON + fabs((double)v1 - (double)iso));
-      const double ws_ = w0 + w1;
-      double pos[3] = {(double)i + (double)x_off, (double)j, (double)k};
-      pos[a] = (pos[a] * w0 + (pos[a] + 1.0) * w1) / ws_;
+      grid_grad(g, c1[0], c1[1], c1[2], g1);
       double n[3];
 #pragma unroll
-      for (int b = 0; b < 3; ++b) n[b] = -((double)g0[b] * w0 + (double)g1[b] * w1);
-      const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-      const double inv = len > 0.0 ? 1.0 / len : 0.0;
+      for (int q = 0; q < 3; ++q) n[q] = -((double)g0[q] * w0 + (double)g1[q] * w1);
+      store_vertex(verts, normals, id, pos, n);
+      ++id;
+    }
+    if ((B.w >> b) & 1u) {                         // calculate_center_vertex: weighted mean of the 8 corners, Lewiner's order
+      double f[3] = {0, 0, 0}, ff = 0, n[3] = {0, 0, 0};
+      for (int L = 0; L < 8; ++L) {
+        const int c = c_lew2my[L];
+        const int ci = i + (c & 1), cj = j + ((c >> 1) & 1), ck = k + ((c >> 2) & 1);
+        const double wc = 1.0 / (kEps + fabs((double)g.vol[((size_t)ci * g.ny + cj) * g.nz + ck] - iso));
 #pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        verts[3 * (size_t)id + b] = (float)pos[b];
-        if (normals) normals[3 * (size_t)id + b] = (float)(n[b] * inv);
+        for (int q = 0; q < 3; ++q) if ((c >> q) & 1) f[q] += wc;
+        ff += wc;
+        float gc[3];
+        grid_grad(g, ci, cj, ck, gc);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) n[q] -= (double)gc[q] * wc;
       }
+      const double pos[3] = {base[0] + f[0] / ff, base[1] + f[1] / ff, base[2] + f[2] / ff};
+      store_vertex(verts, normals, id, pos, n);
       ++id;
     }
   }
 }
 
-// stage 4: triangles.
-__global__ void __launch_bounds__(kLineThreads) mc_emit_triangles(McWs ws, int* __restrict__ faces) {
-  __shared__ unsigned s_warp[kLineThreads / 32];
-  const int ny = ws.ny, nz = ws.nz;
-  const int line = blockIdx.x;
-  const size_t row = (size_t)line * nz;
-  const size_t sx = (size_t)ny * nz, sy = (size_t)nz;
-  const int per = (nz + kLineThreads - 1) / kLineThreads;
-  const int k0 = threadIdx.x * per, k1 = min(nz, k0 + per);
-  unsigned cnt = 0;
-  for (int k = k0; k < k1; ++k) cnt += c_ntri[ws.cube[row + k]];
-  unsigned tid = ws.line_t[line] + block_excl_scan(cnt, s_warp, nullptr);
-  for (int k = k0; k < k1; ++k) {
-    const size_t p = row + k;
-    const unsigned cube = ws.cube[p];
-    const int nt = c_ntri[cube];
-    for (int t = 0; t < nt; ++t) {
+// id of the first vertex owned by grid point (i,j,k) (buffer coordinates) + that point's slot bits
+__device__ __forceinline__ unsigned point_base(const McGrid& g, int i, int j, int k, unsigned* slots) {
+  const long long wq = ((long long)(i - g.p_lo) * g.ny + j) * g.W + (k >> 5);
+  const int b = k & 31;
+  const uint4 B = g.bits[wq];
+  const unsigned lt = (1u << b) - 1u;
+  *slots = ((B.x >> b) & 1u) | (((B.y >> b) & 1u) << 1) | (((B.z >> b) & 1u) << 2);
+  return g.vpre[wq] + __popc(B.x & lt) + __popc(B.y & lt) + __popc(B.z & lt) + __popc(B.w & lt);
+}
+
+__global__ void __launch_bounds__(kBlock) mc_emit_triangles(const McGrid g, long long v_base, int* __restrict__ faces) {
+  const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (wl >= g.nwords_own) return;
+  if ((g.cnt[wl] >> 16) == 0) return;
+  int i, j, w;
+  word_coords(g, wl, &i, &j, &w);
+  const Nbhd n = load_nbhd(g, i, j, w);
+  size_t tid = g.tpre[wl];
+  unsigned act = n.active;
+  while (act) {
+    const int b = __ffs(act) - 1;
+    act &= act - 1;
+    const int k = w * 32 + b;
+    const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
+    const L3Entry* e = &g_l3[resolve_cell(g, cell_mask(n, b), p)];
+    unsigned base[8], slots[8];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int e = c_tri[cube * 15 + 3 * t + c];
-        const int lo = c_edge_lo[e], a = c_edge_axis[e];
-        const size_t q = p + (lo & 1) * sx + ((lo >> 1) & 1) * sy + ((lo >> 2) & 1);
-        faces[3 * (size_t)tid + c] = (int)(ws.vbase[q] + __popc(ws.mask[q] & ((1u << a) - 1u)));
+    for (int c = 0; c < 8; ++c) base[c] = point_base(g, i + (c & 1), j + ((c >> 1) & 1), k + ((c >> 2) & 1), &slots[c]);
+    const int nt = e->ntri;
+    for (int t = 0; t < 3 * nt; ++t) {
+      const int s = e->idx[t];
+      unsigned id;
+      if (s == 12) {
+        id = base[0] + (slots[0] & 1u) + ((slots[0] >> 1) & 1u) + ((slots[0] >> 2) & 1u);
+      } else {
+        const int lo = c_edge_lo[s], a = c_edge_axis[s];
+        id = base[lo] + __popc(slots[lo] & ((1u << a) - 1u));
       }
-      ++tid;
+      faces[3 * tid + t] = (int)(v_base + (long long)id);
     }
+    tid += nt;
   }
 }
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
 
-int carve(void* base, size_t bytes, int nx, int ny, int nz, McWs* ws, size_t* need) {
-  const size_t N = (size_t)nx * ny * nz, L = (size_t)nx * ny;
+int carve(void* base, size_t bytes, McGrid* g, size_t* need) {
+  const size_t nsign = (size_t)g->nb * g->ny * g->W;
+  const size_t nw = (size_t)g->nwords, nblk = (nw + kBlock - 1) / kBlock;
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
-  const size_t o_mask = take(N), o_cube = take(N), o_vb = take(N * 4), o_lv = take(L * 4), o_lt = take(L * 4), o_tot = take(16);
+  const size_t o_sign = take(nsign * 4), o_bits = take(nw * 16), o_cnt = take(nw * 4), o_vp = take((nw + 1) * 4),
+               o_tp = take((nw + 1) * 4), o_blk = take((nblk + 1) * 8), o_tot = take(32);
   *need = off;
   if (!base || bytes < off) return 1;
   char* b = reinterpret_cast<char*>(base);
-  ws->mask = reinterpret_cast<unsigned char*>(b + o_mask);
-  ws->cube = reinterpret_cast<unsigned char*>(b + o_cube);
-  ws->vbase = reinterpret_cast<unsigned int*>(b + o_vb);
-  ws->line_v = reinterpret_cast<unsigned int*>(b + o_lv);
-  ws->line_t = reinterpret_cast<unsigned int*>(b + o_lt);
-  ws->totals = reinterpret_cast<unsigned long long*>(b + o_tot);
-  ws->nx = nx; ws->ny = ny; ws->nz = nz;
+  g->sign = reinterpret_cast<unsigned*>(b + o_sign);
+  g->bits = reinterpret_cast<uint4*>(b + o_bits);
+  g->cnt = reinterpret_cast<unsigned*>(b + o_cnt);
+  g->vpre = reinterpret_cast<unsigned*>(b + o_vp);
+  g->tpre = reinterpret_cast<unsigned*>(b + o_tp);
+  g->blk = reinterpret_cast<unsigned*>(b + o_blk);
+  g->totals = reinterpret_cast<unsigned long long*>(b + o_tot);
+  return 0;
+}
+
+int make_grid(const McShard& s, McGrid* g) {
+  NM_CHECK(s.vol && s.nb >= 1 && s.ny >= 2 && s.nz >= 2, "marching cubes: bad volume shape");
+  NM_CHECK(s.g_x0 >= 0 && s.g_x0 + s.nb <= s.g_nx && s.g_nx >= 2, "marching cubes: buffer planes outside the global grid");
+  NM_CHECK(0 <= s.p_lo && s.p_lo <= s.p_hi && s.p_hi <= s.nb, "marching cubes: bad owned plane range");
+  const bool next_exists = s.g_x0 + s.p_hi < s.g_nx;                    // the plane after the owned ones exists globally
+  NM_CHECK(!next_exists || s.p_hi < s.nb, "marching cubes: plane after the owned range is missing from the buffer");
+  // gradients at the owned planes and at plane p_hi need one more plane on either side (unless it is the global boundary)
+  NM_CHECK(s.p_lo == s.p_hi || s.g_x0 + s.p_lo == 0 || s.p_lo >= 1, "marching cubes: halo plane below the owned range missing");
+  NM_CHECK(!next_exists || s.g_x0 + s.p_hi + 1 >= s.g_nx || s.p_hi + 1 < s.nb, "marching cubes: halo plane above the owned range missing");
+  g->vol = s.vol; g->nb = s.nb; g->ny = s.ny; g->nz = s.nz; g->W = (s.nz + 31) / 32;
+  g->g_x0 = s.g_x0; g->g_nx = s.g_nx; g->p_lo = s.p_lo; g->p_hi = s.p_hi; g->p_end = s.p_hi + (next_exists ? 1 : 0);
+  g->iso = s.iso;
+  g->nwords = (long long)(g->p_end - g->p_lo) * g->ny * g->W;
+  g->nwords_own = (long long)(g->p_hi - g->p_lo) * g->ny * g->W;
   return 0;
 }
 
 }  // namespace
 
-int mc_count(const float* vol, int nx, int ny, int nz, float iso, void** ws_ptr, size_t* ws_bytes, int64_t* counts_host,
-             cudaStream_t st, int64_t* launches) {
-  McWs ws{};
+int mc_count(const McShard& s, void** ws_ptr, size_t* ws_bytes, int64_t* counts_host, cudaStream_t st, int64_t* launches) {
+  McGrid g{};
+  if (int e = make_grid(s, &g)) return e;
   size_t need = 0;
-  if (carve(*ws_ptr, *ws_bytes, nx, ny, nz, &ws, &need)) {
+  if (carve(*ws_ptr, *ws_bytes, &g, &need)) {
     if (*ws_ptr) NM_CUDA(cudaFree(*ws_ptr));
     *ws_ptr = nullptr; *ws_bytes = 0;
     NM_CUDA(cudaMalloc(ws_ptr, need));
     *ws_bytes = need;
-    NM_CHECK(carve(*ws_ptr, *ws_bytes, nx, ny, nz, &ws, &need) == 0, "workspace carve failed");
+    NM_CHECK(carve(*ws_ptr, *ws_bytes, &g, &need) == 0, "workspace carve failed");
   }
-  const int nlines = nx * ny;
-  mc_classify<<<nlines, kLineThreads, 0, st>>>(vol, ws, iso);
+  counts_host[0] = counts_host[1] = 0;
+  if (g.nwords == 0) return 0;
+  const long long nlines = (long long)g.nb * g.ny;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long sign_blocks = (nlines * g.W + (kBlock / 32) * 8 - 1) / ((kBlock / 32) * 8);
+  if (sign_blocks > (long long)sms * 8) sign_blocks = (long long)sms * 8;
+  mc_sign_kernel<<<(unsigned)sign_blocks, kBlock, 0, st>>>(g.vol, nlines, g.nz, g.W, g.iso, g.sign);
   NM_CUDA(cudaGetLastError());
-  mc_scan_lines<<<1, 1024, 0, st>>>(ws, nlines);
+  const long long nblk = (g.nwords + kBlock - 1) / kBlock;
+  NM_CHECK(nblk < (1ll << 31), "marching cubes: volume too large");
+  mc_count_kernel<<<(unsigned)nblk, kBlock, 0, st>>>(g);
   NM_CUDA(cudaGetLastError());
-  unsigned long long h[2];
-  NM_CUDA(cudaMemcpyAsync(h, ws.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
+  mc_scan_blocks<<<1, 1024, 0, st>>>(g, (int)nblk);
+  NM_CUDA(cudaGetLastError());
+  mc_scan_words<<<(unsigned)nblk, kBlock, 0, st>>>(g);
+  NM_CUDA(cudaGetLastError());
+  unsigned long long h[3];
+  NM_CUDA(cudaMemcpyAsync(h, g.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
   NM_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long nv_own = (g.p_end > g.p_hi) ? h[2] : h[0];
   NM_CHECK(h[0] < (1ull << 31) && h[1] < (1ull << 31), "mesh too large for int32 indices");
-  counts_host[0] = (int64_t)h[0];
+  counts_host[0] = (int64_t)nv_own;
   counts_host[1] = (int64_t)h[1];
-  if (launches) *launches += 2;
+  if (launches) *launches += 4;
   return 0;
 }
 
-int mc_emit(const float* vol, int nx, int ny, int nz, float iso, float x_off, void* ws_ptr, float* verts, float* normals,
-            int32_t* faces, cudaStream_t st, int64_t* launches) {
-  McWs ws{};
+int mc_emit(const McShard& s, void* ws_ptr, size_t ws_bytes, long long v_base, float* verts, float* normals, int32_t* faces,
+            cudaStream_t st, int64_t* launches) {
+  McGrid g{};
+  if (int e = make_grid(s, &g)) return e;
   size_t need = 0;
-  NM_CHECK(carve(ws_ptr, (size_t)-1, nx, ny, nz, &ws, &need) == 0, "workspace missing");
-  const int nlines = nx * ny;
-  mc_emit_vertices<<<nlines, kLineThreads, 0, st>>>(vol, ws, iso, x_off, verts, normals);
+  NM_CHECK(carve(ws_ptr, ws_bytes, &g, &need) == 0, "workspace missing (call the count step first, same arguments)");
+  if (g.nwords_own == 0) return 0;
+  const long long nblk = (g.nwords_own + kBlock - 1) / kBlock;
+  mc_emit_vertices<<<(unsigned)nblk, kBlock, 0, st>>>(g, verts, normals);
   NM_CUDA(cudaGetLastError());
-  mc_emit_triangles<<<nlines, kLineThreads, 0, st>>>(ws, faces);
+  mc_emit_triangles<<<(unsigned)nblk, kBlock, 0, st>>>(g, v_base, faces);
   NM_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   return 0;

@@ -363,12 +363,15 @@ class Engine:
         tcgen05 watchdog)."""
         L.check(self.lib.nm_check_flags(self._h, self._stream()))
 
-    def grid_sigma(self, lins, x0=0, x1=None, with_rgb=False):
-        """extract_radiance for planes [x0,x1): lins = three 1-D fp32 tensors (torch.linspace values)."""
+    def grid_sigma(self, lins, x0=0, x1=None, with_rgb=False, out=None):
+        """extract_radiance for planes [x0,x1): lins = three 1-D fp32 tensors (torch.linspace values).  `out`: optional
+        contiguous (x1-x0, n1, n2) device tensor to write the densities into (e.g. the owned planes of a halo buffer)."""
         ls = [np.ascontiguousarray(torch.as_tensor(t).detach().cpu().numpy(), dtype=np.float32) for t in lins]
         n0, n1, n2 = (a.size for a in ls)
         x1 = n0 if x1 is None else x1
-        sigma = torch.empty((x1 - x0, n1, n2), dtype=torch.float32, device=self.device)
+        if out is not None:
+            assert out.shape == (x1 - x0, n1, n2) and out.is_contiguous() and out.dtype == torch.float32 and not with_rgb
+        sigma = out if out is not None else torch.empty((x1 - x0, n1, n2), dtype=torch.float32, device=self.device)
         rgb = torch.empty((x1 - x0, n1, n2, 3), dtype=torch.float32, device=self.device) if with_rgb else None
         L.check(self.lib.nm_grid_sigma(self._h, ls[0].ctypes.data, ls[1].ctypes.data, ls[2].ctypes.data, n0, n1, n2, x0,
                                        x1, _ptr(sigma), _ptr(rgb), self._stream()))
@@ -381,18 +384,35 @@ class Engine:
         L.check(self.lib.nm_volume_stats(self._h, _ptr(v), v.numel(), out))
         return float(out[0]), float(out[1]), float(out[2])
 
-    def marching_cubes(self, vol: torch.Tensor, iso: float, x_off: float = 0.0):
+    def marching_cubes(self, vol: torch.Tensor, iso: float, x_off: int = 0):
+        """skimage.measure.marching_cubes(vol, iso) on the device: (verts (V,3), faces (F,3) int32, normals (V,3))."""
         v = _f32c(vol, self.device)
-        nx, ny, nz = v.shape
+        nv, nt = self.mc_count(v, iso, int(x_off), int(x_off) + v.shape[0], 0, v.shape[0])
+        return self.mc_emit(v, iso, int(x_off), int(x_off) + v.shape[0], 0, v.shape[0], nv, nt, 0)
+
+    def mc_count(self, vol, iso, g_x0, g_nx, p_lo, p_hi):
+        """Count step of one shard (see nm_mc_count): -> (n_vertices owned, n_triangles).  Synchronises."""
+        nb, ny, nz = vol.shape
         counts = (C.c_int64 * 2)()
-        L.check(self.lib.nm_marching_cubes_count(self._h, _ptr(v), nx, ny, nz, float(iso), counts, self._stream()))
-        nv, nt = int(counts[0]), int(counts[1])
-        verts = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
-        normals = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
-        faces = torch.empty((nt, 3), dtype=torch.int32, device=self.device)
+        L.check(self.lib.nm_mc_count(self._h, _ptr(vol), nb, ny, nz, float(iso), int(g_x0), int(g_nx), int(p_lo), int(p_hi),
+                                     counts, self._stream()))
+        return int(counts[0]), int(counts[1])
+
+    def mc_emit(self, vol, iso, g_x0, g_nx, p_lo, p_hi, nv, nt, v_base, out=None):
+        """Emit step: vertices / normals / faces of the shard, faces offset by v_base.  `out`: optional (verts, normals,
+        faces) device tensors to write into (e.g. slices of a gather buffer)."""
+        nb, ny, nz = vol.shape
+        if out is None:
+            verts = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
+            normals = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
+            faces = torch.empty((nt, 3), dtype=torch.int32, device=self.device)
+        else:
+            verts, normals, faces = out
+            assert verts.is_contiguous() and normals.is_contiguous() and faces.is_contiguous() and faces.dtype == torch.int32
+            assert verts.shape[0] >= nv and faces.shape[0] >= nt
         if nv > 0:
-            L.check(self.lib.nm_marching_cubes_emit(self._h, _ptr(v), nx, ny, nz, float(iso), float(x_off), _ptr(verts),
-                                                    _ptr(normals), _ptr(faces), self._stream()))
+            L.check(self.lib.nm_mc_emit(self._h, _ptr(vol), nb, ny, nz, float(iso), int(g_x0), int(g_nx), int(p_lo), int(p_hi),
+                                        int(v_base), _ptr(verts), _ptr(normals), _ptr(faces), self._stream()))
         return verts, faces, normals
 
     # ------------------------------------------------------------------ introspection

@@ -2,9 +2,11 @@
 
 Render: contiguous image-row shards, every rank generates its own rays from the 12-float pose; results are bit-identical
 to the single-GPU image (no cross-shard arithmetic), the exchange is one all_gather of the finished rows.
-Mesh: x-slabs of the density grid with one overlapping plane; per-slab marching cubes in global index coordinates; the
-exchange is an all_gather of the per-slab indexed meshes ("triangle soup", padded to the largest slab) plus three scalar
-all_reduces for the iso-level statistics (extract_iso_level, src/mesh_nerf.py:56-65).
+Mesh: x-slabs of the density grid; every grid point (vertex, cell) is owned by exactly one rank; halo planes by send/recv;
+per-slab marching cubes in global index coordinates with globally consistent vertex ids; the exchange is an all_gather
+of the vertex / triangle counts and ONE all_gather of the per-slab indexed meshes (padded to the largest slab), plus
+scalar all_reduces for the iso-level statistics (extract_iso_level, src/mesh_nerf.py:56-65).  The gathered arrays equal
+the single-GPU arrays bit for bit.
 Training: data parallel over rays — every rank runs forward + backward on its own ray batch (no collective inside), then
 ONE all_reduce of the flattened gradients of both networks (595 k - 1.19 M floats, 4.8 MB) before the optimiser step.
 The collectives go through torch.distributed (NCCL on GPUs, gloo in the CPU tests); there is no data-path collective
@@ -164,7 +166,12 @@ def render_image_sharded(model, pose, H, W, focal, near, far, *, ndc=False, buff
     return ex.gather()
 
 
+SINGLE = "single"        # pass as `group` to run the sharded code paths as ONE shard (tests compare it with the N-rank result)
+
+
 def _rank_world(group=None):
+    if group is SINGLE or group == SINGLE:
+        return 0, 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
@@ -191,36 +198,104 @@ class _StageTimer:
             self.sink[name + "_ms"] = self.sink.get(name + "_ms", 0.0) + a.elapsed_time(b)
 
 
-def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None):
-    """mesh_nerf.extract_geometry on N GPUs: slab sigma sweep -> global iso statistics -> per-slab marching cubes ->
-    all_gather of the slab meshes.  Returns (vertices, triangles, normals, iso) like the single-GPU function (vertices
-    rescaled to (-limit, limit)); the density grid stays sharded.  Works without a process group (one slab)."""
+def slab_layout(n0: int, rank: int, world: int):
+    """x-slab of rank `rank` of a grid with n0 planes: returns (own0, own1, buf0, buf1).
+    Points (and the cells above them) of planes [own0, own1) are OWNED: the n0-1 cell layers are split evenly and the last
+    rank also owns the top plane n0-1.  Marching cubes additionally needs, where they exist, plane own1 (upper corners of
+    the last owned cell layer), own1+1 and own0-1 (central-difference normals): the buffer is planes [buf0, buf1)."""
+    c0, c1 = row_shard(n0 - 1, rank, world)
+    own1 = n0 if rank == world - 1 else c1
+    return c0, own1, max(c0 - 1, 0), min(own1 + 2, n0)
+
+
+def exchange_halo_planes(buf: torch.Tensor, n0: int, rank: int, world: int, group=None):
+    """Fill the halo planes of `buf` (planes [buf0,buf1) of slab_layout) from the neighbouring ranks: this rank's first two
+    owned planes go down to rank-1, its last owned plane goes up to rank+1 — three 4*n1*n2-byte planes per interior rank
+    over NVLink (NCCL send/recv), instead of recomputing 3 planes of MLP per rank.  Needs >= 2 owned planes on every rank."""
+    own0, own1, buf0, buf1 = slab_layout(n0, rank, world)
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, buf[own0 - buf0:own0 - buf0 + 2], rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, buf[0:own0 - buf0], rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, buf[own1 - 1 - buf0:own1 - buf0], rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, buf[own1 - buf0:buf1 - buf0], rank + 1, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+
+def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None, halo="exchange"):
+    """mesh_nerf.extract_geometry (src/mesh_nerf.py:68-92) on N GPUs, x-slabs of the grid:
+      1. every rank sweeps sigma over ITS planes (fused MLP, grid front-end) into its slab buffer;
+      2. halo planes: 3 planes per interior rank by send/recv from the neighbours (`halo="exchange"`), or recomputed;
+      3. extract_iso_level: min / max / std over the whole grid — scalar all_reduces (every plane is owned exactly once);
+      4. marching cubes, count step; all_gather of the (n_vertices, n_triangles) pairs -> every rank's index offset;
+      5. marching cubes, emit step, straight into this rank's segment of the exchange buffer; ONE all_gather of
+         [vertices | normals | faces] (padded to the largest slab) leaves the whole mesh on every rank.
+    A vertex belongs to the rank that owns its grid point, and the last owned cell layer addresses the next rank's
+    vertices by the ids that rank assigns (nm_mc_count / nm_mc_emit), so the concatenation IS the single-GPU mesh — same
+    arrays, bit for bit; there are no duplicates to remove.  Returns (vertices, triangles, normals, iso) like the single-GPU
+    function (vertices rescaled to (-limit, limit) when to_host).  Works without a process group (one slab)."""
+    import numpy as np
     rank, world = _rank_world(group)
     eng = model._engine()
-    res = args.res
+    res, dev = args.res, eng.device
     tm = _StageTimer(timings)
     tiles = [torch.linspace(-args.limit, args.limit, res) for _ in range(3)]
-    x0, x1 = slab_shard(res, rank, world)
+    own0, own1, buf0, buf1 = slab_layout(res, rank, world)
     tm.mark()
-    sigma = eng.grid_sigma(tiles, x0, x1)
-    tm.mark("sweep")
-    own = sigma if rank == world - 1 else sigma[:-1]          # the shared plane is counted once
-    import numpy as np
+    buf = torch.empty((buf1 - buf0, res, res), dtype=torch.float32, device=dev)
+    can_exchange = world > 1 and halo == "exchange" and all(
+        (lambda a: a[1] - a[0] >= 2)(slab_layout(res, r, world)) for r in range(world))
+    if world == 1 or can_exchange:
+        eng.grid_sigma(tiles, own0, own1, out=buf[own0 - buf0:own1 - buf0])
+        tm.mark("sweep")
+        if world > 1:
+            exchange_halo_planes(buf, res, rank, world, group)
+    else:
+        eng.grid_sigma(tiles, buf0, buf1, out=buf)            # halo planes recomputed (bit-identical to the owner's)
+        tm.mark("sweep")
+    own = buf[own0 - buf0:own1 - buf0]
+    tm.mark("halo")
     if world > 1:
         mn, mx, _ = eng.volume_stats(own)
         s = float(own.double().sum())
-        smin, smax, sstd = global_stats(mn, mx, s, lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), sigma.device, group)
+        smin, smax, sstd = global_stats(mn, mx, s, lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), dev, group)
     else:
         smin, smax, sstd = eng.volume_stats(own)
-    iso = min(max(args.iso_level, np.float32(smin) + np.float32(sstd)), np.float32(smax) - np.float32(sstd))
+    iso = float(min(max(args.iso_level, np.float32(smin) + np.float32(sstd)), np.float32(smax) - np.float32(sstd)))
     tm.mark("stats")
-    v, f, n = eng.marching_cubes(sigma, float(iso), x_off=float(x0))
-    tm.mark("mc")
-    if world > 1:
-        v, f, n = gather_mesh(v, f, n, group)
-    tm.mark("gather")
+    shard = (iso, buf0, res, own0 - buf0, own1 - buf0)
+    nv, nt = eng.mc_count(buf, *shard)
+    if world == 1:
+        v, f, n = eng.mc_emit(buf, *shard, nv, nt, 0)
+        tm.mark("mc")
+        tm.mark("gather")
+    else:
+        counts = torch.tensor([nv, nt], dtype=torch.int64, device=dev)
+        allc = torch.empty((world, 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, counts, group=group)
+        allc = allc.cpu()
+        nvs, nts = [int(x) for x in allc[:, 0]], [int(x) for x in allc[:, 1]]
+        v_base = sum(nvs[:rank])
+        if sum(nvs) >= 2 ** 31:
+            raise OverflowError("mesh too large for int32 indices")
+        vmax, tmax = max(max(nvs), 1), max(max(nts), 1)
+        seg = 3 * (2 * vmax + tmax)                               # floats per rank: vertices | normals | faces (int32 bits)
+        local = torch.empty(seg, dtype=torch.float32, device=dev)
+        full = torch.empty(world * seg, dtype=torch.float32, device=dev)
+        views = (local[:3 * vmax].view(vmax, 3), local[3 * vmax:6 * vmax].view(vmax, 3), local[6 * vmax:].view(torch.int32).view(tmax, 3))
+        eng.mc_emit(buf, *shard, nv, nt, v_base, out=views)
+        tm.mark("mc")
+        dist.all_gather_into_tensor(full, local, group=group)
+        full = full.view(world, seg)
+        v = torch.cat([full[r, :3 * nvs[r]] for r in range(world)]).view(-1, 3)
+        n = torch.cat([full[r, 3 * vmax:3 * vmax + 3 * nvs[r]] for r in range(world)]).view(-1, 3)
+        f = torch.cat([full[r, 6 * vmax:6 * vmax + 3 * nts[r]] for r in range(world)]).view(torch.int32).view(-1, 3)
+        tm.mark("gather")
     tm.finish()
     if to_host:
         v = args.limit * (v.cpu() / (res / 2.0) - 1.0)
-        return v, f.cpu(), n.cpu(), float(iso)
-    return v, f, n, float(iso)
+        return v, f.cpu(), n.cpu(), iso
+    return v, f, n, iso

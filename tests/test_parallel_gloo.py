@@ -29,6 +29,18 @@ def test_shard_arithmetic():
             assert sum(e - s - 1 for s, e in slabs) == n0 - 1                      # every cell layer exactly once
 
 
+def test_slab_layout_owns_every_plane_once():
+    for n0 in (512, 40, 9):
+        for world in (1, 2, 4, 8):
+            if n0 - 1 < world:
+                continue
+            lay = [P.slab_layout(n0, r, world) for r in range(world)]
+            assert lay[0][0] == 0 and lay[-1][1] == n0
+            assert all(a[1] == b[0] for a, b in zip(lay, lay[1:]))              # owned point planes tile [0, n0)
+            for own0, own1, buf0, buf1 in lay:
+                assert buf0 == max(own0 - 1, 0) and buf1 == min(own1 + 2, n0)   # one halo plane below, two above
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -54,6 +66,21 @@ def _worker(rank, world, port, q):
         mn, mx, sd = P.global_stats(float(own.min()), float(own.max()), float(own.double().sum()),
                                     lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), torch.device("cpu"))
         ok &= mn == float(vol.min()) and mx == float(vol.max()) and abs(sd - float(vol.double().std(unbiased=False))) < 1e-9
+        # the row exchange: kernels fill `views`, ONE all_gather_into_tensor assembles every map (H not divisible by world)
+        for H2 in (9, 8):
+            ex = P.RowExchange(torch.device("cpu"), H2, W, ("rgb", "acc"))
+            fullrgb = torch.arange(H2 * W * 3, dtype=torch.float32).reshape(H2 * W, 3) + 0.5
+            ex.views["rgb"].copy_(fullrgb[ex.r0 * W:ex.r1 * W])
+            ex.views["acc"].copy_(fullrgb[ex.r0 * W:ex.r1 * W, 1])
+            got = ex.gather()
+            ok &= torch.equal(got["rgb"], fullrgb) and torch.equal(got["acc"], fullrgb[:, 1])
+        # halo planes of an x-slab arrive from the neighbours
+        n0 = 11
+        own0, own1, buf0, buf1 = P.slab_layout(n0, rank, world)
+        buf = torch.full((buf1 - buf0, 5, 6), -1.0)
+        buf[own0 - buf0:own1 - buf0] = vol[own0:own1]
+        P.exchange_halo_planes(buf, n0, rank, world)
+        ok &= torch.equal(buf, vol[buf0:buf1])
         # data-parallel gradient exchange: mean over ranks, one flat all_reduce, parameters without a gradient skipped
         ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(1))]
         ps[0].grad = torch.full((3, 2), float(rank + 1))
