@@ -149,6 +149,11 @@ int nm_grid_sigma(NmHandle h, const float* lin0_host, const float* lin1_host, co
  * {min, max, std}; synchronises. */
 int nm_volume_stats(NmHandle h, const float* vol_dev, int64_t n, float* out_host);
 
+/* The same statistics for a volume sharded over several GPUs, stream-ordered and without host synchronisation: pass 1 writes
+ * out_dev[0..2] = {min, max, sum} of this shard (doubles), pass 2 writes out_dev[3] = sum (x - *mean_dev)^2; the caller
+ * combines the shards between and after the passes (all_gather / all_reduce on the device values). */
+int nm_volume_stats_dev(NmHandle h, const float* vol_dev, int64_t n, int pass, const double* mean_dev, double* out_dev, void* stream);
+
 /* skimage.measure.marching_cubes(volume, level) seam (src/mesh_nerf.py:79) on a device volume (nx,ny,nz) fp32, Lewiner-style
  * topology resolution (face / interior tests, cell-centre vertices): sign bit-volume -> count -> scan -> emit.  Two-call
  * protocol: nm_marching_cubes_count fills counts_host = {n_vertices, n_triangles} (synchronises);

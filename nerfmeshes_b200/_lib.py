@@ -54,6 +54,7 @@ _SIGNATURES = {
     "nm_volume_stats": (C.c_int, [_P, _P, _L, _P]),
     "nm_marching_cubes_count": (C.c_int, [_P, _P, _I, _I, _I, _F, _P, _P]),
     "nm_marching_cubes_emit": (C.c_int, [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, _P]),
+    "nm_volume_stats_dev": (C.c_int, [_P, _P, _L, _I, _P, _P, _P]),
     "nm_mc_count": (C.c_int, [_P, _P, _I, _I, _I, _F, _I, _I, _I, _I, _P, _P]),
     "nm_mc_emit": (C.c_int, [_P, _P, _I, _I, _I, _F, _I, _I, _I, _I, _L, _P, _P, _P, _P]),
     "nm_export_obj": (C.c_int, [C.c_char_p, _P, _L, _P, _L, _P, _L, _P, _L]),

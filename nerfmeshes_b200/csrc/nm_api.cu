@@ -59,6 +59,7 @@ struct NmHandle_t {
   int64_t mlp_points = 0, mlp_launches = 0;
   size_t mc_ws_bytes = 0;
   void* mc_ws_ptr = nullptr;
+  int64_t mc_lists[2] = {0, 0};   // emit-grid sizes left by the last count step
   // training (nm_train.cu): gradient accumulators per network + scratch
   Buf g_wt[2], g_bias[2], g_head[2], train_ws, dout, trans, tr_rgb[2], tr_drgb[2];
   bool grads_ready = false;
@@ -677,20 +678,31 @@ int nm_volume_stats(NmHandle h, const float* vol_dev, int64_t n, float* out_host
   return launch_volume_stats(vol_dev, n, h->d_stats, out_host, h->own_stream, &h->launches);
 }
 
+int nm_volume_stats_dev(NmHandle h, const float* vol_dev, int64_t n, int pass, const double* mean_dev, double* out_dev, void* stream) {
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(vol_dev && out_dev, "null argument");
+  return launch_volume_stats_pass(vol_dev, n, pass, mean_dev, out_dev, (cudaStream_t)stream, &h->launches);
+}
+
 int nm_mc_count(NmHandle h, const float* vol_dev, int nb, int ny, int nz, float iso, int g_x0, int g_nx, int p_lo, int p_hi,
                 int64_t* counts_host, void* stream) {
   if (int e = bind_device(h)) return e;
   NM_CHECK(vol_dev && counts_host, "null argument");
-  const McShard s{vol_dev, nb, ny, nz, iso, g_x0, g_nx, p_lo, p_hi};
-  return mc_count(s, &h->mc_ws_ptr, &h->mc_ws_bytes, counts_host, (cudaStream_t)stream, &h->launches);
+  const McShard s{vol_dev, nb, ny, nz, iso, g_x0, g_nx, p_lo, p_hi, 0};
+  int64_t c[4] = {0, 0, 0, 0};
+  if (int e = mc_count(s, &h->mc_ws_ptr, &h->mc_ws_bytes, c, (cudaStream_t)stream, &h->launches)) return e;
+  counts_host[0] = c[0]; counts_host[1] = c[1];
+  h->mc_lists[0] = c[2]; h->mc_lists[1] = c[3];
+  return 0;
 }
 
 int nm_mc_emit(NmHandle h, const float* vol_dev, int nb, int ny, int nz, float iso, int g_x0, int g_nx, int p_lo, int p_hi,
                int64_t v_base, float* verts_dev, float* normals_dev, int32_t* faces_dev, void* stream) {
   if (int e = bind_device(h)) return e;
   NM_CHECK(vol_dev && verts_dev && faces_dev && h->mc_ws_ptr, "bad arguments (call nm_mc_count first)");
-  const McShard s{vol_dev, nb, ny, nz, iso, g_x0, g_nx, p_lo, p_hi};
-  return mc_emit(s, h->mc_ws_ptr, h->mc_ws_bytes, v_base, verts_dev, normals_dev, faces_dev, (cudaStream_t)stream, &h->launches);
+  const McShard s{vol_dev, nb, ny, nz, iso, g_x0, g_nx, p_lo, p_hi, 0};
+  return mc_emit(s, h->mc_ws_ptr, h->mc_ws_bytes, v_base, h->mc_lists, verts_dev, normals_dev, faces_dev, (cudaStream_t)stream,
+                 &h->launches);
 }
 
 int nm_marching_cubes_count(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, int64_t* counts_host,
@@ -701,10 +713,11 @@ int nm_marching_cubes_count(NmHandle h, const float* vol_dev, int nx, int ny, in
 int nm_marching_cubes_emit(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, float x_off,
                            float* verts_dev, float* normals_dev, int32_t* faces_dev, void* stream) {
   NM_CHECK(x_off >= 0.f && x_off == (float)(int)x_off, "x_off must be a non-negative integer number of planes");
-  // a stand-alone volume whose axis-0 coordinates start at x_off: the count step ran with g_x0 = 0, and only the vertex
-  // coordinates depend on g_x0, so the workspace is reused as is
-  const int x0 = (int)x_off;
-  return nm_mc_emit(h, vol_dev, nx, ny, nz, iso, x0, x0 + nx, 0, nx, 0, verts_dev, normals_dev, faces_dev, stream);
+  // a stand-alone volume whose axis-0 vertex coordinates start at x_off (a pure coordinate shift)
+  if (int e = bind_device(h)) return e;
+  NM_CHECK(vol_dev && verts_dev && faces_dev && h->mc_ws_ptr, "bad arguments (call nm_marching_cubes_count first)");
+  const McShard s{vol_dev, nx, ny, nz, iso, 0, nx, 0, nx, (int)x_off};
+  return mc_emit(s, h->mc_ws_ptr, h->mc_ws_bytes, 0, h->mc_lists, verts_dev, normals_dev, faces_dev, (cudaStream_t)stream, &h->launches);
 }
 
 int nm_query_host(NmHandle h, const float* origins_host, int o_stride, const float* dirs_host, int64_t R,

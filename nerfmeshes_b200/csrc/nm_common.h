@@ -148,6 +148,8 @@ int launch_tree_integrate(const int* idx, const float* w, const float* mw, long 
                           float* scratch2v, cudaStream_t st, int64_t* launches);
 int launch_volume_stats(const float* vol, long long n, double* d_scratch, float* out_host, cudaStream_t st,
                         int64_t* launches);
+int launch_volume_stats_pass(const float* vol, long long n, int pass, const double* mean_dev, double* out_dev, cudaStream_t st,
+                             int64_t* launches);
 // training backward (nm_train.cu)
 size_t train_ws_bytes(const NetProgram& full, long long points, bool use_tc);
 struct TrainMode { int use_tc; int n_passes; int* d_err; };
@@ -168,9 +170,11 @@ struct McShard {
   int nb, ny, nz;
   float iso;
   int g_x0, g_nx, p_lo, p_hi;
+  int x_shift;       // added to the axis-0 vertex coordinates only (stand-alone volumes that are a window of a larger one)
 };
+// counts_host[4]: {vertices owned, triangles, words with vertices, words with triangles}; the last two size the emit grids
 int mc_count(const McShard& s, void** ws, size_t* ws_bytes, int64_t* counts_host, cudaStream_t st, int64_t* launches);
-int mc_emit(const McShard& s, void* ws, size_t ws_bytes, long long v_base, float* verts, float* normals, int32_t* faces,
-            cudaStream_t st, int64_t* launches);
+int mc_emit(const McShard& s, void* ws, size_t ws_bytes, long long v_base, const int64_t* list_sizes, float* verts, float* normals,
+            int32_t* faces, cudaStream_t st, int64_t* launches);
 
 }  // namespace nm

@@ -8,7 +8,8 @@
 //                        only topologically ambiguous ones read their 8 corner values (face tests, interior test).  Writes
 //                        per word: the X/Y/Z/C bit words, vertex + triangle counts; per block: the count sums.
 //   3. mc_scan_blocks / mc_scan_words   two-level exclusive scan of the counts (per-word vertex / triangle prefixes).
-//   4. mc_emit_vertices / mc_emit_triangles   one thread per word again; a vertex id anywhere in the grid is
+//   4. mc_emit_vertices / mc_emit_triangles   one WARP per word that has vertices / triangles (the count pass compacts those
+//                        words into two lists), one lane per grid point of the word; a vertex id anywhere in the grid is
 //                        prefix[word] + popcount(bits below) — no dense per-point id array.
 //
 // Output contract (mirrors the Lewiner output the reference consumes at mesh_nerf.py:79-90): an INDEXED mesh, one vertex
@@ -54,7 +55,7 @@ constexpr double kEps = (double)FLT_EPSILON;
 struct McGrid {
   const float* vol;
   int nb, ny, nz, W;          // buffer planes, lines per plane, points per line, 32-bit words per line
-  int g_x0, g_nx;             // global index of buffer plane 0, planes of the global grid
+  int g_x0, g_nx, x_shift;    // global index of buffer plane 0, planes of the global grid, pure coordinate offset
   int p_lo, p_hi, p_end;      // owned planes [p_lo,p_hi); [p_hi,p_end) = the shadow plane (ids only), 0 or 1 plane
   float iso;
   // workspace
@@ -64,7 +65,9 @@ struct McGrid {
   unsigned* vpre;             // per word: exclusive vertex prefix
   unsigned* tpre;             // per word: exclusive triangle prefix
   unsigned* blk;              // per block of kBlock words: {vertex sum, triangle sum} -> exclusive prefixes
-  unsigned long long* totals; // [n_vertices incl. shadow plane, n_triangles, n_vertices owned]
+  unsigned long long* totals; // [n_vertices incl. shadow plane, n_triangles, n_vertices owned, #words with vertices | #words with triangles << 32]
+  unsigned* list_v;           // owned words that hold at least one vertex (compacted, arbitrary order)
+  unsigned* list_t;           // owned words that hold at least one triangle
   long long nwords;           // words of planes [p_lo,p_end)
   long long nwords_own;       // words of planes [p_lo,p_hi)
 };
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(kBlock) mc_sign_kernel(const float* __restrict
   const long long nw = nlines * W;
   const long long warps = (long long)gridDim.x * (kBlock / 32);
   long long word = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  const bool dense = (nz & 31) == 0;          // lines are whole words: word wd covers vol[32*wd .. 32*wd+31]
   constexpr int U = 8;
   for (; word < nw; word += warps * U) {
     float v[U];
@@ -84,9 +88,13 @@ __global__ void __launch_bounds__(kBlock) mc_sign_kernel(const float* __restrict
       const long long wd = word + warps * u;
       v[u] = -CUDART_INF_F;
       if (wd < nw) {
-        const long long line = wd / W;
-        const int k = (int)(wd - line * W) * 32 + lane;
-        if (k < nz) v[u] = __ldcs(vol + line * nz + k);
+        if (dense) {
+          v[u] = __ldcs(vol + wd * 32 + lane);
+        } else {
+          const unsigned line = (unsigned)((unsigned long long)wd / (unsigned)W);      // nw < 2^32 is checked by the host
+          const int k = (int)((unsigned)wd - line * (unsigned)W) * 32 + lane;
+          if (k < nz) v[u] = __ldcs(vol + (long long)line * nz + k);
+        }
       }
     }
 #pragma unroll
@@ -194,10 +202,12 @@ __device__ __forceinline__ unsigned cell_mask(const Nbhd& n, int b) {   // corne
 }
 
 __device__ __forceinline__ void word_coords(const McGrid& g, long long wl, int* i, int* j, int* w) {
-  const long long line = wl / g.W;
-  *w = (int)(wl - line * g.W);
-  *i = g.p_lo + (int)(line / g.ny);
-  *j = (int)(line % g.ny);
+  const unsigned u = (unsigned)wl;                     // word counts stay below 2^32 (make_grid): 32-bit divisions
+  const unsigned line = u / (unsigned)g.W;
+  *w = (int)(u - line * (unsigned)g.W);
+  const unsigned pi = line / (unsigned)g.ny;
+  *i = g.p_lo + (int)pi;
+  *j = (int)(line - pi * (unsigned)g.ny);
 }
 
 __device__ __forceinline__ unsigned block_sum(unsigned v, unsigned* s_warp) {
@@ -217,6 +227,7 @@ __global__ void __launch_bounds__(kBlock) mc_count_kernel(const McGrid g) {
   __shared__ unsigned s_warp[kBlock / 32];
   const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
   unsigned vc = 0, tc = 0;
+  bool has_v = false, has_t = false;
   if (wl < g.nwords) {
     int i, j, w;
     word_coords(g, wl, &i, &j, &w);
@@ -235,36 +246,60 @@ __global__ void __launch_bounds__(kBlock) mc_count_kernel(const McGrid g) {
     vc = __popc(n.X) + __popc(n.Y) + __popc(n.Z) + __popc(C);
     g.bits[wl] = make_uint4(n.X, n.Y, n.Z, C);
     g.cnt[wl] = vc | (tc << 16);
+    has_v = owned && vc > 0;
+    has_t = tc > 0;
+  }
+  {   // compact the words with vertices / triangles: one atomic per warp and list
+    unsigned* counters = reinterpret_cast<unsigned*>(g.totals + 3);
+    const int lane = threadIdx.x & 31;
+    const unsigned mv = __ballot_sync(0xffffffffu, has_v), mt = __ballot_sync(0xffffffffu, has_t);
+    unsigned bv = 0, bt = 0;
+    if (lane == 0) {
+      if (mv) bv = atomicAdd(counters, __popc(mv));
+      if (mt) bt = atomicAdd(counters + 1, __popc(mt));
+    }
+    bv = __shfl_sync(0xffffffffu, bv, 0); bt = __shfl_sync(0xffffffffu, bt, 0);
+    if (has_v) g.list_v[bv + __popc(mv & ((1u << lane) - 1u))] = (unsigned)wl;
+    if (has_t) g.list_t[bt + __popc(mt & ((1u << lane) - 1u))] = (unsigned)wl;
   }
   const unsigned sv = block_sum(vc, s_warp), stt = block_sum(tc, s_warp);
   if (threadIdx.x == 0) { g.blk[2 * blockIdx.x] = sv; g.blk[2 * blockIdx.x + 1] = stt; }
 }
 
 // ------------------------------------------------------------------------------------------------ 3. scans
-// exclusive scan of the per-block sums (<= a few 1e4 entries: one block, each thread a contiguous chunk)
+// exclusive scan of the per-block sums (a few 1e4 entries): one block, 1024 entries per round, coalesced, running carry
 __global__ void __launch_bounds__(1024) mc_scan_blocks(McGrid g, int nblocks) {
-  __shared__ unsigned long long s_part[2][1024];
-  const int t = threadIdx.x;
-  const int per = (nblocks + 1023) / 1024;
-  const int lo = t * per, hi = min(nblocks, lo + per);
-  unsigned long long sv = 0, stt = 0;
-  for (int l = lo; l < hi; ++l) { sv += g.blk[2 * l]; stt += g.blk[2 * l + 1]; }
-  s_part[0][t] = sv; s_part[1][t] = stt;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 partials
-  for (int o = 1; o < 1024; o <<= 1) {
-    const unsigned long long a = t >= o ? s_part[0][t - o] : 0, b = t >= o ? s_part[1][t - o] : 0;
+  __shared__ unsigned long long s_v[32], s_t[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  unsigned long long carry_v = 0, carry_t = 0;
+  uint2* blk = reinterpret_cast<uint2*>(g.blk);
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int l = base + t;
+    const uint2 c = l < nblocks ? blk[l] : make_uint2(0u, 0u);
+    unsigned long long xv = c.x, xt = c.y;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long yv = __shfl_up_sync(0xffffffffu, xv, o), yt = __shfl_up_sync(0xffffffffu, xt, o);
+      if (lane >= o) { xv += yv; xt += yt; }
+    }
+    if (lane == 31) { s_v[wid] = xv; s_t[wid] = xt; }
     __syncthreads();
-    s_part[0][t] += a; s_part[1][t] += b;
+    if (wid == 0) {
+      unsigned long long av = s_v[lane], at = s_t[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long yv = __shfl_up_sync(0xffffffffu, av, o), yt = __shfl_up_sync(0xffffffffu, at, o);
+        if (lane >= o) { av += yv; at += yt; }
+      }
+      s_v[lane] = av; s_t[lane] = at;                    // inclusive scan of the warp totals
+    }
+    __syncthreads();
+    const unsigned long long wv = wid ? s_v[wid - 1] : 0, wt = wid ? s_t[wid - 1] : 0;
+    if (l < nblocks) blk[l] = make_uint2((unsigned)(carry_v + wv + xv - c.x), (unsigned)(carry_t + wt + xt - c.y));
+    carry_v += s_v[31]; carry_t += s_t[31];
     __syncthreads();
   }
-  unsigned long long av = s_part[0][t] - sv, at = s_part[1][t] - stt;
-  if (t == 1023) { g.totals[0] = s_part[0][t]; g.totals[1] = s_part[1][t]; }
-  for (int l = lo; l < hi; ++l) {
-    const unsigned v = g.blk[2 * l], w = g.blk[2 * l + 1];
-    g.blk[2 * l] = (unsigned)av; g.blk[2 * l + 1] = (unsigned)at;
-    av += v; at += w;
-  }
+  if (t == 0) { g.totals[0] = carry_v; g.totals[1] = carry_t; }
 }
 
 __global__ void __launch_bounds__(kBlock) mc_scan_words(const McGrid g) {
@@ -316,65 +351,63 @@ __device__ __forceinline__ void store_vertex(float* verts, float* normals, size_
   }
 }
 
-__global__ void __launch_bounds__(kBlock) mc_emit_vertices(const McGrid g, float* __restrict__ verts, float* __restrict__ normals) {
-  const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (wl >= g.nwords_own) return;
+__global__ void __launch_bounds__(kBlock) mc_emit_vertices(const McGrid g, unsigned nlist, float* __restrict__ verts,
+                                                           float* __restrict__ normals) {
+  const unsigned item = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if (item >= nlist) return;
+  const int b = threadIdx.x & 31;
+  const long long wl = g.list_v[item];
   const uint4 B = g.bits[wl];
-  unsigned any = B.x | B.y | B.z | B.w;
-  if (!any) return;
+  const unsigned sel[4] = {(B.x >> b) & 1u, (B.y >> b) & 1u, (B.z >> b) & 1u, (B.w >> b) & 1u};
+  if (!(sel[0] | sel[1] | sel[2] | sel[3])) return;
   int i, j, w;
   word_coords(g, wl, &i, &j, &w);
-  size_t id = g.vpre[wl];
+  const unsigned lt = (1u << b) - 1u;
+  size_t id = (size_t)g.vpre[wl] + __popc(B.x & lt) + __popc(B.y & lt) + __popc(B.z & lt) + __popc(B.w & lt);
   const size_t st[3] = {(size_t)g.ny * g.nz, (size_t)g.nz, 1};
   const double iso = (double)g.iso;
-  while (any) {
-    const int b = __ffs(any) - 1;
-    any &= any - 1;
-    const int k = w * 32 + b;
-    const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
-    const double base[3] = {(double)(g.g_x0 + i), (double)j, (double)k};
-    const unsigned bitsel[3] = {(B.x >> b) & 1u, (B.y >> b) & 1u, (B.z >> b) & 1u};
-    float g0[3];
-    double w0 = 0.0;
-    if (bitsel[0] | bitsel[1] | bitsel[2]) {
-      grid_grad(g, i, j, k, g0);
-      w0 = 1.0 / (kEps + fabs((double)g.vol[p] - iso));
+  const int k = w * 32 + b;
+  const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
+  const double base[3] = {(double)(g.g_x0 + i + g.x_shift), (double)j, (double)k};
+  float g0[3];
+  double w0 = 0.0;
+  if (sel[0] | sel[1] | sel[2]) {
+    grid_grad(g, i, j, k, g0);
+    w0 = 1.0 / (kEps + fabs((double)g.vol[p] - iso));
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (!sel[a]) continue;
+    int c1[3] = {i, j, k};
+    c1[a] += 1;
+    const double w1 = 1.0 / (kEps + fabs((double)g.vol[p + st[a]] - iso));
+    const double ff = w0 + w1;
+    double pos[3] = {base[0], base[1], base[2]};
+    pos[a] = base[a] + w1 / ff;                  // x + step * fx / ff with fx = 0*w0 + 1*w1 (scikit-image's form)
+    float g1[3];
+    grid_grad(g, c1[0], c1[1], c1[2], g1);
+    double n[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) n[q] = -((double)g0[q] * w0 + (double)g1[q] * w1);
+    store_vertex(verts, normals, id, pos, n);
+    ++id;
+  }
+  if (sel[3]) {                                  // calculate_center_vertex: weighted mean of the 8 corners, Lewiner's order
+    double f[3] = {0, 0, 0}, ff = 0, n[3] = {0, 0, 0};
+    for (int L = 0; L < 8; ++L) {
+      const int c = c_lew2my[L];
+      const int ci = i + (c & 1), cj = j + ((c >> 1) & 1), ck = k + ((c >> 2) & 1);
+      const double wc = 1.0 / (kEps + fabs((double)g.vol[((size_t)ci * g.ny + cj) * g.nz + ck] - iso));
+#pragma unroll
+      for (int q = 0; q < 3; ++q) if ((c >> q) & 1) f[q] += wc;
+      ff += wc;
+      float gc[3];
+      grid_grad(g, ci, cj, ck, gc);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) n[q] -= (double)gc[q] * wc;
     }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (!bitsel[a]) continue;
-      int c1[3] = {i, j, k};
-      c1[a] += 1;
-      const double w1 = 1.0 / (kEps + fabs((double)g.vol[p + st[a]] - iso));
-      const double ff = w0 + w1;
-      double pos[3] = {base[0], base[1], base[2]};
-      pos[a] = base[a] + w1 / ff;                  // x + step * fx / ff with fx = 0*w0 + 1*w1 (scikit-image's form)
-      float g1[3];
-      grid_grad(g, c1[0], c1[1], c1[2], g1);
-      double n[3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) n[q] = -((double)g0[q] * w0 + (double)g1[q] * w1);
-      store_vertex(verts, normals, id, pos, n);
-      ++id;
-    }
-    if ((B.w >> b) & 1u) {                         // calculate_center_vertex: weighted mean of the 8 corners, Lewiner's order
-      double f[3] = {0, 0, 0}, ff = 0, n[3] = {0, 0, 0};
-      for (int L = 0; L < 8; ++L) {
-        const int c = c_lew2my[L];
-        const int ci = i + (c & 1), cj = j + ((c >> 1) & 1), ck = k + ((c >> 2) & 1);
-        const double wc = 1.0 / (kEps + fabs((double)g.vol[((size_t)ci * g.ny + cj) * g.nz + ck] - iso));
-#pragma unroll
-        for (int q = 0; q < 3; ++q) if ((c >> q) & 1) f[q] += wc;
-        ff += wc;
-        float gc[3];
-        grid_grad(g, ci, cj, ck, gc);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) n[q] -= (double)gc[q] * wc;
-      }
-      const double pos[3] = {base[0] + f[0] / ff, base[1] + f[1] / ff, base[2] + f[2] / ff};
-      store_vertex(verts, normals, id, pos, n);
-      ++id;
-    }
+    const double pos[3] = {base[0] + f[0] / ff, base[1] + f[1] / ff, base[2] + f[2] / ff};
+    store_vertex(verts, normals, id, pos, n);
   }
 }
 
@@ -388,37 +421,41 @@ __device__ __forceinline__ unsigned point_base(const McGrid& g, int i, int j, in
   return g.vpre[wq] + __popc(B.x & lt) + __popc(B.y & lt) + __popc(B.z & lt) + __popc(B.w & lt);
 }
 
-__global__ void __launch_bounds__(kBlock) mc_emit_triangles(const McGrid g, long long v_base, int* __restrict__ faces) {
-  const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (wl >= g.nwords_own) return;
-  if ((g.cnt[wl] >> 16) == 0) return;
+__global__ void __launch_bounds__(kBlock) mc_emit_triangles(const McGrid g, unsigned nlist, long long v_base, int* __restrict__ faces) {
+  const unsigned item = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if (item >= nlist) return;
+  const int b = threadIdx.x & 31;
+  const long long wl = g.list_t[item];
   int i, j, w;
   word_coords(g, wl, &i, &j, &w);
   const Nbhd n = load_nbhd(g, i, j, w);
-  size_t tid = g.tpre[wl];
-  unsigned act = n.active;
-  while (act) {
-    const int b = __ffs(act) - 1;
-    act &= act - 1;
-    const int k = w * 32 + b;
-    const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
-    const L3Entry* e = &g_l3[resolve_cell(g, cell_mask(n, b), p)];
-    unsigned base[8], slots[8];
+  const bool act = (n.active >> b) & 1u;
+  const int k = w * 32 + b;
+  const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
+  const L3Entry* e = nullptr;
+  unsigned nt = 0;
+  if (act) { e = &g_l3[resolve_cell(g, cell_mask(n, b), p)]; nt = e->ntri; }
+  unsigned x = nt;                                // exclusive prefix of the triangle counts over the lanes (cells in k order)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) base[c] = point_base(g, i + (c & 1), j + ((c >> 1) & 1), k + ((c >> 2) & 1), &slots[c]);
-    const int nt = e->ntri;
-    for (int t = 0; t < 3 * nt; ++t) {
-      const int s = e->idx[t];
-      unsigned id;
-      if (s == 12) {
-        id = base[0] + (slots[0] & 1u) + ((slots[0] >> 1) & 1u) + ((slots[0] >> 2) & 1u);
-      } else {
-        const int lo = c_edge_lo[s], a = c_edge_axis[s];
-        id = base[lo] + __popc(slots[lo] & ((1u << a) - 1u));
-      }
-      faces[3 * tid + t] = (int)(v_base + (long long)id);
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+    if (b >= o) x += y;
+  }
+  if (!nt) return;
+  size_t tid = (size_t)g.tpre[wl] + x - nt;
+  unsigned base[8], slots[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) base[c] = point_base(g, i + (c & 1), j + ((c >> 1) & 1), k + ((c >> 2) & 1), &slots[c]);
+  for (unsigned t = 0; t < 3 * nt; ++t) {
+    const int s = e->idx[t];
+    unsigned id;
+    if (s == 12) {
+      id = base[0] + (slots[0] & 1u) + ((slots[0] >> 1) & 1u) + ((slots[0] >> 2) & 1u);
+    } else {
+      const int lo = c_edge_lo[s], a = c_edge_axis[s];
+      id = base[lo] + __popc(slots[lo] & ((1u << a) - 1u));
     }
-    tid += nt;
+    faces[3 * tid + t] = (int)(v_base + (long long)id);
   }
 }
 
@@ -430,7 +467,8 @@ int carve(void* base, size_t bytes, McGrid* g, size_t* need) {
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
   const size_t o_sign = take(nsign * 4), o_bits = take(nw * 16), o_cnt = take(nw * 4), o_vp = take((nw + 1) * 4),
-               o_tp = take((nw + 1) * 4), o_blk = take((nblk + 1) * 8), o_tot = take(32);
+               o_tp = take((nw + 1) * 4), o_blk = take((nblk + 1) * 8), o_tot = take(64),
+               o_lv = take((size_t)g->nwords_own * 4 + 4), o_lt = take((size_t)g->nwords_own * 4 + 4);
   *need = off;
   if (!base || bytes < off) return 1;
   char* b = reinterpret_cast<char*>(base);
@@ -441,6 +479,8 @@ int carve(void* base, size_t bytes, McGrid* g, size_t* need) {
   g->tpre = reinterpret_cast<unsigned*>(b + o_tp);
   g->blk = reinterpret_cast<unsigned*>(b + o_blk);
   g->totals = reinterpret_cast<unsigned long long*>(b + o_tot);
+  g->list_v = reinterpret_cast<unsigned*>(b + o_lv);
+  g->list_t = reinterpret_cast<unsigned*>(b + o_lt);
   return 0;
 }
 
@@ -454,10 +494,11 @@ int make_grid(const McShard& s, McGrid* g) {
   NM_CHECK(s.p_lo == s.p_hi || s.g_x0 + s.p_lo == 0 || s.p_lo >= 1, "marching cubes: halo plane below the owned range missing");
   NM_CHECK(!next_exists || s.g_x0 + s.p_hi + 1 >= s.g_nx || s.p_hi + 1 < s.nb, "marching cubes: halo plane above the owned range missing");
   g->vol = s.vol; g->nb = s.nb; g->ny = s.ny; g->nz = s.nz; g->W = (s.nz + 31) / 32;
-  g->g_x0 = s.g_x0; g->g_nx = s.g_nx; g->p_lo = s.p_lo; g->p_hi = s.p_hi; g->p_end = s.p_hi + (next_exists ? 1 : 0);
+  g->g_x0 = s.g_x0; g->g_nx = s.g_nx; g->x_shift = s.x_shift; g->p_lo = s.p_lo; g->p_hi = s.p_hi; g->p_end = s.p_hi + (next_exists ? 1 : 0);
   g->iso = s.iso;
   g->nwords = (long long)(g->p_end - g->p_lo) * g->ny * g->W;
   g->nwords_own = (long long)(g->p_hi - g->p_lo) * g->ny * g->W;
+  NM_CHECK((long long)s.nb * s.ny * g->W < (1ll << 32), "marching cubes: volume too large (more than 2^32 words)");
   return 0;
 }
 
@@ -477,11 +518,10 @@ int mc_count(const McShard& s, void** ws_ptr, size_t* ws_bytes, int64_t* counts_
   counts_host[0] = counts_host[1] = 0;
   if (g.nwords == 0) return 0;
   const long long nlines = (long long)g.nb * g.ny;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
   long long sign_blocks = (nlines * g.W + (kBlock / 32) * 8 - 1) / ((kBlock / 32) * 8);
   if (sign_blocks > (long long)sms * 8) sign_blocks = (long long)sms * 8;
+  NM_CUDA(cudaMemsetAsync(g.totals, 0, 64, st));
   mc_sign_kernel<<<(unsigned)sign_blocks, kBlock, 0, st>>>(g.vol, nlines, g.nz, g.W, g.iso, g.sign);
   NM_CUDA(cudaGetLastError());
   const long long nblk = (g.nwords + kBlock - 1) / kBlock;
@@ -492,29 +532,35 @@ int mc_count(const McShard& s, void** ws_ptr, size_t* ws_bytes, int64_t* counts_
   NM_CUDA(cudaGetLastError());
   mc_scan_words<<<(unsigned)nblk, kBlock, 0, st>>>(g);
   NM_CUDA(cudaGetLastError());
-  unsigned long long h[3];
+  unsigned long long h[4];
   NM_CUDA(cudaMemcpyAsync(h, g.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
   NM_CUDA(cudaStreamSynchronize(st));
   const unsigned long long nv_own = (g.p_end > g.p_hi) ? h[2] : h[0];
   NM_CHECK(h[0] < (1ull << 31) && h[1] < (1ull << 31), "mesh too large for int32 indices");
   counts_host[0] = (int64_t)nv_own;
   counts_host[1] = (int64_t)h[1];
+  counts_host[2] = (int64_t)(h[3] & 0xffffffffull);       // words with vertices / triangles: grid sizes of the emit step
+  counts_host[3] = (int64_t)(h[3] >> 32);
   if (launches) *launches += 4;
   return 0;
 }
 
-int mc_emit(const McShard& s, void* ws_ptr, size_t ws_bytes, long long v_base, float* verts, float* normals, int32_t* faces,
-            cudaStream_t st, int64_t* launches) {
+int mc_emit(const McShard& s, void* ws_ptr, size_t ws_bytes, long long v_base, const int64_t* list_sizes, float* verts,
+            float* normals, int32_t* faces, cudaStream_t st, int64_t* launches) {
   McGrid g{};
   if (int e = make_grid(s, &g)) return e;
   size_t need = 0;
   NM_CHECK(carve(ws_ptr, ws_bytes, &g, &need) == 0, "workspace missing (call the count step first, same arguments)");
-  if (g.nwords_own == 0) return 0;
-  const long long nblk = (g.nwords_own + kBlock - 1) / kBlock;
-  mc_emit_vertices<<<(unsigned)nblk, kBlock, 0, st>>>(g, verts, normals);
-  NM_CUDA(cudaGetLastError());
-  mc_emit_triangles<<<(unsigned)nblk, kBlock, 0, st>>>(g, v_base, faces);
-  NM_CUDA(cudaGetLastError());
+  const unsigned nlv = (unsigned)list_sizes[0], nlt = (unsigned)list_sizes[1];
+  constexpr unsigned per = kBlock / 32;
+  if (nlv) {
+    mc_emit_vertices<<<(nlv + per - 1) / per, kBlock, 0, st>>>(g, nlv, verts, normals);
+    NM_CUDA(cudaGetLastError());
+  }
+  if (nlt) {
+    mc_emit_triangles<<<(nlt + per - 1) / per, kBlock, 0, st>>>(g, nlt, v_base, faces);
+    NM_CUDA(cudaGetLastError());
+  }
   if (launches) *launches += 2;
   return 0;
 }

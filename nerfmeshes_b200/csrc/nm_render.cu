@@ -430,7 +430,12 @@ __global__ void stats_pass1(const float* __restrict__ v, long long n, double* __
          old = atomicCAS(pmx, assumed, __double_as_longlong((double)mx)); } while (assumed != old);
   }
 }
-__global__ void stats_pass2(const float* __restrict__ v, long long n, double mean, double* __restrict__ acc) {
+__global__ void stats_init(double* __restrict__ acc) {
+  acc[0] = 1e300; acc[1] = -1e300; acc[2] = 0.0; acc[3] = 0.0;
+}
+__global__ void stats_pass2(const float* __restrict__ v, long long n, double mean_val, const double* __restrict__ mean_dev,
+                            double* __restrict__ acc) {
+  const double mean = mean_dev ? *mean_dev : mean_val;
   double s = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double d = (double)v[i] - mean;
@@ -548,7 +553,7 @@ int launch_volume_stats(const float* vol, long long n, double* d_scratch, float*
   NM_CUDA(cudaMemcpyAsync(h, d_scratch, sizeof(h), cudaMemcpyDeviceToHost, st));
   NM_CUDA(cudaStreamSynchronize(st));
   const double mean = h[2] / (double)n;
-  stats_pass2<<<1184, 256, 0, st>>>(vol, n, mean, d_scratch);
+  stats_pass2<<<1184, 256, 0, st>>>(vol, n, mean, nullptr, d_scratch);
   NM_CUDA(cudaGetLastError());
   NM_CUDA(cudaMemcpyAsync(h, d_scratch, sizeof(h), cudaMemcpyDeviceToHost, st));
   NM_CUDA(cudaStreamSynchronize(st));
@@ -556,6 +561,23 @@ int launch_volume_stats(const float* vol, long long n, double* d_scratch, float*
   out_host[1] = (float)h[1];
   out_host[2] = (float)sqrt(h[3] / (double)n);   // numpy .std(): population std (ddof=0)
   if (launches) *launches += 2;
+  return 0;
+}
+
+// asynchronous halves of the same statistics for sharded volumes: pass 1 -> out[0..2] = {min, max, sum} (doubles),
+// pass 2 -> out[3] = sum (x - *mean_dev)^2; the caller reduces across shards between the passes (device tensors, no sync)
+int launch_volume_stats_pass(const float* vol, long long n, int pass, const double* mean_dev, double* out_dev, cudaStream_t st,
+                             int64_t* launches) {
+  NM_CHECK(n > 0 && (pass == 1 || pass == 2), "bad arguments");
+  if (pass == 1) {
+    stats_init<<<1, 1, 0, st>>>(out_dev);
+    stats_pass1<<<1184, 256, 0, st>>>(vol, n, out_dev);
+  } else {
+    NM_CHECK(mean_dev != nullptr, "pass 2 needs the mean");
+    stats_pass2<<<1184, 256, 0, st>>>(vol, n, 0.0, mean_dev, out_dev);
+  }
+  NM_CUDA(cudaGetLastError());
+  if (launches) *launches += 1;
   return 0;
 }
 

@@ -384,11 +384,27 @@ class Engine:
         L.check(self.lib.nm_volume_stats(self._h, _ptr(v), v.numel(), out))
         return float(out[0]), float(out[1]), float(out[2])
 
+    def volume_stats_pass(self, vol: torch.Tensor, pass_no: int, out: torch.Tensor, mean: Optional[torch.Tensor] = None):
+        """Asynchronous half of volume_stats for sharded volumes (nm_volume_stats_dev): out = 4 doubles on the device."""
+        assert out.dtype == torch.float64 and out.numel() >= 4 and out.is_cuda and vol.is_contiguous() and vol.dtype == torch.float32
+        assert mean is None or (mean.dtype == torch.float64 and mean.is_cuda)
+        L.check(self.lib.nm_volume_stats_dev(self._h, _ptr(vol), vol.numel(), int(pass_no), _ptr(mean), _ptr(out), self._stream()))
+
     def marching_cubes(self, vol: torch.Tensor, iso: float, x_off: int = 0):
-        """skimage.measure.marching_cubes(vol, iso) on the device: (verts (V,3), faces (F,3) int32, normals (V,3))."""
+        """skimage.measure.marching_cubes(vol, iso) on the device: (verts (V,3), faces (F,3) int32, normals (V,3)); x_off is
+        added to the axis-0 coordinates of the vertices."""
         v = _f32c(vol, self.device)
-        nv, nt = self.mc_count(v, iso, int(x_off), int(x_off) + v.shape[0], 0, v.shape[0])
-        return self.mc_emit(v, iso, int(x_off), int(x_off) + v.shape[0], 0, v.shape[0], nv, nt, 0)
+        nx, ny, nz = v.shape
+        counts = (C.c_int64 * 2)()
+        L.check(self.lib.nm_marching_cubes_count(self._h, _ptr(v), nx, ny, nz, float(iso), counts, self._stream()))
+        nv, nt = int(counts[0]), int(counts[1])
+        verts = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
+        normals = torch.empty((nv, 3), dtype=torch.float32, device=self.device)
+        faces = torch.empty((nt, 3), dtype=torch.int32, device=self.device)
+        if nv > 0:
+            L.check(self.lib.nm_marching_cubes_emit(self._h, _ptr(v), nx, ny, nz, float(iso), float(int(x_off)), _ptr(verts),
+                                                    _ptr(normals), _ptr(faces), self._stream()))
+        return verts, faces, normals
 
     def mc_count(self, vol, iso, g_x0, g_nx, p_lo, p_hi):
         """Count step of one shard (see nm_mc_count): -> (n_vertices owned, n_triangles).  Synchronises."""

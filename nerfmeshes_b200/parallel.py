@@ -259,9 +259,19 @@ def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None
     own = buf[own0 - buf0:own1 - buf0]
     tm.mark("halo")
     if world > 1:
-        mn, mx, _ = eng.volume_stats(own)
-        s = float(own.double().sum())
-        smin, smax, sstd = global_stats(mn, mx, s, lambda m: float(((own.double() - m) ** 2).sum()), own.numel(), dev, group)
+        # two-pass statistics like the single-GPU nm_volume_stats, shards combined on the device: two tiny all_gathers, and one
+        # host read at the end (every plane is owned exactly once, so sums are exact partitions)
+        acc = torch.empty(5, dtype=torch.float64, device=dev)
+        acc[4] = float(own.numel())
+        eng.volume_stats_pass(own, 1, acc)
+        allacc = torch.empty((world, 5), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allacc, acc, group=group)
+        mean = (allacc[:, 2].sum() / allacc[:, 4].sum()).reshape(1)
+        eng.volume_stats_pass(own, 2, acc, mean)
+        allsq = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allsq, acc[3:4].contiguous(), group=group)
+        res = torch.stack([allacc[:, 0].min(), allacc[:, 1].max(), (allsq.sum() / allacc[:, 4].sum()).sqrt()]).cpu()
+        smin, smax, sstd = (float(np.float32(float(x))) for x in res)
     else:
         smin, smax, sstd = eng.volume_stats(own)
     iso = float(min(max(args.iso_level, np.float32(smin) + np.float32(sstd)), np.float32(smax) - np.float32(sstd)))

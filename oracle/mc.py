@@ -26,7 +26,7 @@ def _load():
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     lib = C.CDLL(_LIB)
     lib.mc_oracle.restype = C.c_int
-    lib.mc_oracle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
+    lib.mc_oracle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
     lib.mc_cell_variant.restype = C.c_int
     lib.mc_cell_variant.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
@@ -41,12 +41,14 @@ def marching_cubes(volume, iso, x_off=0, g_nx=None, own=None, v_base=0, stats=Fa
     lib = _load()
     vol = np.ascontiguousarray(volume, dtype=np.float32)
     nb, ny, nz = vol.shape
-    g_x0 = int(x_off)
-    g_nx = g_x0 + nb if g_nx is None else int(g_nx)
+    if g_nx is None:                 # a stand-alone volume: x_off only shifts the axis-0 coordinates of the vertices
+        g_x0, g_nx, x_shift = 0, nb, int(x_off)
+    else:
+        g_x0, g_nx, x_shift = int(x_off), int(g_nx), 0
     p_lo, p_hi = (0, nb) if own is None else own
     nv, nt = C.c_int64(0), C.c_int64(0)
     st = np.zeros(256, np.int64)
-    args = (vol.ctypes.data, nb, ny, nz, float(iso), g_x0, g_nx, p_lo, p_hi, int(v_base))
+    args = (vol.ctypes.data, nb, ny, nz, float(iso), g_x0, g_nx, p_lo, p_hi, x_shift, int(v_base))
     rc = lib.mc_oracle(*args, None, None, None, C.byref(nv), C.byref(nt), st.ctypes.data)
     assert rc == 0, f"mc_oracle: error {rc}"
     verts = np.empty((nv.value, 3), np.float32)

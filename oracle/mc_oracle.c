@@ -434,7 +434,7 @@ static int grad(const Vol* V, int i, int j, int k, float g[3]) {
   return 0;
 }
 
-int mc_oracle(const float* vol, int nb, int ny, int nz, float iso, int g_x0, int g_nx, int p_lo, int p_hi, long long v_base,
+int mc_oracle(const float* vol, int nb, int ny, int nz, float iso, int g_x0, int g_nx, int p_lo, int p_hi, int x_shift, long long v_base,
               float* verts, float* normals, int32_t* faces, int64_t* nv_out, int64_t* nt_out, int64_t* stats256) {
   init_tables();
   Vol V = {vol, nb, ny, nz, (double)iso, g_x0, g_nx};
@@ -487,7 +487,7 @@ int mc_oracle(const float* vol, int nb, int ny, int nz, float iso, int g_x0, int
           const unsigned mk = mask[p];
           if (!mk) continue;
           int64_t id = vbase[p];
-          const double base[3] = {(double)(g_x0 + i), (double)j, (double)k};
+          const double base[3] = {(double)(g_x0 + i + x_shift), (double)j, (double)k};   /* x_shift: pure coordinate offset */
           for (int a = 0; a < 3; ++a) {
             if (!(mk & (1u << a))) continue;
             int c1[3] = {i, j, k};

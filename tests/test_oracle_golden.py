@@ -118,3 +118,27 @@ def test_fern_ndc_pipeline(fern):
     p_f = O.intervals_to_ray_points(g["t_fine"], g["dirs"], g["origins"])
     raw_f = O.flexible_nerf_forward(fern["fine"], NET, p_f, g["dirs"][:, None, :].expand_as(p_f))
     close(raw_f[..., :3], g["raw_fine"][..., :3], 1e-4)
+
+
+def test_wide_goldens_subset(lego, buff):
+    """The wide end-to-end goldens (make_golden_wide.py: 4096 rays x 3 poses per checkpoint) on a 384-ray subset per
+    checkpoint: the oracle reproduces the reference's maps from the pose alone (ray generation included)."""
+    g = load_npz("golden_wide_lego.npz")
+    H, W, f = int(g["H"]), int(g["W"]), float(g["focal"])
+    for p in (0, 2):
+        o, d = O.get_ray_bundle(H, W, f, g["poses"][p])
+        ids = g["ray_ids"][p][:192].long()
+        bc, bf, _, _ = O.nerf_forward(lego["coarse"], lego["fine"], NET, NET, O.RenderCfg(), o, d.reshape(-1, 3)[ids],
+                                      g["bounds"][0], g["bounds"][1], u=lego["u"])
+        close(bc.rgb_map, g["coarse_rgb"][p][:192], 5e-6)
+        err = (bf.rgb_map - g["rgb"][p][:192]).abs()
+        assert float(err.median()) <= 1e-6 and float(err.max()) <= 1e-3          # max admits one resampling bin flip
+        close((bf.depth_map != 0).float(), (g["depth"][p][:192] != 0).float(), 1.0)
+    gb = load_npz("golden_wide_buff.npz")
+    o, d = O.get_ray_bundle(H, W, f, gb["poses"][1])
+    ids = gb["ray_ids"][1][:192].long()
+    b, t, mask = O.buff_forward(buff["coarse"], NET, O.RenderCfg(num_coarse=192, num_fine=0), buff["voxels"], o[None],
+                                d.reshape(-1, 3)[ids], gb["bounds"][0], gb["bounds"][1])
+    assert torch.equal(mask, gb["ray_mask"][1][:192].bool())
+    close(b.rgb_map, gb["rgb"][1][:192], 1e-5)
+    close(b.acc_map, gb["acc"][1][:192], 1e-5)
