@@ -59,7 +59,9 @@ struct NmHandle_t {
   int64_t mlp_points = 0, mlp_launches = 0;
   size_t mc_ws_bytes = 0;
   void* mc_ws_ptr = nullptr;
-  int64_t mc_lists[2] = {0, 0};   // emit-grid sizes left by the last count step
+  size_t mc_ws2_bytes = 0;
+  void* mc_ws2_ptr = nullptr;
+  int64_t mc_counts[2] = {0, 0};   // {vertices, triangles} of the last count step: sizes of the emit step
   // training (nm_train.cu): gradient accumulators per network + scratch
   Buf g_wt[2], g_bias[2], g_head[2], train_ws, dout, trans, tr_rgb[2], tr_drgb[2];
   bool grads_ready = false;
@@ -435,6 +437,7 @@ int nm_destroy(NmHandle h) {
   for (int i = 0; i < 2; ++i) { h->g_wt[i].release(); h->g_bias[i].release(); h->g_head[i].release(); h->tr_rgb[i].release(); h->tr_drgb[i].release(); }
   h->train_ws.release(); h->dout.release(); h->trans.release();
   if (h->mc_ws_ptr) cudaFree(h->mc_ws_ptr);
+  if (h->mc_ws2_ptr) cudaFree(h->mc_ws2_ptr);
   if (h->h_err) cudaFreeHost(h->h_err);
   cudaFree(h->d_stats);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -689,10 +692,8 @@ int nm_mc_count(NmHandle h, const float* vol_dev, int nb, int ny, int nz, float 
   if (int e = bind_device(h)) return e;
   NM_CHECK(vol_dev && counts_host, "null argument");
   const McShard s{vol_dev, nb, ny, nz, iso, g_x0, g_nx, p_lo, p_hi, 0};
-  int64_t c[4] = {0, 0, 0, 0};
-  if (int e = mc_count(s, &h->mc_ws_ptr, &h->mc_ws_bytes, c, (cudaStream_t)stream, &h->launches)) return e;
-  counts_host[0] = c[0]; counts_host[1] = c[1];
-  h->mc_lists[0] = c[2]; h->mc_lists[1] = c[3];
+  if (int e = mc_count(s, &h->mc_ws_ptr, &h->mc_ws_bytes, counts_host, (cudaStream_t)stream, &h->launches)) return e;
+  h->mc_counts[0] = counts_host[0]; h->mc_counts[1] = counts_host[1];
   return 0;
 }
 
@@ -701,8 +702,8 @@ int nm_mc_emit(NmHandle h, const float* vol_dev, int nb, int ny, int nz, float i
   if (int e = bind_device(h)) return e;
   NM_CHECK(vol_dev && verts_dev && faces_dev && h->mc_ws_ptr, "bad arguments (call nm_mc_count first)");
   const McShard s{vol_dev, nb, ny, nz, iso, g_x0, g_nx, p_lo, p_hi, 0};
-  return mc_emit(s, h->mc_ws_ptr, h->mc_ws_bytes, v_base, h->mc_lists, verts_dev, normals_dev, faces_dev, (cudaStream_t)stream,
-                 &h->launches);
+  return mc_emit(s, h->mc_ws_ptr, h->mc_ws_bytes, &h->mc_ws2_ptr, &h->mc_ws2_bytes, v_base, h->mc_counts[0], h->mc_counts[1],
+                 verts_dev, normals_dev, faces_dev, (cudaStream_t)stream, &h->launches);
 }
 
 int nm_marching_cubes_count(NmHandle h, const float* vol_dev, int nx, int ny, int nz, float iso, int64_t* counts_host,
@@ -717,7 +718,8 @@ int nm_marching_cubes_emit(NmHandle h, const float* vol_dev, int nx, int ny, int
   if (int e = bind_device(h)) return e;
   NM_CHECK(vol_dev && verts_dev && faces_dev && h->mc_ws_ptr, "bad arguments (call nm_marching_cubes_count first)");
   const McShard s{vol_dev, nx, ny, nz, iso, 0, nx, 0, nx, (int)x_off};
-  return mc_emit(s, h->mc_ws_ptr, h->mc_ws_bytes, 0, h->mc_lists, verts_dev, normals_dev, faces_dev, (cudaStream_t)stream, &h->launches);
+  return mc_emit(s, h->mc_ws_ptr, h->mc_ws_bytes, &h->mc_ws2_ptr, &h->mc_ws2_bytes, 0, h->mc_counts[0], h->mc_counts[1], verts_dev,
+                 normals_dev, faces_dev, (cudaStream_t)stream, &h->launches);
 }
 
 int nm_query_host(NmHandle h, const float* origins_host, int o_stride, const float* dirs_host, int64_t R,

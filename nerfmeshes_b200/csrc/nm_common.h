@@ -172,9 +172,9 @@ struct McShard {
   int g_x0, g_nx, p_lo, p_hi;
   int x_shift;       // added to the axis-0 vertex coordinates only (stand-alone volumes that are a window of a larger one)
 };
-// counts_host[4]: {vertices owned, triangles, words with vertices, words with triangles}; the last two size the emit grids
+// counts_host[2]: {vertices owned, triangles}; ws2 is a second grow-only workspace (8 bytes per output vertex / triangle)
 int mc_count(const McShard& s, void** ws, size_t* ws_bytes, int64_t* counts_host, cudaStream_t st, int64_t* launches);
-int mc_emit(const McShard& s, void* ws, size_t ws_bytes, long long v_base, const int64_t* list_sizes, float* verts, float* normals,
-            int32_t* faces, cudaStream_t st, int64_t* launches);
+int mc_emit(const McShard& s, void* ws, size_t ws_bytes, void** ws2, size_t* ws2_bytes, long long v_base, int64_t nv, int64_t nt,
+            float* verts, float* normals, int32_t* faces, cudaStream_t st, int64_t* launches);
 
 }  // namespace nm

@@ -8,9 +8,11 @@
 //                        only topologically ambiguous ones read their 8 corner values (face tests, interior test).  Writes
 //                        per word: the X/Y/Z/C bit words, vertex + triangle counts; per block: the count sums.
 //   3. mc_scan_blocks / mc_scan_words   two-level exclusive scan of the counts (per-word vertex / triangle prefixes).
-//   4. mc_emit_vertices / mc_emit_triangles   one WARP per word that has vertices / triangles (the count pass compacts those
-//                        words into two lists), one lane per grid point of the word; a vertex id anywhere in the grid is
-//                        prefix[word] + popcount(bits below) — no dense per-point id array.
+//   4. mc_expand_kernel  one thread per word: writes, for every vertex id and every triangle id of the word, where it comes
+//                        from (word, bit, slot / table entry, triangle) — an 8-byte record per output element.
+//   5. mc_emit_vertices / mc_emit_triangles   one thread per OUTPUT vertex / triangle (perfectly balanced, coalesced
+//                        stores); a vertex id anywhere in the grid is prefix[word] + popcount(bits below) — no dense
+//                        per-point id array.
 //
 // Output contract (mirrors the Lewiner output the reference consumes at mesh_nerf.py:79-90): an INDEXED mesh, one vertex
 // per crossed grid edge plus Lewiner's cell-centre vertices, vertices (V,3) fp32 in index coordinates (axis0, axis1, axis2),
@@ -65,9 +67,9 @@ struct McGrid {
   unsigned* vpre;             // per word: exclusive vertex prefix
   unsigned* tpre;             // per word: exclusive triangle prefix
   unsigned* blk;              // per block of kBlock words: {vertex sum, triangle sum} -> exclusive prefixes
-  unsigned long long* totals; // [n_vertices incl. shadow plane, n_triangles, n_vertices owned, #words with vertices | #words with triangles << 32]
-  unsigned* list_v;           // owned words that hold at least one vertex (compacted, arbitrary order)
-  unsigned* list_t;           // owned words that hold at least one triangle
+  unsigned long long* totals; // [n_vertices incl. shadow plane, n_triangles, n_vertices owned]
+  unsigned long long* vmap;   // per owned vertex id: word << 7 | bit << 2 | slot            (second workspace, sized after the count)
+  unsigned long long* tmap;   // per triangle id:     word << 32 | L3 entry << 9 | bit << 4 | triangle
   long long nwords;           // words of planes [p_lo,p_end)
   long long nwords_own;       // words of planes [p_lo,p_hi)
 };
@@ -78,23 +80,45 @@ __global__ void __launch_bounds__(kBlock) mc_sign_kernel(const float* __restrict
   const int lane = threadIdx.x & 31;
   const long long nw = nlines * W;
   const long long warps = (long long)gridDim.x * (kBlock / 32);
-  long long word = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-  const bool dense = (nz & 31) == 0;          // lines are whole words: word wd covers vol[32*wd .. 32*wd+31]
+  const long long warp0 = (long long)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+  if ((nz & 127) == 0) {
+    // lines are whole groups of 4 words: one 16-byte load per lane covers 4 points, a warp covers 4 words; the lane's
+    // nibble is OR-reduced over its group of 8 lanes (3 shuffles) and the group leader stores the word
+    const long long ngroups = nw >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(vol);
+    constexpr int U = 4;
+    for (long long grp = warp0; grp < ngroups; grp += warps * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long gq = grp + warps * u;
+        v[u] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        if (gq < ngroups) v[u] = __ldcs(v4 + gq * 32 + lane);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long gq = grp + warps * u;
+        unsigned nib = (v[u].x > iso ? 1u : 0u) | (v[u].y > iso ? 2u : 0u) | (v[u].z > iso ? 4u : 0u) | (v[u].w > iso ? 8u : 0u);
+        nib <<= 4 * (lane & 7);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+        if ((lane & 7) == 0 && gq < ngroups) sign[gq * 4 + (lane >> 3)] = nib;
+      }
+    }
+    return;
+  }
   constexpr int U = 8;
-  for (; word < nw; word += warps * U) {
+  for (long long word = warp0; word < nw; word += warps * U) {
     float v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long wd = word + warps * u;
       v[u] = -CUDART_INF_F;
       if (wd < nw) {
-        if (dense) {
-          v[u] = __ldcs(vol + wd * 32 + lane);
-        } else {
-          const unsigned line = (unsigned)((unsigned long long)wd / (unsigned)W);      // nw < 2^32 is checked by the host
-          const int k = (int)((unsigned)wd - line * (unsigned)W) * 32 + lane;
-          if (k < nz) v[u] = __ldcs(vol + (long long)line * nz + k);
-        }
+        const unsigned line = (unsigned)((unsigned long long)wd / (unsigned)W);      // nw < 2^32 is checked by the host
+        const int k = (int)((unsigned)wd - line * (unsigned)W) * 32 + lane;
+        if (k < nz) v[u] = __ldcs(vol + (long long)line * nz + k);
       }
     }
 #pragma unroll
@@ -227,7 +251,6 @@ __global__ void __launch_bounds__(kBlock) mc_count_kernel(const McGrid g) {
   __shared__ unsigned s_warp[kBlock / 32];
   const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
   unsigned vc = 0, tc = 0;
-  bool has_v = false, has_t = false;
   if (wl < g.nwords) {
     int i, j, w;
     word_coords(g, wl, &i, &j, &w);
@@ -246,21 +269,6 @@ __global__ void __launch_bounds__(kBlock) mc_count_kernel(const McGrid g) {
     vc = __popc(n.X) + __popc(n.Y) + __popc(n.Z) + __popc(C);
     g.bits[wl] = make_uint4(n.X, n.Y, n.Z, C);
     g.cnt[wl] = vc | (tc << 16);
-    has_v = owned && vc > 0;
-    has_t = tc > 0;
-  }
-  {   // compact the words with vertices / triangles: one atomic per warp and list
-    unsigned* counters = reinterpret_cast<unsigned*>(g.totals + 3);
-    const int lane = threadIdx.x & 31;
-    const unsigned mv = __ballot_sync(0xffffffffu, has_v), mt = __ballot_sync(0xffffffffu, has_t);
-    unsigned bv = 0, bt = 0;
-    if (lane == 0) {
-      if (mv) bv = atomicAdd(counters, __popc(mv));
-      if (mt) bt = atomicAdd(counters + 1, __popc(mt));
-    }
-    bv = __shfl_sync(0xffffffffu, bv, 0); bt = __shfl_sync(0xffffffffu, bt, 0);
-    if (has_v) g.list_v[bv + __popc(mv & ((1u << lane) - 1u))] = (unsigned)wl;
-    if (has_t) g.list_t[bt + __popc(mt & ((1u << lane) - 1u))] = (unsigned)wl;
   }
   const unsigned sv = block_sum(vc, s_warp), stt = block_sum(tc, s_warp);
   if (threadIdx.x == 0) { g.blk[2 * blockIdx.x] = sv; g.blk[2 * blockIdx.x + 1] = stt; }
@@ -351,48 +359,75 @@ __device__ __forceinline__ void store_vertex(float* verts, float* normals, size_
   }
 }
 
-__global__ void __launch_bounds__(kBlock) mc_emit_vertices(const McGrid g, unsigned nlist, float* __restrict__ verts,
+// 4. expansion: where every output vertex / triangle comes from
+__global__ void __launch_bounds__(kBlock) mc_expand_kernel(const McGrid g) {
+  const long long wl = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (wl >= g.nwords_own) return;
+  const unsigned c = g.cnt[wl];
+  if (c == 0) return;
+  if (c & 0xffffu) {
+    const uint4 B = g.bits[wl];
+    unsigned long long id = g.vpre[wl];
+    unsigned any = B.x | B.y | B.z | B.w;
+    while (any) {
+      const int b = __ffs(any) - 1;
+      any &= any - 1;
+      const unsigned sel = ((B.x >> b) & 1u) | (((B.y >> b) & 1u) << 1) | (((B.z >> b) & 1u) << 2) | (((B.w >> b) & 1u) << 3);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if ((sel >> a) & 1u) g.vmap[id++] = ((unsigned long long)wl << 7) | ((unsigned long long)b << 2) | (unsigned long long)a;
+    }
+  }
+  if (c >> 16) {
+    int i, j, w;
+    word_coords(g, wl, &i, &j, &w);
+    const Nbhd n = load_nbhd(g, i, j, w);
+    unsigned long long tid = g.tpre[wl];
+    unsigned act = n.active;
+    while (act) {
+      const int b = __ffs(act) - 1;
+      act &= act - 1;
+      const size_t p = ((size_t)i * g.ny + j) * g.nz + (size_t)w * 32 + b;
+      const unsigned e = (unsigned)resolve_cell(g, cell_mask(n, b), p);
+      const unsigned nt = g_l3[e].ntri;
+      for (unsigned t = 0; t < nt; ++t)
+        g.tmap[tid++] = ((unsigned long long)wl << 32) | ((unsigned long long)e << 9) | ((unsigned long long)b << 4) | t;
+    }
+  }
+}
+
+// 5. one thread per output vertex
+__global__ void __launch_bounds__(kBlock) mc_emit_vertices(const McGrid g, unsigned nv, float* __restrict__ verts,
                                                            float* __restrict__ normals) {
-  const unsigned item = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-  if (item >= nlist) return;
-  const int b = threadIdx.x & 31;
-  const long long wl = g.list_v[item];
-  const uint4 B = g.bits[wl];
-  const unsigned sel[4] = {(B.x >> b) & 1u, (B.y >> b) & 1u, (B.z >> b) & 1u, (B.w >> b) & 1u};
-  if (!(sel[0] | sel[1] | sel[2] | sel[3])) return;
+  const unsigned id = blockIdx.x * kBlock + threadIdx.x;
+  if (id >= nv) return;
+  const unsigned long long rec = g.vmap[id];
+  const long long wl = (long long)(rec >> 7);
+  const int b = (int)((rec >> 2) & 31u), slot = (int)(rec & 3u);
   int i, j, w;
   word_coords(g, wl, &i, &j, &w);
-  const unsigned lt = (1u << b) - 1u;
-  size_t id = (size_t)g.vpre[wl] + __popc(B.x & lt) + __popc(B.y & lt) + __popc(B.z & lt) + __popc(B.w & lt);
   const size_t st[3] = {(size_t)g.ny * g.nz, (size_t)g.nz, 1};
   const double iso = (double)g.iso;
   const int k = w * 32 + b;
   const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
   const double base[3] = {(double)(g.g_x0 + i + g.x_shift), (double)j, (double)k};
-  float g0[3];
-  double w0 = 0.0;
-  if (sel[0] | sel[1] | sel[2]) {
+  if (slot < 3) {
+    const int a = slot;
+    float g0[3], g1[3];
     grid_grad(g, i, j, k, g0);
-    w0 = 1.0 / (kEps + fabs((double)g.vol[p] - iso));
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    if (!sel[a]) continue;
     int c1[3] = {i, j, k};
     c1[a] += 1;
+    grid_grad(g, c1[0], c1[1], c1[2], g1);
+    const double w0 = 1.0 / (kEps + fabs((double)g.vol[p] - iso));
     const double w1 = 1.0 / (kEps + fabs((double)g.vol[p + st[a]] - iso));
     const double ff = w0 + w1;
     double pos[3] = {base[0], base[1], base[2]};
     pos[a] = base[a] + w1 / ff;                  // x + step * fx / ff with fx = 0*w0 + 1*w1 (scikit-image's form)
-    float g1[3];
-    grid_grad(g, c1[0], c1[1], c1[2], g1);
     double n[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) n[q] = -((double)g0[q] * w0 + (double)g1[q] * w1);
     store_vertex(verts, normals, id, pos, n);
-    ++id;
-  }
-  if (sel[3]) {                                  // calculate_center_vertex: weighted mean of the 8 corners, Lewiner's order
+  } else {                                       // calculate_center_vertex: weighted mean of the 8 corners, Lewiner's order
     double f[3] = {0, 0, 0}, ff = 0, n[3] = {0, 0, 0};
     for (int L = 0; L < 8; ++L) {
       const int c = c_lew2my[L];
@@ -411,52 +446,37 @@ __global__ void __launch_bounds__(kBlock) mc_emit_vertices(const McGrid g, unsig
   }
 }
 
-// id of the first vertex owned by grid point (i,j,k) (buffer coordinates) + that point's slot bits
-__device__ __forceinline__ unsigned point_base(const McGrid& g, int i, int j, int k, unsigned* slots) {
+// id of the vertex in slot `a` (0..2 edge along axis a, 3 centre) of grid point (i,j,k) (buffer coordinates)
+__device__ __forceinline__ unsigned vertex_id(const McGrid& g, int i, int j, int k, int a) {
   const long long wq = ((long long)(i - g.p_lo) * g.ny + j) * g.W + (k >> 5);
   const int b = k & 31;
   const uint4 B = g.bits[wq];
   const unsigned lt = (1u << b) - 1u;
-  *slots = ((B.x >> b) & 1u) | (((B.y >> b) & 1u) << 1) | (((B.z >> b) & 1u) << 2);
-  return g.vpre[wq] + __popc(B.x & lt) + __popc(B.y & lt) + __popc(B.z & lt) + __popc(B.w & lt);
+  const unsigned slots = ((B.x >> b) & 1u) | (((B.y >> b) & 1u) << 1) | (((B.z >> b) & 1u) << 2);
+  return g.vpre[wq] + __popc(B.x & lt) + __popc(B.y & lt) + __popc(B.z & lt) + __popc(B.w & lt) + __popc(slots & ((1u << a) - 1u));
 }
 
-__global__ void __launch_bounds__(kBlock) mc_emit_triangles(const McGrid g, unsigned nlist, long long v_base, int* __restrict__ faces) {
-  const unsigned item = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-  if (item >= nlist) return;
-  const int b = threadIdx.x & 31;
-  const long long wl = g.list_t[item];
+// one thread per output triangle
+__global__ void __launch_bounds__(kBlock) mc_emit_triangles(const McGrid g, unsigned nt, long long v_base, int* __restrict__ faces) {
+  const unsigned tid = blockIdx.x * kBlock + threadIdx.x;
+  if (tid >= nt) return;
+  const unsigned long long rec = g.tmap[tid];
+  const long long wl = (long long)(rec >> 32);
+  const unsigned e = (unsigned)((rec >> 9) & 0x7fffffu), b = (unsigned)((rec >> 4) & 31u), t = (unsigned)(rec & 15u);
   int i, j, w;
   word_coords(g, wl, &i, &j, &w);
-  const Nbhd n = load_nbhd(g, i, j, w);
-  const bool act = (n.active >> b) & 1u;
-  const int k = w * 32 + b;
-  const size_t p = ((size_t)i * g.ny + j) * g.nz + k;
-  const L3Entry* e = nullptr;
-  unsigned nt = 0;
-  if (act) { e = &g_l3[resolve_cell(g, cell_mask(n, b), p)]; nt = e->ntri; }
-  unsigned x = nt;                                // exclusive prefix of the triangle counts over the lanes (cells in k order)
+  const int k = w * 32 + (int)b;
+  const unsigned char* idx = g_l3[e].idx + 3 * t;
+  int out[3];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-    if (b >= o) x += y;
-  }
-  if (!nt) return;
-  size_t tid = (size_t)g.tpre[wl] + x - nt;
-  unsigned base[8], slots[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) base[c] = point_base(g, i + (c & 1), j + ((c >> 1) & 1), k + ((c >> 2) & 1), &slots[c]);
-  for (unsigned t = 0; t < 3 * nt; ++t) {
-    const int s = e->idx[t];
+  for (int c = 0; c < 3; ++c) {
+    const int s = idx[c];
     unsigned id;
-    if (s == 12) {
-      id = base[0] + (slots[0] & 1u) + ((slots[0] >> 1) & 1u) + ((slots[0] >> 2) & 1u);
-    } else {
-      const int lo = c_edge_lo[s], a = c_edge_axis[s];
-      id = base[lo] + __popc(slots[lo] & ((1u << a) - 1u));
-    }
-    faces[3 * tid + t] = (int)(v_base + (long long)id);
+    if (s == 12) id = vertex_id(g, i, j, k, 3);
+    else { const int lo = c_edge_lo[s]; id = vertex_id(g, i + (lo & 1), j + ((lo >> 1) & 1), k + ((lo >> 2) & 1), c_edge_axis[s]); }
+    out[c] = (int)(v_base + (long long)id);
   }
+  faces[3 * (size_t)tid] = out[0]; faces[3 * (size_t)tid + 1] = out[1]; faces[3 * (size_t)tid + 2] = out[2];
 }
 
 size_t align_up(size_t x) { return (x + 255) / 256 * 256; }
@@ -467,8 +487,7 @@ int carve(void* base, size_t bytes, McGrid* g, size_t* need) {
   size_t off = 0;
   auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
   const size_t o_sign = take(nsign * 4), o_bits = take(nw * 16), o_cnt = take(nw * 4), o_vp = take((nw + 1) * 4),
-               o_tp = take((nw + 1) * 4), o_blk = take((nblk + 1) * 8), o_tot = take(64),
-               o_lv = take((size_t)g->nwords_own * 4 + 4), o_lt = take((size_t)g->nwords_own * 4 + 4);
+               o_tp = take((nw + 1) * 4), o_blk = take((nblk + 1) * 8), o_tot = take(64);
   *need = off;
   if (!base || bytes < off) return 1;
   char* b = reinterpret_cast<char*>(base);
@@ -479,8 +498,6 @@ int carve(void* base, size_t bytes, McGrid* g, size_t* need) {
   g->tpre = reinterpret_cast<unsigned*>(b + o_tp);
   g->blk = reinterpret_cast<unsigned*>(b + o_blk);
   g->totals = reinterpret_cast<unsigned long long*>(b + o_tot);
-  g->list_v = reinterpret_cast<unsigned*>(b + o_lv);
-  g->list_t = reinterpret_cast<unsigned*>(b + o_lt);
   return 0;
 }
 
@@ -520,7 +537,7 @@ int mc_count(const McShard& s, void** ws_ptr, size_t* ws_bytes, int64_t* counts_
   const long long nlines = (long long)g.nb * g.ny;
   static int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
   long long sign_blocks = (nlines * g.W + (kBlock / 32) * 8 - 1) / ((kBlock / 32) * 8);
-  if (sign_blocks > (long long)sms * 8) sign_blocks = (long long)sms * 8;
+  if (sign_blocks > (long long)sms * 4) sign_blocks = (long long)sms * 4;       // one resident wave, grid-stride
   NM_CUDA(cudaMemsetAsync(g.totals, 0, 64, st));
   mc_sign_kernel<<<(unsigned)sign_blocks, kBlock, 0, st>>>(g.vol, nlines, g.nz, g.W, g.iso, g.sign);
   NM_CUDA(cudaGetLastError());
@@ -532,36 +549,46 @@ int mc_count(const McShard& s, void** ws_ptr, size_t* ws_bytes, int64_t* counts_
   NM_CUDA(cudaGetLastError());
   mc_scan_words<<<(unsigned)nblk, kBlock, 0, st>>>(g);
   NM_CUDA(cudaGetLastError());
-  unsigned long long h[4];
+  unsigned long long h[3];
   NM_CUDA(cudaMemcpyAsync(h, g.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
   NM_CUDA(cudaStreamSynchronize(st));
   const unsigned long long nv_own = (g.p_end > g.p_hi) ? h[2] : h[0];
   NM_CHECK(h[0] < (1ull << 31) && h[1] < (1ull << 31), "mesh too large for int32 indices");
   counts_host[0] = (int64_t)nv_own;
   counts_host[1] = (int64_t)h[1];
-  counts_host[2] = (int64_t)(h[3] & 0xffffffffull);       // words with vertices / triangles: grid sizes of the emit step
-  counts_host[3] = (int64_t)(h[3] >> 32);
   if (launches) *launches += 4;
   return 0;
 }
 
-int mc_emit(const McShard& s, void* ws_ptr, size_t ws_bytes, long long v_base, const int64_t* list_sizes, float* verts,
-            float* normals, int32_t* faces, cudaStream_t st, int64_t* launches) {
+int mc_emit(const McShard& s, void* ws_ptr, size_t ws_bytes, void** ws2_ptr, size_t* ws2_bytes, long long v_base, int64_t nv,
+            int64_t nt, float* verts, float* normals, int32_t* faces, cudaStream_t st, int64_t* launches) {
   McGrid g{};
   if (int e = make_grid(s, &g)) return e;
   size_t need = 0;
   NM_CHECK(carve(ws_ptr, ws_bytes, &g, &need) == 0, "workspace missing (call the count step first, same arguments)");
-  const unsigned nlv = (unsigned)list_sizes[0], nlt = (unsigned)list_sizes[1];
-  constexpr unsigned per = kBlock / 32;
-  if (nlv) {
-    mc_emit_vertices<<<(nlv + per - 1) / per, kBlock, 0, st>>>(g, nlv, verts, normals);
+  if (g.nwords_own == 0 || (nv == 0 && nt == 0)) return 0;
+  NM_CHECK(g.nwords_own < (1ll << 32) && nv >= 0 && nt >= 0, "bad counts");
+  const size_t need2 = align_up((size_t)nv * 8 + 8) + (size_t)nt * 8 + 8;
+  if (*ws2_bytes < need2) {
+    if (*ws2_ptr) NM_CUDA(cudaFree(*ws2_ptr));
+    *ws2_ptr = nullptr; *ws2_bytes = 0;
+    NM_CUDA(cudaMalloc(ws2_ptr, need2 + need2 / 4));
+    *ws2_bytes = need2 + need2 / 4;
+  }
+  g.vmap = reinterpret_cast<unsigned long long*>(*ws2_ptr);
+  g.tmap = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(*ws2_ptr) + align_up((size_t)nv * 8 + 8));
+  const long long nblk = (g.nwords_own + kBlock - 1) / kBlock;
+  mc_expand_kernel<<<(unsigned)nblk, kBlock, 0, st>>>(g);
+  NM_CUDA(cudaGetLastError());
+  if (nv) {
+    mc_emit_vertices<<<(unsigned)((nv + kBlock - 1) / kBlock), kBlock, 0, st>>>(g, (unsigned)nv, verts, normals);
     NM_CUDA(cudaGetLastError());
   }
-  if (nlt) {
-    mc_emit_triangles<<<(nlt + per - 1) / per, kBlock, 0, st>>>(g, nlt, v_base, faces);
+  if (nt) {
+    mc_emit_triangles<<<(unsigned)((nt + kBlock - 1) / kBlock), kBlock, 0, st>>>(g, (unsigned)nt, v_base, faces);
     NM_CUDA(cudaGetLastError());
   }
-  if (launches) *launches += 2;
+  if (launches) *launches += 3;
   return 0;
 }
 

@@ -270,8 +270,8 @@ def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None
         eng.volume_stats_pass(own, 2, acc, mean)
         allsq = torch.empty(world, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allsq, acc[3:4].contiguous(), group=group)
-        res = torch.stack([allacc[:, 0].min(), allacc[:, 1].max(), (allsq.sum() / allacc[:, 4].sum()).sqrt()]).cpu()
-        smin, smax, sstd = (float(np.float32(float(x))) for x in res)
+        st3 = torch.stack([allacc[:, 0].min(), allacc[:, 1].max(), (allsq.sum() / allacc[:, 4].sum()).sqrt()]).cpu()
+        smin, smax, sstd = (float(np.float32(float(x))) for x in st3)
     else:
         smin, smax, sstd = eng.volume_stats(own)
     iso = float(min(max(args.iso_level, np.float32(smin) + np.float32(sstd)), np.float32(smax) - np.float32(sstd)))
