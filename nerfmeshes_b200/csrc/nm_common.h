@@ -91,6 +91,18 @@ struct MlpInput {
   long long M = 0;               // number of points
 };
 
+// Optional by-products of a fused-MLP launch for the training backward (nm_train.cu): per layer (nullptr = not wanted)
+//   packT  the layer's output as the point-major bf16 hi/lo operand pack of the weight-gradient GEMM (nm_gemm.h: tiles of
+//          128 features x 64 points, [feature block][point block], `kbt` point blocks per feature block; rows >= M zero)
+//   bits   its relu mask, one bit per element (halfword [m * n_out/16 + n/16], bit n%16)
+//   act    its fp32 value (M, n_out) row-major (the layers the SIMT head kernels read)
+struct MlpEmit {
+  uint8_t* packT[kMaxLayers];
+  uint32_t* bits[kMaxLayers];
+  float* act[kMaxLayers];
+  int kbt;
+};
+
 int build_programs(const NmNetDesc& d, NetProgram* full, NetProgram* sigma);
 // Packs host fp32 reference tensors into the device layouts.  `get(name, &numel)` returns the host tensor.
 struct WeightSource {
@@ -108,7 +120,7 @@ int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, Net
 
 // kernel launchers (return 0 / <0; count launches via *launches)
 int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
-                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches);
+                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit = nullptr);
 int launch_mlp_simt(const NetDev& net, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st,
                     int64_t* launches);
 

@@ -26,6 +26,7 @@
 //   d_full[n]      (4 commits)  every issuer is done with accumulator chunk n           -> epilogue may drain it
 //   kb_free[k]     (4 commits)  every issuer is done reading activation K-block k       -> epilogue may overwrite it
 //   chunk_ready[n] (4 arrives)  chunk n drained + zeroed, K-block n of the new layer written -> issuers may use both
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -67,7 +68,10 @@ struct TcParams {
   unsigned long long* trace;   // NM_TC_TRACE: CTA 0 logs (kind, id, index, layer, t0..t3) records; trace[0] = count
   int dbg;   // bring-up switches (env NM_TC_DEBUG): 1 = no MMA issue, 2 = no epilogue math, 4 = no weight copies
   uint32_t off_pe, off_bias, off_head, off_red, off_bars;
+  int has_emit;     // training: the epilogue also writes the backward pass's operands (MlpEmit)
+  MlpEmit emit;
 };
+static_assert(sizeof(TcParams) <= 4096, "TcParams must fit the 4 KB kernel-parameter window");
 
 // barrier slots (8 B each) relative to off_bars
 constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
@@ -223,6 +227,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 }
                 part[hh] = acc;
               }
+              if (P.has_emit) {
+                // by-products for the training backward: relu mask, fp32 copy (layers the head kernels read) and the
+                // point-major bf16 hi/lo pack the weight-gradient GEMM consumes (rows past M are written as zeros)
+                const bool valid = m < P.in.M;
+                if (P.emit.bits[li] && valid) {
+                  uint32_t mk = 0;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) mk |= (v[j] > 0.f ? 1u : 0u) << j;
+                  P.emit.bits[li][(size_t)m * (size_t)(L.n_out >> 5) + (size_t)(col0 >> 5)] = mk;
+                }
+                if (P.emit.act[li] && valid) {
+                  float4* dst = reinterpret_cast<float4*>(P.emit.act[li] + (size_t)m * L.n_out + col0);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (P.emit.packT[li]) {
+                  const long long pt = tile * kTileM + row;
+                  uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u;
+                  const uint32_t c8 = (uint32_t)((pt & 63) >> 3), e2 = (uint32_t)(pt & 7) * 2u;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    const uint32_t rf = (uint32_t)((col0 + j) & 127);
+                    const uint32_t o = rf * 128u + ((c8 ^ (rf & 7u)) << 4) + e2;
+                    const float x = valid ? v[j] : 0.f;
+                    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+                    *reinterpret_cast<uint16_t*>(tb + o) = __bfloat16_as_ushort(h);
+                    *reinterpret_cast<uint16_t*>(tb + 16384u + o) = __bfloat16_as_ushort(l);
+                  }
+                }
+              }
               if (writes_a) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
@@ -264,13 +299,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             ptx::named_bar_sync(1, kEpiWarps * 32);
             if (hcol == 0) {
               sigma_val = part[0] + s_red[row] + hb[0];
-              if (L.is_final && m < P.in.M) P.out[m] = sigma_val;   // sigma-only program
+              if (L.is_final && m < P.in.M && P.out) P.out[m] = sigma_val;   // sigma-only program
             }
           } else {
             float* r4 = s_red + 128 + 4 * row;
             if (hcol == 1) { r4[0] = part[0]; r4[1] = part[1]; r4[2] = part[2]; r4[3] = part[3]; }
             ptx::named_bar_sync(2, kEpiWarps * 32);
-            if (hcol == 0 && m < P.in.M) {
+            if (hcol == 0 && m < P.in.M && P.out) {
               float o[4];
 #pragma unroll
               for (int hh = 0; hh < 4; ++hh) o[hh] = (hh < heads) ? part[hh] + r4[hh] + hb[hh] : 0.f;
@@ -452,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 }  // namespace
 
 int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
-                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches) {
+                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit) {
   if (in.M <= 0) return 0;
   const NetProgram& hp = sigma_only ? net.sigma : net.full;
   TcParams P{};
@@ -468,6 +503,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.act_inv_scale = ldexpf(1.f, -act_scale_log2);
   P.n_tiles = (in.M + kTileM - 1) / kTileM;
   P.err = d_err;
+  if (emit) { P.has_emit = 1; P.emit = *emit; }
   {
     const char* e = getenv("NM_TC_DEBUG");
     P.dbg = e ? atoi(e) : 0;

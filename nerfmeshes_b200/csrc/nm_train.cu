@@ -571,7 +571,23 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   auto tc_base = [&]() { TcGemmParams T{}; T.n_passes = mode.n_passes; T.err = mode.d_err; return T; };
 
   // ---- forward recompute: act[l] = act_l([act[l-1] | PE] W^T + b)
-  for (int l = 0; l < G.n_layers; ++l) {
+  // Tensor-core path: ONE launch of the fused forward kernel (nm_mlp_tc.cu) whose epilogue also emits what the backward
+  // needs — relu masks, the point-major bf16 packs of every hidden activation (B operand of the weight-gradient GEMMs) and
+  // the fp32 activations the head kernels read — instead of a chain of layer GEMMs round-tripping through HBM.  The masks
+  // are by construction the forward pass's own.  NM_TRAIN_LAYERWISE=1 keeps the layer-by-layer GEMM chain (debugging).
+  static const bool layerwise = [] { const char* e = getenv("NM_TRAIN_LAYERWISE"); return e && atoi(e) != 0; }();
+  if (tc && !layerwise) {
+    MlpEmit E{};
+    E.kbt = kbtP;
+    for (int l = 0; l < G.n_layers; ++l) {
+      const LayerProg& L = G.layers[l];
+      if (l + 1 < G.n_layers) E.packT[l] = W.pkt_act[l];
+      if (L.relu) E.bits[l] = reinterpret_cast<uint32_t*>(W.bits[l]);
+      if (L.kind != KIND_HIDDEN) E.act[l] = W.act[l];
+    }
+    if (int e = launch_mlp_tc(net, false, mode.n_passes, 0, in, nullptr, num_sms, mode.d_err, st, launches, &E)) return e;
+  }
+  for (int l = 0; l < G.n_layers && !(tc && !layerwise); ++l) {
     const LayerProg& L = G.layers[l];
     const int N = L.n_out, Kt = L.k_act + L.k_pe;
     GemmEpi fin{};
