@@ -50,6 +50,11 @@ struct NetDev {
   size_t tcw_bytes = 0;
   size_t tcw_fwd_off[kMaxLayers] = {}, tcw_bwd_off[kMaxLayers] = {};
   bool tcw_valid = false;
+  // fused data-gradient chain (nm_mlp_tc.cu, mode 2): backward program + W^T stages (bf16 hi/lo), rebuilt lazily
+  NetProgram bwd{};
+  NetProgram* d_bwd = nullptr;
+  uint8_t* d_wpack_bwd = nullptr;
+  bool bwd_valid = false;
   std::vector<std::string> names;    // per layer of `full`: weight, bias, head weight, head bias ("" if none)
 };
 
@@ -104,6 +109,8 @@ struct MlpEmit {
 };
 
 int build_programs(const NmNetDesc& d, NetProgram* full, NetProgram* sigma);
+int build_backward_program(const NetProgram& full, NetProgram* bwd);
+int build_backward_stream(NetDev* net, cudaStream_t st, int64_t* launches);
 // Packs host fp32 reference tensors into the device layouts.  `get(name, &numel)` returns the host tensor.
 struct WeightSource {
   int n = 0;
@@ -121,6 +128,8 @@ int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, Net
 // kernel launchers (return 0 / <0; count launches via *launches)
 int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
                   int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit = nullptr);
+int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout, float* colsum_out,
+                      const MlpEmit& io, int n_passes, int num_sms, int* d_err, cudaStream_t st, int64_t* launches);
 int launch_mlp_simt(const NetDev& net, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st,
                     int64_t* launches);
 

@@ -70,6 +70,13 @@ struct TcParams {
   uint32_t off_pe, off_bias, off_head, off_red, off_bars;
   int has_emit;     // training: the epilogue also writes the backward pass's operands (MlpEmit)
   MlpEmit emit;
+  // mode 2: the data-gradient chain of the training backward (a KIND_LOAD / KIND_BWD program, W^T stages in bf16 hi/lo):
+  // emit.bits[li] is the INPUT relu mask of that layer, emit.packT[li] receives dZ, column sums go to colsum_out
+  int mode;
+  const float* dz_in;     // (M, dz_ld) fp32: dZ of the last forward layer
+  int dz_ld;
+  const float* dout;      // (M, 4): compositor adjoint, column 3 = d sigma
+  float* colsum_out;      // bias-gradient array (forward bias offsets)
 };
 static_assert(sizeof(TcParams) <= 4096, "TcParams must fit the 4 KB kernel-parameter window");
 
@@ -107,6 +114,8 @@ __device__ __forceinline__ uint32_t swz_off(int r, int c) {
   return (uint32_t)r * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
 }
 
+// MODE 0: inference; 1: training forward (the epilogue also emits the backward's operands); 2: data-gradient chain
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = ptx::smem_u32(smem);
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   {
     uint4* z = reinterpret_cast<uint4*>(smem + P.off_pe);
     for (int i = threadIdx.x; i < (int)(kPeTotal / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) s_bias[i] = P.bias[i];
+    for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) s_bias[i] = (MODE == 2) ? 0.f : P.bias[i];   // mode 2: column-sum accumulators
     for (int i = threadIdx.x; i < P.net.n_head; i += kThreads) s_head[i] = P.head[i];
   }
   ptx::fence_proxy_async_smem();
@@ -180,7 +189,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       for (int li = 0; li < n_layers; ++li, ++gl) {
         const LayerProg& L = P.net.layers[li];
         const int NC = L.n_out >> 6;
-        const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
+        const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final) || (L.kind == KIND_LOAD) ||
+                              (L.kind == KIND_BWD && !L.is_final);
+        constexpr bool bwd = MODE == 2;
         const int heads = L.kind == KIND_SIGMA ? 1 : (L.kind == KIND_RGB ? 3 : (L.kind == KIND_OUT4 ? 4 : 0));
         float part[4] = {0.f, 0.f, 0.f, 0.f};
         // Warp set `hcol` (warps 4*hcol..4*hcol+3, one per TMEM lane quarter) owns accumulator chunks hcol and hcol+2:
@@ -198,21 +209,80 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             for (int half = 0; half < 2; ++half) {
               uint32_t r[32];
               const int col0 = n * 64 + half * 32;
-              NM_TMEM_LD32(tmem + lane_addr + (uint32_t)col0, r);
-              ptx::tmem_wait_ld();
-              const float4* b4 = reinterpret_cast<const float4*>(s_bias + L.bias_off + col0);
               float v[32];
+              if (MODE == 2 && L.kind == KIND_LOAD) {
+                // top of the data-gradient chain: dZ of the last forward layer, from HBM (rows past M are zero)
+                const bool valid = m < P.in.M;
+                const float4* src = reinterpret_cast<const float4*>(P.dz_in + (size_t)(valid ? m : 0) * P.dz_ld + col0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = b4[j];
-                v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), so, bb.x);
-                v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), so, bb.y);
-                v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), so, bb.z);
-                v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), so, bb.w);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 x = valid ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                  v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+                }
+              } else {
+                NM_TMEM_LD32(tmem + lane_addr + (uint32_t)col0, r);
+                ptx::tmem_wait_ld();
               }
-              if (L.relu) {
+              if (MODE == 2 && L.kind == KIND_BWD) {
+                // dA = dZ W (+ d sigma * w_alpha), masked by relu' of the forward layer below; column sums = its bias gradient
+                const bool valid = m < P.in.M;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * so;
+                if (L.aux2) {
+                  const float dsg = valid ? P.dout[(size_t)m * 4 + 3] : 0.f;
+                  const float4* w4 = reinterpret_cast<const float4*>(s_head + L.head_off + col0);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 ww = w4[j];
+                    v[4 * j + 0] = fmaf(dsg, ww.x, v[4 * j + 0]); v[4 * j + 1] = fmaf(dsg, ww.y, v[4 * j + 1]);
+                    v[4 * j + 2] = fmaf(dsg, ww.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(dsg, ww.w, v[4 * j + 3]);
+                  }
+                }
+                uint32_t mk = valid ? 0xffffffffu : 0u;
+                if (L.relu && valid) mk = P.emit.bits[li][(size_t)m * (size_t)(L.n_out >> 5) + (size_t)(col0 >> 5)];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ((mk >> j) & 1u) ? v[j] : 0.f;
+                {   // column sums over this warp's 32 rows: reduce-scatter (31 shuffles), lane j ends with column col0 + j
+                  float t16[16], t8[8], t4[4], t2[2];
+                  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float rcv = __shfl_xor_sync(0xffffffffu, u16 ? v[j] : v[j + 16], 16);
+                    t16[j] = (u16 ? v[j + 16] : v[j]) + rcv;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float rcv = __shfl_xor_sync(0xffffffffu, u8 ? t16[j] : t16[j + 8], 8);
+                    t8[j] = (u8 ? t16[j + 8] : t16[j]) + rcv;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float rcv = __shfl_xor_sync(0xffffffffu, u4 ? t8[j] : t8[j + 4], 4);
+                    t4[j] = (u4 ? t8[j + 4] : t8[j]) + rcv;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const float rcv = __shfl_xor_sync(0xffffffffu, u2 ? t4[j] : t4[j + 2], 2);
+                    t2[j] = (u2 ? t4[j + 2] : t4[j]) + rcv;
+                  }
+                  const float rcv = __shfl_xor_sync(0xffffffffu, u1 ? t2[0] : t2[1], 1);
+                  const float cs = (u1 ? t2[1] : t2[0]) + rcv;
+                  atomicAdd(s_bias + L.bias_off + col0 + lane, cs);
+                }
+              } else if (MODE != 2 || L.kind != KIND_LOAD) {
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + L.bias_off + col0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 bb = b4[j];
+                  v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), so, bb.x);
+                  v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), so, bb.y);
+                  v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), so, bb.z);
+                  v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), so, bb.w);
+                }
+                if (L.relu) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
               }
               for (int hh = 0; hh < heads; ++hh) {
                 const float4* w4 = reinterpret_cast<const float4*>(s_head + L.head_off + hh * L.n_out + col0);
@@ -227,22 +297,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 }
                 part[hh] = acc;
               }
-              if (P.has_emit) {
+              if (MODE >= 1) {
                 // by-products for the training backward: relu mask, fp32 copy (layers the head kernels read) and the
                 // point-major bf16 hi/lo pack the weight-gradient GEMM consumes (rows past M are written as zeros)
                 const bool valid = m < P.in.M;
-                if (P.emit.bits[li] && valid) {
+                if (!bwd && P.emit.bits[li] && valid) {
                   uint32_t mk = 0;
 #pragma unroll
                   for (int j = 0; j < 32; ++j) mk |= (v[j] > 0.f ? 1u : 0u) << j;
                   P.emit.bits[li][(size_t)m * (size_t)(L.n_out >> 5) + (size_t)(col0 >> 5)] = mk;
                 }
-                if (P.emit.act[li] && valid) {
+                if (!bwd && P.emit.act[li] && valid) {
                   float4* dst = reinterpret_cast<float4*>(P.emit.act[li] + (size_t)m * L.n_out + col0);
 #pragma unroll
                   for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                if (P.emit.packT[li]) {
+                if (P.emit.packT[li] && !writes_a) {     // (layers that write the A operand emit from it after the hand-over, below)
                   const long long pt = tile * kTileM + row;
                   uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u;
                   const uint32_t c8 = (uint32_t)((pt & 63) >> 3), e2 = (uint32_t)(pt & 7) * 2u;
@@ -260,12 +330,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               }
               if (writes_a) {
                 uint32_t hi[16], lo[16];
+                if (bwd) {     // gradients: bf16 hi/lo (fp32's exponent range)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float a0 = v[2 * j] * si, a1 = v[2 * j + 1] * si;
-                  hi[j] = ptx::pack_f16x2_sat(a0, a1);
-                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
-                  lo[j] = ptx::pack_f16x2_sat(a0 - f.x, a1 - f.y);
+                  for (int j = 0; j < 16; ++j) {
+                    const float a0 = v[2 * j] * si, a1 = v[2 * j + 1] * si;
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+                    const float2 f = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - f.x, a1 - f.y);
+                    hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float a0 = v[2 * j] * si, a1 = v[2 * j + 1] * si;
+                    hi[j] = ptx::pack_f16x2_sat(a0, a1);
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi[j]));
+                    lo[j] = ptx::pack_f16x2_sat(a0 - f.x, a1 - f.y);
+                  }
                 }
                 if (half == 0) {
                   if (P.trace) tr2 = clock64();
@@ -290,6 +372,48 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bars + kBarChunk + 8 * n);
           if (P.trace && (warp & 3) == 0 && lane == 0) trace_rec(P, 2, hcol, n, gl, tr0, tr1, tr2, clock64(), trace_cursor);
+          if (MODE >= 1 && writes_a && n < NC && P.emit.packT[li]) {
+            // Off the critical path: the chunk has been handed back to the issuers; its values are read back from the A operand
+            // this warp has just written (hi + lo 16-bit halves; it stays untouched until this warp's next epilogue of chunk n)
+            // and stored as the point-major bf16 hi/lo pack of the weight-gradient GEMM (rows past M as zeros).
+            const bool valid = m < P.in.M;
+            const long long pt = tile * kTileM + row;
+            const uint32_t c8 = (uint32_t)((pt & 63) >> 3), e2 = (uint32_t)(pt & 7) * 2u;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              uint32_t h16[16], l16[16];
+              const uint32_t acol = (uint32_t)(n * 32 + half * 16);
+              NM_TMEM_LD16(tmem + lane_addr + kColAhi + acol, h16);
+              if (n_passes == 3) NM_TMEM_LD16(tmem + lane_addr + kColAlo + acol, l16);
+              ptx::tmem_wait_ld();
+              const int col0 = n * 64 + half * 32;
+              uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                uint16_t oh[2], ol[2];
+                if (MODE == 2) {        // already bf16 hi / lo
+                  oh[0] = (uint16_t)(h16[j] & 0xffffu); oh[1] = (uint16_t)(h16[j] >> 16);
+                  ol[0] = (n_passes == 3) ? (uint16_t)(l16[j] & 0xffffu) : (uint16_t)0; ol[1] = (n_passes == 3) ? (uint16_t)(l16[j] >> 16) : (uint16_t)0;
+                } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
+                  const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
+                  float2 fl = make_float2(0.f, 0.f);
+                  if (n_passes == 3) fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
+                  const float x0 = (fh.x + fl.x) * so, x1 = (fh.y + fl.y) * so;
+                  const __nv_bfloat16 b0 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
+                  oh[0] = __bfloat16_as_ushort(b0); oh[1] = __bfloat16_as_ushort(b1);
+                  ol[0] = __bfloat16_as_ushort(__float2bfloat16_rn(x0 - __bfloat162float(b0)));
+                  ol[1] = __bfloat16_as_ushort(__float2bfloat16_rn(x1 - __bfloat162float(b1)));
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const uint32_t rf = (uint32_t)((col0 + 2 * j + q) & 127);
+                  const uint32_t o = rf * 128u + ((c8 ^ (rf & 7u)) << 4) + e2;
+                  *reinterpret_cast<uint16_t*>(tb + o) = valid ? oh[q] : (uint16_t)0;
+                  *reinterpret_cast<uint16_t*>(tb + 16384u + o) = valid ? ol[q] : (uint16_t)0;
+                }
+              }
+            }
+          }
         }
         if (heads) {
           // the two chunk sets of a row live in warps w and w+4: combine their partial dot products through smem
@@ -336,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1;
       ptx::mbar_wait(bars + kBarPeEmpty + 8 * buf, ((it >> 1) & 1) ^ 1, P.err, ERR_PE_EMPTY);
+      if (MODE == 2) { ptx::mbar_arrive(bars + kBarPeFull + 8 * buf); continue; }   // no encodings in the data-gradient chain
       long long m = tile * kTileM + r;
       if (m >= P.in.M) m = P.in.M - 1;
       float p[3], d[3];
@@ -388,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     // =============================================================== MMA issuers (4 converged warps)
     const int w = warp - kMmaWarp0;
     const uint32_t acc_only = P.net.accumulate_only ? 1u : 0u;
-    const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk);
+    const uint32_t idesc = ptx::make_idesc_f16(kTileM, kChunk) | (MODE == 2 ? ((1u << 7) | (1u << 10)) : 0u);   // mode 2: A, B = bf16
     int slot = 0;
     uint32_t ph = 0, gl = 0, it = 0, cur_pos = 0;
     unsigned trace_cursor = 0;
@@ -481,36 +606,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   // ---------------------------------------------------------------- teardown
   ptx::tc_fence_before();
   __syncthreads();
+  if (MODE == 2 && P.colsum_out) {
+    for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) {
+      const float x = s_bias[i];
+      if (x != 0.f) atomicAdd(P.colsum_out + i, x);
+    }
+  }
   if (warp == kProdWarp) ptx::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
 
-int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
-                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit) {
-  if (in.M <= 0) return 0;
-  const NetProgram& hp = sigma_only ? net.sigma : net.full;
-  TcParams P{};
-  P.net = hp;
-  P.wpack = sigma_only ? net.d_wpack_sigma : net.d_wpack_full;
-  P.bias = net.d_bias;
-  P.head = net.d_head;
-  P.in = in;
-  P.out = out;
-  P.out_sigma_only = sigma_only ? 1 : 0;
-  P.n_passes = n_passes;
-  P.act_scale = ldexpf(1.f, act_scale_log2);
-  P.act_inv_scale = ldexpf(1.f, -act_scale_log2);
-  P.n_tiles = (in.M + kTileM - 1) / kTileM;
-  P.err = d_err;
-  if (emit) { P.has_emit = 1; P.emit = *emit; }
+// shared-memory layout + launch of a prepared parameter block
+static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* launches) {
+  const NetProgram& hp = P.net;
   {
     const char* e = getenv("NM_TC_DEBUG");
     P.dbg = e ? atoi(e) : 0;
-    const char* ns_env = getenv("NM_TC_STAGES");
-    (void)ns_env;
   }
-
   auto align_up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
   int dev = 0, max_smem = 0;
   NM_CUDA(cudaGetDevice(&dev));
@@ -530,10 +643,12 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.off_bars = off; off += kBarBytes;
   NM_CHECK((int)off <= max_smem, "shared-memory layout overflow");
 
-  static thread_local unsigned configured_devs = 0;        // per-device opt-in to the large dynamic shared memory window
-  if (!(configured_devs & (1u << (dev & 31)))) {
-    NM_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    configured_devs |= 1u << (dev & 31);
+  const int mode = P.mode == 2 ? 2 : (P.has_emit ? 1 : 0);
+  auto kern = mode == 2 ? mlp_tc_kernel<2> : (mode == 1 ? mlp_tc_kernel<1> : mlp_tc_kernel<0>);
+  static thread_local unsigned configured_devs[3] = {0, 0, 0};   // per-device opt-in to the large dynamic shared memory window
+  if (!(configured_devs[mode] & (1u << (dev & 31)))) {
+    NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    configured_devs[mode] |= 1u << (dev & 31);
   }
   long long grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
   const char* trace_path = getenv("NM_TC_TRACE");
@@ -542,7 +657,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
     NM_CUDA(cudaMalloc(&P.trace, trace_words * 8));
     NM_CUDA(cudaMemset(P.trace, 0, trace_words * 8));
   }
-  mlp_tc_kernel<<<(unsigned)grid, kThreads, off, st>>>(P);
+  kern<<<(unsigned)grid, kThreads, off, st>>>(P);
   NM_CUDA(cudaGetLastError());
   if (trace_path) {   // debugging aid: synchronous dump of CTA 0's event log
     NM_CUDA(cudaStreamSynchronize(st));
@@ -553,6 +668,50 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   }
   if (launches) ++*launches;
   return 0;
+}
+
+int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
+                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit) {
+  if (in.M <= 0) return 0;
+  const NetProgram& hp = sigma_only ? net.sigma : net.full;
+  TcParams P{};
+  P.net = hp;
+  P.wpack = sigma_only ? net.d_wpack_sigma : net.d_wpack_full;
+  P.bias = net.d_bias;
+  P.head = net.d_head;
+  P.in = in;
+  P.out = out;
+  P.out_sigma_only = sigma_only ? 1 : 0;
+  P.n_passes = n_passes;
+  P.act_scale = ldexpf(1.f, act_scale_log2);
+  P.act_inv_scale = ldexpf(1.f, -act_scale_log2);
+  P.n_tiles = (in.M + kTileM - 1) / kTileM;
+  P.err = d_err;
+  if (emit) { P.has_emit = 1; P.emit = *emit; }
+  return launch_prepared(P, num_sms, st, launches);
+}
+
+// The data-gradient chain of the training backward for M points (nm_train.cu): dz_in (M, dz_ld) fp32 = dZ of the last
+// forward layer; for every backward layer li (net.bwd): io.bits[li] = relu mask to apply (input), io.packT[li] = where dZ
+// goes as the weight-gradient operand; column sums (bias gradients) are accumulated into colsum_out.
+int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout, float* colsum_out,
+                      const MlpEmit& io, int n_passes, int num_sms, int* d_err, cudaStream_t st, int64_t* launches) {
+  if (M <= 0) return 0;
+  NM_CHECK(net.bwd_valid && net.d_wpack_bwd, "backward weight stream not built");
+  NM_CHECK((dz_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(dz_in) & 15) == 0, "dz_in must be 16-byte aligned rows");
+  TcParams P{};
+  P.net = net.bwd;
+  P.wpack = net.d_wpack_bwd;
+  P.bias = net.d_bias;
+  P.head = net.d_head;
+  P.in.M = M;
+  P.n_passes = n_passes;
+  P.act_scale = 1.f; P.act_inv_scale = 1.f;
+  P.n_tiles = (M + kTileM - 1) / kTileM;
+  P.err = d_err;
+  P.has_emit = 1; P.emit = io;
+  P.mode = 2; P.dz_in = dz_in; P.dz_ld = dz_ld; P.dout = dout; P.colsum_out = colsum_out;
+  return launch_prepared(P, num_sms, st, launches);
 }
 
 }  // namespace nm

@@ -3,6 +3,7 @@
 //   (a) 16 KB tensor-core stages [hi | lo] fp16, K-major, 128B-swizzled, in schedule order (one linear stream the
 //       kernel's producer warp walks with cp.async.bulk), and
 //   (b) transposed fp32 Wt[k][n] for the CUDA-core kernel.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cmath>
@@ -65,65 +66,10 @@ static bool is_skip(const NmNetDesc& d, int i) {  // src/nerf/models.py:36-42,64
   return (i % d.skip_step == 0) && i > 0 && i != d.num_layers - 1;
 }
 
-static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::vector<LayerNames>* names) {
-  memset(p, 0, sizeof(*p));
-  const int h = d.hidden_size;
-  NM_CHECK(h == 128 || h == 256, "hidden_size %d unsupported (128 or 256)", h);
-  NM_CHECK(d.num_layers >= 1 && d.num_layers + 2 <= kMaxLayers, "num_layers %d unsupported", d.num_layers);
-  NM_CHECK(d.skip_step >= 1, "skip_step must be >= 1");
-  NM_CHECK(d.num_encoding_fn_xyz >= 0 && d.num_encoding_fn_xyz <= 10, "num_encoding_fn_xyz must be in [0,10]");
-  NM_CHECK(d.num_encoding_fn_dir >= 0 && d.num_encoding_fn_dir <= 10, "num_encoding_fn_dir must be in [0,10]");
-  p->hidden = h;
-  p->L_xyz = d.num_encoding_fn_xyz;
-  p->L_dir = d.num_encoding_fn_dir;
-  p->inc_xyz = d.include_input_xyz ? 1 : 0;
-  p->inc_dir = d.include_input_dir ? 1 : 0;
-  p->dim_xyz = 6 * p->L_xyz + (p->inc_xyz ? 3 : 0);
-  p->dim_dir = d.use_viewdirs ? 6 * p->L_dir + (p->inc_dir ? 3 : 0) : 0;
-  NM_CHECK(p->dim_xyz >= 1 && p->dim_xyz <= 64, "xyz encoding width %d unsupported", p->dim_xyz);
-  NM_CHECK(p->dim_dir <= 64 && (!d.use_viewdirs || p->dim_dir >= 1), "dir encoding width %d unsupported", p->dim_dir);
-  freq_bands(p->L_xyz, d.log_sampling_xyz, p->freq_xyz);
-  freq_bands(p->L_dir, d.log_sampling_dir, p->freq_dir);
-
-  int nl = 0, bias = 0, head = 0, wt = 0;
-  auto add = [&](int n_out, int k_act, int pe_src, int k_pe, int relu, const std::string& base) -> LayerProg& {
-    LayerProg& L = p->layers[nl++];
-    L.n_out = n_out; L.k_act = k_act; L.pe_src = pe_src; L.k_pe = k_pe; L.relu = relu; L.kind = KIND_HIDDEN;
-    L.bias_off = bias; bias += n_out;
-    L.wt_off = wt; wt += (k_act + k_pe) * n_out;
-    names->push_back({base + ".weight", base + ".bias", "", ""});
-    return L;
-  };
-  add(h, 0, SRC_PE_XYZ, p->dim_xyz, 0, "layer1");
-  for (int i = 0; i < d.num_layers - 1; ++i) {
-    bool sk = is_skip(d, i);
-    add(h, h, sk ? SRC_PE_XYZ : 0, sk ? p->dim_xyz : 0, 1, "layers_xyz." + std::to_string(i));
-  }
-  {
-    LayerProg& T = p->layers[nl - 1];
-    T.head_off = head;
-    if (d.use_viewdirs) {
-      T.kind = KIND_SIGMA; head += h + 1;
-      names->back().head_w = "fc_alpha.weight"; names->back().head_b = "fc_alpha.bias";
-    } else {
-      T.kind = KIND_OUT4; head += 4 * h + 4; T.is_final = 1;
-      names->back().head_w = "fc_out.weight"; names->back().head_b = "fc_out.bias";
-    }
-  }
-  if (d.use_viewdirs) {
-    if (sigma_only) {
-      p->layers[nl - 1].is_final = 1;
-    } else {
-      add(h, h, 0, 0, 1, "fc_feat");
-      LayerProg& D = add(h / 2, h, SRC_PE_DIR, p->dim_dir, 1, "layers_dir.0");
-      head = (head + 3) & ~3;                       // the epilogue reads head rows as float4
-      D.kind = KIND_RGB; D.is_final = 1; D.head_off = head; head += 3 * (h / 2) + 3;
-      names->back().head_w = "fc_rgb.weight"; names->back().head_b = "fc_rgb.bias";
-    }
-  }
-  p->n_layers = nl; p->n_bias = bias; p->n_head = head;
-  for (int i = 0; i < nl; ++i) if (p->layers[i].pe_src == SRC_PE_DIR) p->uses_dir = 1;
-
+// Tensor-core block schedule of a layer list (forward or backward program): fills blocks[], blk_begin/end, the per-issuer
+// bookkeeping and n_blocks from each layer's n_out / k_act / pe_src / k_pe.
+static int schedule_blocks(NetProgram* p) {
+  const int nl = p->n_layers;
   // tensor-core schedule.  Block (k,n) needs epilogue chunks 0..max(k,n) of the previous layer (group): chunk k
   // supplies activation K-block k, chunk n frees accumulator chunk n.  The TMEM A region is single-buffered and is
   // overwritten in place by the epilogue; the kernel's kb_free barriers (not the block order) make that safe.
@@ -141,6 +87,10 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
     const int KB = L.k_act / kChunk, NC = L.n_out / kChunk;
     NM_CHECK(KB <= 4 && NC <= 4, "layer wider than 256");
     L.blk_begin = nb;
+    if (L.kind == KIND_LOAD) {      // no MMA blocks: every issuer has "nothing to do" on every chunk / K-block
+      L.blk_end = nb; L.none_d = 0xFFFF; L.none_k = 0xFFFF; L.first_blk = -1;
+      continue;
+    }
     int started[4] = {0, 0, 0, 0};
     int lastblk[4] = {-1, -1, -1, -1};
     auto push = [&](int src, int kb, int nc, int ksteps, int group) {
@@ -202,6 +152,95 @@ static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::ve
   return 0;
 }
 
+static int build_one(const NmNetDesc& d, bool sigma_only, NetProgram* p, std::vector<LayerNames>* names) {
+  memset(p, 0, sizeof(*p));
+  const int h = d.hidden_size;
+  NM_CHECK(h == 128 || h == 256, "hidden_size %d unsupported (128 or 256)", h);
+  NM_CHECK(d.num_layers >= 1 && d.num_layers + 2 <= kMaxLayers, "num_layers %d unsupported", d.num_layers);
+  NM_CHECK(d.skip_step >= 1, "skip_step must be >= 1");
+  NM_CHECK(d.num_encoding_fn_xyz >= 0 && d.num_encoding_fn_xyz <= 10, "num_encoding_fn_xyz must be in [0,10]");
+  NM_CHECK(d.num_encoding_fn_dir >= 0 && d.num_encoding_fn_dir <= 10, "num_encoding_fn_dir must be in [0,10]");
+  p->hidden = h;
+  p->L_xyz = d.num_encoding_fn_xyz;
+  p->L_dir = d.num_encoding_fn_dir;
+  p->inc_xyz = d.include_input_xyz ? 1 : 0;
+  p->inc_dir = d.include_input_dir ? 1 : 0;
+  p->dim_xyz = 6 * p->L_xyz + (p->inc_xyz ? 3 : 0);
+  p->dim_dir = d.use_viewdirs ? 6 * p->L_dir + (p->inc_dir ? 3 : 0) : 0;
+  NM_CHECK(p->dim_xyz >= 1 && p->dim_xyz <= 64, "xyz encoding width %d unsupported", p->dim_xyz);
+  NM_CHECK(p->dim_dir <= 64 && (!d.use_viewdirs || p->dim_dir >= 1), "dir encoding width %d unsupported", p->dim_dir);
+  freq_bands(p->L_xyz, d.log_sampling_xyz, p->freq_xyz);
+  freq_bands(p->L_dir, d.log_sampling_dir, p->freq_dir);
+
+  int nl = 0, bias = 0, head = 0, wt = 0;
+  auto add = [&](int n_out, int k_act, int pe_src, int k_pe, int relu, const std::string& base) -> LayerProg& {
+    LayerProg& L = p->layers[nl++];
+    L.n_out = n_out; L.k_act = k_act; L.pe_src = pe_src; L.k_pe = k_pe; L.relu = relu; L.kind = KIND_HIDDEN;
+    L.bias_off = bias; bias += n_out;
+    L.wt_off = wt; wt += (k_act + k_pe) * n_out;
+    names->push_back({base + ".weight", base + ".bias", "", ""});
+    return L;
+  };
+  add(h, 0, SRC_PE_XYZ, p->dim_xyz, 0, "layer1");
+  for (int i = 0; i < d.num_layers - 1; ++i) {
+    bool sk = is_skip(d, i);
+    add(h, h, sk ? SRC_PE_XYZ : 0, sk ? p->dim_xyz : 0, 1, "layers_xyz." + std::to_string(i));
+  }
+  {
+    LayerProg& T = p->layers[nl - 1];
+    T.head_off = head;
+    if (d.use_viewdirs) {
+      T.kind = KIND_SIGMA; head += h + 1;
+      names->back().head_w = "fc_alpha.weight"; names->back().head_b = "fc_alpha.bias";
+    } else {
+      T.kind = KIND_OUT4; head += 4 * h + 4; T.is_final = 1;
+      names->back().head_w = "fc_out.weight"; names->back().head_b = "fc_out.bias";
+    }
+  }
+  if (d.use_viewdirs) {
+    if (sigma_only) {
+      p->layers[nl - 1].is_final = 1;
+    } else {
+      add(h, h, 0, 0, 1, "fc_feat");
+      LayerProg& D = add(h / 2, h, SRC_PE_DIR, p->dim_dir, 1, "layers_dir.0");
+      head = (head + 3) & ~3;                       // the epilogue reads head rows as float4
+      D.kind = KIND_RGB; D.is_final = 1; D.head_off = head; head += 3 * (h / 2) + 3;
+      names->back().head_w = "fc_rgb.weight"; names->back().head_b = "fc_rgb.bias";
+    }
+  }
+  p->n_layers = nl; p->n_bias = bias; p->n_head = head;
+  for (int i = 0; i < nl; ++i) if (p->layers[i].pe_src == SRC_PE_DIR) p->uses_dir = 1;
+
+  return schedule_blocks(p);
+}
+
+// Data-gradient program of the training backward (nm_train.cu): layer 0 loads dZ of the last forward layer, then one
+// KIND_BWD layer per forward layer l = last..1 computing dZ_{l-1} = (dZ_l W_l[:, :k_act] (+ dsigma w_alpha)) * relu'_{l-1}.
+// bias_off / head_off are those of forward layer l-1: the column sums of dZ_{l-1} ARE its bias gradient, and the
+// rank-1 term reads fc_alpha's row from the same head array.
+int build_backward_program(const NetProgram& F, NetProgram* B) {
+  memset(B, 0, sizeof(*B));
+  B->hidden = F.hidden; B->n_bias = F.n_bias; B->n_head = F.n_head;
+  const int last = F.n_layers - 1;
+  NM_CHECK(last >= 1 && last + 1 <= kMaxLayers, "network too shallow / deep for the fused backward");
+  int nl = 0;
+  {
+    LayerProg& L = B->layers[nl++];
+    L.kind = KIND_LOAD; L.n_out = F.layers[last].n_out; L.aux = last;
+  }
+  for (int l = last; l >= 1; --l) {
+    const LayerProg& Fl = F.layers[l];
+    const LayerProg& Fp = F.layers[l - 1];
+    NM_CHECK(Fl.k_act == Fp.n_out, "layer chain mismatch");
+    LayerProg& L = B->layers[nl++];
+    L.kind = KIND_BWD; L.n_out = Fl.k_act; L.k_act = Fl.n_out; L.relu = Fp.relu; L.is_final = (l == 1);
+    L.bias_off = Fp.bias_off; L.head_off = Fp.head_off; L.wt_off = Fl.wt_off;
+    L.aux = l; L.aux2 = (Fp.kind == KIND_SIGMA) ? 1 : 0;
+  }
+  B->n_layers = nl;
+  return schedule_blocks(B);
+}
+
 int build_programs(const NmNetDesc& d, NetProgram* full, NetProgram* sigma) {
   std::vector<LayerNames> n1, n2;
   if (int e = build_one(d, false, full, &n1)) return e;
@@ -258,6 +297,7 @@ int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, Net
 void free_network(NetDev* net) {
   cudaFree(net->d_full); cudaFree(net->d_sigma); cudaFree(net->d_wpack_full); cudaFree(net->d_wpack_sigma);
   cudaFree(net->d_bias); cudaFree(net->d_head); cudaFree(net->d_wt); cudaFree(net->d_w); cudaFree(net->d_tcw);
+  cudaFree(net->d_bwd); cudaFree(net->d_wpack_bwd);
   *net = NetDev{};
 }
 
@@ -360,7 +400,47 @@ __global__ void __launch_bounds__(256) pack_stream_kernel(const NetProgram* __re
   }
 }
 
+// stages of the backward program: block (kb, nc) of layer L holds rows n' = nc*64.. (input feature of forward layer L.aux)
+// and columns k' = kb*64.. (its output feature) of W^T, i.e. Wt[n'][k'] with Wt = the transposed fp32 weights (ld = the
+// forward layer's n_out); bf16 hi/lo split (gradients span fp32's exponent range)
+__global__ void __launch_bounds__(256) pack_bwd_stream_kernel(const NetProgram* __restrict__ prog, const float* __restrict__ wt,
+                                                              uint8_t* __restrict__ out) {
+  const NetProgram& P = *prog;
+  const int b = blockIdx.x;
+  int li = 0;
+  while (li + 1 < P.n_layers && b >= P.layers[li].blk_end) ++li;
+  const LayerProg& L = P.layers[li];
+  const BlockProg B = P.blocks[b];
+  const int ld = L.k_act;                          // forward n_out
+  const float* W = wt + L.wt_off;
+  uint8_t* st = out + (size_t)b * kStageBytes;
+  for (int e = threadIdx.x; e < kChunk * kChunk; e += blockDim.x) {
+    const int r = e >> 6, c = e & 63;
+    const int n = B.nc * kChunk + r, k = B.kb * kChunk + c;
+    const float w = (n < L.n_out && k < L.k_act) ? W[(size_t)n * ld + k] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    *reinterpret_cast<__nv_bfloat16*>(st + swz_off_dev(r, c)) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(st + kHalfStage + swz_off_dev(r, c)) = lo;
+  }
+}
+
 }  // namespace
+
+// (re)build the backward program and its weight stream from the current transposed weights (device, stream-ordered)
+int build_backward_stream(NetDev* net, cudaStream_t st, int64_t* launches) {
+  if (!net->d_bwd) {
+    if (int e = build_backward_program(net->full, &net->bwd)) return e;
+    NM_CUDA(cudaMalloc(&net->d_bwd, sizeof(NetProgram)));
+    NM_CUDA(cudaMemcpyAsync(net->d_bwd, &net->bwd, sizeof(NetProgram), cudaMemcpyHostToDevice, st));
+    NM_CUDA(cudaMalloc(&net->d_wpack_bwd, (size_t)net->bwd.n_blocks * kStageBytes));
+  }
+  pack_bwd_stream_kernel<<<net->bwd.n_blocks, 256, 0, st>>>(net->d_bwd, net->d_wt, net->d_wpack_bwd);
+  NM_CUDA(cudaGetLastError());
+  if (launches) ++*launches;
+  net->bwd_valid = true;
+  return 0;
+}
 
 int load_network_dev(const NmNetDesc& d, const WeightSource& src, NetDev* net, cudaStream_t st, int64_t* launches) {
   std::vector<LayerNames> nf, ns;
@@ -412,6 +492,7 @@ int load_network_dev(const NmNetDesc& d, const WeightSource& src, NetDev* net, c
   NM_CUDA(cudaGetLastError());
   if (launches) *launches += 2;
   net->tcw_valid = false;
+  net->bwd_valid = false;
   net->loaded = true;
   return 0;
 }

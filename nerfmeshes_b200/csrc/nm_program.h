@@ -22,7 +22,10 @@ enum : int {
   KIND_HIDDEN = 0,   // y = act(Wx+b) becomes the next layer's A operand
   KIND_SIGMA = 1,    // hidden + the fc_alpha head (256->1) as a dot product in the epilogue
   KIND_RGB = 2,      // layers_dir.0 + the fc_rgb head (->3, sigmoid) in the epilogue; nothing written back
-  KIND_OUT4 = 3      // use_viewdirs=False: trunk output + fc_out head (->4)
+  KIND_OUT4 = 3,     // use_viewdirs=False: trunk output + fc_out head (->4)
+  // backward (data-gradient) program of the training step, nm_train.cu: the same machine walks the layers in reverse
+  KIND_LOAD = 4,     // no MMA: the epilogue loads the top gradient dZ (fp32, HBM) into the A operand
+  KIND_BWD = 5       // dA = dZ W (+ dsigma w_alpha) masked by relu' of forward layer aux-1 -> next A, its pack, column sums
 };
 
 struct LayerProg {
@@ -41,6 +44,8 @@ struct LayerProg {
   // no block into accumulator chunk i (none_d) / no block reading activation K-block i (none_k) in this layer
   int32_t none_d, none_k;
   int32_t first_blk;  // byte w = offset from blk_begin of issuer w's first block in this layer, 0xFF = none
+  int32_t aux;        // backward program: forward layer l whose W^T this layer streams (it produces dZ of layer l-1)
+  int32_t aux2;       // backward program: 1 = add dsigma * w_alpha (forward layer l-1 carries the fc_alpha head)
 };
 
 // One (K-block, N-chunk) step of the tensor-core schedule == one 16 KB weight stage.

@@ -461,6 +461,7 @@ size_t up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 struct TrainWs {
   float *pe_x, *pe_d, *dbuf[2], *act[kMaxLayers];
   uint8_t *pk_a[2], *pk_pex, *pk_ped, *pkt_a, *pkt_act[kMaxLayers], *pkt_pex, *pkt_ped;
+  uint8_t* pkt_dz[kMaxLayers];    // point-major bf16 packs of every layer's dZ (fused data-gradient chain: A operands of dW)
   uint16_t* bits[kMaxLayers];     // relu masks of the recomputed activations, 1 bit per element (tensor-core path)
   size_t bytes;
 };
@@ -485,6 +486,7 @@ TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
     w.pkt_pex = take(pack_bytes(kPeLd, P128));
     w.pkt_ped = take(pack_bytes(kPeLd, P128));
     for (int l = 0; l < G.n_layers; ++l) w.bits[l] = (uint16_t*)take((size_t)P * (G.layers[l].n_out / 16) * 2);
+    for (int l = 0; l < G.n_layers; ++l) w.pkt_dz[l] = take(pack_bytes(G.layers[l].n_out, P128));
   }
   w.bytes = off;
   return w;
@@ -627,6 +629,58 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   size_t gw_off[kMaxLayers];
   int gw_ld[kMaxLayers];
   grad_layout(G, gw_off, gw_ld);
+  if (tc && !layerwise) {
+    // Fused: the SIMT heads produce dZ of the last layer; ONE launch of the fused kernel on the backward program walks the
+    // data gradient down the whole network with dZ in TMEM (W^T streamed through shared memory, relu masks from the recompute,
+    // the rank-1 d sigma term, bias gradients as column sums) and leaves every layer's dZ as the point-major pack the
+    // long-K weight-gradient GEMMs consume — no per-layer round trip of dZ / masks / row packs through HBM.
+    if (!net.bwd_valid)
+      if (int e = build_backward_stream(&net, st, launches)) return e;
+    const int last = G.n_layers - 1;
+    const LayerProg& Ltop = G.layers[last];
+    NM_CHECK(Ltop.kind == KIND_RGB || Ltop.kind == KIND_OUT4, "the last layer must carry the colour head");
+    const int p_per_block = (P + 8 * num_sms - 1) / (8 * num_sms);
+    const int hb_blocks = (P + p_per_block - 1) / p_per_block;
+    float* dZ = W.dbuf[0];
+    head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 0, Ltop.kind == KIND_RGB ? 3 : 4, W.act[last], Ltop.n_out, P,
+                                                   net.d_head + Ltop.head_off, g->head + Ltop.head_off, dZ, Ltop.relu, p_per_block,
+                                                   g->bias + Ltop.bias_off);
+    NM_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    for (int l = 0; l < last; ++l) {
+      const LayerProg& L = G.layers[l];
+      if (L.kind != KIND_SIGMA) continue;       // weight / bias gradient of fc_alpha (its data-gradient term is in the chain)
+      head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 3, 1, W.act[l], L.n_out, P, net.d_head + L.head_off,
+                                                     g->head + L.head_off, nullptr, 0, p_per_block, nullptr);
+      NM_CUDA(cudaGetLastError());
+      if (launches) ++*launches;
+    }
+    if (int e = launch_pack_cols(dZ, Ltop.n_out, P, Ltop.n_out, W.pkt_dz[last], kbtP, 0, st, launches)) return e;
+    MlpEmit io{};
+    io.kbt = kbtP;
+    for (int li = 1; li < net.bwd.n_layers; ++li) {
+      const int l = net.bwd.layers[li].aux;      // this backward layer streams W_l^T and produces dZ of forward layer l-1
+      io.packT[li] = W.pkt_dz[l - 1];
+      if (G.layers[l - 1].relu) io.bits[li] = reinterpret_cast<uint32_t*>(W.bits[l - 1]);
+    }
+    if (int e = launch_mlp_tc_bwd(net, P, dZ, Ltop.n_out, dout, g->bias, io, mode.n_passes, num_sms, mode.d_err, st, launches)) return e;
+    for (int l = last; l >= 0; --l) {            // weight gradients dW (N, Kt) += dZ^T [act[l-1] | PE]: long-K GEMMs, fp32 atomics
+      const LayerProg& L = G.layers[l];
+      TcGemmParams T = tc_base();
+      T.nseg = 1; T.atomic = 1; T.ldd = gw_ld[l]; T.M = L.n_out;
+      if (L.k_act > 0) {
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP};
+        T.D = g->w + gw_off[l]; T.N = L.k_act;
+        if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
+      }
+      if (L.pe_src) {
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, pkt_pe_of(L), kbtP, kbtP};
+        T.D = g->w + gw_off[l] + L.k_act; T.N = L.k_pe;
+        if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
+      }
+    }
+    return 0;
+  }
   int cur = 0;
   bool dz_packed = false;      // W.pk_a[cur] already holds the bf16 row pack of dbuf[cur]
   bool dz_colpacked = false;   // W.pkt_a already holds the point-major bf16 pack of dbuf[cur]

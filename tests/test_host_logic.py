@@ -45,7 +45,7 @@ def test_fails_loudly_without_gpu():
 # ------------------------------------------------------------------------------------------ program + packing
 class LayerProg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_out", "k_act", "pe_src", "k_pe", "relu", "kind", "is_final", "bias_off",
-                                         "head_off", "blk_begin", "blk_end", "wt_off", "none_d", "none_k", "first_blk")]
+                                         "head_off", "blk_begin", "blk_end", "wt_off", "none_d", "none_k", "first_blk", "aux", "aux2")]
 
 
 class BlockProg(C.Structure):

@@ -13,13 +13,52 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def lego(a):
+    """wall-clock and CUDA-event stage times of the full mesh path on the lego checkpoint."""
+    import nerfmeshes_b200 as nm
+    from nerfmeshes_b200 import parallel as par
+    from bench import load_npz, model_cfg
+    model = nm.NeRFModel.from_npz(model_cfg(2.0, 6.0), load_npz("weights_lego_nerf.npz")).eval().cuda()
+    eng = model._engine()
+    wall = {}
+
+    def wrap(name):
+        fn = getattr(eng, name)
+
+        def timed(*args, **kw):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn(*args, **kw)
+            torch.cuda.synchronize()
+            wall[name] = wall.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+            return out
+        setattr(eng, name, timed)
+    for name in ("grid_sigma", "volume_stats", "mc_count", "mc_emit"):
+        wrap(name)
+
+    class Args:
+        res, limit, iso_level = a.res, 1.2, 32.0
+    for rep in range(a.reps):
+        wall.clear()
+        tm = {}
+        t0 = time.perf_counter()
+        v, f, n, iso = par.extract_geometry_sharded(model, Args, to_host=False, timings=tm)
+        torch.cuda.synchronize()
+        print(f"rep {rep}: total wall {1e3 * (time.perf_counter() - t0):.2f} ms | events " +
+              ", ".join(f"{k} {x:.3f}" for k, x in tm.items()) + " | wall per call " + ", ".join(f"{k} {x:.3f}" for k, x in wall.items()) +
+              f" | {v.shape[0]} vertices {f.shape[0]} triangles")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--volume")
     ap.add_argument("--iso", type=float, default=0.0)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--lego", action="store_true", help="time parallel.extract_geometry_sharded (lego sigma sweep + MC) stage by stage")
     a = ap.parse_args()
+    if a.lego:
+        return lego(a)
     from nerfmeshes_b200.nerf_api import _engine
     eng = _engine()
     if a.volume:
