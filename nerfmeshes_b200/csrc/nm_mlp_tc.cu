@@ -314,17 +314,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 }
                 if (P.emit.packT[li] && !writes_a) {     // (layers that write the A operand emit from it after the hand-over, below)
                   const long long pt = tile * kTileM + row;
-                  uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u;
-                  const uint32_t c8 = (uint32_t)((pt & 63) >> 3), e2 = (uint32_t)(pt & 7) * 2u;
+                  // element (feature f, point pt) of a tile: row f%128, 16-byte chunk ((pt%64)/8) ^ (f%8), 2-byte slot pt%8.
+                  // col0 is a multiple of 32, so f%8 = j%8: one base address per j%8, the rest are immediates
+                  uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
+                                (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
+                  const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    const uint32_t rf = (uint32_t)((col0 + j) & 127);
-                    const uint32_t o = rf * 128u + ((c8 ^ (rf & 7u)) << 4) + e2;
-                    const float x = valid ? v[j] : 0.f;
-                    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-                    *reinterpret_cast<uint16_t*>(tb + o) = __bfloat16_as_ushort(h);
-                    *reinterpret_cast<uint16_t*>(tb + 16384u + o) = __bfloat16_as_ushort(l);
+                  for (int q = 0; q < 8; ++q) {
+                    uint8_t* bq = tb + ((c8 ^ (uint32_t)q) << 4);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                      const int j = q + 8 * rr;
+                      const float x = valid ? v[j] : 0.f;
+                      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                      const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+                      *reinterpret_cast<uint16_t*>(bq + j * 128) = __bfloat16_as_ushort(h);
+                      *reinterpret_cast<uint16_t*>(bq + j * 128 + 16384) = __bfloat16_as_ushort(l);
+                    }
                   }
                 }
               }
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             // and stored as the point-major bf16 hi/lo pack of the weight-gradient GEMM (rows past M as zeros).
             const bool valid = m < P.in.M;
             const long long pt = tile * kTileM + row;
-            const uint32_t c8 = (uint32_t)((pt & 63) >> 3), e2 = (uint32_t)(pt & 7) * 2u;
+            const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
               uint32_t h16[16], l16[16];
@@ -387,29 +393,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
               if (n_passes == 3) NM_TMEM_LD16(tmem + lane_addr + kColAlo + acol, l16);
               ptx::tmem_wait_ld();
               const int col0 = n * 64 + half * 32;
-              uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u;
+              if (!valid) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                uint16_t oh[2], ol[2];
-                if (MODE == 2) {        // already bf16 hi / lo
-                  oh[0] = (uint16_t)(h16[j] & 0xffffu); oh[1] = (uint16_t)(h16[j] >> 16);
-                  ol[0] = (n_passes == 3) ? (uint16_t)(l16[j] & 0xffffu) : (uint16_t)0; ol[1] = (n_passes == 3) ? (uint16_t)(l16[j] >> 16) : (uint16_t)0;
-                } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
-                  const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
-                  float2 fl = make_float2(0.f, 0.f);
-                  if (n_passes == 3) fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
-                  const float x0 = (fh.x + fl.x) * so, x1 = (fh.y + fl.y) * so;
-                  const __nv_bfloat16 b0 = __float2bfloat16_rn(x0), b1 = __float2bfloat16_rn(x1);
-                  oh[0] = __bfloat16_as_ushort(b0); oh[1] = __bfloat16_as_ushort(b1);
-                  ol[0] = __bfloat16_as_ushort(__float2bfloat16_rn(x0 - __bfloat162float(b0)));
-                  ol[1] = __bfloat16_as_ushort(__float2bfloat16_rn(x1 - __bfloat162float(b1)));
-                }
+                for (int j = 0; j < 16; ++j) { h16[j] = 0u; l16[j] = 0u; }
+              } else if (n_passes != 3) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  const uint32_t rf = (uint32_t)((col0 + 2 * j + q) & 127);
-                  const uint32_t o = rf * 128u + ((c8 ^ (rf & 7u)) << 4) + e2;
-                  *reinterpret_cast<uint16_t*>(tb + o) = valid ? oh[q] : (uint16_t)0;
-                  *reinterpret_cast<uint16_t*>(tb + 16384u + o) = valid ? ol[q] : (uint16_t)0;
+                for (int j = 0; j < 16; ++j) l16[j] = 0u;
+              }
+              // one base address per (feature % 8) — see the inline variant above; features 2j, 2j+1 sit in register j
+              uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
+                            (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                uint8_t* bq = tb + ((c8 ^ (uint32_t)q) << 4);
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                  const int f = q + 8 * rr, j = f >> 1, odd = f & 1;
+                  uint16_t oh, ol;
+                  if (MODE == 2) {        // already bf16 hi / lo
+                    oh = (uint16_t)(odd ? (h16[j] >> 16) : (h16[j] & 0xffffu));
+                    ol = (uint16_t)(odd ? (l16[j] >> 16) : (l16[j] & 0xffffu));
+                  } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
+                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
+                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
+                    const float x = ((odd ? fh.y : fh.x) + (odd ? fl.y : fl.x)) * so;
+                    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+                    oh = __bfloat16_as_ushort(b0);
+                    ol = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(b0)));
+                  }
+                  *reinterpret_cast<uint16_t*>(bq + f * 128) = oh;
+                  *reinterpret_cast<uint16_t*>(bq + f * 128 + 16384) = ol;
                 }
               }
             }
