@@ -97,9 +97,8 @@ struct MlpInput {
 };
 
 // Optional by-products of a fused-MLP launch for the training backward (nm_train.cu): per layer (nullptr = not wanted)
-//   packT  the layer's output as the point-major hi/lo operand pack of the weight-gradient GEMM (nm_gemm.h: tiles of 128
-//          features x 64 points, [feature block][point block], `kbt` point blocks per feature block; rows >= M zero):
-//          fp16 halves for activations (training forward; needs act_scale 1), bf16 halves for dZ (data-gradient chain)
+//   packT  the layer's output as the point-major bf16 hi/lo operand pack of the weight-gradient GEMM (nm_gemm.h: tiles of
+//          128 features x 64 points, [feature block][point block], `kbt` point blocks per feature block; rows >= M zero)
 //   bits   its relu mask, one bit per element (halfword [m * n_out/16 + n/16], bit n%16)
 //   act    its fp32 value (M, n_out) row-major (the layers the SIMT head kernels read)
 struct MlpEmit {

@@ -32,9 +32,7 @@ struct TcGemmParams {
   TcSeg seg[2];
   int nseg;
   int n_passes;            // 3: hi*hi + lo*hi + hi*lo;  1: hi*hi
-  int fp16;                // operand packs are fp16 halves (else bf16)
-  int b_fp16;              // with fp16 == 0: the B operand alone is fp16 (A bf16): kind::f16 takes the two formats independently
-                           //   (weight gradients: A = dZ in bf16, B = activations exactly as the forward kernel holds them)
+  int fp16;                // operand packs are fp16 halves (else bf16); both operands must use the same format
   float* D;                // (M,N) fp32 row-major
   int ldd, M, N;
   int atomic;              // D += via atomicAdd, K split over CTAs (weight gradients); the epilogue fields are ignored

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer (whole warp converged; one lane issues)
-    const uint32_t idesc = P.fp16 ? kIdescF16 : (P.b_fp16 ? (kIdescF16 | (1u << 7)) : kIdescBf16);
+    const uint32_t idesc = P.fp16 ? kIdescF16 : kIdescBf16;
     int it = 0, i = 0;
     for (int t = t_first; t < n_tiles; t += t_step, ++i) {
       const int nbv = min(NB, P.n_rb_b - tile_cb0(t));

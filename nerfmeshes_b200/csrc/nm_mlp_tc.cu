@@ -326,16 +326,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                     for (int rr = 0; rr < 4; ++rr) {
                       const int j = q + 8 * rr;
                       const float x = valid ? v[j] : 0.f;
-                      if (MODE == 2) {     // dZ: bf16 hi / lo
-                        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-                        *reinterpret_cast<uint16_t*>(bq + j * 128) = __bfloat16_as_ushort(h);
-                        *reinterpret_cast<uint16_t*>(bq + j * 128 + 16384) = __bfloat16_as_ushort(l);
-                      } else {             // activations: fp16 hi / lo like the A operand
-                        const uint16_t h = f16_bits_sat(x);
-                        *reinterpret_cast<uint16_t*>(bq + j * 128) = h;
-                        *reinterpret_cast<uint16_t*>(bq + j * 128 + 16384) = f16_bits_sat(x - f16_bits_to_float(h));
-                      }
+                      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                      const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+                      *reinterpret_cast<uint16_t*>(bq + j * 128) = __bfloat16_as_ushort(h);
+                      *reinterpret_cast<uint16_t*>(bq + j * 128 + 16384) = __bfloat16_as_ushort(l);
                     }
                   }
                 }
@@ -415,10 +409,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                   const int f = q + 8 * rr, j = f >> 1, odd = f & 1;
-                  // the halves are already in the pack's format: fp16 hi / lo of the activation (training forward, act_scale 1)
-                  // or bf16 hi / lo of dZ (data-gradient chain) — a plain copy
-                  *reinterpret_cast<uint16_t*>(bq + f * 128) = (uint16_t)(odd ? (h16[j] >> 16) : (h16[j] & 0xffffu));
-                  *reinterpret_cast<uint16_t*>(bq + f * 128 + 16384) = (uint16_t)(odd ? (l16[j] >> 16) : (l16[j] & 0xffffu));
+                  uint16_t oh, ol;
+                  if (MODE == 2) {        // already bf16 hi / lo
+                    oh = (uint16_t)(odd ? (h16[j] >> 16) : (h16[j] & 0xffffu));
+                    ol = (uint16_t)(odd ? (l16[j] >> 16) : (l16[j] & 0xffffu));
+                  } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
+                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
+                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
+                    const float x = ((odd ? fh.y : fh.x) + (odd ? fl.y : fl.x)) * so;
+                    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+                    oh = __bfloat16_as_ushort(b0);
+                    ol = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(b0)));
+                  }
+                  *reinterpret_cast<uint16_t*>(bq + f * 128) = oh;
+                  *reinterpret_cast<uint16_t*>(bq + f * 128 + 16384) = ol;
                 }
               }
             }

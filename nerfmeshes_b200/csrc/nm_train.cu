@@ -559,18 +559,12 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   encode_kernel<<<(P + 127) / 128, 128, 0, st>>>(in, net.d_full, W.pe_x, W.pe_d);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
-  // NM_TRAIN_LAYERWISE=1 keeps the round-1 layer-by-layer GEMM chain (debugging / comparison)
-  static const bool layerwise = [] { const char* e = getenv("NM_TRAIN_LAYERWISE"); return e && atoi(e) != 0; }();
-  const bool fused = tc && !layerwise;
-  // fused path: the B operands of the weight-gradient GEMMs (activations, encodings) are fp16 hi/lo, exactly the halves the
-  // forward kernel holds in tensor memory (copied out, no conversion); the A operands (dZ) are bf16 hi/lo
-  const int b_fp16 = fused ? 1 : 0;
   if (tc) {
-    if (!fused) if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
-    if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, kbtP, b_fp16, st, launches)) return e;
+    if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
+    if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, kbtP, 0, st, launches)) return e;
     if (G.dim_dir > 0) {
-      if (!fused) if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
-      if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, kbtP, b_fp16, st, launches)) return e;
+      if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
+      if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, kbtP, 0, st, launches)) return e;
     }
   }
   auto pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? W.pe_x : W.pe_d; };
@@ -582,8 +576,9 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   // Tensor-core path: ONE launch of the fused forward kernel (nm_mlp_tc.cu) whose epilogue also emits what the backward
   // needs — relu masks, the point-major bf16 packs of every hidden activation (B operand of the weight-gradient GEMMs) and
   // the fp32 activations the head kernels read — instead of a chain of layer GEMMs round-tripping through HBM.  The masks
-  // are by construction the forward pass's own.
-  if (fused) {
+  // are by construction the forward pass's own.  NM_TRAIN_LAYERWISE=1 keeps the layer-by-layer GEMM chain (debugging).
+  static const bool layerwise = [] { const char* e = getenv("NM_TRAIN_LAYERWISE"); return e && atoi(e) != 0; }();
+  if (tc && !layerwise) {
     MlpEmit E{};
     E.kbt = kbtP;
     for (int l = 0; l < G.n_layers; ++l) {
@@ -594,7 +589,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
     }
     if (int e = launch_mlp_tc(net, false, mode.n_passes, 0, in, nullptr, num_sms, mode.d_err, st, launches, &E)) return e;
   }
-  for (int l = 0; l < G.n_layers && !fused; ++l) {
+  for (int l = 0; l < G.n_layers && !(tc && !layerwise); ++l) {
     const LayerProg& L = G.layers[l];
     const int N = L.n_out, Kt = L.k_act + L.k_pe;
     GemmEpi fin{};
@@ -634,7 +629,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   size_t gw_off[kMaxLayers];
   int gw_ld[kMaxLayers];
   grad_layout(G, gw_off, gw_ld);
-  if (fused) {
+  if (tc && !layerwise) {
     // Fused: the SIMT heads produce dZ of the last layer; ONE launch of the fused kernel on the backward program walks the
     // data gradient down the whole network with dZ in TMEM (W^T streamed through shared memory, relu masks from the recompute,
     // the rank-1 d sigma term, bias gradients as column sums) and leaves every layer's dZ as the point-major pack the
@@ -672,7 +667,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
     for (int l = last; l >= 0; --l) {            // weight gradients dW (N, Kt) += dZ^T [act[l-1] | PE]: long-K GEMMs, fp32 atomics
       const LayerProg& L = G.layers[l];
       TcGemmParams T = tc_base();
-      T.nseg = 1; T.atomic = 1; T.ldd = gw_ld[l]; T.M = L.n_out; T.b_fp16 = 1;
+      T.nseg = 1; T.atomic = 1; T.ldd = gw_ld[l]; T.M = L.n_out;
       if (L.k_act > 0) {
         T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP};
         T.D = g->w + gw_off[l]; T.N = L.k_act;
