@@ -112,7 +112,7 @@ int check_kernel_flags(NmHandle h) {
 }
 
 // one fused-MLP launch in the configured arithmetic
-int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st) {
+int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st, const MlpEmit* emit = nullptr) {
   const NetDev& net = h->nets[which];
   NM_CHECK(net.loaded, "weights of network %d not loaded", which);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -128,7 +128,7 @@ int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* o
   int rc;
   if (h->cfg.precision == NM_PREC_FP32) rc = launch_mlp_simt(net, sigma_only, in, out, st, &h->launches);
   else rc = launch_mlp_tc(net, sigma_only, h->cfg.precision == NM_PREC_FAST ? 1 : 3, h->cfg.act_scale_log2, in, out,
-                          h->num_sms, h->d_err, st, &h->launches);
+                          h->num_sms, h->d_err, st, &h->launches, emit);
   if (rc) return rc;
   if (h->timing) {
     NM_CUDA(cudaEventRecord(e1, st));
@@ -148,7 +148,9 @@ struct RayBatch {
 float* off(float* p, long long n) { return p ? p + n : nullptr; }
 
 // NeRFModel.forward / BuFFModel.forward for one chunk of rays; `o` already offset to the chunk.
-int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const NmRenderOut& o, cudaStream_t st) {
+// emit_c / emit_f: training only — the coarse (or only) / fine network's forward also leaves the backward's operands (MlpEmit)
+int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const NmRenderOut& o, cudaStream_t st,
+                 const MlpEmit* emit_c = nullptr, const MlpEmit* emit_f = nullptr) {
   const NmRenderCfg& c = h->cfg;
   const long long R = rb.R;
   const int Nc = c.num_coarse;
@@ -194,12 +196,12 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
     if (int e = launch_aabb(h->voxels.as<float>(), h->V, rb.origins, rb.o_stride, rb.dirs, R, rb.nf[0], rb.nf[1], Nc,
                             h->s_table.as<float>(), t_c, z, nullptr, h->d_err + 1, st, &h->launches)) return e;
     if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
-    if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(z, Nc), h->raw_c.as<float>(), st)) return e;
+    if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(z, Nc), h->raw_c.as<float>(), st, emit_c)) return e;
     if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, z, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
     return composite(h->raw_c.as<float>(), z, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
   }
   if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
-  if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(t_c, Nc), h->raw_c.as<float>(), st)) return e;
+  if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(t_c, Nc), h->raw_c.as<float>(), st, emit_c)) return e;
   if (Nf == 0) {
     if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, t_c, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
     return composite(h->raw_c.as<float>(), t_c, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
@@ -213,7 +215,7 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
   if (!t_f) { if (int e = h->t_f.ensure((size_t)R * S * 4)) return e; t_f = h->t_f.as<float>(); }
   if (int e = launch_invcdf(t_c, w_c, h->u_table.as<float>(), Nc, Nf, R, c.perturb, seed ^ 0x9e3779b9u, t_f, st, &h->launches)) return e;
   if (int e = h->raw_f.ensure((size_t)R * S * 16)) return e;
-  if (int e = run_mlp(h, NM_NET_FINE, false, rays_input(t_f, S), h->raw_f.as<float>(), st)) return e;
+  if (int e = run_mlp(h, NM_NET_FINE, false, rays_input(t_f, S), h->raw_f.as<float>(), st, emit_f)) return e;
   return composite(h->raw_f.as<float>(), t_f, S, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
 }
 
@@ -304,7 +306,29 @@ int train_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const 
   if (int e = h->tr_rgb[0].ensure((size_t)R * 12)) return e;
   o.rgb = h->tr_rgb[0].as<float>();
   if (two) { if (int e = h->tr_rgb[1].ensure((size_t)R * 12)) return e; o.coarse_rgb = h->tr_rgb[1].as<float>(); }
-  if (int e = render_chunk(h, rb, flags, seed, o, st)) return e;
+  // Direct mode: when the backward's workspace for ALL points of the chunk fits the budget (NM_TRAIN_DIRECT_GB, default 48),
+  // the training forward itself emits the masks / activation packs and the backward skips its recompute launch; larger
+  // chunks are walked in sub-chunks with a recompute each (below).
+  const bool use_tc = c.precision != NM_PREC_FP32;
+  const char* dg_env = getenv("NM_TRAIN_DIRECT_GB");      // read per call: the tests flip it to cover both walks
+  const double direct_gb = dg_env ? atof(dg_env) : 48.0;
+  const size_t ws_main = train_fused(use_tc) && c.act_scale_log2 == 0 ? train_ws_bytes(h->nets[two ? NM_NET_FINE : NM_NET_COARSE].full, R * S, true) + 1024 : 0;
+  const size_t ws_coarse = (ws_main && two) ? train_ws_bytes(h->nets[NM_NET_COARSE].full, R * Nc, true) + 1024 : 0;
+  const bool direct = ws_main > 0 && (double)(ws_main + ws_coarse) <= direct_gb * 1e9 && (d_rgb || target) && (!two || d_rgb_coarse || target);
+  float *ws_m = nullptr, *ws_c = nullptr;
+  MlpEmit em_main{}, em_coarse{};
+  if (direct) {
+    if (int e = h->train_ws.ensure(ws_main + ws_coarse + 2048)) return e;
+    ws_m = reinterpret_cast<float*>(((uintptr_t)h->train_ws.p + 1023) & ~(uintptr_t)1023);
+    train_emit_setup(h->nets[two ? NM_NET_FINE : NM_NET_COARSE].full, R * S, ws_m, &em_main);
+    if (two) {
+      ws_c = reinterpret_cast<float*>(((uintptr_t)ws_m + ws_main + 1023) & ~(uintptr_t)1023);
+      train_emit_setup(h->nets[NM_NET_COARSE].full, R * Nc, ws_c, &em_coarse);
+    }
+    if (int e = render_chunk(h, rb, flags, seed, o, st, two ? &em_coarse : &em_main, two ? &em_main : nullptr)) return e;
+  } else {
+    if (int e = render_chunk(h, rb, flags, seed, o, st)) return e;
+  }
   if (target) {
     for (int i = 0; i < (two ? 2 : 1); ++i) {
       if (int e = h->tr_drgb[i].ensure((size_t)R * 12)) return e;
@@ -331,8 +355,16 @@ int train_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const 
     if (int e = h->trans.ensure((size_t)R * P.s * 4)) return e;
     if (int e = launch_composite_backward(P.raw, P.t, rb.dirs, P.g, R, P.s, c.noise_std, seed ^ P.salt,
                                           c.white_background, h->trans.as<float>(), h->dout.as<float>(), st, &h->launches)) return e;
-    // sub-chunks of `waves` full waves of 128-point row blocks (148 SMs): bounds the activation workspace (~17 KB per point)
-    const bool use_tc = c.precision != NM_PREC_FP32;
+    NetGrads gd{h->g_wt[P.which].as<float>(), h->g_bias[P.which].as<float>(), h->g_head[P.which].as<float>()};
+    TrainMode md{use_tc ? 1 : 0, c.precision == NM_PREC_FAST ? 1 : 3, h->d_err};
+    if (direct) {
+      MlpInput in{};
+      in.mode = IN_RAYS; in.dirs = rb.dirs; in.ray_o = rb.origins; in.o_stride = rb.o_stride; in.t = P.t; in.S = P.s; in.M = R * P.s;
+      float* wsp = (two && P.which == NM_NET_COARSE) ? ws_c : ws_m;
+      if (int e = mlp_backward(h->nets[P.which], in, h->dout.as<float>(), wsp, &gd, h->num_sms, md, st, &h->launches, 1)) return e;
+      continue;
+    }
+    // sub-chunks of `waves` full waves of 128-point row blocks (148 SMs): bounds the activation workspace (~20 KB per point)
     static const int waves = [] { const char* e = getenv("NM_TRAIN_WAVES"); int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
     long long rays_sub = ((long long)h->num_sms * 128 * waves) / P.s;
     if (rays_sub < 1) rays_sub = 1;

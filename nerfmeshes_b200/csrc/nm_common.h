@@ -175,7 +175,9 @@ int launch_volume_stats_pass(const float* vol, long long n, int pass, const doub
 size_t train_ws_bytes(const NetProgram& full, long long points, bool use_tc);
 struct TrainMode { int use_tc; int n_passes; int* d_err; };
 int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws, NetGrads* g, int num_sms,
-                 const TrainMode& mode, cudaStream_t st, int64_t* launches);
+                 const TrainMode& mode, cudaStream_t st, int64_t* launches, int have_acts = 0);
+bool train_fused(bool use_tc);
+void train_emit_setup(const NetProgram& full, long long points, float* ws, MlpEmit* emit);
 int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_cols, int b_cols, int k_split, int n_passes,
                   int fp16, int atomic, float* D, uint8_t* scratch, size_t scratch_bytes, int num_sms, int* d_err, cudaStream_t st,
                   int64_t* launches);

@@ -465,23 +465,32 @@ struct TrainWs {
   uint16_t* bits[kMaxLayers];     // relu masks of the recomputed activations, 1 bit per element (tensor-core path)
   size_t bytes;
 };
+bool train_layerwise() {
+  static const bool v = [] { const char* e = getenv("NM_TRAIN_LAYERWISE"); return e && atoi(e) != 0; }();
+  return v;
+}
+
 TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
   TrainWs w{};
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += up(bytes); return p; };
   const int h = G.hidden;
+  const bool fused = use_tc && !train_layerwise();    // fused chains: no row packs, fp32 activations only where the heads read them
   w.pe_x = (float*)take((size_t)P * kPeLd * 4);
   w.pe_d = (float*)take((size_t)P * kPeLd * 4);
   w.dbuf[0] = (float*)take((size_t)P * h * 4);
-  w.dbuf[1] = (float*)take((size_t)P * h * 4);
-  for (int l = 0; l < G.n_layers; ++l) w.act[l] = (float*)take((size_t)P * G.layers[l].n_out * 4);
+  if (!fused) w.dbuf[1] = (float*)take((size_t)P * h * 4);
+  for (int l = 0; l < G.n_layers; ++l)
+    if (!fused || G.layers[l].kind != KIND_HIDDEN) w.act[l] = (float*)take((size_t)P * G.layers[l].n_out * 4);
   if (use_tc) {
-    w.pk_a[0] = take(pack_bytes((int)P, h));
-    w.pk_a[1] = take(pack_bytes((int)P, h));
-    w.pk_pex = take(pack_bytes((int)P, kPeLd));
-    w.pk_ped = take(pack_bytes((int)P, kPeLd));
+    if (!fused) {
+      w.pk_a[0] = take(pack_bytes((int)P, h));
+      w.pk_a[1] = take(pack_bytes((int)P, h));
+      w.pk_pex = take(pack_bytes((int)P, kPeLd));
+      w.pk_ped = take(pack_bytes((int)P, kPeLd));
+    }
     const int P128 = (int)((P + 127) / 128) * 128;     // K blocks of the point-major packs come in pairs (one per 128-row tile)
-    w.pkt_a = take(pack_bytes(h, P128));
+    if (!fused) w.pkt_a = take(pack_bytes(h, P128));
     for (int l = 0; l + 1 < G.n_layers; ++l) w.pkt_act[l] = take(pack_bytes(G.layers[l].n_out, P128));
     w.pkt_pex = take(pack_bytes(kPeLd, P128));
     w.pkt_ped = take(pack_bytes(kPeLd, P128));
@@ -523,6 +532,22 @@ int build_weight_packs(NetDev& net, cudaStream_t st, int64_t* launches) {
 
 size_t train_ws_bytes(const NetProgram& G, long long points, bool use_tc) { return carve(G, points, use_tc, nullptr).bytes; }
 
+bool train_fused(bool use_tc) { return use_tc && !train_layerwise(); }
+
+// The by-products a training forward must leave in `ws` (same carving as mlp_backward) so that the backward can skip its
+// recompute launch: see MlpEmit.
+void train_emit_setup(const NetProgram& G, long long P, float* ws_base, MlpEmit* E) {
+  const TrainWs W = carve(G, P, true, reinterpret_cast<uint8_t*>(ws_base));
+  *E = MlpEmit{};
+  E->kbt = 2 * (int)((P + 127) / 128);
+  for (int l = 0; l < G.n_layers; ++l) {
+    const LayerProg& L = G.layers[l];
+    if (l + 1 < G.n_layers) E->packT[l] = W.pkt_act[l];
+    if (L.relu) E->bits[l] = reinterpret_cast<uint32_t*>(W.bits[l]);
+    if (L.kind != KIND_HIDDEN) E->act[l] = W.act[l];
+  }
+}
+
 int launch_composite_backward(const float* raw, const float* t, const float* dirs, const float* d_rgb, long long R, int S,
                               float noise_std, uint64_t seed, int white_bg, float* scratch, float* dout,
                               cudaStream_t st, int64_t* launches) {
@@ -546,7 +571,7 @@ int launch_mse_grad(const float* rgb, const float* target, long long n, long lon
 // Backward of one network over P = in.M points.  dout (P,4).  ws: train_ws_bytes(full, P, use_tc) bytes, 1 KB aligned.
 // Weight gradients accumulate in the reference's (out,in) layout at the offsets of NetDev.d_w.
 int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_base, NetGrads* g, int num_sms,
-                 const TrainMode& mode, cudaStream_t st, int64_t* launches) {
+                 const TrainMode& mode, cudaStream_t st, int64_t* launches, int have_acts) {
   const NetProgram& G = net.full;
   const int P = (int)in.M;
   if (P <= 0) return 0;
@@ -560,10 +585,11 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   if (tc) {
-    if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
+    const bool rows = train_layerwise();      // row packs feed the layer-wise forward GEMMs only
+    if (rows) if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
     if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, kbtP, 0, st, launches)) return e;
     if (G.dim_dir > 0) {
-      if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
+      if (rows) if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
       if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, kbtP, 0, st, launches)) return e;
     }
   }
@@ -577,16 +603,10 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   // needs — relu masks, the point-major bf16 packs of every hidden activation (B operand of the weight-gradient GEMMs) and
   // the fp32 activations the head kernels read — instead of a chain of layer GEMMs round-tripping through HBM.  The masks
   // are by construction the forward pass's own.  NM_TRAIN_LAYERWISE=1 keeps the layer-by-layer GEMM chain (debugging).
-  static const bool layerwise = [] { const char* e = getenv("NM_TRAIN_LAYERWISE"); return e && atoi(e) != 0; }();
-  if (tc && !layerwise) {
+  const bool layerwise = train_layerwise();
+  if (tc && !layerwise && !have_acts) {       // have_acts: the training forward itself already left them in `ws` (nm_api.cu)
     MlpEmit E{};
-    E.kbt = kbtP;
-    for (int l = 0; l < G.n_layers; ++l) {
-      const LayerProg& L = G.layers[l];
-      if (l + 1 < G.n_layers) E.packT[l] = W.pkt_act[l];
-      if (L.relu) E.bits[l] = reinterpret_cast<uint32_t*>(W.bits[l]);
-      if (L.kind != KIND_HIDDEN) E.act[l] = W.act[l];
-    }
+    train_emit_setup(G, P, ws_base, &E);
     if (int e = launch_mlp_tc(net, false, mode.n_passes, 0, in, nullptr, num_sms, mode.d_err, st, launches, &E)) return e;
   }
   for (int l = 0; l < G.n_layers && !(tc && !layerwise); ++l) {

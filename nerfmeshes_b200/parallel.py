@@ -166,6 +166,20 @@ def render_image_sharded(model, pose, H, W, focal, near, far, *, ndc=False, buff
     return ex.gather()
 
 
+_MESH_BUFFERS = {}
+
+
+def _scratch(key, numel, dtype, device):
+    """Grow-only scratch tensors of the mesh path (slab buffer, exchange segments, single-GPU outputs): steady-state calls
+    make no allocator traffic.  Tensors returned by extract_geometry_sharded(to_host=False) are views of these buffers
+    and stay valid until the next call."""
+    t = _MESH_BUFFERS.get((key, str(device)))
+    if t is None or t.numel() < numel or t.dtype != dtype:
+        t = torch.empty(int(numel * 1.25) + 16, dtype=dtype, device=device)
+        _MESH_BUFFERS[(key, str(device))] = t
+    return t[:numel]
+
+
 SINGLE = "single"        # pass as `group` to run the sharded code paths as ONE shard (tests compare it with the N-rank result)
 
 
@@ -245,7 +259,7 @@ def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None
     tiles = [torch.linspace(-args.limit, args.limit, res) for _ in range(3)]
     own0, own1, buf0, buf1 = slab_layout(res, rank, world)
     tm.mark()
-    buf = torch.empty((buf1 - buf0, res, res), dtype=torch.float32, device=dev)
+    buf = _scratch("slab", (buf1 - buf0) * res * res, torch.float32, dev).view(buf1 - buf0, res, res)
     can_exchange = world > 1 and halo == "exchange" and all(
         (lambda a: a[1] - a[0] >= 2)(slab_layout(res, r, world)) for r in range(world))
     if world == 1 or can_exchange:
@@ -279,7 +293,9 @@ def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None
     shard = (iso, buf0, res, own0 - buf0, own1 - buf0)
     nv, nt = eng.mc_count(buf, *shard)
     if world == 1:
-        v, f, n = eng.mc_emit(buf, *shard, nv, nt, 0)
+        outs = (_scratch("v", 3 * nv, torch.float32, dev).view(nv, 3), _scratch("n", 3 * nv, torch.float32, dev).view(nv, 3),
+                _scratch("f", 3 * nt, torch.int32, dev).view(nt, 3))
+        v, f, n = eng.mc_emit(buf, *shard, nv, nt, 0, out=outs)
         tm.mark("mc")
         tm.mark("gather")
     else:
@@ -293,8 +309,8 @@ def extract_geometry_sharded(model, args, group=None, to_host=True, timings=None
             raise OverflowError("mesh too large for int32 indices")
         vmax, tmax = max(max(nvs), 1), max(max(nts), 1)
         seg = 3 * (2 * vmax + tmax)                               # floats per rank: vertices | normals | faces (int32 bits)
-        local = torch.empty(seg, dtype=torch.float32, device=dev)
-        full = torch.empty(world * seg, dtype=torch.float32, device=dev)
+        local = _scratch("local", seg, torch.float32, dev)
+        full = _scratch("full", world * seg, torch.float32, dev)
         views = (local[:3 * vmax].view(vmax, 3), local[3 * vmax:6 * vmax].view(vmax, 3), local[6 * vmax:].view(torch.int32).view(tmax, 3))
         eng.mc_emit(buf, *shard, nv, nt, v_base, out=views)
         tm.mark("mc")

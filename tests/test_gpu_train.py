@@ -168,6 +168,38 @@ def test_fused_loss_backward_equals_autograd_path_and_accumulates():
     assert lc2 != lc and not torch.equal(gc2["layer1.weight"], gc["layer1.weight"])
 
 
+def test_direct_and_subchunk_walks_agree(monkeypatch):
+    """The backward either reuses what the training forward emitted (whole chunk in the workspace, the default) or walks
+    sub-chunks with a recompute each (NM_TRAIN_DIRECT_GB=0, what a chunk beyond the budget gets; 6000 rays x 64 samples take
+    two sub-chunks of 16 waves).  Same masks, same operands: they differ by atomic order only."""
+    import nerfmeshes_b200 as nm
+    net = O.NetCfg()
+    cfg = _cfg(net, net, nc=24, nf=40)
+    cfg.update({"nerf.train.perturb": True, "nerf.train.radiance_field_noise_std": 0.5})
+    model = nm.NeRFModel(cfg).cuda().train()
+    model.model_coarse.load_state_dict(O.init_weights(net, 3), strict=False)
+    model.model_fine.load_state_dict(O.init_weights(net, 4), strict=False)
+    g = torch.Generator().manual_seed(8)
+    R = 6000
+    o = (torch.randn(3, generator=g) * 0.2).cuda()
+    d = torch.randn(R, 3, generator=g).cuda()
+    target = torch.rand(R, 3, generator=g).cuda()
+    eng = model._engine()
+
+    def run():
+        eng.zero_grad()
+        loss = eng.loss_backward(o, d, 0.5, 3.0, target, training=True, seed=77)
+        return ([float(x) for x in loss[:2]],
+                {k: eng.get_grad(0, k, p).cpu() for k, p in model.model_coarse.named_parameters()},
+                {k: eng.get_grad(1, k, p).cpu() for k, p in model.model_fine.named_parameters()})
+    l_dir, c_dir, f_dir = run()
+    monkeypatch.setenv("NM_TRAIN_DIRECT_GB", "0")
+    l_sub, c_sub, f_sub = run()
+    assert l_dir == l_sub
+    compare(c_sub, c_dir, rel_max=2e-5, name="walks coarse")
+    compare(f_sub, f_dir, rel_max=2e-5, name="walks fine")
+
+
 def test_buff_backward_matches_autograd():
     import nerfmeshes_b200 as nm
     z = load_npz("weights_lego_buff.npz")
