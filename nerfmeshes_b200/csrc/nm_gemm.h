@@ -27,6 +27,7 @@ struct TcSeg {             // one K segment: packs ordered [row block][K block],
   const uint8_t* b;
   int b_kbt;
   int nkb;                 // K blocks of this segment
+  int mn = 0;              // bit 0 / bit 1: the A / B pack is MN-major (K = the source's rows: pack_cols, the fused kernels' emissions)
 };
 struct TcGemmParams {
   TcSeg seg[2];

@@ -138,12 +138,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
         ptx::mbar_wait(full(s), (uint32_t)((it / NS) & 1), P.err, 92);
         ptx::tc_fence_after();
         const uint32_t a = sbase + (uint32_t)s * STAGE;
-        const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a), a_lo = ptx::make_kmajor_sw128_desc(a + kPtileHalf);
+        const int mn = P.seg[kk < n0 ? 0 : 1].mn;
+        const bool amn = mn & 1, bmn = mn & 2;
+        const uint32_t idesc_s = idesc | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
+        const uint64_t a_step = amn ? 128u : 2u, b_step = bmn ? 128u : 2u;       // per k16: 2048 B (MN-major) / 32 B (K-major)
+        const uint64_t a_hi = amn ? ptx::make_mnmajor_sw128_desc(a) : ptx::make_kmajor_sw128_desc(a);
+        const uint64_t a_lo = amn ? ptx::make_mnmajor_sw128_desc(a + kPtileHalf) : ptx::make_kmajor_sw128_desc(a + kPtileHalf);
         for (int j = 0; j < ((P.dbg & 1) ? 0 : nbv); ++j) {
           const uint32_t bs = a + kPtileBytes * (uint32_t)(1 + j);
-          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(bs), b_lo = ptx::make_kmajor_sw128_desc(bs + kPtileHalf);
-          if (P.n_passes == 3) ptx::mma_block_ss3(dacc + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, kk > 0 ? 1u : 0u, 4u);
-          else ptx::mma_block_ss1(dacc + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc, kk > 0 ? 1u : 0u, 4u);
+          const uint64_t b_hi = bmn ? ptx::make_mnmajor_sw128_desc(bs) : ptx::make_kmajor_sw128_desc(bs);
+          const uint64_t b_lo = bmn ? ptx::make_mnmajor_sw128_desc(bs + kPtileHalf) : ptx::make_kmajor_sw128_desc(bs + kPtileHalf);
+          if (P.n_passes == 3) ptx::mma_block_ss3g(dacc + 128u * j, a_hi, a_lo, b_hi, b_lo, idesc_s, kk > 0 ? 1u : 0u, 4u, a_step, b_step);
+          else ptx::mma_block_ss1g(dacc + 128u * j, a_hi, b_hi, idesc_s, kk > 0 ? 1u : 0u, 4u, a_step, b_step);
         }
         ptx::tc_commit_elect(empty(s));
       }
@@ -260,19 +266,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
                 }
               }
             }
-            if (P.packT_out) {   // the finished 32x16 block, transposed: lane = (column f, pair of 8-row chunks)
+            if (P.packT_out) {   // the finished 32x16 block as an MN-major pack (K = rows): lane = row, 16 columns = 2 chunks
               __syncwarp();
-              const int f = lane & 15, ch0 = (lane >> 4) * 2;
-              const int nf = (cb0 + j) * 128 + c0 + f;
-              const int row = nf & 127;
-              uint8_t* tile = P.packT_out + ((size_t)(nf >> 7) * P.packT_kbt + (rb * 2 + (lg >> 1))) * kPtileBytes;
+              const int nf0 = (cb0 + j) * 128 + c0;
+              const int krow = (lg & 1) * 32 + lane;
+              uint8_t* tile = P.packT_out + ((size_t)(nf0 >> 7) * P.packT_kbt + (rb * 2 + (lg >> 1))) * kPtileBytes +
+                              (size_t)((nf0 & 127) >> 6) * 8192u + (size_t)krow * 128u;
 #pragma unroll
-              for (int c = ch0; c < ch0 + 2; ++c) {
+              for (int c = 0; c < 2; ++c) {
                 __align__(16) uint16_t hi[8], lo[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split16(stg[(c * 8 + e) * 17 + f], 0, &hi[e], &lo[e]);
-                const int c8 = (lg & 1) * 4 + c;
-                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4);
+                for (int e = 0; e < 8; ++e) split16(stg[lane * 17 + c * 8 + e], 0, &hi[e], &lo[e]);
+                const uint32_t off = (uint32_t)(((((nf0 & 63) >> 3) + c) ^ (krow & 7)) << 4);
                 *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
                 *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
               }
@@ -336,40 +341,39 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
   }
 }
 
-// K along the source's rows (points): operand row r = source column f (f < F valid), K index = source row p (p < P).
-// grid (K blocks over points, row blocks over features); the 64 x 128 fp32 source block goes through shared memory.
+// K along the source's rows (points): operand row = source column f (f < F valid), K index = source row p (p < P).
+// MN-major tiles (ptx::make_mnmajor_sw128_desc): tile [feature block of 128][64-point K block] = [feature group of 64]
+// [point row][128 B = 64 features]; a source row segment is copied as it lies, no transposition.  grid (K blocks over
+// points, row blocks over features); 256 threads: 8 lanes cover one 128-byte line, 4 passes of 32 point rows, 2 groups.
 __global__ void __launch_bounds__(256) pack_cols_kernel(const float* __restrict__ src, int ld, int P, int F,
                                                         uint8_t* __restrict__ out, int kbt, int fp16) {
-  __shared__ float t[64][129];
   const int kb = blockIdx.x, rb = blockIdx.y;
   uint8_t* tile = out + ((size_t)rb * kbt + kb) * kPtileBytes;
-  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && rb * 128 + 128 <= F;
-  if (vec) {
-    for (int e = threadIdx.x; e < 64 * 32; e += 256) {           // 64 points x 32 float4
-      const int p = e >> 5, f4 = (e & 31) * 4;
-      const int gp = kb * 64 + p;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gp < P) x = *reinterpret_cast<const float4*>(src + (size_t)gp * ld + rb * 128 + f4);
-      t[p][f4] = x.x; t[p][f4 + 1] = x.y; t[p][f4 + 2] = x.z; t[p][f4 + 3] = x.w;
-    }
-  } else {
-    for (int e = threadIdx.x; e < 64 * 128; e += 256) {
-      const int p = e >> 7, f = e & 127;
-      const int gp = kb * 64 + p, gf = rb * 128 + f;
-      t[p][f] = (gp < P && gf < F) ? src[(size_t)gp * ld + gf] : 0.f;
-    }
-  }
-  __syncthreads();
   const int c8 = threadIdx.x & 7;
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
 #pragma unroll
-  for (int pass = 0; pass < 4; ++pass) {
-    const int r = pass * 32 + (threadIdx.x >> 3);
-    __align__(16) uint16_t hi[8], lo[8];
+  for (int g = 0; g < 2; ++g) {
+    const int col = rb * 128 + g * 64 + c8 * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split16(t[c8 * 8 + i][r], fp16, &hi[i], &lo[i]);
-    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+    for (int pass = 0; pass < 2; ++pass) {
+      const int r = pass * 32 + (threadIdx.x >> 3);            // point row of the K block
+      const int gp = kb * 64 + r;
+      float v[8];
+      if (vec && gp < P && col + 8 <= F) {
+        const float4 x0 = *reinterpret_cast<const float4*>(src + (size_t)gp * ld + col);
+        const float4 x1 = *reinterpret_cast<const float4*>(src + (size_t)gp * ld + col + 4);
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (gp < P && col + i < F) ? src[(size_t)gp * ld + col + i] : 0.f;
+      }
+      __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) split16(v[i], fp16, &hi[i], &lo[i]);
+      const uint32_t off = (uint32_t)g * 8192u + (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+    }
   }
 }
 

@@ -313,24 +313,27 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                   for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
                 if (P.emit.packT[li] && !writes_a) {     // (layers that write the A operand emit from it after the hand-over, below)
+                  // MN-major pack (nm_ptx.cuh make_mnmajor_sw128_desc): a point's 64 features of one group are one 128-byte
+                  // line, 16-byte chunks XOR-swizzled by the point row; this thread owns 32 features = 4 chunks, hi and lo
                   const long long pt = tile * kTileM + row;
-                  // element (feature f, point pt) of a tile: row f%128, 16-byte chunk ((pt%64)/8) ^ (f%8), 2-byte slot pt%8.
-                  // col0 is a multiple of 32, so f%8 = j%8: one base address per j%8, the rest are immediates
-                  uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
-                                (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
-                  const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
+                  uint8_t* line = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
+                                  (size_t)((col0 & 127) >> 6) * 8192u + (size_t)(pt & 63) * 128u;
+                  const uint32_t c0 = (uint32_t)((col0 & 63) >> 3), sw = (uint32_t)(pt & 7);
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    uint8_t* bq = tb + ((c8 ^ (uint32_t)q) << 4);
+                  for (int c = 0; c < 4; ++c) {
+                    uint32_t h4[4], l4[4];
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                      const int j = q + 8 * rr;
-                      const float x = valid ? v[j] : 0.f;
-                      const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                      const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-                      *reinterpret_cast<uint16_t*>(bq + j * 128) = __bfloat16_as_ushort(h);
-                      *reinterpret_cast<uint16_t*>(bq + j * 128 + 16384) = __bfloat16_as_ushort(l);
+                    for (int e = 0; e < 4; ++e) {
+                      const float x0 = valid ? v[c * 8 + 2 * e] : 0.f, x1 = valid ? v[c * 8 + 2 * e + 1] : 0.f;
+                      const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                      const float2 f = __bfloat1622float2(h2);
+                      const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+                      h4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                      l4[e] = *reinterpret_cast<const uint32_t*>(&l2);
                     }
+                    const uint32_t off = ((c0 + (uint32_t)c) ^ sw) << 4;
+                    *reinterpret_cast<uint4*>(line + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                    *reinterpret_cast<uint4*>(line + 16384u + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
                   }
                 }
               }
@@ -400,30 +403,32 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) l16[j] = 0u;
               }
-              // one base address per (feature % 8) — see the inline variant above; features 2j, 2j+1 sit in register j
-              uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
-                            (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
+              // MN-major pack, as the inline variant above: 4 chunks of 8 features; features 2j, 2j+1 sit in register j
+              uint8_t* line = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
+                              (size_t)((col0 & 127) >> 6) * 8192u + (size_t)(pt & 63) * 128u;
+              const uint32_t c0 = (uint32_t)((col0 & 63) >> 3), sw = (uint32_t)(pt & 7);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                uint8_t* bq = tb + ((c8 ^ (uint32_t)q) << 4);
+              for (int c = 0; c < 4; ++c) {
+                uint32_t h4[4], l4[4];
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                  const int f = q + 8 * rr, j = f >> 1, odd = f & 1;
-                  uint16_t oh, ol;
+                for (int e = 0; e < 4; ++e) {
+                  const int j = c * 4 + e;
                   if (MODE == 2) {        // already bf16 hi / lo
-                    oh = (uint16_t)(odd ? (h16[j] >> 16) : (h16[j] & 0xffffu));
-                    ol = (uint16_t)(odd ? (l16[j] >> 16) : (l16[j] & 0xffffu));
+                    h4[e] = h16[j]; l4[e] = l16[j];
                   } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
                     const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
                     const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
-                    const float x = ((odd ? fh.y : fh.x) + (odd ? fl.y : fl.x)) * so;
-                    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
-                    oh = __bfloat16_as_ushort(b0);
-                    ol = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(b0)));
+                    const float x0 = (fh.x + fl.x) * so, x1 = (fh.y + fl.y) * so;
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                    const float2 f = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+                    h4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                    l4[e] = *reinterpret_cast<const uint32_t*>(&l2);
                   }
-                  *reinterpret_cast<uint16_t*>(bq + f * 128) = oh;
-                  *reinterpret_cast<uint16_t*>(bq + f * 128 + 16384) = ol;
                 }
+                const uint32_t off = ((c0 + (uint32_t)c) ^ sw) << 4;
+                *reinterpret_cast<uint4*>(line + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                *reinterpret_cast<uint4*>(line + 16384u + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
               }
             }
           }

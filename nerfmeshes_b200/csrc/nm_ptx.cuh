@@ -201,6 +201,58 @@ __device__ __forceinline__ void mma_block_ss1(uint32_t d_tmem, uint64_t a_hi, ui
       ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_first), "r"(ksteps)
       : "memory");
 }
+// The same blocks with the per-k16 descriptor advance given by the caller (>>4 units): K-major SWIZZLE_128B operands step
+// by 32 B (2), MN-major ones by two 8-row groups = 2048 B (128).
+__device__ __forceinline__ void mma_block_ss3g(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                               uint32_t idesc, uint32_t acc_first, uint32_t ksteps, uint64_t a_step, uint64_t b_step) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pk, pacc, pt;\n\t.reg .b64 a, b;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pacc, %6, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "setp.gt.u32 pk, %7, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 0;\n\tadd.u64 b, %3, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pacc;\n\t"
+      "setp.gt.u32 pk, %7, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %2, 0;\n\tadd.u64 b, %3, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 0;\n\tadd.u64 b, %4, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "setp.gt.u32 pk, %7, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %8;\n\tadd.u64 b, b, %9;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(acc_first), "r"(ksteps), "l"(a_step), "l"(b_step)
+      : "memory");
+}
+__device__ __forceinline__ void mma_block_ss1g(uint32_t d_tmem, uint64_t a_hi, uint64_t b_hi, uint32_t idesc, uint32_t acc_first,
+                                               uint32_t ksteps, uint64_t a_step, uint64_t b_step) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pk, pacc, pt;\n\t.reg .b64 a, b;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 pacc, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+      "setp.gt.u32 pk, %5, 0;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, %1, 0;\n\tadd.u64 b, %2, 0;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pacc;\n\t"
+      "setp.gt.u32 pk, %5, 1;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %6;\n\tadd.u64 b, b, %7;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "setp.gt.u32 pk, %5, 2;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %6;\n\tadd.u64 b, b, %7;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "setp.gt.u32 pk, %5, 3;\n\tand.pred pk, pk, pe;\n\tadd.u64 a, a, %6;\n\tadd.u64 b, b, %7;\n\t"
+      "@pk tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, pt;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_hi), "l"(b_hi), "r"(idesc), "r"(acc_first), "r"(ksteps), "l"(a_step), "l"(b_step)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
@@ -212,6 +264,14 @@ __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
 // layout_type=2 (SWIZZLE_128B) [61,64).  Tile base must be 1024-byte aligned; advancing K by 16 fp16 = +32 B = +2.
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// MN-major, SWIZZLE_128B descriptor of a 128 (M or N) x 64 (K) tile of 16-bit elements stored as [MN group of 64][K row][128 B]:
+// the 64 MN elements of one K index are one 128-byte line (16-byte chunks XOR-swizzled by the K row % 8, as in the K-major
+// case), 8 K rows make a 1024-byte group (SBO), the second MN group of 64 follows at LBO = 64 rows * 128 B = 8192 B.
+// Canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute mma_traits_sm100.hpp).  Advancing K by 16 = +2048 B.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B fp16 (0), both K-major,

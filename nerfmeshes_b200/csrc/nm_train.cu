@@ -19,6 +19,8 @@
 
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "nm_common.h"
 #include "nm_frontend.cuh"
 #include "nm_gemm.h"
@@ -43,6 +45,47 @@ __global__ void encode_kernel(const __grid_constant__ MlpInput in, const NetProg
     float* pd = pe_d + m * kPeLd;
     for (int j = G.dim_dir; j < kPeLd; ++j) pd[j] = 0.f;
     positional_encoding(d, G.L_dir, G.inc_dir, G.freq_dir, [&](int j, float v) { pd[j] = v; });
+  }
+}
+
+// Tensor-core path: the encodings are only ever read as the B operand of the weight-gradient GEMMs, so they go straight
+// into the point-major (MN-major) bf16 hi/lo packs (pack_cols_kernel's layout, nm_gemm_tc.cu: tile = 64-point K block,
+// [feature group of 64][point row][128 B], 16-byte chunks XOR-swizzled by the row) without an fp32 round trip.  One CTA per
+// 64 points: threads 0..63 encode xyz, 64..127 the direction; a thread writes its point's 128-byte line (feature group 1
+// is padding, written as zeros).
+__global__ void __launch_bounds__(128) encode_pack_kernel(const __grid_constant__ MlpInput in, const NetProgram* __restrict__ prog,
+                                                          uint8_t* __restrict__ pkt_x, uint8_t* __restrict__ pkt_d) {
+  const NetProgram& G = *prog;
+  const int kb = blockIdx.x;
+  const int which = threadIdx.x >> 6, pt = threadIdx.x & 63;
+  if ((which ? G.dim_dir : G.dim_xyz) <= 0) return;
+  const long long m = (long long)kb * 64 + pt;
+  __shared__ float stage[128][65];                       // a thread's 64 features (dynamic index j: not a register array)
+  float* f = stage[threadIdx.x];
+  for (int j = 0; j < 64; ++j) f[j] = 0.f;
+  if (m < in.M) {
+    float p[3], d[3];
+    fetch_point(in, m, p, d);
+    if (which == 0) positional_encoding(p, G.L_xyz, G.inc_xyz, G.freq_xyz, [&](int j, float v) { f[j] = v; });
+    else positional_encoding(d, G.L_dir, G.inc_dir, G.freq_dir, [&](int j, float v) { f[j] = v; });
+  }
+  uint8_t* line = (which ? pkt_d : pkt_x) + (size_t)kb * kPtileBytes + (size_t)pt * 128u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x = f[c * 8 + i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+      hi[i] = __bfloat16_as_ushort(h); lo[i] = __bfloat16_as_ushort(l);
+    }
+    const uint32_t off = (uint32_t)((c ^ (pt & 7)) << 4);
+    *reinterpret_cast<uint4*>(line + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(line + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+    // feature group 1 (rows 64..127 of the operand): zero padding
+    *reinterpret_cast<uint4*>(line + 8192u + off) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(line + kPtileHalf + 8192u + off) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -302,58 +345,97 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ Z
 // dout: (P,4) = [d rgb_raw(3), d sigma].  col0: first dout column this head consumes.
 // Accumulates g_head (weight rows then bias, the layout of NetDev.d_head) and, if dX != nullptr, writes
 // dX[p][k] = relu'(act[p][k]) * sum_h dout[p][col0+h] * W[h][k].
+// Thread layout: N/4 column threads (one float4 of the activation row each) x 1024/N row groups; every thread keeps 4 rows
+// in flight (16-byte loads: 64 B per thread outstanding), the row groups are folded through shared memory before the
+// atomics.  N must be a multiple of 4 and <= 256 (hidden width).
 __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restrict__ dout, int col0, int heads,
                                                             const float* __restrict__ act, int N, int P,
                                                             const float* __restrict__ hw, float* __restrict__ g_head,
                                                             float* __restrict__ dX, int relu_mask, int p_per_block,
                                                             float* __restrict__ g_bias) {
-  const int k = threadIdx.x;
+  __shared__ float red[256][4 * 4 + 4 + 1];
+  const int nct = N >> 2;                                 // column threads per row group
+  const int groups = 256 / nct;                           // row groups (N=128: 8, N=256: 4)
+  const int ct = threadIdx.x % nct, grp = threadIdx.x / nct;
+  const bool live = grp < groups;
+  const int k = ct * 4;
   const int p0 = blockIdx.x * p_per_block, p1 = min(P, p0 + p_per_block);
-  float w[4] = {0.f, 0.f, 0.f, 0.f}, gw[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
-  float dsum = 0.f;                                     // column sum of dX: the layer's bias gradient
-  if (k < N)
-    for (int h = 0; h < heads; ++h) w[h] = hw[h * N + k];
-  for (int pb = p0; pb < p1; pb += 4) {                 // 4 points per trip: independent loads in flight
-    float a4[4];
-    float4 d4[4];
+  float w[4][4], gw[4][4], gb[4] = {0.f, 0.f, 0.f, 0.f}, dsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = min(pb + u, p1 - 1);
-      d4[u] = *reinterpret_cast<const float4*>(dout + (size_t)p * 4);
-      a4[u] = (k < N) ? act[(size_t)p * N + k] : 0.f;
-    }
+  for (int h = 0; h < 4; ++h)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = pb + u;
-      if (p >= p1) break;
-      const float dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
-      if (k < N) {
-        const float a = a4[u];
-        float dx = 0.f;
-        for (int h = 0; h < heads; ++h) {
-          const float g = dd[col0 + h];
-          gw[h] = fmaf(g, a, gw[h]);
-          dx = fmaf(g, w[h], dx);
-        }
-        if (relu_mask && !(a > 0.f)) dx = 0.f;
-        if (dX) dX[(size_t)p * N + k] = dx;
-        dsum += dx;
+    for (int c = 0; c < 4; ++c) { w[h][c] = (live && h < heads) ? hw[h * N + k + c] : 0.f; gw[h][c] = 0.f; }
+  if (live)
+    for (int pb = p0 + grp * 4; pb < p1; pb += groups * 4) {
+      float4 a4[4], d4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = min(pb + u, p1 - 1);
+        d4[u] = *reinterpret_cast<const float4*>(dout + (size_t)p * 4);
+        a4[u] = *reinterpret_cast<const float4*>(act + (size_t)p * N + k);
       }
-      if (k == 0)
-        for (int h = 0; h < heads; ++h) gb[h] += dd[col0 + h];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = pb + u;
+        if (p >= p1) break;
+        const float dd[4] = {d4[u].x, d4[u].y, d4[u].z, d4[u].w};
+        const float a[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
+        float dx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (h >= heads) break;
+          const float g = col0 ? dd[3] : dd[h];             // col0 is 0 (colour heads) or 3 (the single sigma head)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { gw[h][c] = fmaf(g, a[c], gw[h][c]); dx[c] = fmaf(g, w[h][c], dx[c]); }
+          if (ct == 0) gb[h] += g;
+        }
+        if (dX) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (relu_mask && !(a[c] > 0.f)) dx[c] = 0.f;
+            dsum[c] += dx[c];
+          }
+          *reinterpret_cast<float4*>(dX + (size_t)p * N + k) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+        }
+      }
+    }
+  float* mine = red[threadIdx.x];
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mine[h * 4 + c] = gw[h][c];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) mine[16 + c] = dsum[c];
+  __syncthreads();
+  // fold the row groups: 20 slots (16 head-weight partials, 4 column sums) x nct column threads
+  for (int item = threadIdx.x; item < nct * 20; item += 256) {
+    const int c_t = item % nct, slot = item / nct;        // slot: 0..15 = gw[h][c], 16..19 = dsum[c]
+    float acc = 0.f;
+    for (int g2 = 0; g2 < groups; ++g2) acc += red[g2 * nct + c_t][slot];
+    if (slot < 16) {
+      const int h = slot >> 2, c = slot & 3;
+      if (h < heads) atomicAdd(g_head + h * N + c_t * 4 + c, acc);
+    } else if (g_bias && dX) {
+      atomicAdd(g_bias + c_t * 4 + (slot - 16), acc);
     }
   }
-  if (k < N && g_bias && dX) atomicAdd(g_bias + k, dsum);
-  if (k < N)
-    for (int h = 0; h < heads; ++h) atomicAdd(g_head + h * N + k, gw[h]);
-  if (k == 0)
-    for (int h = 0; h < heads; ++h) atomicAdd(g_head + heads * N + h, gb[h]);
+  // head bias gradient (sum of the upstream gradient columns): the ct == 0 thread of every group holds a partial
+  __syncthreads();
+  if (ct == 0 && live)
+#pragma unroll
+    for (int h = 0; h < 4; ++h) red[grp][h] = gb[h];
+  __syncthreads();
+  if (threadIdx.x < heads) {
+    float acc = 0.f;
+    for (int g2 = 0; g2 < groups; ++g2) acc += red[g2][threadIdx.x];
+    atomicAdd(g_head + heads * N + threadIdx.x, acc);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ compositor adjoint
 // VolumeRenderer.forward (src/nerf/modules.py:67-121) differentiated w.r.t. the raw network outputs, for a loss that
 // reads rgb_map only (model_nerf.py:118-126).  raw = (sigmoid rgb, raw sigma) as the forward kernels store it.
-// Same arithmetic / noise stream as composite_kernel (nm_render.cu).  One thread per ray; T_i goes through `scratch`.
+// Same arithmetic / noise stream as composite_kernel (nm_render.cu).
 __device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -380,52 +462,91 @@ struct CompositeBwdArgs {
   float* dout;        // (R,S,4)
 };
 
-__global__ void composite_backward_kernel(const __grid_constant__ CompositeBwdArgs a) {
-  const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per ray (a training chunk has a few thousand rays: a thread per ray leaves the GPU idle behind a serial
+// 2 x S-step dependency chain).  Lane l owns the contiguous samples [l*seg, (l+1)*seg): transmittance = exclusive product
+// scan of the segment products across lanes times the running product inside the segment; the suffix sum the same way
+// from the other end.  Association differs from the forward kernel's serial product by rounding only.
+constexpr int kCbSeg = 16;                  // samples per lane held in registers: S <= 512
+__global__ void __launch_bounds__(128) composite_backward_kernel(const __grid_constant__ CompositeBwdArgs a) {
+  const long long ray = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ray >= a.R) return;
+  const int lane = threadIdx.x & 31;
   const int S = a.S;
+  const int seg = (S + 31) / 32;
+  const int i0 = lane * seg, i1 = min(S, i0 + seg);
   const float4* raw = reinterpret_cast<const float4*>(a.raw) + ray * S;
   const float* t = a.t + ray * S;
-  float* Ts = a.scratch + ray * S;
   float4* dout = reinterpret_cast<float4*>(a.dout) + ray * S;
   const float dx = a.dirs[3 * ray], dy = a.dirs[3 * ray + 1], dz = a.dirs[3 * ray + 2];
   const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
   const float gr = a.d_rgb[3 * ray], gg = a.d_rgb[3 * ray + 1], gb = a.d_rgb[3 * ray + 2];
   const float gbg = a.white_bg ? (gr + gg + gb) : 0.f;
-  auto sample = [&](int i, float* dist, float* pre) {
-    *dist = ((i + 1 < S) ? (t[i + 1] - t[i]) : 1e10f) * nrm;
-    float sg = raw[i].w;
-    if (a.noise_std > 0.f) sg = sg + randn(a.seed, (uint64_t)(ray * S + i)) * a.noise_std;
-    *pre = sg;
-  };
-  float T = 1.0f;
-  for (int i = 0; i < S; ++i) {
-    float dist, pre;
-    sample(i, &dist, &pre);
-    const float alpha = 1.0f - expf(-fmaxf(pre, 0.f) * dist);
-    Ts[i] = T;
-    T = T * (1.0f - alpha + 1e-10f);
+  float4 q[kCbSeg];
+  float dist[kCbSeg], pre[kCbSeg], keep[kCbSeg];
+  float prod = 1.0f;
+#pragma unroll
+  for (int u = 0; u < kCbSeg; ++u) {
+    const int i = i0 + u;
+    if (u < seg && i < i1) {
+      q[u] = raw[i];
+      dist[u] = ((i + 1 < S) ? (t[i + 1] - t[i]) : 1e10f) * nrm;
+      float sg = q[u].w;
+      if (a.noise_std > 0.f) sg = sg + randn(a.seed, (uint64_t)(ray * S + i)) * a.noise_std;
+      pre[u] = sg;
+      const float alpha = 1.0f - expf(-fmaxf(sg, 0.f) * dist[u]);
+      keep[u] = 1.0f - alpha + 1e-10f;
+      prod *= keep[u];
+    }
   }
-  float suffix = 0.f;                       // sum_{j>i} G_j w_j
-  for (int i = S - 1; i >= 0; --i) {
-    float dist, pre;
-    sample(i, &dist, &pre);
-    const float4 q = raw[i];
-    const float sg = fmaxf(pre, 0.f);
-    const float e = expf(-sg * dist);
-    const float alpha = 1.0f - e;
-    const float Ti = Ts[i];
-    const float w = alpha * Ti;
-    const float G = (gr * q.x + gg * q.y + gb * q.z) - gbg;          // dL/dw_i
-    const float dalpha = G * Ti - suffix / (1.0f - alpha + 1e-10f);
-    suffix = suffix + G * w;
-    float4 o;
-    o.x = gr * w * q.x * (1.0f - q.x);                               // through the sigmoid
-    o.y = gg * w * q.y * (1.0f - q.y);
-    o.z = gb * w * q.z * (1.0f - q.z);
-    o.w = (pre > 0.f) ? dalpha * dist * e : 0.f;                     // relu, alpha = 1 - exp(-sigma dist)
-    if (!isfinite(o.w)) o.w = 0.f;                                   // dist = 1e10 on the last sample: 1e10 * 0
-    dout[i] = o;
+  // exclusive product scan over lanes
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= v;
+  }
+  float T = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) T = 1.0f;
+  float Ti[kCbSeg], gsum = 0.f;
+#pragma unroll
+  for (int u = 0; u < kCbSeg; ++u) {
+    const int i = i0 + u;
+    if (u < seg && i < i1) {
+      Ti[u] = T;
+      const float alpha = 1.0f - expf(-fmaxf(pre[u], 0.f) * dist[u]);
+      const float G = (gr * q[u].x + gg * q[u].y + gb * q[u].z) - gbg;
+      gsum += G * alpha * T;
+      T *= keep[u];
+    }
+  }
+  // exclusive suffix sum over lanes: sum of G_j w_j of all samples in higher lanes
+  float sincl = gsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_down_sync(0xffffffffu, sincl, o);
+    if (lane + o < 32) sincl += v;
+  }
+  float suffix = __shfl_down_sync(0xffffffffu, sincl, 1);
+  if (lane == 31) suffix = 0.f;
+#pragma unroll
+  for (int u = kCbSeg - 1; u >= 0; --u) {
+    const int i = i0 + u;
+    if (u < seg && i < i1) {
+      const float sg = fmaxf(pre[u], 0.f);
+      const float e = expf(-sg * dist[u]);
+      const float alpha = 1.0f - e;
+      const float w = alpha * Ti[u];
+      const float G = (gr * q[u].x + gg * q[u].y + gb * q[u].z) - gbg;        // dL/dw_i
+      const float dalpha = G * Ti[u] - suffix / (1.0f - alpha + 1e-10f);
+      suffix = suffix + G * w;
+      float4 o;
+      o.x = gr * w * q[u].x * (1.0f - q[u].x);                               // through the sigmoid
+      o.y = gg * w * q[u].y * (1.0f - q[u].y);
+      o.z = gb * w * q[u].z * (1.0f - q[u].z);
+      o.w = (pre[u] > 0.f) ? dalpha * dist[u] * e : 0.f;                     // relu, alpha = 1 - exp(-sigma dist)
+      if (!isfinite(o.w)) o.w = 0.f;                                         // dist = 1e10 on the last sample: 1e10 * 0
+      dout[i] = o;
+    }
   }
 }
 
@@ -476,8 +597,10 @@ TrainWs carve(const NetProgram& G, long long P, bool use_tc, uint8_t* base) {
   auto take = [&](size_t bytes) { uint8_t* p = base ? base + off : nullptr; off += up(bytes); return p; };
   const int h = G.hidden;
   const bool fused = use_tc && !train_layerwise();    // fused chains: no row packs, fp32 activations only where the heads read them
-  w.pe_x = (float*)take((size_t)P * kPeLd * 4);
-  w.pe_d = (float*)take((size_t)P * kPeLd * 4);
+  if (!fused) {
+    w.pe_x = (float*)take((size_t)P * kPeLd * 4);
+    w.pe_d = (float*)take((size_t)P * kPeLd * 4);
+  }
   w.dbuf[0] = (float*)take((size_t)P * h * 4);
   if (!fused) w.dbuf[1] = (float*)take((size_t)P * h * 4);
   for (int l = 0; l < G.n_layers; ++l)
@@ -552,8 +675,9 @@ int launch_composite_backward(const float* raw, const float* t, const float* dir
                               float noise_std, uint64_t seed, int white_bg, float* scratch, float* dout,
                               cudaStream_t st, int64_t* launches) {
   if (R <= 0) return 0;
+  NM_CHECK(S <= 32 * kCbSeg, "sample count %d exceeds the compositor adjoint's limit (%d)", S, 32 * kCbSeg);
   CompositeBwdArgs a{raw, t, dirs, d_rgb, R, S, noise_std, seed, white_bg, scratch, dout};
-  composite_backward_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(a);
+  composite_backward_kernel<<<(unsigned)((R + 3) / 4), 128, 0, st>>>(a);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -581,16 +705,22 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
     if (int e = build_weight_packs(net, st, launches)) return e;
   const int kbtP = 2 * ((P + 127) / 128);      // K blocks of the point-major packs (zero-filled beyond P)
 
-  encode_kernel<<<(P + 127) / 128, 128, 0, st>>>(in, net.d_full, W.pe_x, W.pe_d);
-  NM_CUDA(cudaGetLastError());
-  if (launches) ++*launches;
-  if (tc) {
-    const bool rows = train_layerwise();      // row packs feed the layer-wise forward GEMMs only
-    if (rows) if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
-    if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, kbtP, 0, st, launches)) return e;
-    if (G.dim_dir > 0) {
-      if (rows) if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
-      if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, kbtP, 0, st, launches)) return e;
+  if (tc && !train_layerwise()) {               // fused chains: the encodings are needed as weight-gradient operands only
+    NM_CHECK(G.dim_xyz <= kPeLd && G.dim_dir <= kPeLd, "encoding wider than %d", kPeLd);
+    encode_pack_kernel<<<kbtP, 128, 0, st>>>(in, net.d_full, W.pkt_pex, W.pkt_ped);
+    NM_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+  } else {
+    encode_kernel<<<(P + 127) / 128, 128, 0, st>>>(in, net.d_full, W.pe_x, W.pe_d);
+    NM_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    if (tc) {                                   // layer-wise chain: row packs feed the forward GEMMs, column packs the dW GEMMs
+      if (int e = launch_pack_rows(W.pe_x, kPeLd, P, G.dim_xyz, W.pk_pex, 1, st, launches)) return e;
+      if (int e = launch_pack_cols(W.pe_x, kPeLd, P, G.dim_xyz, W.pkt_pex, kbtP, 0, st, launches)) return e;
+      if (G.dim_dir > 0) {
+        if (int e = launch_pack_rows(W.pe_d, kPeLd, P, G.dim_dir, W.pk_ped, 1, st, launches)) return e;
+        if (int e = launch_pack_cols(W.pe_d, kPeLd, P, G.dim_dir, W.pkt_ped, kbtP, 0, st, launches)) return e;
+      }
     }
   }
   auto pe_of = [&](const LayerProg& L) { return L.pe_src == SRC_PE_XYZ ? W.pe_x : W.pe_d; };
@@ -661,6 +791,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
     NM_CHECK(Ltop.kind == KIND_RGB || Ltop.kind == KIND_OUT4, "the last layer must carry the colour head");
     const int p_per_block = (P + 8 * num_sms - 1) / (8 * num_sms);
     const int hb_blocks = (P + p_per_block - 1) / p_per_block;
+    NM_CHECK((Ltop.n_out & 3) == 0 && Ltop.n_out <= 1024 && (G.hidden & 3) == 0 && G.hidden <= 1024, "head widths must be multiples of 4, <= 1024");
     float* dZ = W.dbuf[0];
     head_backward_kernel<<<hb_blocks, 256, 0, st>>>(dout, 0, Ltop.kind == KIND_RGB ? 3 : 4, W.act[last], Ltop.n_out, P,
                                                    net.d_head + Ltop.head_off, g->head + Ltop.head_off, dZ, Ltop.relu, p_per_block,
@@ -675,9 +806,9 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       NM_CUDA(cudaGetLastError());
       if (launches) ++*launches;
     }
-    if (int e = launch_pack_cols(dZ, Ltop.n_out, P, Ltop.n_out, W.pkt_dz[last], kbtP, 0, st, launches)) return e;
     MlpEmit io{};
     io.kbt = kbtP;
+    io.packT[0] = W.pkt_dz[last];               // the chain's load stage emits the top dZ's pack too
     for (int li = 1; li < net.bwd.n_layers; ++li) {
       const int l = net.bwd.layers[li].aux;      // this backward layer streams W_l^T and produces dZ of forward layer l-1
       io.packT[li] = W.pkt_dz[l - 1];
@@ -689,12 +820,12 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       TcGemmParams T = tc_base();
       T.nseg = 1; T.atomic = 1; T.ldd = gw_ld[l]; T.M = L.n_out;
       if (L.k_act > 0) {
-        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP};
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP, 3};
         T.D = g->w + gw_off[l]; T.N = L.k_act;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
       if (L.pe_src) {
-        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, pkt_pe_of(L), kbtP, kbtP};
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, pkt_pe_of(L), kbtP, kbtP, 3};
         T.D = g->w + gw_off[l] + L.k_act; T.N = L.k_pe;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
@@ -707,6 +838,8 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
   bool bias_done = false;      // the kernel that produced dbuf[cur] already accumulated its column sums (bias gradient)
   const int p_per_block = (P + 8 * num_sms - 1) / (8 * num_sms);      // 8 CTAs per SM keep enough loads in flight
   const int hb_blocks = (P + p_per_block - 1) / p_per_block;
+  for (int l = 0; l < G.n_layers; ++l)
+    NM_CHECK(G.layers[l].kind == KIND_HIDDEN || ((G.layers[l].n_out & 3) == 0 && G.layers[l].n_out <= 1024), "head widths must be multiples of 4, <= 1024");
   for (int l = G.n_layers - 1; l >= 0; --l) {
     const LayerProg& L = G.layers[l];
     const int N = L.n_out;
@@ -735,12 +868,12 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       TcGemmParams T = tc_base();
       T.nseg = 1; T.atomic = 1; T.ldd = ldg; T.M = N;
       if (L.k_act > 0) {
-        T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_act[l - 1], kbtP, kbtP};
+        T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_act[l - 1], kbtP, kbtP, 3};
         T.D = gW; T.N = L.k_act;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
       if (L.pe_src) {
-        T.seg[0] = TcSeg{W.pkt_a, kbtP, pkt_pe_of(L), kbtP, kbtP};
+        T.seg[0] = TcSeg{W.pkt_a, kbtP, pkt_pe_of(L), kbtP, kbtP, 3};
         T.D = gW + L.k_act; T.N = L.k_pe;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
@@ -816,7 +949,7 @@ int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_col
   } else {
     if (int e = a_cols ? launch_pack_cols(A, M, K, M, pa, 0, fp16, st, launches) : launch_pack_rows(A, K, M, K, pa, fp16, st, launches)) return e;
     T.nseg = 1;
-    T.seg[0] = TcSeg{pa, kbt, pb, kbt, kbt};
+    T.seg[0] = TcSeg{pa, kbt, pb, kbt, kbt, (a_cols ? 1 : 0) | (b_cols ? 2 : 0)};
   }
   int repeat = 1;
   if (const char* e = getenv("NM_GEMM_REPEAT")) repeat = atoi(e) > 0 ? atoi(e) : 1;     // timing aid (tools/gemm_bench.py)

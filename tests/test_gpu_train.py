@@ -195,7 +195,7 @@ def test_direct_and_subchunk_walks_agree(monkeypatch):
     l_dir, c_dir, f_dir = run()
     monkeypatch.setenv("NM_TRAIN_DIRECT_GB", "0")
     l_sub, c_sub, f_sub = run()
-    assert l_dir == l_sub
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l_dir, l_sub))      # the loss is an atomic sum of block partials
     compare(c_sub, c_dir, rel_max=2e-5, name="walks coarse")
     compare(f_sub, f_dir, rel_max=2e-5, name="walks fine")
 
@@ -329,6 +329,45 @@ def test_backward_tensor_core_vs_cuda_core_yardstick():
     _, _, gc32, gf32 = model_grads(model, o, d, bounds, target, seed=5)
     compare(gc, gc32, rel_max=3e-2, rel_l2=6e-3, name="tc vs fp32 coarse")
     compare(gf, gf32, rel_max=3e-2, rel_l2=6e-3, name="tc vs fp32 fine")
+
+
+@pytest.mark.parametrize("case", ["nerf256", "skip2_no_viewdirs"])
+def test_backward_fp32_mode_matches_autograd_per_layer(case):
+    """NM_PREC_FP32 (plain fp32 FMAs, the same arithmetic class as torch on the CPU) against autograd through the oracle,
+    per parameter tensor: relative L2 <= 1.5e-3 (measured on a B200: <= 6.1e-4, worst at the first layer where the most
+    relu gates sit within fp32 summation-order noise of 0; upper layers 1e-6..2e-4).  This is the net under the tensor-core
+    tests' gate-flip floor (6e-3): a scaling / indexing error confined to ONE layer's gradient (1 % would do) cannot pass
+    here, and the tensor-core path is tied to this one by test_backward_tensor_core_vs_cuda_core_yardstick."""
+    import nerfmeshes_b200 as nm
+    from nerfmeshes_b200 import _lib as L
+    if case == "nerf256":
+        net = O.NetCfg()
+        nc, nf = 24, 40
+    else:
+        net = O.NetCfg(num_layers=6, hidden_size=256, skip_step=2, num_encoding_fn_xyz=8, use_viewdirs=False)
+        nc, nf = 16, 17
+    sdc, sdf = O.init_weights(net, 31), O.init_weights(net, 32)
+    for sd in (sdc, sdf):
+        if "fc_alpha.bias" in sd:
+            sd["fc_alpha.bias"] = sd["fc_alpha.bias"] + 0.6
+        else:
+            sd["fc_out.bias"] = sd["fc_out.bias"] + torch.tensor([0.0, 0.0, 0.0, 0.6])
+    model = nm.NeRFModel(_cfg(net, net, nc=nc, nf=nf)).cuda().train()
+    model.precision = L.PREC_FP32
+    model.model_coarse.load_state_dict(sdc, strict=False)
+    model.model_fine.load_state_dict(sdf, strict=False)
+    g = torch.Generator().manual_seed(6)
+    R = 257
+    o = torch.randn(R, 3, generator=g) * 0.3
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    target = torch.rand(R, 3, generator=g)
+    near, far = torch.tensor(0.5), torch.tensor(3.5)
+    rc = O.RenderCfg(num_coarse=nc, num_fine=nf)
+    lc_ref, lf_ref, gc_ref, gf_ref = oracle_grads(sdc, sdf, net, net, rc, o, d, near, far, target)
+    lc, lf, gc, gf = model_grads(model, o.cuda(), d.cuda(), (near, far), target.cuda())
+    assert abs(lc - lc_ref) <= 1e-5 * abs(lc_ref) and abs(lf - lf_ref) <= 1e-5 * abs(lf_ref)
+    w = max(compare(gc, gc_ref, rel_l2=1.5e-3, name=f"fp32 {case} coarse"), compare(gf, gf_ref, rel_l2=1.5e-3, name=f"fp32 {case} fine"))
+    print(f"fp32 {case}: worst max-err / max|ref| = {w:.2e}")
 
 
 def test_fused_training_step_matches_autograd_route():
