@@ -231,7 +231,8 @@ int nm_tree_integrate(NmHandle h, const int32_t* idx_dev, const float* weights_d
 
 /* Test hook for the tensor-core GEMM of the backward pass (nm_gemm_tc.cu): D (M,N) = A (M,K) B (N,K)^T from fp32
  * row-major device arrays through the bf16 hi/lo operand packs.  a_cols / b_cols: that operand is given transposed
- * ((K,M) / (K,N)) and packed along its rows (the weight-gradient operands); k_split: feed K as two segments;
+ * ((K,M) / (K,N)) and packed along its rows (the weight-gradient operands; 1 = K-major tiles, 2 = MN-major tiles read
+ * through MN-major shared-memory descriptors); k_split: feed K as two segments;
  * fp16: fp16 halves instead of bf16; atomic: D += with K split over CTAs. */
 int nm_debug_gemm(NmHandle h, const float* a_dev, const float* b_dev, int M, int N, int K, int a_cols, int b_cols,
                   int k_split, int n_passes, int fp16, int atomic, float* d_dev, void* stream);

@@ -128,7 +128,7 @@ int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, Net
 // kernel launchers (return 0 / <0; count launches via *launches)
 int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
                   int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit = nullptr);
-int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout, float* colsum_out,
+int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout,
                       const MlpEmit& io, int n_passes, int num_sms, int* d_err, cudaStream_t st, int64_t* launches);
 int launch_mlp_simt(const NetDev& net, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st,
                     int64_t* launches);

@@ -27,7 +27,7 @@ struct TcSeg {             // one K segment: packs ordered [row block][K block],
   const uint8_t* b;
   int b_kbt;
   int nkb;                 // K blocks of this segment
-  int mn = 0;              // bit 0 / bit 1: the A / B pack is MN-major (K = the source's rows: pack_cols, the fused kernels' emissions)
+  int mn = 0;              // bit 0 / bit 1: the A / B pack is an MN-major tile (pack_cols with mn=1) instead of a K-major one
 };
 struct TcGemmParams {
   TcSeg seg[2];
@@ -39,6 +39,8 @@ struct TcGemmParams {
   int atomic;              // D += via atomicAdd, K split over CTAs (weight gradients); the epilogue fields are ignored
   GemmEpi epi;
   float* colsum;           // optional: colsum[n] += sum_m D[m][n] (bias gradient of the layer whose dZ this GEMM produces)
+  float* a_rowsum;         // optional (split-K, K-major bf16 A): a_rowsum[m] += sum_k A[m][k], taken from the staged A tiles by the
+                           //   otherwise idle epilogue warps — with A = dZ^T this is the layer's bias gradient
   uint8_t* pack_out;       // optional: the epilogue also writes D as the row pack ([row block][K block = column / 64]) the
   int pack_kbt;            //   next GEMM of the chain consumes as its A operand (saves a pack_rows pass over D)
   int pack_fp16;
@@ -55,7 +57,7 @@ struct TcGemmParams {
 
 size_t pack_bytes(int rows, int k);
 int launch_pack_rows(const float* src, int ld, int R, int C, uint8_t* out, int fp16, cudaStream_t st, int64_t* launches);
-int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int kbt, int fp16, cudaStream_t st, int64_t* launches);
+int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int kbt, int fp16, cudaStream_t st, int64_t* launches, int mn = 0);
 int launch_tc_gemm(TcGemmParams P, int num_sms, cudaStream_t st, int64_t* launches);
 
 }  // namespace nm

@@ -83,9 +83,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
   const int n0 = k1 - k0;
   const int nk = n0 + (P.nseg > 1 ? P.seg[1].nkb : 0);
 
+  // split-K with a_rowsum: the CTAs of the first column group also sum the rows of every A tile they stage (bias gradient)
+  const bool sum_rows = !pers && P.a_rowsum != nullptr && blockIdx.y == 0;
   if (threadIdx.x == 0) {
     if (sbase & 1023u) { if (P.err) atomicExch(P.err, 90); __trap(); }
-    for (int s = 0; s < NS; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), 1); }
+    for (int s = 0; s < NS; ++s) { ptx::mbar_init(full(s), 1); ptx::mbar_init(empty(s), sum_rows ? 1 + kEpiWarps : 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full(b), 1); ptx::mbar_init(acc_empty(b), kEpiWarps); }
     ptx::fence_mbar_init();
   }
@@ -161,6 +163,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
     // 32 rows x 16 columns.  A thread owns one accumulator row; each block is transposed through a per-warp staging tile
     // so that global accesses are contiguous row segments: a lane then handles 4 columns of rows sub, sub+8, ...
     // The epilogue is instruction-latency bound, hence many warps with short dependent chains rather than few wide ones.
+    if (sum_rows) {
+      // Row sums of the A tiles while the MMA warp consumes them: warp w owns rows 8w..8w+7, 8 lanes cover one 128-byte row
+      // (64 K elements; the swizzle only permutes chunks within the row, irrelevant for a sum), hi + lo halves.
+      float acc[2] = {0.f, 0.f};
+      const int r0 = warp * 8 + (lane >> 3);
+      for (int kk = 0; kk < nk; ++kk) {
+        const int s = kk % NS;
+        ptx::mbar_wait(full(s), (uint32_t)((kk / NS) & 1), P.err, 95);
+        const uint8_t* at = smem + (size_t)s * STAGE + (size_t)(lane & 7) * 16u;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint4 h = *reinterpret_cast<const uint4*>(at + (size_t)(r0 + 4 * u) * 128u);
+          const uint4 l = *reinterpret_cast<const uint4*>(at + kPtileHalf + (size_t)(r0 + 4 * u) * 128u);
+          const uint32_t w[8] = {h.x, h.y, h.z, h.w, l.x, l.y, l.z, l.w};
+          float t = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t += __uint_as_float(w[e] << 16) + __uint_as_float(w[e] & 0xffff0000u);
+          acc[u] += t;
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(empty(s));
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float t = acc[u];
+        t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
+        const int row = (int)blockIdx.x * 128 + r0 + 4 * u;
+        if ((lane & 7) == 0 && row < P.M) atomicAdd(P.a_rowsum + row, t);
+      }
+    }
     float* stg = reinterpret_cast<float*>(smem + kStgOff + (uint32_t)warp * kStgWarp);     // 32 rows, pitch 17 floats
     const int lg = warp & 3, quarter = warp >> 2;
     const int sub = lane >> 2, q4 = (lane & 3) * 4;
@@ -266,18 +298,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
                 }
               }
             }
-            if (P.packT_out) {   // the finished 32x16 block as an MN-major pack (K = rows): lane = row, 16 columns = 2 chunks
+            if (P.packT_out) {   // the finished 32x16 block, transposed: lane = (column f, pair of 8-row chunks)
               __syncwarp();
-              const int nf0 = (cb0 + j) * 128 + c0;
-              const int krow = (lg & 1) * 32 + lane;
-              uint8_t* tile = P.packT_out + ((size_t)(nf0 >> 7) * P.packT_kbt + (rb * 2 + (lg >> 1))) * kPtileBytes +
-                              (size_t)((nf0 & 127) >> 6) * 8192u + (size_t)krow * 128u;
+              const int f = lane & 15, ch0 = (lane >> 4) * 2;
+              const int nf = (cb0 + j) * 128 + c0 + f;
+              const int row = nf & 127;
+              uint8_t* tile = P.packT_out + ((size_t)(nf >> 7) * P.packT_kbt + (rb * 2 + (lg >> 1))) * kPtileBytes;
 #pragma unroll
-              for (int c = 0; c < 2; ++c) {
+              for (int c = ch0; c < ch0 + 2; ++c) {
                 __align__(16) uint16_t hi[8], lo[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) split16(stg[lane * 17 + c * 8 + e], 0, &hi[e], &lo[e]);
-                const uint32_t off = (uint32_t)(((((nf0 & 63) >> 3) + c) ^ (krow & 7)) << 4);
+                for (int e = 0; e < 8; ++e) split16(stg[(c * 8 + e) * 17 + f], 0, &hi[e], &lo[e]);
+                const int c8 = (lg & 1) * 4 + c;
+                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4);
                 *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
                 *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
               }
@@ -341,11 +374,47 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict_
   }
 }
 
-// K along the source's rows (points): operand row = source column f (f < F valid), K index = source row p (p < P).
-// MN-major tiles (ptx::make_mnmajor_sw128_desc): tile [feature block of 128][64-point K block] = [feature group of 64]
+// K along the source's rows (points): operand row r = source column f (f < F valid), K index = source row p (p < P).
+// grid (K blocks over points, row blocks over features); the 64 x 128 fp32 source block goes through shared memory.
+__global__ void __launch_bounds__(256) pack_cols_kernel(const float* __restrict__ src, int ld, int P, int F,
+                                                        uint8_t* __restrict__ out, int kbt, int fp16) {
+  __shared__ float t[64][129];
+  const int kb = blockIdx.x, rb = blockIdx.y;
+  uint8_t* tile = out + ((size_t)rb * kbt + kb) * kPtileBytes;
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && rb * 128 + 128 <= F;
+  if (vec) {
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {           // 64 points x 32 float4
+      const int p = e >> 5, f4 = (e & 31) * 4;
+      const int gp = kb * 64 + p;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gp < P) x = *reinterpret_cast<const float4*>(src + (size_t)gp * ld + rb * 128 + f4);
+      t[p][f4] = x.x; t[p][f4 + 1] = x.y; t[p][f4 + 2] = x.z; t[p][f4 + 3] = x.w;
+    }
+  } else {
+    for (int e = threadIdx.x; e < 64 * 128; e += 256) {
+      const int p = e >> 7, f = e & 127;
+      const int gp = kb * 64 + p, gf = rb * 128 + f;
+      t[p][f] = (gp < P && gf < F) ? src[(size_t)gp * ld + gf] : 0.f;
+    }
+  }
+  __syncthreads();
+  const int c8 = threadIdx.x & 7;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int r = pass * 32 + (threadIdx.x >> 3);
+    __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split16(t[c8 * 8 + i][r], fp16, &hi[i], &lo[i]);
+    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// The same operand as pack_cols_kernel (operand row = source column f, K index = source row p) stored as MN-major tiles (ptx::make_mnmajor_sw128_desc): tile [feature block of 128][64-point K block] = [feature group of 64]
 // [point row][128 B = 64 features]; a source row segment is copied as it lies, no transposition.  grid (K blocks over
 // points, row blocks over features); 256 threads: 8 lanes cover one 128-byte line, 4 passes of 32 point rows, 2 groups.
-__global__ void __launch_bounds__(256) pack_cols_kernel(const float* __restrict__ src, int ld, int P, int F,
+__global__ void __launch_bounds__(256) pack_cols_mn_kernel(const float* __restrict__ src, int ld, int P, int F,
                                                         uint8_t* __restrict__ out, int kbt, int fp16) {
   const int kb = blockIdx.x, rb = blockIdx.y;
   uint8_t* tile = out + ((size_t)rb * kbt + kb) * kPtileBytes;
@@ -390,11 +459,12 @@ int launch_pack_rows(const float* src, int ld, int R, int C, uint8_t* out, int f
   return 0;
 }
 
-int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int kbt, int fp16, cudaStream_t st, int64_t* launches) {
+int launch_pack_cols(const float* src, int ld, int P, int F, uint8_t* out, int kbt, int fp16, cudaStream_t st, int64_t* launches, int mn) {
   if (P <= 0 || F <= 0) return 0;
   if (kbt <= 0) kbt = (P + 63) / 64;                  // callers may ask for zero-filled K blocks beyond P
   dim3 grid(kbt, (F + 127) / 128);
-  pack_cols_kernel<<<grid, 256, 0, st>>>(src, ld, P, F, out, kbt, fp16);
+  if (mn) pack_cols_mn_kernel<<<grid, 256, 0, st>>>(src, ld, P, F, out, kbt, fp16);
+  else pack_cols_kernel<<<grid, 256, 0, st>>>(src, ld, P, F, out, kbt, fp16);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   return 0;
@@ -409,6 +479,7 @@ int launch_tc_gemm(TcGemmParams P, int num_sms, cudaStream_t st, int64_t* launch
   const int col_groups = (P.n_rb_b + NB - 1) / NB;
   int splits = 1;
   P.kb_per_split = 0;
+  NM_CHECK(!P.a_rowsum || (P.atomic && !P.fp16 && !(P.seg[0].mn & 1)), "a_rowsum needs split-K with a K-major bf16 A operand");
   if (P.atomic) {
     NM_CHECK(P.nseg == 1, "split-K takes one K segment");
     const int tiles = n_rb_a * col_groups;

@@ -71,12 +71,11 @@ struct TcParams {
   int has_emit;     // training: the epilogue also writes the backward pass's operands (MlpEmit)
   MlpEmit emit;
   // mode 2: the data-gradient chain of the training backward (a KIND_LOAD / KIND_BWD program, W^T stages in bf16 hi/lo):
-  // emit.bits[li] is the INPUT relu mask of that layer, emit.packT[li] receives dZ, column sums go to colsum_out
+  // emit.bits[li] is the INPUT relu mask of that layer, emit.packT[li] receives dZ
   int mode;
   const float* dz_in;     // (M, dz_ld) fp32: dZ of the last forward layer
   int dz_ld;
   const float* dout;      // (M, 4): compositor adjoint, column 3 = d sigma
-  float* colsum_out;      // bias-gradient array (forward bias offsets)
 };
 static_assert(sizeof(TcParams) <= 4096, "TcParams must fit the 4 KB kernel-parameter window");
 
@@ -146,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   {
     uint4* z = reinterpret_cast<uint4*>(smem + P.off_pe);
     for (int i = threadIdx.x; i < (int)(kPeTotal / 16); i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) s_bias[i] = (MODE == 2) ? 0.f : P.bias[i];   // mode 2: column-sum accumulators
+    for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) s_bias[i] = (MODE == 2) ? 0.f : P.bias[i];
     for (int i = threadIdx.x; i < P.net.n_head; i += kThreads) s_head[i] = P.head[i];
   }
   ptx::fence_proxy_async_smem();
@@ -175,6 +174,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   const float so = P.act_scale, si = P.act_inv_scale;
   const int n_passes = P.n_passes;
 
+  // Mode 2 (data-gradient chain): the epilogue holds a 32-column slab, its bf16 hi/lo halves and the mask at once and spilled
+  // under the 96-register launch budget (17 warps: one SM sub-partition hosts five).  Its front-end warps are idle and the
+  // issuers are light, so the register file is re-divided per warpgroup: per sub-partition 2 x 144 (epilogue) + 40 (front
+  // end) + 56 (producer / issuer) [+ 96 for the 17th warp, which is in no complete warpgroup] = the 4 (5) x 96 it was given.
+  if (MODE == 2) {
+    if (warp < kEpiWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
+    else if (warp < kProdWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else if (warp < kProdWarp + 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
   if (warp < kEpiWarps) {
     // =============================================================== epilogue warps
     const int q = warp & 3, hcol = warp >> 2;
@@ -224,7 +232,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 ptx::tmem_wait_ld();
               }
               if (MODE == 2 && L.kind == KIND_BWD) {
-                // dA = dZ W (+ d sigma * w_alpha), masked by relu' of the forward layer below; column sums = its bias gradient
+                // dA = dZ W (+ d sigma * w_alpha), masked by relu' of the forward layer below.  (Its column sums — the bias
+                // gradient — are taken by the weight-gradient GEMM from the pack emitted below: nm_gemm_tc.cu a_rowsum.)
                 const bool valid = m < P.in.M;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * so;
@@ -242,33 +251,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 if (L.relu && valid) mk = P.emit.bits[li][(size_t)m * (size_t)(L.n_out >> 5) + (size_t)(col0 >> 5)];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = ((mk >> j) & 1u) ? v[j] : 0.f;
-                {   // column sums over this warp's 32 rows: reduce-scatter (31 shuffles), lane j ends with column col0 + j
-                  float t16[16], t8[8], t4[4], t2[2];
-                  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const float rcv = __shfl_xor_sync(0xffffffffu, u16 ? v[j] : v[j + 16], 16);
-                    t16[j] = (u16 ? v[j + 16] : v[j]) + rcv;
-                  }
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float rcv = __shfl_xor_sync(0xffffffffu, u8 ? t16[j] : t16[j + 8], 8);
-                    t8[j] = (u8 ? t16[j + 8] : t16[j]) + rcv;
-                  }
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float rcv = __shfl_xor_sync(0xffffffffu, u4 ? t8[j] : t8[j + 4], 4);
-                    t4[j] = (u4 ? t8[j + 4] : t8[j]) + rcv;
-                  }
-#pragma unroll
-                  for (int j = 0; j < 2; ++j) {
-                    const float rcv = __shfl_xor_sync(0xffffffffu, u2 ? t4[j] : t4[j + 2], 2);
-                    t2[j] = (u2 ? t4[j + 2] : t4[j]) + rcv;
-                  }
-                  const float rcv = __shfl_xor_sync(0xffffffffu, u1 ? t2[0] : t2[1], 1);
-                  const float cs = (u1 ? t2[1] : t2[0]) + rcv;
-                  atomicAdd(s_bias + L.bias_off + col0 + lane, cs);
-                }
               } else if (MODE != 2 || L.kind != KIND_LOAD) {
                 const float4* b4 = reinterpret_cast<const float4*>(s_bias + L.bias_off + col0);
 #pragma unroll
@@ -313,27 +295,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                   for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
                 if (P.emit.packT[li] && !writes_a) {     // (layers that write the A operand emit from it after the hand-over, below)
-                  // MN-major pack (nm_ptx.cuh make_mnmajor_sw128_desc): a point's 64 features of one group are one 128-byte
-                  // line, 16-byte chunks XOR-swizzled by the point row; this thread owns 32 features = 4 chunks, hi and lo
                   const long long pt = tile * kTileM + row;
-                  uint8_t* line = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
-                                  (size_t)((col0 & 127) >> 6) * 8192u + (size_t)(pt & 63) * 128u;
-                  const uint32_t c0 = (uint32_t)((col0 & 63) >> 3), sw = (uint32_t)(pt & 7);
+                  // element (feature f, point pt) of a tile: row f%128, 16-byte chunk ((pt%64)/8) ^ (f%8), 2-byte slot pt%8.
+                  // col0 is a multiple of 32, so f%8 = j%8: one base address per j%8, the rest are immediates
+                  uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
+                                (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
+                  const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) {
-                    uint32_t h4[4], l4[4];
+                  for (int q = 0; q < 8; ++q) {
+                    uint8_t* bq = tb + ((c8 ^ (uint32_t)q) << 4);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float x0 = valid ? v[c * 8 + 2 * e] : 0.f, x1 = valid ? v[c * 8 + 2 * e + 1] : 0.f;
-                      const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-                      const float2 f = __bfloat1622float2(h2);
-                      const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
-                      h4[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                      l4[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                    for (int rr = 0; rr < 4; ++rr) {
+                      const int j = q + 8 * rr;
+                      const float x = valid ? v[j] : 0.f;
+                      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                      const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+                      *reinterpret_cast<uint16_t*>(bq + j * 128) = __bfloat16_as_ushort(h);
+                      *reinterpret_cast<uint16_t*>(bq + j * 128 + 16384) = __bfloat16_as_ushort(l);
                     }
-                    const uint32_t off = ((c0 + (uint32_t)c) ^ sw) << 4;
-                    *reinterpret_cast<uint4*>(line + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                    *reinterpret_cast<uint4*>(line + 16384u + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
                   }
                 }
               }
@@ -403,32 +382,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) l16[j] = 0u;
               }
-              // MN-major pack, as the inline variant above: 4 chunks of 8 features; features 2j, 2j+1 sit in register j
-              uint8_t* line = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
-                              (size_t)((col0 & 127) >> 6) * 8192u + (size_t)(pt & 63) * 128u;
-              const uint32_t c0 = (uint32_t)((col0 & 63) >> 3), sw = (uint32_t)(pt & 7);
+              // one base address per (feature % 8) — see the inline variant above; features 2j, 2j+1 sit in register j
+              uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
+                            (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint32_t h4[4], l4[4];
+              for (int q = 0; q < 8; ++q) {
+                uint8_t* bq = tb + ((c8 ^ (uint32_t)q) << 4);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = c * 4 + e;
+                for (int rr = 0; rr < 4; ++rr) {
+                  const int f = q + 8 * rr, j = f >> 1, odd = f & 1;
+                  uint16_t oh, ol;
                   if (MODE == 2) {        // already bf16 hi / lo
-                    h4[e] = h16[j]; l4[e] = l16[j];
+                    oh = (uint16_t)(odd ? (h16[j] >> 16) : (h16[j] & 0xffffu));
+                    ol = (uint16_t)(odd ? (l16[j] >> 16) : (l16[j] & 0xffffu));
                   } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
                     const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
                     const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
-                    const float x0 = (fh.x + fl.x) * so, x1 = (fh.y + fl.y) * so;
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-                    const float2 f = __bfloat1622float2(h2);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
-                    h4[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                    l4[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                    const float x = ((odd ? fh.y : fh.x) + (odd ? fl.y : fl.x)) * so;
+                    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+                    oh = __bfloat16_as_ushort(b0);
+                    ol = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(b0)));
                   }
+                  *reinterpret_cast<uint16_t*>(bq + f * 128) = oh;
+                  *reinterpret_cast<uint16_t*>(bq + f * 128 + 16384) = ol;
                 }
-                const uint32_t off = ((c0 + (uint32_t)c) ^ sw) << 4;
-                *reinterpret_cast<uint4*>(line + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-                *reinterpret_cast<uint4*>(line + 16384u + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
               }
             }
           }
@@ -624,12 +601,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   // ---------------------------------------------------------------- teardown
   ptx::tc_fence_before();
   __syncthreads();
-  if (MODE == 2 && P.colsum_out) {
-    for (int i = threadIdx.x; i < P.net.n_bias; i += kThreads) {
-      const float x = s_bias[i];
-      if (x != 0.f) atomicAdd(P.colsum_out + i, x);
-    }
-  }
   if (warp == kProdWarp) ptx::tmem_dealloc(tmem, 512);
 }
 
@@ -711,8 +682,8 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
 
 // The data-gradient chain of the training backward for M points (nm_train.cu): dz_in (M, dz_ld) fp32 = dZ of the last
 // forward layer; for every backward layer li (net.bwd): io.bits[li] = relu mask to apply (input), io.packT[li] = where dZ
-// goes as the weight-gradient operand; column sums (bias gradients) are accumulated into colsum_out.
-int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout, float* colsum_out,
+// goes as the weight-gradient operand (its row sums there are the bias gradients: launch_tc_gemm a_rowsum).
+int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout,
                       const MlpEmit& io, int n_passes, int num_sms, int* d_err, cudaStream_t st, int64_t* launches) {
   if (M <= 0) return 0;
   NM_CHECK(net.bwd_valid && net.d_wpack_bwd, "backward weight stream not built");
@@ -728,7 +699,7 @@ int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz
   P.n_tiles = (M + kTileM - 1) / kTileM;
   P.err = d_err;
   P.has_emit = 1; P.emit = io;
-  P.mode = 2; P.dz_in = dz_in; P.dz_ld = dz_ld; P.dout = dout; P.colsum_out = colsum_out;
+  P.mode = 2; P.dz_in = dz_in; P.dz_ld = dz_ld; P.dout = dout;
   return launch_prepared(P, num_sms, st, launches);
 }
 

@@ -49,43 +49,49 @@ __global__ void encode_kernel(const __grid_constant__ MlpInput in, const NetProg
 }
 
 // Tensor-core path: the encodings are only ever read as the B operand of the weight-gradient GEMMs, so they go straight
-// into the point-major (MN-major) bf16 hi/lo packs (pack_cols_kernel's layout, nm_gemm_tc.cu: tile = 64-point K block,
-// [feature group of 64][point row][128 B], 16-byte chunks XOR-swizzled by the row) without an fp32 round trip.  One CTA per
-// 64 points: threads 0..63 encode xyz, 64..127 the direction; a thread writes its point's 128-byte line (feature group 1
-// is padding, written as zeros).
-__global__ void __launch_bounds__(128) encode_pack_kernel(const __grid_constant__ MlpInput in, const NetProgram* __restrict__ prog,
+// into the point-major bf16 hi/lo packs (pack_cols_kernel's layout, nm_gemm_tc.cu: tile = [feature block][64-point K
+// block], 128 feature rows x 64 points, 128-byte swizzle) without an fp32 round trip.  One CTA per 64 points: threads
+// 0..63 encode xyz, 64..127 the direction, all 256 write the two tiles from shared memory.
+__global__ void __launch_bounds__(256) encode_pack_kernel(const __grid_constant__ MlpInput in, const NetProgram* __restrict__ prog,
                                                           uint8_t* __restrict__ pkt_x, uint8_t* __restrict__ pkt_d) {
+  __shared__ float t[2][64][65];                           // [encoding][feature][point]
   const NetProgram& G = *prog;
   const int kb = blockIdx.x;
   const int which = threadIdx.x >> 6, pt = threadIdx.x & 63;
-  if ((which ? G.dim_dir : G.dim_xyz) <= 0) return;
-  const long long m = (long long)kb * 64 + pt;
-  __shared__ float stage[128][65];                       // a thread's 64 features (dynamic index j: not a register array)
-  float* f = stage[threadIdx.x];
-  for (int j = 0; j < 64; ++j) f[j] = 0.f;
-  if (m < in.M) {
-    float p[3], d[3];
-    fetch_point(in, m, p, d);
-    if (which == 0) positional_encoding(p, G.L_xyz, G.inc_xyz, G.freq_xyz, [&](int j, float v) { f[j] = v; });
-    else positional_encoding(d, G.L_dir, G.inc_dir, G.freq_dir, [&](int j, float v) { f[j] = v; });
-  }
-  uint8_t* line = (which ? pkt_d : pkt_x) + (size_t)kb * kPtileBytes + (size_t)pt * 128u;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    __align__(16) uint16_t hi[8], lo[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float x = f[c * 8 + i];
-      const __nv_bfloat16 h = __float2bfloat16_rn(x);
-      const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-      hi[i] = __bfloat16_as_ushort(h); lo[i] = __bfloat16_as_ushort(l);
+  if (which < 2) {
+    float (*tt)[65] = t[which];
+    const long long m = (long long)kb * 64 + pt;
+    const int dim = which ? G.dim_dir : G.dim_xyz;
+    for (int j = dim; j < 64; ++j) tt[j][pt] = 0.f;
+    if (m < in.M && dim > 0) {
+      float p[3], d[3];
+      fetch_point(in, m, p, d);
+      if (which == 0) positional_encoding(p, G.L_xyz, G.inc_xyz, G.freq_xyz, [&](int j, float v) { tt[j][pt] = v; });
+      else positional_encoding(d, G.L_dir, G.inc_dir, G.freq_dir, [&](int j, float v) { tt[j][pt] = v; });
+    } else {
+      for (int j = 0; j < dim; ++j) tt[j][pt] = 0.f;
     }
-    const uint32_t off = (uint32_t)((c ^ (pt & 7)) << 4);
-    *reinterpret_cast<uint4*>(line + off) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(line + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
-    // feature group 1 (rows 64..127 of the operand): zero padding
-    *reinterpret_cast<uint4*>(line + 8192u + off) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(line + kPtileHalf + 8192u + off) = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const int c8 = threadIdx.x & 7;
+  for (int e = 0; e < 2; ++e) {
+    if (e == 1 && G.dim_dir <= 0) break;
+    uint8_t* tile = (e ? pkt_d : pkt_x) + (size_t)kb * kPtileBytes;        // one feature block: tile index = kb
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int r = pass * 32 + (threadIdx.x >> 3);        // feature row of the tile; rows >= 64 are zero padding
+      __align__(16) uint16_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = r < 64 ? t[e][r][c8 * 8 + i] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+        hi[i] = __bfloat16_as_ushort(h); lo[i] = __bfloat16_as_ushort(l);
+      }
+      const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c8 ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(tile + off) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(tile + kPtileHalf + off) = *reinterpret_cast<const uint4*>(lo);
+    }
   }
 }
 
@@ -707,7 +713,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
 
   if (tc && !train_layerwise()) {               // fused chains: the encodings are needed as weight-gradient operands only
     NM_CHECK(G.dim_xyz <= kPeLd && G.dim_dir <= kPeLd, "encoding wider than %d", kPeLd);
-    encode_pack_kernel<<<kbtP, 128, 0, st>>>(in, net.d_full, W.pkt_pex, W.pkt_ped);
+    encode_pack_kernel<<<kbtP, 256, 0, st>>>(in, net.d_full, W.pkt_pex, W.pkt_ped);
     NM_CUDA(cudaGetLastError());
     if (launches) ++*launches;
   } else {
@@ -814,18 +820,22 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       io.packT[li] = W.pkt_dz[l - 1];
       if (G.layers[l - 1].relu) io.bits[li] = reinterpret_cast<uint32_t*>(W.bits[l - 1]);
     }
-    if (int e = launch_mlp_tc_bwd(net, P, dZ, Ltop.n_out, dout, g->bias, io, mode.n_passes, num_sms, mode.d_err, st, launches)) return e;
+    if (int e = launch_mlp_tc_bwd(net, P, dZ, Ltop.n_out, dout, io, mode.n_passes, num_sms, mode.d_err, st, launches)) return e;
     for (int l = last; l >= 0; --l) {            // weight gradients dW (N, Kt) += dZ^T [act[l-1] | PE]: long-K GEMMs, fp32 atomics
       const LayerProg& L = G.layers[l];
       TcGemmParams T = tc_base();
       T.nseg = 1; T.atomic = 1; T.ldd = gw_ld[l]; T.M = L.n_out;
+      // bias gradient = row sums of dZ^T, taken by the first GEMM that stages this layer's dZ pack (the top layer's comes
+      // from head_backward_kernel)
+      T.a_rowsum = l < last ? g->bias + L.bias_off : nullptr;
       if (L.k_act > 0) {
-        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP, 3};
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP};
         T.D = g->w + gw_off[l]; T.N = L.k_act;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
+        T.a_rowsum = nullptr;
       }
       if (L.pe_src) {
-        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, pkt_pe_of(L), kbtP, kbtP, 3};
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, pkt_pe_of(L), kbtP, kbtP};
         T.D = g->w + gw_off[l] + L.k_act; T.N = L.k_pe;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
@@ -868,12 +878,12 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       TcGemmParams T = tc_base();
       T.nseg = 1; T.atomic = 1; T.ldd = ldg; T.M = N;
       if (L.k_act > 0) {
-        T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_act[l - 1], kbtP, kbtP, 3};
+        T.seg[0] = TcSeg{W.pkt_a, kbtP, W.pkt_act[l - 1], kbtP, kbtP};
         T.D = gW; T.N = L.k_act;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
       if (L.pe_src) {
-        T.seg[0] = TcSeg{W.pkt_a, kbtP, pkt_pe_of(L), kbtP, kbtP, 3};
+        T.seg[0] = TcSeg{W.pkt_a, kbtP, pkt_pe_of(L), kbtP, kbtP};
         T.D = gW + L.k_act; T.N = L.k_pe;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
@@ -925,7 +935,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
 
 // standalone entry for tests of the tensor-core GEMM: D (M,N) = A (M,K) B (N,K)^T from fp32 row-major device
 // arrays.  a_cols / b_cols != 0: the operand is given transposed ((K,M) / (K,N) row-major) and packed with
-// pack_cols.  k_split > 0 (multiple of 64, row-packed operands only): the K range is fed as two segments.
+// pack_cols (1: K-major tiles, 2: MN-major tiles consumed through MN-major descriptors).  k_split > 0 (multiple of 64, row-packed operands only): the K range is fed as two segments.
 int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_cols, int b_cols, int k_split, int n_passes,
                   int fp16, int atomic, float* D, uint8_t* scratch, size_t scratch_bytes, int num_sms, int* d_err, cudaStream_t st,
                   int64_t* launches) {
@@ -937,7 +947,7 @@ int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_col
   TcGemmParams T{};
   T.n_passes = n_passes; T.fp16 = fp16; T.err = d_err; T.atomic = atomic; T.D = D; T.ldd = N; T.M = M; T.N = N;
   const int kbt = (K + 63) / 64;
-  if (int e = b_cols ? launch_pack_cols(B, N, K, N, pb, 0, fp16, st, launches) : launch_pack_rows(B, K, N, K, pb, fp16, st, launches)) return e;
+  if (int e = b_cols ? launch_pack_cols(B, N, K, N, pb, 0, fp16, st, launches, b_cols == 2) : launch_pack_rows(B, K, N, K, pb, fp16, st, launches)) return e;
   if (k_split > 0) {
     NM_CHECK(!a_cols && !b_cols && k_split % 64 == 0 && k_split < K && !atomic, "bad k_split");
     if (int e = launch_pack_rows(A, K, M, k_split, pa, fp16, st, launches)) return e;
@@ -947,9 +957,9 @@ int debug_tc_gemm(const float* A, const float* B, int M, int N, int K, int a_col
     T.seg[0] = TcSeg{pa, kb0, pb, kbt, kb0};
     T.seg[1] = TcSeg{pa2, kb1, pb + (size_t)kb0 * kPtileBytes, kbt, kb1};
   } else {
-    if (int e = a_cols ? launch_pack_cols(A, M, K, M, pa, 0, fp16, st, launches) : launch_pack_rows(A, K, M, K, pa, fp16, st, launches)) return e;
+    if (int e = a_cols ? launch_pack_cols(A, M, K, M, pa, 0, fp16, st, launches, a_cols == 2) : launch_pack_rows(A, K, M, K, pa, fp16, st, launches)) return e;
     T.nseg = 1;
-    T.seg[0] = TcSeg{pa, kbt, pb, kbt, kbt, (a_cols ? 1 : 0) | (b_cols ? 2 : 0)};
+    T.seg[0] = TcSeg{pa, kbt, pb, kbt, kbt, (a_cols == 2 ? 1 : 0) | (b_cols == 2 ? 2 : 0)};
   }
   int repeat = 1;
   if (const char* e = getenv("NM_GEMM_REPEAT")) repeat = atoi(e) > 0 ? atoi(e) : 1;     // timing aid (tools/gemm_bench.py)
