@@ -87,7 +87,9 @@ typedef struct NmRenderOut {
 enum {
   NM_FLAG_TRAINING = 1,    /* module.training: no depth threshold, train noise_std            */
   NM_FLAG_BUFF = 2,        /* BuFFModel.forward: AABB-clipped sampling, single net (coarse slot) */
-  NM_FLAG_TEACHER_T = 4    /* t_vals is an INPUT: skip sampling, run net `which`=fine-if-present on it */
+  NM_FLAG_TEACHER_T = 4,   /* t_vals is an INPUT: skip sampling, run net `which`=fine-if-present on it */
+  NM_FLAG_RANDOM_VOXELS = 8 /* with NM_FLAG_BUFF: cfg.tree.use_random_sampling — multinomial voxel draws + uniform depth inside
+                               the voxel (src/nerf/tree.py:280-297) instead of the deterministic placement; uses `seed` */
 };
 
 /* ---- lifecycle -------------------------------------------------------------------------------------- */
@@ -220,12 +222,16 @@ int nm_get_grad(NmHandle h, int which, const char* name, float* out_dev, int64_t
  * nm_ray_voxel_indices: the `indices` output of TreeSampling.batch_ray_voxel_intersect (src/nerf/tree.py:215-343,
  *   deterministic branch) for cfg.num_coarse samples per ray: the voxel (row of the nm_set_tree list) every sample lies
  *   in, int32 (R,S), -1 on rays that hit no voxel; z_out_dev (R,S) optionally receives the sample distances with the
- *   uniform fallback on those rays (model_buff.py:52-53).
+ *   uniform fallback on those rays (model_buff.py:52-53).  _ex: flags = NM_FLAG_RANDOM_VOXELS selects the random branch
+ *   (tree.py:280-297) with `seed` — pass the seed of the render call whose samples are being attributed.
  * nm_tree_integrate: TreeSampling.ray_batch_integration (tree.py:177-206) past its step gate: memm[v] +=
  *   (sum of weights / sum of weight masks of the samples in v - memm[v]) / counter for every voxel that received a sample.
  *   idx/weights/mask: n = R*S entries (whole batch, idx -1 skipped, or only the rows of rays that hit). */
 int nm_ray_voxel_indices(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
                          const float* near_far_host, float* z_out_dev, int32_t* idx_out_dev, void* stream);
+int nm_ray_voxel_indices_ex(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                            const float* near_far_host, int flags, uint64_t seed, float* z_out_dev, int32_t* idx_out_dev,
+                            void* stream);
 int nm_tree_integrate(NmHandle h, const int32_t* idx_dev, const float* weights_dev, const float* mask_weights_dev, int64_t n,
                       float* memm_dev, int32_t V, int32_t counter, void* stream);
 

@@ -31,7 +31,7 @@ class NmRenderOut(C.Structure):
 
 
 PREC_EXACT, PREC_FAST, PREC_FP32 = 0, 1, 2
-FLAG_TRAINING, FLAG_BUFF, FLAG_TEACHER_T = 1, 2, 4
+FLAG_TRAINING, FLAG_BUFF, FLAG_TEACHER_T, FLAG_RANDOM_VOXELS = 1, 2, 4, 8
 NET_COARSE, NET_FINE = 0, 1
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -66,6 +66,7 @@ _SIGNATURES = {
     "nm_loss_backward": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _I, C.c_uint64, _P, _P, _P]),
     "nm_get_grad": (C.c_int, [_P, _I, C.c_char_p, _P, _L, _P]),
     "nm_ray_voxel_indices": (C.c_int, [_P, _P, _I, _P, _L, _P, _P, _P, _P]),
+    "nm_ray_voxel_indices_ex": (C.c_int, [_P, _P, _I, _P, _L, _P, _I, C.c_uint64, _P, _P, _P]),
     "nm_tree_integrate": (C.c_int, [_P, _P, _P, _P, _L, _P, C.c_int32, C.c_int32, _P]),
     "nm_debug_gemm": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "nm_debug_pack": (C.c_int, [C.POINTER(NmNetDesc), _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64), _I, _P,

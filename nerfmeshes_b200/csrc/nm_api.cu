@@ -194,7 +194,8 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
     if (int e = h->t_u.ensure((size_t)R * Nc * 4)) return e;
     float* z = h->t_u.as<float>();
     if (int e = launch_aabb(h->voxels.as<float>(), h->V, rb.origins, rb.o_stride, rb.dirs, R, rb.nf[0], rb.nf[1], Nc,
-                            h->s_table.as<float>(), t_c, z, nullptr, h->d_err + 1, st, &h->launches)) return e;
+                            h->s_table.as<float>(), t_c, z, nullptr, h->d_err + 1, st, &h->launches,
+                            (flags & NM_FLAG_RANDOM_VOXELS) ? 1 : 0, seed)) return e;
     if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
     if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(z, Nc), h->raw_c.as<float>(), st, emit_c)) return e;
     if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, z, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
@@ -656,6 +657,12 @@ int nm_debug_gemm(NmHandle h, const float* a_dev, const float* b_dev, int M, int
 // ---------------------------------------------------------------------------------------------- BuFF tree maintenance
 int nm_ray_voxel_indices(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
                          const float* near_far_host, float* z_out_dev, int32_t* idx_out_dev, void* stream) {
+  return nm_ray_voxel_indices_ex(h, origins_dev, o_stride, dirs_dev, R, near_far_host, 0, 0, z_out_dev, idx_out_dev, stream);
+}
+
+int nm_ray_voxel_indices_ex(NmHandle h, const float* origins_dev, int o_stride, const float* dirs_dev, int64_t R,
+                            const float* near_far_host, int flags, uint64_t seed, float* z_out_dev, int32_t* idx_out_dev,
+                            void* stream) {
   if (int e = bind_checked(h)) return e;
   NM_CHECK(origins_dev && dirs_dev && near_far_host && idx_out_dev, "null argument");
   NM_CHECK(o_stride == 0 || o_stride == 3, "o_stride must be 0 or 3");
@@ -669,8 +676,16 @@ int nm_ray_voxel_indices(NmHandle h, const float* origins_dev, int o_stride, con
     if (int e = launch_stratified(h->s_table.as<float>(), S, R, near_far_host, nullptr, nullptr, h->cfg.lindisp, 0, 0, t_u, st,
                                   &h->launches)) return e;
   }
-  return launch_aabb(h->voxels.as<float>(), h->V, origins_dev, o_stride, dirs_dev, R, near_far_host[0], near_far_host[1], S,
-                     h->s_table.as<float>(), t_u, z_out_dev, idx_out_dev, h->d_err + 1, st, &h->launches);
+  // walked in the render calls' ray chunks with their per-chunk seeds, so that a random draw repeats the render's own
+  const long long kChunk = chunk_rays();
+  for (long long r0 = 0; r0 < R; r0 += kChunk) {
+    const long long n = (R - r0 < kChunk) ? R - r0 : kChunk;
+    if (int e = launch_aabb(h->voxels.as<float>(), h->V, origins_dev + (long long)o_stride * r0, o_stride, dirs_dev + 3 * r0, n,
+                            near_far_host[0], near_far_host[1], S, h->s_table.as<float>(), t_u ? t_u + r0 * S : nullptr,
+                            z_out_dev ? z_out_dev + r0 * S : nullptr, idx_out_dev + r0 * S, h->d_err + 1, st, &h->launches,
+                            (flags & NM_FLAG_RANDOM_VOXELS) ? 1 : 0, seed + (uint64_t)r0)) return e;
+  }
+  return 0;
 }
 
 int nm_tree_integrate(NmHandle h, const int32_t* idx_dev, const float* weights_dev, const float* mask_weights_dev, int64_t n,

@@ -164,7 +164,7 @@ int launch_invcdf(const float* t_c, const float* w_c, const float* u_table, int 
                   uint64_t seed, float* t_f, cudaStream_t st, int64_t* launches);
 int launch_aabb(const float* voxels, int V, const float* origins, int o_stride, const float* dirs, long long R,
                 float near, float far, int S, const float* s_table, const float* t_uniform, float* z_out, int* idx_out,
-                int* d_overflow, cudaStream_t st, int64_t* launches);
+                int* d_overflow, cudaStream_t st, int64_t* launches, int random = 0, uint64_t seed = 0);
 int launch_tree_integrate(const int* idx, const float* w, const float* mw, long long n, float* memm, int V, int counter,
                           float* scratch2v, cudaStream_t st, int64_t* launches);
 int launch_volume_stats(const float* vol, long long n, double* d_scratch, float* out_host, cudaStream_t st,

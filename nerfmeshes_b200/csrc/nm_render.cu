@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(kInvWarps * 32) invcdf_kernel(const float* __r
                                                               float* __restrict__ t_f) {
   __shared__ float s_bins[kInvWarps][kMaxCoarse];
   __shared__ float s_cdf[kInvWarps][kMaxCoarse];
-  __shared__ float s_all[kInvWarps][kMaxTotal];
+  __shared__ float s_all[kInvWarps][2 * kMaxTotal];      // coarse depths, then the new samples padded to a power of two
+  __shared__ float s_out[kInvWarps][kMaxTotal];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ray = (long long)blockIdx.x * kInvWarps + wid;
   if (ray >= R) return;
@@ -208,12 +209,36 @@ __global__ void __launch_bounds__(kInvWarps * 32) invcdf_kernel(const float* __r
     const float tt = (u - cb) / denom;
     all[Nc + j] = bb + tt * (ba - bb);
   }
-  int n2 = 1;
-  while (n2 < total) n2 <<= 1;
-  for (int i = total + lane; i < n2; i += 32) all[i] = CUDART_INF_F;
   __syncwarp();
-  warp_bitonic_sort(all, n2, lane);
-  for (int i = lane; i < total; i += 32) t_f[ray * total + i] = all[i];
+  // torch.sort(cat(t, samples)) as a merge.  The coarse depths ascend; the new samples ascend too whenever u does (the
+  // shipped validation tables; up to a rounding ulp at bin edges) — checked here, and sorted on their own when they do not
+  // (training draws u at random).  An element's place in the merged order is its own index plus the number of elements of
+  // the other list that come before it; equal values are interchangeable, so the output equals the full sort's bit for bit.
+  float* smp = all + Nc;
+  bool ok = true;
+  for (int j = lane; j + 1 < Nf; j += 32) ok &= !(smp[j] > smp[j + 1]);
+  if (!__all_sync(0xffffffffu, ok)) {
+    int n2 = 1;
+    while (n2 < Nf) n2 <<= 1;
+    for (int i = Nf + lane; i < n2; i += 32) smp[i] = CUDART_INF_F;
+    __syncwarp();
+    warp_bitonic_sort(smp, n2, lane);
+  }
+  float* outp = s_out[wid];
+  for (int i = lane; i < Nc; i += 32) {         // coarse depth i: samples strictly below it come first
+    const float x = all[i];
+    int lo = 0, hi = Nf;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (smp[mid] < x) lo = mid + 1; else hi = mid; }
+    outp[i + lo] = x;
+  }
+  for (int j = lane; j < Nf; j += 32) {         // sample j: coarse depths <= it come first
+    const float x = smp[j];
+    int lo = 0, hi = Nc;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (all[mid] <= x) lo = mid + 1; else hi = mid; }
+    outp[j + lo] = x;
+  }
+  __syncwarp();
+  for (int i = lane; i < total; i += 32) t_f[ray * total + i] = outp[i];
 }
 
 // ------------------------------------------------------------------------------------------------ a10
@@ -268,7 +293,7 @@ __global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __re
                                                               float far, int S, const float* __restrict__ s_table,
                                                               const float* __restrict__ t_uniform,
                                                               float* __restrict__ z_out, int* __restrict__ idx_out,
-                                                              int* __restrict__ overflow) {
+                                                              int* __restrict__ overflow, int random, uint64_t seed) {
   __shared__ int s_vox[kAabbWarps][kMaxHits];
   __shared__ float s_lo[kAabbWarps][kMaxHits];
   __shared__ float s_hi[kAabbWarps][kMaxHits];
@@ -328,6 +353,29 @@ __global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __re
     }
     return;
   }
+  if (random) {
+    // cfg.tree.use_random_sampling (tree.py:280-297): S draws with replacement from a multinomial that weighs every hit voxel 1
+    // (and every miss 1e-12: a 1e-9-probability event per draw that would sample a non-intersection's garbage interval —
+    // not reproduced), each placed uniformly inside its voxel's [entry, exit]; then the common sort below.  Distributional
+    // parity only: torch's generator stream cannot be matched.
+    for (int k = lane; k < S; k += 32) {
+      const uint64_t c = (uint64_t)(ray * S + k);
+      const int h = min((int)(u01(seed ^ 0x5bd1e995u, 2 * c) * (float)H), H - 1);
+      z[k] = lo[h] + (hi[h] - lo[h]) * u01(seed ^ 0x5bd1e995u, 2 * c + 1);
+      bucket[k] = vox[h];
+    }
+    __syncwarp();
+    int m2 = 1;
+    while (m2 < S) m2 <<= 1;
+    for (int i = S + lane; i < m2; i += 32) { z[i] = CUDART_INF_F; bucket[i] = -1; }
+    __syncwarp();
+    warp_bitonic_sort_tagged(z, bucket, m2, lane);
+    for (int k = lane; k < S; k += 32) {
+      if (z_out) z_out[ray * S + k] = z[k];
+      if (idx_out) idx_out[ray * S + k] = bucket[k];
+    }
+    return;
+  }
   int n2 = 1;
   while (n2 < H) n2 <<= 1;
   for (int i = H + lane; i < n2; i += 32) { lo[i] = CUDART_INF_F; hi[i] = CUDART_INF_F; vox[i] = -1; }
@@ -355,11 +403,17 @@ __global__ void __launch_bounds__(kAabbWarps * 32) aabb_kernel(const float* __re
   }
   __syncwarp();
   for (int k = lane; k < S; k += 32) bucket[k] = vox[bucket[k]];      // sample -> voxel id (tree.py:333-335)
-  int m2 = 1;
-  while (m2 < S) m2 <<= 1;
-  for (int i = S + lane; i < m2; i += 32) { z[i] = CUDART_INF_F; bucket[i] = -1; }
-  __syncwarp();
-  warp_bitonic_sort_tagged(z, bucket, m2, lane);                      // (:338-341) ids follow their samples
+  // (:338-341) sort the samples, ids following.  Leaf boxes do not overlap, so the buckets' intervals are disjoint and the
+  // samples already ascend (up to a rounding ulp at a bucket edge): the sort network only runs for a ray where they do not.
+  bool asc = true;
+  for (int k = lane; k + 1 < S; k += 32) asc &= !(z[k] > z[k + 1]);
+  if (!__all_sync(0xffffffffu, asc)) {
+    int m2 = 1;
+    while (m2 < S) m2 <<= 1;
+    for (int i = S + lane; i < m2; i += 32) { z[i] = CUDART_INF_F; bucket[i] = -1; }
+    __syncwarp();
+    warp_bitonic_sort_tagged(z, bucket, m2, lane);
+  }
   for (int k = lane; k < S; k += 32) {
     if (z_out) z_out[ray * S + k] = z[k];
     if (idx_out) idx_out[ray * S + k] = bucket[k];
@@ -513,12 +567,12 @@ int launch_invcdf(const float* t_c, const float* w_c, const float* u_table, int 
 
 int launch_aabb(const float* voxels, int V, const float* origins, int o_stride, const float* dirs, long long R,
                      float near, float far, int S, const float* s_table, const float* t_uniform, float* z_out, int* idx_out,
-                     int* d_overflow, cudaStream_t st, int64_t* launches) {
+                     int* d_overflow, cudaStream_t st, int64_t* launches, int random, uint64_t seed) {
   NM_CHECK(S <= kMaxTotal, "sample count %d exceeds the AABB sampler limit", S);
   NM_CHECK(z_out == nullptr || t_uniform != nullptr, "z output needs the uniform fallback samples");
   if (R <= 0) return 0;
   aabb_kernel<<<(unsigned)((R + kAabbWarps - 1) / kAabbWarps), kAabbWarps * 32, 0, st>>>(
-      voxels, V, origins, o_stride, dirs, R, near, far, S, s_table, t_uniform, z_out, idx_out, d_overflow);
+      voxels, V, origins, o_stride, dirs, R, near, far, S, s_table, t_uniform, z_out, idx_out, d_overflow, random, seed);
   NM_CUDA(cudaGetLastError());
   if (launches) ++*launches;
   return 0;

@@ -197,7 +197,7 @@ class Engine:
         else:
             assert o.shape == (R, 3), "origins must be (3,), (1,3) or (R,3)"
             o_stride = 3
-        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        flags = self._flags(training, buff)
         S = self.num_samples(buff)
         per_ray = isinstance(near, torch.Tensor) and near.dim() > 0 and near.shape[0] == R and near.numel() == R and R > 1
         nf = (C.c_float * 2)(0.0, 0.0)
@@ -252,7 +252,7 @@ class Engine:
         g = None if d_rgb is None else _f32c(d_rgb, d.device)
         gc = None if d_coarse_rgb is None else _f32c(d_coarse_rgb, d.device)
         assert (g is None or g.shape == (R, 3)) and (gc is None or gc.shape == (R, 3))
-        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        flags = self._flags(training, buff)
         if R:
             L.check(self.lib.nm_backward_rays(self._h, _ptr(o), o_stride, _ptr(d), R, nf, _ptr(near_d), _ptr(far_d), flags,
                                               seed, _ptr(g), _ptr(gc), self._stream()))
@@ -264,7 +264,7 @@ class Engine:
         tgt = _f32c(target_rgb, d.device)
         assert tgt.shape == (R, 3)
         loss = torch.zeros(2, dtype=torch.float32, device=d.device)
-        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        flags = self._flags(training, buff)
         if R:
             L.check(self.lib.nm_loss_backward(self._h, _ptr(o), o_stride, _ptr(d), R, nf, _ptr(near_d), _ptr(far_d), flags,
                                               seed, _ptr(tgt), _ptr(loss), self._stream()))
@@ -276,8 +276,14 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ BuFF tree maintenance
-    def ray_voxel_indices(self, origins, dirs, near, far, want_z=False):
-        """(R,S) int32 voxel index of every AABB sample (-1 on rays without a hit) [, (R,S) sample distances]."""
+    def _flags(self, training, buff):
+        """render-call flags; `voxel_random` mirrors cfg.tree.use_random_sampling (src/nerf/tree.py:280)."""
+        return ((L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0) |
+                (L.FLAG_RANDOM_VOXELS if buff and getattr(self, "voxel_random", False) else 0))
+
+    def ray_voxel_indices(self, origins, dirs, near, far, want_z=False, seed=0):
+        """(R,S) int32 voxel index of every AABB sample (-1 on rays without a hit) [, (R,S) sample distances].  With
+        `voxel_random` set, `seed` must be the render call's seed for the indices to describe that call's samples."""
         o, o_stride, d, R, nf, near_d, far_d = self._ray_args(origins, dirs, near, far)
         if nf is None:
             raise L.NmError("the BuFF sampler takes scalar near/far")
@@ -285,7 +291,8 @@ class Engine:
         idx = torch.empty((R, S), dtype=torch.int32, device=d.device)
         z = torch.empty((R, S), dtype=torch.float32, device=d.device) if want_z else None
         if R:
-            L.check(self.lib.nm_ray_voxel_indices(self._h, _ptr(o), o_stride, _ptr(d), R, nf, _ptr(z), _ptr(idx), self._stream()))
+            L.check(self.lib.nm_ray_voxel_indices_ex(self._h, _ptr(o), o_stride, _ptr(d), R, nf, self._flags(False, True) & L.FLAG_RANDOM_VOXELS,
+                                                     int(seed), _ptr(z), _ptr(idx), self._stream()))
         return (idx, z) if want_z else idx
 
     def tree_integrate(self, idx, weights, mask_weights, memm, counter):
@@ -315,7 +322,7 @@ class Engine:
         R = (row1 - row0) * W
         p = np.ascontiguousarray(torch.as_tensor(pose).detach().cpu().numpy()[:3, :4], dtype=np.float32)
         nf = (C.c_float * 2)(float(near), float(far))
-        flags = (L.FLAG_TRAINING if training else 0) | (L.FLAG_BUFF if buff else 0)
+        flags = self._flags(training, buff)
         S = self.num_samples(buff)
         if to_host:
             if host_out is not None:

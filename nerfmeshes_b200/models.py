@@ -437,13 +437,14 @@ class BuFFModel(BaseModel):
             raise IndexError("BuFFModel needs ray origins of shape (1,3) or (R,3) (src/nerf/tree.py:231)")
         eng = self._engine()
         self._sync_tree(eng)
+        eng.voxel_random = bool(_cfg_get(self.cfg, "tree.use_random_sampling", False))      # src/nerf/tree.py:280
         o = eng.render_rays(ray_origins, ray_directions, near, far, training=self.training, buff=True, seed=seed,
                             want=["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights", "t_vals"])
         if self.training and o["rgb"].is_cuda:
             # accumulate the (detached) sample weights into the voxels (model_buff.py:65-66; tree.py:177-206)
             step_gate = int(_cfg_get(self.cfg, "tree.step_size_integration_offset", 0) or 0)
             if self.global_step >= step_gate:
-                idx = eng.ray_voxel_indices(ray_origins, ray_directions, near, far)
+                idx = eng.ray_voxel_indices(ray_origins, ray_directions, near, far, seed=seed)
                 eng.check_flags()      # a truncated hit list (> 512 voxels on a ray) must not reach the tree statistics
                 self.tree.ray_batch_integration(self.global_step, idx, o["weights"], o["mask_weights"])
         o["rgb"], _ = self._attach_grad((ray_origins, ray_directions, near, far), seed, True, o["rgb"])

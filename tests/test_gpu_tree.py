@@ -108,3 +108,49 @@ def test_buff_training_step_updates_weights_tree_and_schedule():
     assert sizes[0] == (n0, 1) and sizes[1] == (n0, 1) and sizes[2] == (n0, 2) and sizes[3] == (n0, 3)
     assert sizes[4][1] == 1 and sizes[4][0] != n0
     assert abs(out["log"]["train/psnr"] + 10 * np.log10(out["loss"])) < 1e-6 and np.isfinite(losses).all()
+
+
+def test_random_voxel_sampling_branch(buff):
+    """cfg.tree.use_random_sampling (src/nerf/tree.py:280-297): multinomial voxel draws with replacement, a uniform depth
+    inside the drawn voxel's [entry, exit], then the common sort.  torch's generator stream cannot be matched, so the parity
+    is distributional and structural: every sample lies inside the interval of the voxel it is attributed to, that voxel is
+    one the ray hits (the oracle's hit mask), samples ascend, rays without a hit keep the uniform fallback / index -1, every
+    hit voxel of a ray is drawn about S/H times, the render with the flag uses exactly these samples, and a new seed draws
+    new ones."""
+    g = load_npz("golden_lego_buff.npz")
+    vox = load_npz("weights_lego_buff.npz")["voxels"].float()
+    near, far = float(g["bounds"][0]), float(g["bounds"][1])
+    eng = buff._engine()
+    buff._sync_tree(eng)
+    o, d = g["origin"][None], g["dirs"]
+    _, _, mask = O.batch_ray_voxel_intersect(vox, o, d, near, far, 192, return_indices=True)
+    eng.voxel_random = True
+    try:
+        idx, z = eng.ray_voxel_indices(o.cuda(), d.cuda(), near, far, want_z=True, seed=11)
+        idx2, z2 = eng.ray_voxel_indices(o.cuda(), d.cuda(), near, far, want_z=True, seed=12)
+        out = eng.render_rays(o.cuda(), d.cuda(), near, far, buff=True, seed=11, want=["rgb", "t_vals"])
+    finally:
+        eng.voxel_random = False
+    idx, z = idx.cpu(), z.cpu()
+    assert torch.equal(out["t_vals"].cpu(), z)                           # the render's own samples
+    assert bool((idx[~mask] == -1).all()) and torch.equal(z[~mask], g["z"][~mask])
+    assert bool((z[:, 1:] >= z[:, :-1]).all())
+    assert not torch.equal(z2.cpu()[mask], z[mask])
+    # slab intersection per (ray, voxel) in float64 — interval membership with a few ulps of slack
+    inv = 1.0 / d.double()
+    a0 = (vox[None, :, 0].double() - o.double()[:, None]) * inv[:, None]     # (R,V,3)
+    a1 = (vox[None, :, 1].double() - o.double()[:, None]) * inv[:, None]
+    lo_c, hi_c = torch.minimum(a0, a1), torch.maximum(a0, a1)
+    t_in, t_out = lo_c.max(-1).values, hi_c.min(-1).values                 # (R,V)
+    hit = (t_in <= t_out) & (t_in >= near) & (t_out <= far)
+    rows = torch.nonzero(mask).flatten()
+    for r in rows.tolist():
+        v = idx[r].long()
+        assert bool((v >= 0).all()) and bool(hit[r, v].all())
+        assert bool((z[r].double() >= t_in[r, v] - 1e-5).all()) and bool((z[r].double() <= t_out[r, v] + 1e-5).all())
+        H = int(hit[r].sum())
+        counts = torch.bincount(v, minlength=vox.shape[0])[hit[r]]
+        assert int(counts.sum()) == 192
+        if H <= 24:                                                       # expected 192/H >= 8 per voxel: none may starve
+            assert int(counts.min()) >= 1 and int(counts.max()) <= 192 // H * 4 + 8
+    assert torch.isfinite(out["rgb"]).all()
