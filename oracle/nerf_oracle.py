@@ -318,8 +318,12 @@ def sample_pdf_forward(t_coarse, weights, num_fine, perturb=False, u=None, gener
 # a10: AABB-clipped sampling (BuFF)
 # --------------------------------------------------------------------------------------
 def batch_ray_voxel_intersect(voxels: torch.Tensor, origins: torch.Tensor, dirs: torch.Tensor, near, far,
-                              samples_count: int, return_indices: bool = False, literal_sort: bool = False):
-    """src/nerf/tree.py:215-343, deterministic branch (use_random_sampling False in every shipped config).
+                              samples_count: int, return_indices: bool = False, literal_sort: bool = False,
+                              use_random_sampling: bool = False, generator: Optional[torch.Generator] = None):
+    """src/nerf/tree.py:215-343: the deterministic branch (use_random_sampling False in every shipped config) and, with
+    use_random_sampling=True, the random one (:280-297: multinomial over voxels weighted 1 on a hit / 1e-12 on a miss, with
+    replacement, then a uniform depth inside the drawn voxel's interval; the draws come from torch's generator, so only the
+    distribution is comparable with another implementation).
 
     voxels (V,2,3) [min,max]; origins (1,3) or (R,3); dirs (R,3).  Returns z (R,S) ascending and ray_mask (R,).
     Restated in the textbook slab form, which SURVEY D.3 verified equal to the reference's sequential
@@ -354,6 +358,14 @@ def batch_ray_voxel_intersect(voxels: torch.Tensor, origins: torch.Tensor, dirs:
     z = torch.zeros(R, samples_count)
     if ray_mask.sum() == 0:
         return (z, torch.ones(R, samples_count, dtype=torch.long), ray_mask) if return_indices else (z, ray_mask)
+    if use_random_sampling:                                       # (:280-297)
+        weights = torch.ones(R, V)
+        weights[~mask] = 1e-12
+        samples = torch.multinomial(weights, samples_count, replacement=True, generator=generator)
+        v_lo, v_hi = tmin.gather(-1, samples), tmax.gather(-1, samples)
+        z = v_lo + (v_hi - v_lo) * torch.rand(v_lo.shape, generator=generator)
+        z, perm = z.sort(-1)                                      # (:338-341)
+        return (z, samples.gather(-1, perm), ray_mask) if return_indices else (z, ray_mask)
     # hits sorted by entry distance, compacted to the front (:299-308)
     order = tmin.sort(-1)
     tmin_s = order.values

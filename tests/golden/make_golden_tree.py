@@ -3,6 +3,7 @@
   * per-sample voxel indices of batch_ray_voxel_intersect on the golden BuFF rays        (tree.py:215-343)
   * memm after one and two ray_batch_integration calls                                    (tree.py:177-206)
   * voxel lists of a small synthetic tree before / after two consolidate() calls          (tree.py:127-175)
+  * the random sampling branch (use_random_sampling) under torch.manual_seed(4321), 48 samples (tree.py:280-297)
 """
 import os
 import sys
@@ -39,6 +40,13 @@ def main():
         t.ray_batch_integration(step - 5, idx[mask], w[mask], mw[mask])          # before the offset: no-op
         assert torch.equal(t.memm, memm2) and t.counter == 3
 
+        # the random branch (tree.py:280-297) under a fixed global seed: pins the oracle's restatement draw for draw
+        mb.tree.config.tree.use_random_sampling = True
+        torch.manual_seed(4321)
+        z_r, idx_r, mask_r = mb.tree.batch_ray_voxel_intersect(o[None], dirs, near, far, samples_count=48)
+        mb.tree.config.tree.use_random_sampling = False
+        assert torch.equal(mask_r, mask)
+
         cfg = NS(dataset=NS(near=2.0, far=6.0),
                  tree=NS(subdivision_outer_count=3, subdivision_inner_count=2, max_depth=3, eps=0.3, max_voxel_count=60,
                          use_random_sampling=False, step_size_integration_offset=10, step_size_tree=4))
@@ -56,7 +64,7 @@ def main():
         ticks = np.array([int(ts.ticked(s)) for s in range(0, 30)], dtype=np.int32)
     np.savez_compressed(os.path.join(HERE, "golden_tree.npz"), idx=idx.numpy().astype(np.int32), ray_mask=mask.numpy(),
                         memm1=memm1.numpy(), memm2=memm2.numpy(), v0=v0.numpy(), m1=m1.numpy(), v1=v1.numpy(), m2=m2.numpy(),
-                        v2=v2.numpy(), ticks=ticks)
+                        v2=v2.numpy(), ticks=ticks, z_random=z_r.numpy(), idx_random=idx_r.numpy().astype(np.int32))
     print("idx", idx.shape, "memm nonzero", int((memm1 != 0).sum()), "voxels", v0.shape[0], v1.shape[0], v2.shape[0])
 
 

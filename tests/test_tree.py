@@ -46,6 +46,20 @@ def test_oracle_voxel_indices_and_integration_match_reference():
     assert counter == 3 and float((memm - torch.from_numpy(G["memm2"])).abs().max()) < 1e-6
 
 
+def test_oracle_random_sampling_branch_repeats_the_reference_draw_for_draw():
+    """cfg.tree.use_random_sampling (src/nerf/tree.py:280-297): under the same torch seed the oracle's restatement consumes the
+    global generator exactly like the reference (one multinomial, one rand_like) — depths and voxel ids bit-identical."""
+    g = load_npz("golden_lego_buff.npz")
+    vox = load_npz("weights_lego_buff.npz")["voxels"].float()
+    near, far = float(g["bounds"][0]), float(g["bounds"][1])
+    torch.manual_seed(4321)
+    z, idx, mask = O.batch_ray_voxel_intersect(vox, g["origin"][None], g["dirs"], near, far, 48, return_indices=True,
+                                               use_random_sampling=True)
+    assert torch.equal(mask, torch.from_numpy(G["ray_mask"]))
+    assert torch.equal(z[mask], torch.from_numpy(G["z_random"])[mask])
+    assert torch.equal(idx[mask].int(), torch.from_numpy(G["idx_random"])[mask])
+
+
 def _cfg():
     return NS(dataset=NS(near=2.0, far=6.0),
               tree=NS(subdivision_outer_count=3, subdivision_inner_count=2, max_depth=3, eps=0.3, max_voxel_count=60,
