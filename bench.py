@@ -50,9 +50,13 @@ def load_npz(name):
     return {k: torch.from_numpy(z[k]) for k in z.files if z[k].dtype.kind == "f"}
 
 
+# one FlexibleNeRFModel of the shipped configs (config/*.yml models.coarse / models.fine; src/nerf/models.py:5-58)
+NET = {"num_layers": 8, "hidden_size": 256, "skip_step": 4, "num_encoding_fn_xyz": 10, "num_encoding_fn_dir": 4,
+       "include_input_xyz": True, "include_input_dir": True, "log_sampling_xyz": True, "log_sampling_dir": True, "use_viewdirs": True}
+
+
 def model_cfg(near, far, buff=False):
-    from oracle.nerf_oracle import NetCfg
-    net = NetCfg().__dict__
+    net = dict(NET)
     cfg = {"experiment.model": "BuFFModel" if buff else "NeRFModel", "dataset.near": near, "dataset.far": far,
            "dataset.white_background": False,
            "models.coarse_type": "FlexibleNeRFModel", "models.fine_type": "FlexibleNeRFModel", "models.use_fine": not buff,
@@ -65,8 +69,19 @@ def model_cfg(near, far, buff=False):
     return cfg
 
 
+def pose_spherical(theta, phi, radius):
+    """camera-to-world of the benchmark orbit (the Blender datasets' render path, src/data/data_helpers.py:10-37): a camera at
+    distance `radius` looking at the origin, elevation phi, azimuth theta (degrees), in the z-up world frame."""
+    th, ph = theta / 180.0 * np.pi, phi / 180.0 * np.pi          # trig in double, matrices in fp32 (like the source)
+    c2w = np.eye(4, dtype=np.float32)
+    c2w[2, 3] = radius
+    rx = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1]], dtype=np.float32)
+    ry = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1]], dtype=np.float32)
+    flip = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.float32)
+    return torch.from_numpy((flip @ (ry @ (rx @ c2w))).astype(np.float32))
+
+
 def poses120():
-    from oracle.nerf_oracle import pose_spherical
     return [pose_spherical(float(a), -30.0, 4.0) for a in np.linspace(-270, 90, 120, endpoint=False)]
 
 
@@ -335,12 +350,10 @@ def run_render(nm, name, ctx, steps, warmup, precision, with_e2e, clocks=None):
 
     if with_e2e:
         # host buffers through the C ABI: rays (H2D from pinned memory), render, [all_gather,] rgb + disp back (D2H), sync
-        from oracle.nerf_oracle import get_ray_bundle, ndc_rays
-        o_h, d_h = get_ray_bundle(H, W, focal, poses[0])
-        if wl["ndc"]:
-            o_h, d_h = ndc_rays(H, W, focal, 1.0, o_h.expand(d_h.shape), d_h)
-            o_h = o_h.reshape(-1, 3).contiguous()
-        d_h = d_h.reshape(-1, 3).contiguous()
+        o_g, d_g = eng.ray_bundle(poses[0], H, W, focal, ndc=wl["ndc"])      # the caller's host ray buffers (made once, untimed)
+        o_h = o_g.reshape(-1, 3).cpu().contiguous()
+        d_h = d_g.reshape(-1, 3).cpu().contiguous()
+        del o_g, d_g
         host_want = ["rgb", "disp"]
         if rows:
             ex = par.row_exchange(eng.device, H, W, host_want)
@@ -567,15 +580,16 @@ def main():
             result["mesh"] = mesh_block(run_mesh(nm, ctx, 2, 1, a.precision), 2)
         t = run_train(nm, ctx, a.precision)
         train_ms = ctx.max_over_ranks(t["ms"])[0]
-        flops = t["rays"] * (64 + 192) * FLOP_PER_POINT * 4
+        flops = t["rays"] * (64 + 192) * FLOP_PER_POINT * 3
         result["train"] = {"metric": "train-rays/sec", "value": t["rays"] * ctx.world / (train_ms * 1e-3), "unit": "rays/s",
                            "rays_per_step_per_gpu": t["rays"], "ms_per_step": train_ms, "launches_per_step": int(t["launches"]),
                            "workload": "nm_loss_backward: fused forward + mse(coarse)+mse(fine) + backward of both 8x256 networks "
                                        "(64+192 samples per ray), gradients accumulated on device; no optimiser step; data parallel over rays",
                            "loss": t["loss"], "algorithmic_tflops": flops / (train_ms * 1e-3) / 1e12,
                            "frac_of_tensor_peak": flops / (train_ms * 1e-3) / 1e12 / peak_tf,
-                           "note": "4x forward FLOPs per step: forward, recompute, data gradient, weight gradient; exact mode issues 3 "
-                                   "MMAs per product, so tensor-pipe work is 3x the algorithmic figure"}
+                           "note": "3x forward FLOPs per step: forward (which also emits the backward's operands: no recompute), data "
+                                   "gradient, weight gradient; exact mode issues 3 MMAs per product, so tensor-pipe work is 3x the "
+                                   "algorithmic figure.  The step is bound by the HBM traffic of the operand packs (DESIGN 4.4)"}
     if ctx.rank != 0:
         if ctx.dist is not None:
             ctx.dist.destroy_process_group()

@@ -38,11 +38,15 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
 def full(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[-1]
-    print(f"# ncu --set full --clock-control none, kernel {vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else ''}")
-    for h, u, v in zip(hdr, units, vals):
-        if any(h == k or h.startswith(k + " ") or (k in h and h.endswith(k.split('.')[-1])) for k in KEYS) and any(h.startswith(k) for k in KEYS):
-            print(f"{h} [{u}] = {v}")
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:                      # one block per captured launch
+        if len(vals) != len(hdr):
+            continue
+        print(f"# ncu --set full --clock-control none, kernel {vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else ''}")
+        for h, u, v in zip(hdr, units, vals):
+            if any(h == k or h.startswith(k + " ") or (k in h and h.endswith(k.split('.')[-1])) for k in KEYS) and any(h.startswith(k) for k in KEYS):
+                print(f"{h} [{u}] = {v}")
+        print()
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "nerfmeshes_b200", "lib", "libnerfmeshes_b200.so")
-MN = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "HGMMA", "LDGSTS", "DFMA", "ATOMS", "RED"]
+MN = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "USETMAXREG", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "HGMMA", "LDGSTS", "DFMA", "ATOMS", "RED"]
 
 
 def main():
