@@ -112,7 +112,8 @@ int check_kernel_flags(NmHandle h) {
 }
 
 // one fused-MLP launch in the configured arithmetic
-int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st, const MlpEmit* emit = nullptr) {
+int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st, const MlpEmit* emit = nullptr,
+            const CompositeArgs* comp = nullptr) {
   const NetDev& net = h->nets[which];
   NM_CHECK(net.loaded, "weights of network %d not loaded", which);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -128,7 +129,7 @@ int run_mlp(NmHandle h, int which, bool sigma_only, const MlpInput& in, float* o
   int rc;
   if (h->cfg.precision == NM_PREC_FP32) rc = launch_mlp_simt(net, sigma_only, in, out, st, &h->launches);
   else rc = launch_mlp_tc(net, sigma_only, h->cfg.precision == NM_PREC_FAST ? 1 : 3, h->cfg.act_scale_log2, in, out,
-                          h->num_sms, h->d_err, st, &h->launches, emit);
+                          h->num_sms, h->d_err, st, &h->launches, emit, comp);
   if (rc) return rc;
   if (h->timing) {
     NM_CUDA(cudaEventRecord(e1, st));
@@ -149,8 +150,10 @@ float* off(float* p, long long n) { return p ? p + n : nullptr; }
 
 // NeRFModel.forward / BuFFModel.forward for one chunk of rays; `o` already offset to the chunk.
 // emit_c / emit_f: training only — the coarse (or only) / fine network's forward also leaves the backward's operands (MlpEmit)
+// need_raw: the caller reads h->raw_c / h->raw_f afterwards (the training backward) — otherwise the compositor runs inside the
+// MLP kernel and the per-sample network outputs never reach HBM (NM_FUSED_COMPOSITE=0 keeps the two-kernel path for A/B tests).
 int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const NmRenderOut& o, cudaStream_t st,
-                 const MlpEmit* emit_c = nullptr, const MlpEmit* emit_f = nullptr) {
+                 const MlpEmit* emit_c = nullptr, const MlpEmit* emit_f = nullptr, bool need_raw = false) {
   const NmRenderCfg& c = h->cfg;
   const long long R = rb.R;
   const int Nc = c.num_coarse;
@@ -160,27 +163,33 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
   const int Nf = (h->has_fine && !buff) ? c.num_fine : 0;
   const int S = Nc + Nf;
   // the coarse and the fine compositor draw independent sigma noise (two torch.randn calls in the reference): distinct salts
-  auto composite = [&](const float* raw, const float* t, int s, float* rgb, float* depth, float* depth_raw, float* acc,
-                       float* disp, float* w, float* mw, uint64_t salt = kNoiseSaltMain) {
-    CompositeArgs a{};
-    a.raw = raw; a.t = t; a.dirs = rb.dirs; a.R = R; a.S = s; a.noise_std = c.noise_std; a.seed = seed ^ salt;
-    a.white_bg = c.white_background; a.training = training ? 1 : 0; a.thr = c.attenuation_threshold;
-    a.rgb = rgb; a.depth = depth; a.depth_raw = depth_raw; a.acc = acc; a.disp = disp; a.weights = w; a.mask_weights = mw;
-    return launch_composite(a, st, &h->launches);
-  };
   auto rays_input = [&](const float* t, int s) {
     MlpInput in{};
     in.mode = IN_RAYS; in.dirs = rb.dirs; in.ray_o = rb.origins; in.o_stride = rb.o_stride; in.t = t; in.S = s;
     in.M = R * s;
     return in;
   };
+  const char* fe = getenv("NM_FUSED_COMPOSITE");       // read per call: the tests flip it to compare the two paths
+  const bool fused_env = !fe || atoi(fe) != 0;
+  // network `which` on the samples t (R,s) + VolumeRenderer: one launch when eligible, else raw (R,s,4) through `raw_buf`
+  auto mlp_composite = [&](int which, Buf& raw_buf, const MlpEmit* emit, const float* t, int s, float* rgb, float* depth,
+                           float* depth_raw, float* acc, float* disp, float* w, float* mw, uint64_t salt = kNoiseSaltMain) -> int {
+    CompositeArgs a{};
+    a.t = t; a.dirs = rb.dirs; a.R = R; a.S = s; a.noise_std = c.noise_std; a.seed = seed ^ salt;
+    a.white_bg = c.white_background; a.training = training ? 1 : 0; a.thr = c.attenuation_threshold;
+    a.rgb = rgb; a.depth = depth; a.depth_raw = depth_raw; a.acc = acc; a.disp = disp; a.weights = w; a.mask_weights = mw;
+    const bool fuse = fused_env && !need_raw && !emit && c.precision != NM_PREC_FP32 && mlp_tc_composite_group(s) > 0;
+    if (fuse) return run_mlp(h, which, false, rays_input(t, s), nullptr, st, nullptr, &a);
+    if (int e = raw_buf.ensure((size_t)R * s * 16)) return e;
+    if (int e = run_mlp(h, which, false, rays_input(t, s), raw_buf.as<float>(), st, emit)) return e;
+    a.raw = raw_buf.as<float>();
+    return launch_composite(a, st, &h->launches);
+  };
 
   if (teacher) {
     NM_CHECK(o.t_vals != nullptr, "NM_FLAG_TEACHER_T needs out.t_vals as input");
     const int which = (h->has_fine && !buff) ? NM_NET_FINE : NM_NET_COARSE;
-    if (int e = h->raw_f.ensure((size_t)R * S * 16)) return e;
-    if (int e = run_mlp(h, which, false, rays_input(o.t_vals, S), h->raw_f.as<float>(), st)) return e;
-    return composite(h->raw_f.as<float>(), o.t_vals, S, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+    return mlp_composite(which, h->raw_f, nullptr, o.t_vals, S, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
   }
 
   // coarse / uniform samples (a3)
@@ -196,28 +205,22 @@ int render_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const
     if (int e = launch_aabb(h->voxels.as<float>(), h->V, rb.origins, rb.o_stride, rb.dirs, R, rb.nf[0], rb.nf[1], Nc,
                             h->s_table.as<float>(), t_c, z, nullptr, h->d_err + 1, st, &h->launches,
                             (flags & NM_FLAG_RANDOM_VOXELS) ? 1 : 0, seed)) return e;
-    if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
-    if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(z, Nc), h->raw_c.as<float>(), st, emit_c)) return e;
     if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, z, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
-    return composite(h->raw_c.as<float>(), z, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+    return mlp_composite(NM_NET_COARSE, h->raw_c, emit_c, z, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
   }
-  if (int e = h->raw_c.ensure((size_t)R * Nc * 16)) return e;
-  if (int e = run_mlp(h, NM_NET_COARSE, false, rays_input(t_c, Nc), h->raw_c.as<float>(), st, emit_c)) return e;
   if (Nf == 0) {
     if (o.t_vals) NM_CUDA(cudaMemcpyAsync(o.t_vals, t_c, (size_t)R * Nc * 4, cudaMemcpyDeviceToDevice, st));
-    return composite(h->raw_c.as<float>(), t_c, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+    return mlp_composite(NM_NET_COARSE, h->raw_c, emit_c, t_c, Nc, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
   }
   float* w_c = o.coarse_weights;
   if (!w_c) { if (int e = h->w_c.ensure((size_t)R * Nc * 4)) return e; w_c = h->w_c.as<float>(); }
-  if (int e = composite(h->raw_c.as<float>(), t_c, Nc, o.coarse_rgb, nullptr, nullptr, o.coarse_acc, o.coarse_disp, w_c, nullptr,
-                        kNoiseSaltCoarse)) return e;
+  if (int e = mlp_composite(NM_NET_COARSE, h->raw_c, emit_c, t_c, Nc, o.coarse_rgb, nullptr, nullptr, o.coarse_acc, o.coarse_disp, w_c,
+                            nullptr, kNoiseSaltCoarse)) return e;
   // inverse-CDF resampling + merge (a8)
   float* t_f = o.t_vals;
   if (!t_f) { if (int e = h->t_f.ensure((size_t)R * S * 4)) return e; t_f = h->t_f.as<float>(); }
   if (int e = launch_invcdf(t_c, w_c, h->u_table.as<float>(), Nc, Nf, R, c.perturb, seed ^ 0x9e3779b9u, t_f, st, &h->launches)) return e;
-  if (int e = h->raw_f.ensure((size_t)R * S * 16)) return e;
-  if (int e = run_mlp(h, NM_NET_FINE, false, rays_input(t_f, S), h->raw_f.as<float>(), st, emit_f)) return e;
-  return composite(h->raw_f.as<float>(), t_f, S, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
+  return mlp_composite(NM_NET_FINE, h->raw_f, emit_f, t_f, S, o.rgb, o.depth, o.depth_raw, o.acc, o.disp, o.weights, o.mask_weights);
 }
 
 NmRenderOut offset_out(const NmRenderOut& o, long long r0, int S, int Nc) {
@@ -326,9 +329,9 @@ int train_chunk(NmHandle h, const RayBatch& rb, int flags, uint64_t seed, const 
       ws_c = reinterpret_cast<float*>(((uintptr_t)ws_m + ws_main + 1023) & ~(uintptr_t)1023);
       train_emit_setup(h->nets[NM_NET_COARSE].full, R * Nc, ws_c, &em_coarse);
     }
-    if (int e = render_chunk(h, rb, flags, seed, o, st, two ? &em_coarse : &em_main, two ? &em_main : nullptr)) return e;
+    if (int e = render_chunk(h, rb, flags, seed, o, st, two ? &em_coarse : &em_main, two ? &em_main : nullptr, true)) return e;
   } else {
-    if (int e = render_chunk(h, rb, flags, seed, o, st)) return e;
+    if (int e = render_chunk(h, rb, flags, seed, o, st, nullptr, nullptr, true)) return e;
   }
   if (target) {
     for (int i = 0; i < (two ? 2 : 1); ++i) {

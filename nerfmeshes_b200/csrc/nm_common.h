@@ -126,8 +126,13 @@ int debug_pack(const NmNetDesc& d, const WeightSource& src, bool sigma_only, Net
                size_t* need);
 
 // kernel launchers (return 0 / <0; count launches via *launches)
+struct CompositeArgs;
+// comp != nullptr (inference on ray inputs): the compositor runs inside the kernel on the staged outputs of every tile and
+// writes the per-ray maps (and weights, if asked); `out` is not written.  mlp_tc_composite_group(S) == 0: not eligible.
+int mlp_tc_composite_group(int samples_per_ray);
 int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
-                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit = nullptr);
+                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit = nullptr,
+                  const CompositeArgs* comp = nullptr);
 int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout,
                       const MlpEmit& io, int n_passes, int num_sms, int* d_err, cudaStream_t st, int64_t* launches);
 int launch_mlp_simt(const NetDev& net, bool sigma_only, const MlpInput& in, float* out, cudaStream_t st,

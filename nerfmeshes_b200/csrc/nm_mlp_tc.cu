@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "nm_common.h"
+#include "nm_composite.cuh"
 #include "nm_frontend.cuh"
 #include "nm_ptx.cuh"
 
@@ -76,16 +77,23 @@ struct TcParams {
   const float* dz_in;     // (M, dz_ld) fp32: dZ of the last forward layer
   int dz_ld;
   const float* dout;      // (M, 4): compositor adjoint, column 3 = d sigma
+  // fused compositor (mode 0, ray inputs): the last layer's (rgb, sigma) of a tile go to the front-end warps through shared
+  // memory instead of to `out`; they composite every ray in sample order (nm_composite.cuh) and write the per-ray maps.
+  int comp_on;
+  int tile_group;         // tiles per scheduling group = lcm(S, 128) / 128 when compositing (rays never straddle groups), else 1
+  uint32_t off_comp;      // shared memory: [128] float4 staging block, then the carry of the ray cut by the tile edge
+  CompositeArgs comp;
 };
 static_assert(sizeof(TcParams) <= 4096, "TcParams must fit the 4 KB kernel-parameter window");
 
 // barrier slots (8 B each) relative to off_bars
 constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
                    kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kLoadedCnt = 264, kBarDirFull = 272, kBarDirEmpty = 280,
-                   kBarBytes = 320;
+                   kBarRawFull = 288, kBarRawEmpty = 296, kBarBytes = 320;
+constexpr uint32_t kCompBytes = 128 * 16 + 64;
 
 enum : int { ERR_ALIGN = 1, ERR_W_EMPTY = 2, ERR_W_FULL = 3, ERR_PE_FULL = 4, ERR_PE_EMPTY = 5, ERR_CHUNK = 6,
-             ERR_DFULL = 7, ERR_KBFREE = 8 };
+             ERR_DFULL = 7, ERR_KBFREE = 8, ERR_RAW = 9 };
 
 __device__ __forceinline__ uint16_t f16_bits_sat(float a) {
   uint16_t h;
@@ -134,6 +142,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bars + kBarPeFull + 8 * i, 128); ptx::mbar_init(bars + kBarPeEmpty + 8 * i, kIssuers); }
     ptx::mbar_init(bars + kBarDirFull, 128);
     ptx::mbar_init(bars + kBarDirEmpty, kIssuers);
+    ptx::mbar_init(bars + kBarRawFull, 128);
+    ptx::mbar_init(bars + kBarRawEmpty, 1);
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(bars + kBarChunk + 8 * i, 4);
       ptx::mbar_init(bars + kBarDFull + 8 * i, kIssuers);
@@ -173,6 +183,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 
   const float so = P.act_scale, si = P.act_inv_scale;
   const int n_passes = P.n_passes;
+  // i-th tile of this CTA: groups of `tile_group` consecutive tiles are dealt round-robin to the CTAs (group size 1: the plain
+  // strided order).  Returns -1 past the end.
+  const uint32_t Gt = (uint32_t)P.tile_group;
+  auto tile_of = [&](uint32_t i) -> long long {
+    const long long g = (long long)blockIdx.x + (long long)(i / Gt) * (long long)gridDim.x;
+    const long long t = g * (long long)Gt + (long long)(i % Gt);
+    return t < P.n_tiles ? t : -1;
+  };
 
   // Mode 2 (data-gradient chain): the epilogue holds a 32-column slab, its bf16 hi/lo halves and the mask at once and spilled
   // under the 96-register launch budget (17 warps: one SM sub-partition hosts five).  Its front-end warps are idle and the
@@ -192,7 +210,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     uint32_t gl = 0;
     unsigned trace_cursor = 0;
     float sigma_val = 0.f;
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    for (uint32_t it = 0;; ++it) {
+      const long long tile = tile_of(it);
+      if (tile < 0) break;
       const long long m = tile * kTileM + row;
       for (int li = 0; li < n_layers; ++li, ++gl) {
         const LayerProg& L = P.net.layers[li];
@@ -424,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             float* r4 = s_red + 128 + 4 * row;
             if (hcol == 1) { r4[0] = part[0]; r4[1] = part[1]; r4[2] = part[2]; r4[3] = part[3]; }
             ptx::named_bar_sync(2, kEpiWarps * 32);
-            if (hcol == 0 && m < P.in.M && P.out) {
+            if (hcol == 0 && (P.comp_on || (m < P.in.M && P.out))) {
               float o[4];
 #pragma unroll
               for (int hh = 0; hh < 4; ++hh) o[hh] = (hh < heads) ? part[hh] + r4[hh] + hb[hh] : 0.f;
@@ -437,7 +457,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 res.y = 1.f / (1.f + expf(-o[1]));
                 res.z = 1.f / (1.f + expf(-o[2]));
                 res.w = sg;
-                reinterpret_cast<float4*>(P.out)[m] = res;
+                if (MODE == 0 && P.comp_on) {
+                  // hand the tile's outputs to the front-end warps (single staging block: they are a whole tile ahead of us)
+                  ptx::mbar_wait(bars + kBarRawEmpty, (it & 1) ^ 1, P.err, ERR_RAW);
+                  reinterpret_cast<float4*>(smem + P.off_comp)[row] = res;
+                  ptx::mbar_arrive(bars + kBarRawFull);
+                } else {
+                  reinterpret_cast<float4*>(P.out)[m] = res;
+                }
               }
             }
           }
@@ -451,8 +478,47 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const int has_dir = P.net.uses_dir;
     const float* fx = P.net.freq_xyz;
     const float* fd = P.net.freq_dir;
+    // Fused compositor: tile `itp` of this CTA, whose last layer the epilogue has staged in shared memory.  Thread k takes the
+    // k-th ray that has samples in the tile and walks them in order (the same sequential arithmetic as composite_kernel); the
+    // ray cut by the tile's upper edge leaves its running state in the carry slot for thread 0 of the next tile — tiles of a
+    // group are consecutive and groups start on ray boundaries, so that next tile is this CTA's next iteration.
+    auto composite_tile = [&](uint32_t itp) {
+      const long long tp = tile_of(itp);
+      const CompositeArgs& A = P.comp;
+      ptx::mbar_wait(bars + kBarRawFull, itp & 1, P.err, ERR_RAW);
+      const float4* stage = reinterpret_cast<const float4*>(smem + P.off_comp);
+      float* carry = reinterpret_cast<float*>(smem + P.off_comp + 128 * 16);
+      const long long p0 = tp * kTileM, p1 = min(p0 + (long long)kTileM, P.in.M);
+      const int S = A.S;
+      const long long ray = p0 / S + r;
+      const long long s0 = max(ray * (long long)S, p0), s1 = min((ray + 1) * (long long)S, p1);
+      if (s0 < s1) {
+        CompState cs;
+        if (s0 > ray * (long long)S) { cs.T = carry[0]; cs.acc = carry[1]; cs.depth = carry[2]; cs.r = carry[3]; cs.g = carry[4]; cs.b = carry[5]; }
+        else comp_init(cs);
+        const float nrm = comp_ray_norm(A.dirs, ray);
+        const float* tr = A.t + ray * S;
+        int i = (int)(s0 - ray * (long long)S);
+        const int i1 = (int)(s1 - ray * (long long)S);
+        float tc = tr[i];
+        for (; i < i1; ++i) {
+          const float tn = (i + 1 < S) ? tr[i + 1] : 0.f;
+          float mk;
+          const float w = comp_step(cs, A, ray, i, tc, tn, nrm, stage[ray * S + i - p0], &mk);
+          if (A.weights) A.weights[ray * S + i] = w;
+          if (A.mask_weights) A.mask_weights[ray * S + i] = mk;
+          tc = tn;
+        }
+        if (i1 == S) comp_finish(cs, A, ray);
+        else { carry[0] = cs.T; carry[1] = cs.acc; carry[2] = cs.depth; carry[3] = cs.r; carry[4] = cs.g; carry[5] = cs.b; }
+      }
+      ptx::named_bar_sync(3, 128);                 // staging block consumed, carry visible to the next tile's thread 0
+      if (r == 0) ptx::mbar_arrive(bars + kBarRawEmpty);
+    };
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+    for (;; ++it) {
+      const long long tile = tile_of(it);
+      if (tile < 0) break;
       const uint32_t buf = it & 1;
       ptx::mbar_wait(bars + kBarPeEmpty + 8 * buf, ((it >> 1) & 1) ^ 1, P.err, ERR_PE_EMPTY);
       if (MODE == 2) { ptx::mbar_arrive(bars + kBarPeFull + 8 * buf); continue; }   // no encodings in the data-gradient chain
@@ -477,7 +543,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(bars + kBarDirFull);
       }
+      if (MODE == 0 && P.comp_on && it > 0) composite_tile(it - 1);     // the previous tile is finishing while this one starts
     }
+    if (MODE == 0 && P.comp_on && it > 0) composite_tile(it - 1);
   } else if (warp == kProdWarp) {
     // =============================================================== weight producer
     if (lane == 0) {
@@ -485,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       uint32_t ph = 0, issued = 0;
       const uint32_t cnt_addr = bars + kLoadedCnt;
       const uint32_t bytes = (n_passes == 3) ? (uint32_t)kStageBytes : (uint32_t)kHalfStage;
-      for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      for (uint32_t itile = 0; tile_of(itile) >= 0; ++itile) {
         for (int b = 0; b < n_blocks; ++b) {
           ptx::mbar_wait(bars + kBarWEmpty + 8 * slot, ph ^ 1, P.err, ERR_W_EMPTY);
           if (P.dbg & 4) {
@@ -513,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     uint32_t ph = 0, gl = 0, it = 0, cur_pos = 0;
     unsigned trace_cursor = 0;
     const uint32_t cnt_addr = bars + kLoadedCnt;
-    for (long long tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++it) {
+    for (; tile_of(it) >= 0; ++it) {
       const uint32_t buf = it & 1;
       ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
       ptx::tc_fence_after();
@@ -618,7 +686,7 @@ static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* l
   NM_CUDA(cudaGetDevice(&dev));
   NM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const uint32_t fixed = kPeTotal + align_up(hp.n_bias * 4, 16) + align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16) +
-                         (128 + 512) * 4 + kBarBytes;
+                         (128 + 512) * 4 + kBarBytes + (P.comp_on ? kCompBytes : 0u);
   int ns = ((int)max_smem - (int)fixed) / kStageBytes;
   if (ns > kMaxStages) ns = kMaxStages;
   if (const char* e = getenv("NM_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v < ns) ns = v; }
@@ -630,6 +698,8 @@ static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* l
   P.off_head = off; off += align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16);
   P.off_red = off; off += (128 + 512) * 4;
   P.off_bars = off; off += kBarBytes;
+  P.off_comp = off; off += P.comp_on ? kCompBytes : 0u;
+  if (P.tile_group < 1) P.tile_group = 1;
   NM_CHECK((int)off <= max_smem, "shared-memory layout overflow");
 
   const int mode = P.mode == 2 ? 2 : (P.has_emit ? 1 : 0);
@@ -639,7 +709,8 @@ static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* l
     NM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     configured_devs[mode] |= 1u << (dev & 31);
   }
-  long long grid = P.n_tiles < num_sms ? P.n_tiles : num_sms;
+  const long long n_groups = (P.n_tiles + P.tile_group - 1) / P.tile_group;
+  long long grid = n_groups < num_sms ? n_groups : num_sms;
   const char* trace_path = getenv("NM_TC_TRACE");
   const size_t trace_words = 1 + 6 * (size_t)kTraceRegion * 5;
   if (trace_path) {
@@ -659,8 +730,18 @@ static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* l
   return 0;
 }
 
+// Tiles per scheduling group for a fused compositor over S samples per ray (0: not eligible — fall back to raw + composite_kernel)
+int mlp_tc_composite_group(int S) {
+  if (S <= 0) return 0;
+  int a = S, b = kTileM;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const long long l = (long long)S / a * kTileM;      // lcm(S, 128)
+  const long long g = l / kTileM;
+  return g <= 8 ? (int)g : 0;                          // long groups would unbalance the CTAs
+}
+
 int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scale_log2, const MlpInput& in, float* out,
-                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit) {
+                  int num_sms, int* d_err, cudaStream_t st, int64_t* launches, const MlpEmit* emit, const CompositeArgs* comp) {
   if (in.M <= 0) return 0;
   const NetProgram& hp = sigma_only ? net.sigma : net.full;
   TcParams P{};
@@ -677,6 +758,14 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.n_tiles = (in.M + kTileM - 1) / kTileM;
   P.err = d_err;
   if (emit) { P.has_emit = 1; P.emit = *emit; }
+  P.tile_group = 1;
+  if (comp) {
+    NM_CHECK(!emit && !sigma_only && in.mode == IN_RAYS && comp->S == in.S && comp->R * (long long)comp->S == in.M && comp->t == in.t,
+             "fused compositor: needs the ray front end on the compositor's own samples");
+    P.tile_group = mlp_tc_composite_group(comp->S);
+    NM_CHECK(P.tile_group > 0, "fused compositor: %d samples per ray not supported", comp->S);
+    P.comp_on = 1; P.comp = *comp; P.out = nullptr;
+  }
   return launch_prepared(P, num_sms, st, launches);
 }
 

@@ -6,22 +6,10 @@
 #include <math_constants.h>
 
 #include "nm_common.h"
+#include "nm_composite.cuh"
 
 namespace nm {
 namespace {
-
-// counter-based uniform [0,1): splitmix64 of (seed, index).  Used only for perturb / noise (distributional parity).
-__device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
-}
-__device__ __forceinline__ float randn(uint64_t seed, uint64_t idx) {
-  const float a = fmaxf(u01(seed, 2 * idx), 1e-7f), b = u01(seed, 2 * idx + 1);
-  return sqrtf(-2.f * logf(a)) * cospif(2.f * b);
-}
 
 // ------------------------------------------------------------------------------------------------ a1 / a2
 // get_ray_bundle (src/nerf/nerf_helpers.py:226-277) and ndc_rays (:280-307).
@@ -110,36 +98,19 @@ __global__ void composite_kernel(const __grid_constant__ CompositeArgs a) {
   const int S = a.S;
   const float4* raw = reinterpret_cast<const float4*>(a.raw) + ray * S;
   const float* t = a.t + ray * S;
-  const float dx = a.dirs[3 * ray], dy = a.dirs[3 * ray + 1], dz = a.dirs[3 * ray + 2];
-  const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-  float T = 1.0f, acc = 0.f, depth = 0.f, r = 0.f, g = 0.f, b = 0.f;
+  const float nrm = comp_ray_norm(a.dirs, ray);
+  CompState cs;
+  comp_init(cs);
   float tc = t[0];
-  for (int i = 0; i < S; ++i) {
+  for (int i = 0; i < S; ++i) {        // the arithmetic lives in nm_composite.cuh, shared with the fused compositor (nm_mlp_tc.cu)
     const float tn = (i + 1 < S) ? t[i + 1] : 0.f;
-    const float dist = ((i + 1 < S) ? (tn - tc) : 1e10f) * nrm;
-    const float4 q = raw[i];
-    float sg = q.w;
-    if (a.noise_std > 0.f) sg = sg + randn(a.seed, (uint64_t)(ray * S + i)) * a.noise_std;
-    sg = fmaxf(sg, 0.f);
-    const float alpha = 1.0f - expf(-sg * dist);
-    const float w = alpha * T;
+    float mk;
+    const float w = comp_step(cs, a, ray, i, tc, tn, nrm, raw[i], &mk);
     if (a.weights) a.weights[ray * S + i] = w;
-    if (a.mask_weights) a.mask_weights[ray * S + i] = (T > a.thr) ? 1.f : 0.f;
-    r = r + w * q.x; g = g + w * q.y; b = b + w * q.z;
-    acc = acc + w;
-    depth = depth + w * tc;
-    T = T * (1.0f - alpha + 1e-10f);
+    if (a.mask_weights) a.mask_weights[ray * S + i] = mk;
     tc = tn;
   }
-  float disp = 1.0f / fmaxf(1e-10f, depth / acc);
-  if (isnan(disp)) disp = 0.f;          // fmaxf drops a NaN operand; torch.max propagates it, then :107 zeroes it
-  if (isnan(depth / acc)) disp = 0.f;
-  if (a.depth_raw) a.depth_raw[ray] = depth;
-  if (a.depth) a.depth[ray] = (!a.training && acc < 1.0f) ? 0.f : depth;
-  if (a.white_bg) { const float bg = 1.0f - acc; r = r + bg; g = g + bg; b = b + bg; }
-  if (a.rgb) { a.rgb[3 * ray] = r; a.rgb[3 * ray + 1] = g; a.rgb[3 * ray + 2] = b; }
-  if (a.acc) a.acc[ray] = acc;
-  if (a.disp) a.disp[ray] = disp;
+  comp_finish(cs, a, ray);
 }
 
 // ------------------------------------------------------------------------------------------------ a8

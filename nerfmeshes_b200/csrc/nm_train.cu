@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 
 #include "nm_common.h"
+#include "nm_composite.cuh"
 #include "nm_frontend.cuh"
 #include "nm_gemm.h"
 
@@ -442,18 +443,6 @@ __global__ void __launch_bounds__(256) head_backward_kernel(const float* __restr
 // VolumeRenderer.forward (src/nerf/modules.py:67-121) differentiated w.r.t. the raw network outputs, for a loss that
 // reads rgb_map only (model_nerf.py:118-126).  raw = (sigmoid rgb, raw sigma) as the forward kernels store it.
 // Same arithmetic / noise stream as composite_kernel (nm_render.cu).
-__device__ __forceinline__ float u01(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
-}
-__device__ __forceinline__ float randn(uint64_t seed, uint64_t idx) {
-  const float a = fmaxf(u01(seed, 2 * idx), 1e-7f), b = u01(seed, 2 * idx + 1);
-  return sqrtf(-2.f * logf(a)) * cospif(2.f * b);
-}
-
 struct CompositeBwdArgs {
   const float* raw;   // (R,S,4)
   const float* t;     // (R,S)
@@ -497,7 +486,7 @@ __global__ void __launch_bounds__(128) composite_backward_kernel(const __grid_co
       q[u] = raw[i];
       dist[u] = ((i + 1 < S) ? (t[i + 1] - t[i]) : 1e10f) * nrm;
       float sg = q[u].w;
-      if (a.noise_std > 0.f) sg = sg + randn(a.seed, (uint64_t)(ray * S + i)) * a.noise_std;
+      if (a.noise_std > 0.f) sg = __fadd_rn(sg, __fmul_rn(randn(a.seed, (uint64_t)(ray * S + i)), a.noise_std));   // as comp_step
       pre[u] = sg;
       const float alpha = 1.0f - expf(-fmaxf(sg, 0.f) * dist[u]);
       keep[u] = 1.0f - alpha + 1e-10f;

@@ -397,3 +397,59 @@ def test_eval_loop_device_resident(lego_model, tmp_path):
     assert torch.equal(q.rgb_map.view(H, W, 3).cpu(), res["rgb"][0])   # same rays -> bit-identical (deterministic path)
     oo, dd = O.get_ray_bundle(H, W, f, torch.as_tensor(poses[0], dtype=torch.float32))
     close(d.cpu(), dd, 2e-6, name="eval rays vs oracle rays")
+
+
+@pytest.mark.parametrize("case", ["lego_64_128", "s96_group3", "s48_white_training_noise", "s16_coarse_only", "s33_not_eligible", "buff_192"])
+def test_fused_compositor_equals_two_kernel_path(case, monkeypatch):
+    """The compositor fused into the MLP kernel (the last layer's outputs go to the front-end warps through shared memory; per-
+    sample network outputs never reach HBM) against the two-kernel path (raw (R,S,4) to HBM + composite_kernel): the same
+    sequential arithmetic (csrc/nm_composite.cuh) => every output map, weights and masks included, bit-identical.  Cases:
+    rays of 0.5 / 1.5 tiles (lego), 0.75 tiles in groups of 3 (S=96), S=48 with a white background, training mode, jitter
+    and sigma noise (same seed), 8 rays per tile (S=16), a sample count whose group would be too long (S=33: falls back),
+    the BuFF sampler; ragged ray counts throughout."""
+    import nerfmeshes_b200 as nm
+    all_out = ["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights", "t_vals", "coarse_rgb", "coarse_acc", "coarse_disp",
+               "coarse_weights"]
+    training, buff, seed = False, False, 3
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    if case == "buff_192":
+        model = nm.BuFFModel.from_npz(BUFF_CFG, load_npz("weights_lego_buff.npz")).cuda().eval()
+        gg = load_npz("golden_lego_buff.npz")
+        o, d, near, far, buff = gg["origin"][None].cuda(), gg["dirs"].cuda(), float(gg["bounds"][0]), float(gg["bounds"][1]), True
+        model._sync_tree(model._engine())
+        want = all_out[:8]
+    else:
+        net = O.NetCfg() if case == "lego_64_128" else O.NetCfg(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)
+        nc, nf = {"lego_64_128": (64, 128), "s96_group3": (40, 56), "s48_white_training_noise": (20, 28), "s16_coarse_only": (16, 0),
+                  "s33_not_eligible": (33, 31)}[case]
+        cfg = _cfg(net, net if nf else None, nc=nc, nf=nf, white=case.startswith("s48"))
+        if case.startswith("s48"):
+            cfg.update({"nerf.train.perturb": True, "nerf.train.radiance_field_noise_std": 0.7})
+            training = True
+        model = nm.NeRFModel(cfg).cuda()
+        model = model.train() if training else model.eval()
+        model.model_coarse.load_state_dict(O.init_weights(net, 41), strict=False)
+        if nf:
+            model.model_fine.load_state_dict(O.init_weights(net, 42), strict=False)
+        R = 4099 if case == "lego_64_128" else 1237
+        o = (torch.randn(3, generator=g) * 0.2).cuda()
+        d = torch.randn(R, 3, generator=g).cuda()
+        near, far = 0.5, 3.0
+        want = all_out if nf else all_out[:8]
+    eng = model._engine()
+
+    def run():
+        with torch.no_grad():
+            return {k: v.clone() for k, v in eng.render_rays(o, d, near, far, training=training, buff=buff, seed=seed, want=want).items()}
+    monkeypatch.setenv("NM_FUSED_COMPOSITE", "0")
+    n0 = eng.launch_count()
+    two = run()
+    monkeypatch.setenv("NM_FUSED_COMPOSITE", "1")
+    n1 = eng.launch_count()
+    one = run()
+    n2 = eng.launch_count()
+    passes = 2 if "coarse_rgb" in want else 1
+    assert (n1 - n0) - (n2 - n1) == (0 if case == "s33_not_eligible" else passes)      # one composite_kernel less per network pass
+    for k in want:
+        assert torch.equal(one[k], two[k]), (case, k, float((one[k] - two[k]).abs().max()))
+    assert torch.isfinite(one["rgb"]).all() and float(one["acc"].max()) > 0.0
