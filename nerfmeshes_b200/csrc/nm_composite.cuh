@@ -38,17 +38,27 @@ __device__ __forceinline__ float comp_ray_norm(const float* __restrict__ dirs, l
   return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
 
-// sample i of `ray`: tc = t[i], tn = t[i+1] (unused for the last sample), q = (sigmoid rgb, raw sigma).  Returns the weight.
-__device__ __forceinline__ float comp_step(CompState& s, const CompositeArgs& a, long long ray, int i, float tc, float tn,
-                                           float nrm, float4 q, float* mask_out) {
+// sample i of `ray`: tc = t[i], tn = t[i+1] (unused for the last sample), sigma_raw = the network's raw density.
+// Returns alpha_i; *keep = 1 - alpha_i + 1e-10, the factor of the transmittance product.
+__device__ __forceinline__ float comp_alpha(const CompositeArgs& a, long long ray, int i, float tc, float tn, float nrm,
+                                            float sigma_raw, float* keep) {
   const int S = a.S;
   const float dist = __fmul_rn((i + 1 < S) ? __fsub_rn(tn, tc) : 1e10f, nrm);
-  float sg = q.w;
+  float sg = sigma_raw;
   if (a.noise_std > 0.f) sg = __fadd_rn(sg, __fmul_rn(randn(a.seed, (uint64_t)(ray * S + i)), a.noise_std));
   sg = fmaxf(sg, 0.f);
   float e = expf(__fmul_rn(-sg, dist));
   asm volatile("" : "+f"(e));
   const float alpha = __fsub_rn(1.0f, e);
+  *keep = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+  return alpha;
+}
+
+// one sample of the sequential walk: q = (sigmoid rgb, raw sigma).  Returns the weight.
+__device__ __forceinline__ float comp_step(CompState& s, const CompositeArgs& a, long long ray, int i, float tc, float tn,
+                                           float nrm, float4 q, float* mask_out) {
+  float keep;
+  const float alpha = comp_alpha(a, ray, i, tc, tn, nrm, q.w, &keep);
   const float w = __fmul_rn(alpha, s.T);
   *mask_out = (s.T > a.thr) ? 1.f : 0.f;
   s.r = __fadd_rn(s.r, __fmul_rn(w, q.x));
@@ -56,7 +66,7 @@ __device__ __forceinline__ float comp_step(CompState& s, const CompositeArgs& a,
   s.b = __fadd_rn(s.b, __fmul_rn(w, q.z));
   s.acc = __fadd_rn(s.acc, w);
   s.depth = __fadd_rn(s.depth, __fmul_rn(w, tc));
-  s.T = __fmul_rn(s.T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+  s.T = __fmul_rn(s.T, keep);
   return w;
 }
 

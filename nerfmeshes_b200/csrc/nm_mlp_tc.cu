@@ -81,7 +81,7 @@ struct TcParams {
   // memory instead of to `out`; they composite every ray in sample order (nm_composite.cuh) and write the per-ray maps.
   int comp_on;
   int tile_group;         // tiles per scheduling group = lcm(S, 128) / 128 when compositing (rays never straddle groups), else 1
-  uint32_t off_comp;      // shared memory: [128] float4 staging block, then the carry of the ray cut by the tile edge
+  uint32_t off_comp;      // shared memory of the fused compositor (kCompBytes)
   CompositeArgs comp;
 };
 static_assert(sizeof(TcParams) <= 4096, "TcParams must fit the 4 KB kernel-parameter window");
@@ -90,7 +90,7 @@ static_assert(sizeof(TcParams) <= 4096, "TcParams must fit the 4 KB kernel-param
 constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
                    kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kLoadedCnt = 264, kBarDirFull = 272, kBarDirEmpty = 280,
                    kBarRawFull = 288, kBarRawEmpty = 296, kBarBytes = 320;
-constexpr uint32_t kCompBytes = 128 * 16 + 64;
+constexpr uint32_t kCompBytes = 128 * 16 + 128 * 4 + 128 * 4 + 64;   // staged q / products, keep / T, weights, two carry slots
 
 enum : int { ERR_ALIGN = 1, ERR_W_EMPTY = 2, ERR_W_FULL = 3, ERR_PE_FULL = 4, ERR_PE_EMPTY = 5, ERR_CHUNK = 6,
              ERR_DFULL = 7, ERR_KBFREE = 8, ERR_RAW = 9 };
@@ -478,41 +478,88 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     const int has_dir = P.net.uses_dir;
     const float* fx = P.net.freq_xyz;
     const float* fd = P.net.freq_dir;
-    // Fused compositor: tile `itp` of this CTA, whose last layer the epilogue has staged in shared memory.  Thread k takes the
-    // k-th ray that has samples in the tile and walks them in order (the same sequential arithmetic as composite_kernel); the
-    // ray cut by the tile's upper edge leaves its running state in the carry slot for thread 0 of the next tile — tiles of a
-    // group are consecutive and groups start on ray boundaries, so that next tile is this CTA's next iteration.
+    // Fused compositor: tile `itp` of this CTA, whose last layer the epilogue has staged in shared memory.  Same arithmetic,
+    // in the same order, as composite_kernel (nm_composite.cuh) — but laid out for few issue slots, because these warps share
+    // their schedulers with the epilogue warps:  A  every thread takes ONE sample: alpha, keep (the exp lives here);
+    // B  one thread per ray segment runs the transmittance product chain through shared memory;  C  every thread: weight,
+    // mask, the four products;  D  one lane per (segment, accumulator) runs the five ordered sums.  The ray cut by the tile's
+    // upper edge leaves T and its partial sums in a carry slot for the next tile (tiles of a group are consecutive in this
+    // CTA and groups start on ray boundaries).
     auto composite_tile = [&](uint32_t itp) {
       const long long tp = tile_of(itp);
       const CompositeArgs& A = P.comp;
       ptx::mbar_wait(bars + kBarRawFull, itp & 1, P.err, ERR_RAW);
-      const float4* stage = reinterpret_cast<const float4*>(smem + P.off_comp);
-      float* carry = reinterpret_cast<float*>(smem + P.off_comp + 128 * 16);
+      float4* stage = reinterpret_cast<float4*>(smem + P.off_comp);            // q per sample, later (w r, w g, w b, w t)
+      float* keepT = reinterpret_cast<float*>(smem + P.off_comp + 2048);       // keep per sample, later T
+      float* wv = keepT + 128;                                                 // weight per sample
+      const float* carry_in = wv + 128 + ((itp & 1) ^ 1) * 8;                  // written by the previous tile
+      float* carry_out = wv + 128 + (itp & 1) * 8;
       const long long p0 = tp * kTileM, p1 = min(p0 + (long long)kTileM, P.in.M);
       const int S = A.S;
-      const long long ray = p0 / S + r;
-      const long long s0 = max(ray * (long long)S, p0), s1 = min((ray + 1) * (long long)S, p1);
-      if (s0 < s1) {
-        CompState cs;
-        if (s0 > ray * (long long)S) { cs.T = carry[0]; cs.acc = carry[1]; cs.depth = carry[2]; cs.r = carry[3]; cs.g = carry[4]; cs.b = carry[5]; }
-        else comp_init(cs);
-        const float nrm = comp_ray_norm(A.dirs, ray);
+      const long long ray_first = p0 / S;
+      const int n_seg = (int)((p1 - 1) / S - ray_first) + 1;
+      // ---- A
+      const long long p = p0 + r;
+      const bool live = p < p1;
+      float tc = 0.f, alpha = 0.f;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const long long ray = p / S;
+        const int i = (int)(p - ray * S);
         const float* tr = A.t + ray * S;
-        int i = (int)(s0 - ray * (long long)S);
-        const int i1 = (int)(s1 - ray * (long long)S);
-        float tc = tr[i];
-        for (; i < i1; ++i) {
-          const float tn = (i + 1 < S) ? tr[i + 1] : 0.f;
-          float mk;
-          const float w = comp_step(cs, A, ray, i, tc, tn, nrm, stage[ray * S + i - p0], &mk);
-          if (A.weights) A.weights[ray * S + i] = w;
-          if (A.mask_weights) A.mask_weights[ray * S + i] = mk;
-          tc = tn;
-        }
-        if (i1 == S) comp_finish(cs, A, ray);
-        else { carry[0] = cs.T; carry[1] = cs.acc; carry[2] = cs.depth; carry[3] = cs.r; carry[4] = cs.g; carry[5] = cs.b; }
+        tc = tr[i];
+        const float tn = (i + 1 < S) ? tr[i + 1] : 0.f;
+        q = stage[r];
+        float keep;
+        alpha = comp_alpha(A, ray, i, tc, tn, comp_ray_norm(A.dirs, ray), q.w, &keep);
+        keepT[r] = keep;
       }
-      ptx::named_bar_sync(3, 128);                 // staging block consumed, carry visible to the next tile's thread 0
+      ptx::named_bar_sync(3, 128);
+      // ---- B
+      for (int k = r; k < n_seg; k += 128) {
+        const long long rayk = ray_first + k;
+        const long long s0 = max(rayk * (long long)S, p0), s1 = min((rayk + 1) * (long long)S, p1);
+        float T = (s0 > rayk * (long long)S) ? carry_in[0] : 1.0f;
+        for (int j = (int)(s0 - p0); j < (int)(s1 - p0); ++j) { const float kp = keepT[j]; keepT[j] = T; T = __fmul_rn(T, kp); }
+        if (s1 < (rayk + 1) * (long long)S) carry_out[0] = T;
+      }
+      ptx::named_bar_sync(3, 128);
+      // ---- C
+      if (live) {
+        const float T = keepT[r];
+        const float w = __fmul_rn(alpha, T);
+        if (A.weights) A.weights[p] = w;
+        if (A.mask_weights) A.mask_weights[p] = (T > A.thr) ? 1.f : 0.f;
+        wv[r] = w;
+        stage[r] = make_float4(__fmul_rn(w, q.x), __fmul_rn(w, q.y), __fmul_rn(w, q.z), __fmul_rn(w, tc));
+      }
+      ptx::named_bar_sync(3, 128);
+      // ---- D: lane c of an 8-lane group owns accumulator c (r, g, b, acc, depth) of the group's segment
+      for (int k0 = 0; k0 < n_seg; k0 += 16) {
+        const int k = k0 + (r >> 3), c = r & 7;
+        const long long rayk = ray_first + k;
+        const long long s0 = max(rayk * (long long)S, p0), s1 = min((rayk + 1) * (long long)S, p1);
+        const bool act = k < n_seg && c < 5;
+        float sum = 0.f;
+        if (act) {
+          if (s0 > rayk * (long long)S) sum = carry_in[1 + c];
+          const float* src = (c == 3) ? wv : reinterpret_cast<const float*>(stage) + (c == 4 ? 3 : c);
+          const int stride = (c == 3) ? 1 : 4;
+          for (int j = (int)(s0 - p0); j < (int)(s1 - p0); ++j) sum = __fadd_rn(sum, src[j * stride]);
+        }
+        const float s_g = __shfl_down_sync(0xffffffffu, sum, 1), s_b = __shfl_down_sync(0xffffffffu, sum, 2);
+        const float s_a = __shfl_down_sync(0xffffffffu, sum, 3), s_d = __shfl_down_sync(0xffffffffu, sum, 4);
+        if (act && c == 0) {
+          if (s1 == (rayk + 1) * (long long)S) {
+            CompState cs;
+            cs.T = 0.f; cs.r = sum; cs.g = s_g; cs.b = s_b; cs.acc = s_a; cs.depth = s_d;
+            comp_finish(cs, A, rayk);
+          } else {
+            carry_out[1] = sum; carry_out[2] = s_g; carry_out[3] = s_b; carry_out[4] = s_a; carry_out[5] = s_d;
+          }
+        }
+      }
+      ptx::named_bar_sync(3, 128);                 // staging block consumed, carry visible to the next tile
       if (r == 0) ptx::mbar_arrive(bars + kBarRawEmpty);
     };
     uint32_t it = 0;
