@@ -559,11 +559,13 @@ def main():
         r["dev_ms"] = dev_ms
         blk = render_block(prim, r, ctx, a.steps, peak_tf, peak_src)
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_mlp_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_mlp_traffic.json")
         if os.path.exists(tp) and prim == "lego":
             traffic = json.load(open(tp)).get("mean_bytes_per_launch")       # ncu dram read+write per MLP launch, full-image launch
         blk["roofline"]["traffic"] = traffic
-        blk["roofline"]["traffic_note"] = ("DRAM bytes per full-image launch (ncu, profiles/); algorithmic 20 B/point (t in, raw out)")
+        blk["roofline"]["traffic_note"] = ("mean DRAM bytes per full-image MLP launch (ncu, profiles/r02_mlp_traffic.json): the compositor runs "
+                                           "inside the kernel, so a launch reads t (4 B/sample) and writes the per-ray maps (+ the coarse pass's "
+                                           "weights, 4 B/sample); round 1 wrote raw (R,S,4): 1.62 GB per launch")
         result.update({"value": blk["value"], "ms_per_step": blk["ms_per_step"], "clocks": r["clk"], "finite": r["finite"],
                        "gpu_launches": r["launches"], "roofline": blk["roofline"],
                        "e2e": {"value": r["rays"] / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": r["h2d"],
