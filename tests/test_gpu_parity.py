@@ -454,3 +454,27 @@ def test_fused_compositor_equals_two_kernel_path(case, monkeypatch):
     fewer = {"s33_not_eligible": 1 if "coarse_rgb" in want else 0}.get(case, passes)    # S=33+31=64 still fuses the fine pass
     assert (n1 - n0) - (n2 - n1) == fewer, (n0, n1, n2)                                  # one composite_kernel less per fused pass
     assert torch.isfinite(one["rgb"]).all() and float(one["acc"].max()) > 0.0
+
+
+def test_edge_cases_empty_single_and_one_past_a_tile():
+    """Empty batches are legal no-ops with correctly shaped outputs; a single ray, and ray counts that put one sample past a
+    128-point tile (the fused compositor's carry across a tile edge with nothing after it), agree with the oracle."""
+    import nerfmeshes_b200 as nm
+    net = O.NetCfg(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)
+    sdc, sdf = O.init_weights(net, 51), O.init_weights(net, 52)
+    model = nm.NeRFModel(_cfg(net, net, nc=64, nf=128)).cuda().eval()
+    model.model_coarse.load_state_dict(sdc, strict=False)
+    model.model_fine.load_state_dict(sdf, strict=False)
+    eng = model._engine()
+    o = torch.tensor([0.1, -0.2, 0.3])
+    out = eng.render_rays(o.cuda(), torch.zeros(0, 3).cuda(), 0.5, 3.0, want=["rgb", "acc", "weights", "t_vals"])
+    assert out["rgb"].shape == (0, 3) and out["acc"].shape == (0,) and out["weights"].shape == (0, 192) and out["t_vals"].shape == (0, 192)
+    pts = eng.point_mlp(0, torch.zeros(0, 3).cuda(), torch.zeros(0, 3).cuda())
+    assert pts.shape[0] == 0
+    g = torch.Generator().manual_seed(77)
+    for R in (1, 2, 3):           # 192, 384, 576 fine samples: 1.5, 3, 4.5 tiles; 64, 128, 192 coarse samples
+        d = torch.randn(R, 3, generator=g)
+        got = eng.render_rays(o.cuda(), d.cuda(), 0.5, 3.0, want=["rgb", "acc", "depth_raw", "coarse_rgb"])
+        bc, bf, _, _ = O.nerf_forward(sdc, sdf, net, net, O.RenderCfg(), o[None], d, torch.tensor(0.5), torch.tensor(3.0))
+        assert float((got["rgb"].cpu() - bf.rgb_map).abs().max()) <= 1e-4 and float((got["coarse_rgb"].cpu() - bc.rgb_map).abs().max()) <= 1e-4
+        assert float((got["acc"].cpu() - bf.acc_map).abs().max()) <= 1e-4
