@@ -250,6 +250,11 @@ int nm_debug_pack(const NmNetDesc* desc, int n_tensors, const char* const* names
                   const int64_t* numel, int sigma_only, void* program_out, size_t program_cap, uint8_t* pack_out,
                   size_t pack_cap, size_t* pack_need);
 
+/* Host-only: how the fused compositor deals tiles to CTAs for `samples_per_ray` samples (nm_mlp_tc.cu).  Returns the group
+ * size g = lcm(S,128)/128 (0: the fused compositor is not used for this S); if tiles_out != NULL it receives the tile
+ * indices CTA `cta` of `grid` CTAs processes, in order, for a launch of n_tiles tiles (at most cap entries; *n_out = count). */
+int nm_debug_tile_schedule(int samples_per_ray, int64_t n_tiles, int grid, int cta, int64_t* tiles_out, int64_t cap, int64_t* n_out);
+
 /* Device-side error flags, readable even after a kernel trapped: out2[0] = tcgen05 pipeline watchdog code (0 = ok),
  * out2[1] = AABB hit-list overflow. */
 int nm_kernel_flags(NmHandle h, int32_t* out2);

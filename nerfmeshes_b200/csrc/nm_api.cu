@@ -860,6 +860,22 @@ int nm_kernel_flags(NmHandle h, int32_t* out2) {
 
 int64_t nm_launch_count(NmHandle h) { return h ? h->launches : -1; }
 
+int nm_debug_tile_schedule(int samples_per_ray, int64_t n_tiles, int grid, int cta, int64_t* tiles_out, int64_t cap, int64_t* n_out) {
+  const int g = mlp_tc_composite_group(samples_per_ray);
+  if (tiles_out && n_out) {
+    const int64_t gt = g > 0 ? g : 1;       // the kernel's tile_of(): groups of gt consecutive tiles dealt round-robin
+    int64_t n = 0;
+    for (int64_t i = 0;; ++i) {
+      const int64_t grp = cta + (i / gt) * grid, t = grp * gt + (i % gt);
+      if (t >= n_tiles) break;
+      if (n < cap) tiles_out[n] = t;
+      ++n;
+    }
+    *n_out = n;
+  }
+  return g;
+}
+
 int nm_set_timing(NmHandle h, int enable) {
   NM_CHECK(h, "null handle");
   h->timing = enable != 0;

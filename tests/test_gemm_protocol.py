@@ -85,3 +85,68 @@ def test_persistent_gemm_protocol_all_small_shapes():
     for NS, nk, tiles in itertools.product((2, 3), (1, 2, 3, 4, 5, 7), (1, 2, 3, 5, 16)):
         for seed in range(3):
             run(NS, nk, tiles, seed)
+
+
+def run_split_k_with_row_sums(NS, nk, seed):
+    """The split-K (weight-gradient) variant with a_rowsum: one tile per CTA, and the 16 epilogue warps first walk the stage
+    ring as READERS of the A tiles (row sums = bias gradient), arriving on empty[s] next to the MMA warp's commit — so
+    empty[s] counts 1 + 16 arrivals and the producer may only refill a stage once both kinds of consumer are done."""
+    full = [Bar(f"full{s}", 1) for s in range(NS)]
+    empty = [Bar(f"empty{s}", 1 + EPI_WARPS) for s in range(NS)]
+    acc_full = Bar("acc_full", 1)
+    stage = [None] * NS
+    summed = [[] for _ in range(EPI_WARPS)]
+    done = []
+
+    def wait(bar, k):
+        while not bar.done(k):
+            yield
+
+    def producer():
+        for it in range(nk):
+            s = it % NS
+            if it >= NS:
+                yield from wait(empty[s], it // NS - 1)
+            stage[s] = it
+            full[s].arrive()
+            yield
+
+    def mma():
+        for it in range(nk):
+            s = it % NS
+            yield from wait(full[s], it // NS)
+            assert stage[s] == it
+            empty[s].arrive()
+            yield
+        acc_full.arrive()
+
+    def epilogue(w):
+        for it in range(nk):                            # row-sum readers
+            s = it % NS
+            yield from wait(full[s], it // NS)
+            assert stage[s] == it, f"row-sum warp {w} expected K block {it}, stage {s} holds {stage[s]}"
+            summed[w].append(it)
+            yield
+            empty[s].arrive()
+        yield from wait(acc_full, 0)
+        done.append(w)
+
+    agents = [producer(), mma()] + [epilogue(w) for w in range(EPI_WARPS)]
+    rng = random.Random(seed)
+    alive = list(range(len(agents)))
+    for _ in range(400000):
+        if not alive:
+            break
+        a = rng.choice(alive)
+        try:
+            next(agents[a])
+        except StopIteration:
+            alive.remove(a)
+    assert not alive, f"deadlock: NS={NS} nk={nk}, agents left {alive}"
+    assert sorted(done) == list(range(EPI_WARPS)) and all(x == list(range(nk)) for x in summed)
+
+
+def test_split_k_row_sum_readers_share_the_stage_ring():
+    for NS, nk in itertools.product((2, 3), (1, 2, 3, 4, 7, 9, 16)):
+        for seed in range(3):
+            run_split_k_with_row_sums(NS, nk, seed)

@@ -378,3 +378,37 @@ def test_configure_optimizers_matches_reference_schedule():
     cfg2 = {**cfg, "scheduler.type": "StepLR", "scheduler.options.gamma": 0.5, "scheduler.options.step_size": 10}
     (opt2,), (sd2,) = nm.NeRFModel(cfg2).configure_optimizers()
     assert isinstance(sd2["scheduler"], torch.optim.lr_scheduler.StepLR)
+
+
+def test_fused_compositor_tile_schedule_covers_every_tile_once_and_never_splits_a_ray_across_ctas():
+    """nm_mlp_tc.cu deals tiles to CTAs in groups of lcm(S,128)/128 consecutive tiles when the compositor is fused (host mirror
+    of the kernel's tile_of(), nm_debug_tile_schedule): every tile exactly once, a CTA's tiles of one group consecutive and in
+    order (the carry of a ray cut by a tile edge goes to that CTA's NEXT iteration), groups starting on ray boundaries."""
+    import ctypes as C
+    import math
+    from nerfmeshes_b200 import _lib as L
+    lib = L.load()
+    for S in (1, 16, 32, 33, 48, 64, 96, 100, 128, 192, 256, 320, 384):
+        g = lib.nm_debug_tile_schedule(S, 0, 1, 0, None, 0, None)
+        lcm = S * 128 // math.gcd(S, 128)
+        assert g == (lcm // 128 if lcm // 128 <= 8 else 0), (S, g)
+        if g == 0:
+            continue
+        for rays, grid in ((1, 3), (7, 2), (1000, 148), (12345, 148)):
+            n_tiles = (rays * S + 127) // 128
+            grid = min(grid, (n_tiles + g - 1) // g)
+            seen = []
+            for cta in range(grid):
+                buf = (C.c_int64 * (n_tiles + 1))()
+                n = C.c_int64()
+                assert lib.nm_debug_tile_schedule(S, n_tiles, grid, cta, buf, n_tiles + 1, C.byref(n)) == g
+                mine = list(buf[:n.value])
+                seen += mine
+                for a, b in zip(mine, mine[1:]):
+                    if b // g == a // g:
+                        assert b == a + 1                       # inside a group: consecutive tiles, consecutive iterations
+                    else:
+                        assert a % g == g - 1 or a == n_tiles - 1   # a group is finished before the next one starts
+                        assert b % g == 0 and (b * 128) % S == 0    # and the next one starts on a ray boundary
+                assert not mine or (mine[0] * 128) % S == 0
+            assert sorted(seen) == list(range(n_tiles)), (S, rays, grid)
