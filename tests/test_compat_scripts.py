@@ -62,3 +62,28 @@ def test_overlay_modules_serve_the_mesh_script_call_sequence(tmp_path):
         sys.path.remove(os.path.join(ROOT, "compat"))
         for m in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "nerf" or k.startswith("nerf.") or k.startswith("skimage")]:
             del sys.modules[m]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF + "/src"), reason="reference tree not on this machine")
+def test_reference_databundle_ndc_reaches_the_library_through_the_overlay(tmp_path):
+    """The reference's only caller of ndc_rays is DataBundle.ndc() (src/data/data_helpers.py:164-167), which passes the rays
+    positionally.  With compat/ in front of the reference's src/ its `from nerf.nerf_helpers import ndc_rays` binds the
+    overlay's function; the call must reach nm_ndc_rays — on a machine without a GPU that means the library's loud
+    'needs a CUDA device' error, not a signature error and not a CPU fallback."""
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {REF + '/src'!r}); sys.path.insert(0, {os.path.join(ROOT, 'compat')!r}); sys.path.insert(0, {ROOT!r})\n"
+        "from data.data_helpers import DataBundle\n"
+        "H, W, f = 6, 8, 7.5\n"
+        "b = DataBundle(ray_origins=torch.tensor([0.1, 0.2, 0.9]), ray_directions=-torch.rand(H, W, 3) - 0.1, hwf=(H, W, f))\n"
+        "try:\n"
+        "    b.ndc()\n"
+        "    print('NDC_OK', tuple(b.ray_origins.shape), tuple(b.ray_directions.shape))\n"
+        "except Exception as e:\n"
+        "    print('NDC_ERR', type(e).__name__, e)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    out = r.stdout + r.stderr
+    if torch.cuda.is_available():
+        assert "NDC_OK (6, 8, 3) (6, 8, 3)" in out, out[-2000:]
+    else:
+        assert "NDC_ERR" in out and "CUDA device" in out and "TypeError" not in out and "ValueError" not in out, out[-2000:]

@@ -154,6 +154,14 @@ def test_ray_bundle_and_ndc():
     close(on, g["ndc_o"], 5e-6, 5e-6, name="ndc origins")
     close(dn, g["ndc_d"], 5e-6, 5e-6, name="ndc dirs")
     assert np.array_equal(nm.pose_spherical(30.0, -30.0, 4.0), O.pose_spherical(30.0, -30.0, 4.0).numpy())
+    # the reference's positional call — DataBundle.ndc(): ndc_rays(*hwf, 1.0, ray_origins[None, None, :], ray_directions)
+    # (src/data/data_helpers.py:164-167) — on caller-supplied rays, CPU tensors in / CPU tensors out, and CUDA in / CUDA out
+    on2, dn2 = nm.ndc_rays(H, W, f, 1.0, g["origin"][None, None, :], g["dirs"])
+    assert not on2.is_cuda and on2.shape == g["dirs"].shape
+    close(on2, g["ndc_o"], 5e-6, 5e-6, name="ndc origins (positional)")
+    close(dn2, g["ndc_d"], 5e-6, 5e-6, name="ndc dirs (positional)")
+    on3, dn3 = nm.ndc_rays(H, W, f, 1.0, g["origin"].cuda()[None, None, :], g["dirs"].cuda())
+    assert on3.is_cuda and torch.equal(on3.cpu(), on2) and torch.equal(dn3.cpu(), dn2)
 
 
 # ----------------------------------------------------------------------------------------------------- NeRF pipeline
