@@ -163,7 +163,51 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const __grid_c
     // 32 rows x 16 columns.  A thread owns one accumulator row; each block is transposed through a per-warp staging tile
     // so that global accesses are contiguous row segments: a lane then handles 4 columns of rows sub, sub+8, ...
     // The epilogue is instruction-latency bound, hence many warps with short dependent chains rather than few wide ones.
-    if (sum_rows) {
+    if (sum_rows && (P.seg[0].mn & 1)) {
+      // MN-major A tile: [feature group of 64][K row (point) 0..63][128 B = 8 chunks of 8 features, chunk ^= row & 7].  Thread t
+      // owns the 8 features of chunk column fc = t % 16 (group fc / 8, chunk fc % 8) over the two K rows 2 * (t / 16) + {0, 1}.
+      const int t = (int)threadIdx.x;                      // 0..511: the 16 epilogue warps
+      const int fc = t & 15, r2 = (t >> 4) * 2;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      for (int kk = 0; kk < nk; ++kk) {
+        const int s = kk % NS;
+        ptx::mbar_wait(full(s), (uint32_t)((kk / NS) & 1), P.err, 95);
+        const uint8_t* at = smem + (size_t)s * STAGE + (size_t)(fc >> 3) * 8192u;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int row = r2 + u;
+          const uint32_t off = (uint32_t)row * 128u + (uint32_t)((((fc & 7) ^ (row & 7))) << 4);
+          const uint4 h = *reinterpret_cast<const uint4*>(at + off);
+          const uint4 l = *reinterpret_cast<const uint4*>(at + kPtileHalf + off);
+          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[2 * e] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            acc[2 * e + 1] += __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(empty(s));
+      }
+      // fold the 32 row slices: lanes l and l ^ 16 share fc; then one shared-memory accumulator per feature across the warps
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+      float* red = reinterpret_cast<float*>(smem + kStgOff);            // epilogue staging, not in use yet
+      if (t < 128) red[t] = 0.f;
+      ptx::named_bar_sync(1, kEpiWarps * 32);
+      if (lane < 16) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(red + fc * 8 + e, acc[e]);
+      }
+      ptx::named_bar_sync(1, kEpiWarps * 32);
+      if (t < 128) {
+        const int row = (int)blockIdx.x * 128 + t;
+        if (row < P.M) atomicAdd(P.a_rowsum + row, red[t]);
+      }
+      ptx::named_bar_sync(1, kEpiWarps * 32);                           // red[] is the staging area of the epilogue below
+    } else if (sum_rows) {
       // Row sums of the A tiles while the MMA warp consumes them: warp w owns rows 8w..8w+7, 8 lanes cover one 128-byte row
       // (64 K elements; the swizzle only permutes chunks within the row, irrelevant for a sum), hi + lo halves.
       float acc[2] = {0.f, 0.f};
@@ -479,7 +523,7 @@ int launch_tc_gemm(TcGemmParams P, int num_sms, cudaStream_t st, int64_t* launch
   const int col_groups = (P.n_rb_b + NB - 1) / NB;
   int splits = 1;
   P.kb_per_split = 0;
-  NM_CHECK(!P.a_rowsum || (P.atomic && !P.fp16 && !(P.seg[0].mn & 1)), "a_rowsum needs split-K with a K-major bf16 A operand");
+  NM_CHECK(!P.a_rowsum || (P.atomic && !P.fp16), "a_rowsum needs split-K with a bf16 A operand");
   if (P.atomic) {
     NM_CHECK(P.nseg == 1, "split-K takes one K segment");
     const int tiles = n_rb_a * col_groups;

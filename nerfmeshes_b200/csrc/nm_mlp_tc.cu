@@ -77,6 +77,7 @@ struct TcParams {
   const float* dz_in;     // (M, dz_ld) fp32: dZ of the last forward layer
   int dz_ld;
   const float* dout;      // (M, 4): compositor adjoint, column 3 = d sigma
+  int emit_mn;            // mode 2: dZ packs as MN-major tiles, written by per-warp bulk stores from a shared-memory staging block
   // fused compositor (mode 0, ray inputs): the last layer's (rgb, sigma) of a tile go to the front-end warps through shared
   // memory instead of to `out`; they composite every ray in sample order (nm_composite.cuh) and write the per-ray maps.
   int comp_on;
@@ -387,6 +388,47 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             const bool valid = m < P.in.M;
             const long long pt = tile * kTileM + row;
             const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
+            if (MODE == 2 && P.emit_mn) {
+              // MN-major pack (ptx::make_mnmajor_sw128_desc: a point's 64 features of a group are one 128-byte line, chunks
+              // XOR-swizzled by the row).  Sixteen-byte global stores from here would touch 32 lines per instruction; instead the
+              // warp lays its 32 rows x 128 B (hi, lo) out in a private shared-memory block — exactly the contiguous 4 KB the rows
+              // occupy in the global tile — and one lane hands each to the bulk-copy engine.  The encoding buffers, unused by
+              // the data-gradient chain, hold the eight 8 KB blocks.
+              uint8_t* stg = smem + P.off_pe + (uint32_t)warp * 8192u;
+              if (lane == 0) ptx::bulk_wait_group_read0();          // the previous chunk's stores have drained this block
+              __syncwarp();
+#pragma unroll 1
+              for (int half = 0; half < 2; ++half) {
+                uint32_t h16[16], l16[16];
+                const uint32_t acol = (uint32_t)(n * 32 + half * 16);
+                NM_TMEM_LD16(tmem + lane_addr + kColAhi + acol, h16);
+                if (n_passes == 3) NM_TMEM_LD16(tmem + lane_addr + kColAlo + acol, l16);
+                ptx::tmem_wait_ld();
+                if (!valid) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) { h16[j] = 0u; l16[j] = 0u; }
+                } else if (n_passes != 3) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) l16[j] = 0u;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const uint32_t off = (uint32_t)lane * 128u + ((((uint32_t)(half * 4 + c)) ^ ((uint32_t)lane & 7u)) << 4);
+                  *reinterpret_cast<uint4*>(stg + off) = make_uint4(h16[4 * c], h16[4 * c + 1], h16[4 * c + 2], h16[4 * c + 3]);
+                  *reinterpret_cast<uint4*>(stg + 4096u + off) = make_uint4(l16[4 * c], l16[4 * c + 1], l16[4 * c + 2], l16[4 * c + 3]);
+                }
+              }
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                // rows q*32.. of the tile = rows (q&1)*32.. of K block tile*2 + (q>>1); feature block n>>1, feature group n&1
+                uint8_t* dst = P.emit.packT[li] + ((size_t)(n >> 1) * (size_t)P.emit.kbt + (size_t)(tile * 2 + (q >> 1))) * 32768u +
+                               (size_t)(n & 1) * 8192u + (size_t)((q & 1) * 32) * 128u;
+                ptx::bulk_s2g(dst, ptx::smem_u32(stg), 4096u);
+                ptx::bulk_s2g(dst + 16384u, ptx::smem_u32(stg) + 4096u, 4096u);
+                ptx::bulk_commit_group();
+              }
+            } else
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
               uint32_t h16[16], l16[16];
@@ -471,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         }
       }
     }
+    if (MODE == 2 && lane == 0) ptx::bulk_wait_group0();      // outstanding pack stores (emit_mn) before the block goes away
   } else if (warp < kProdWarp) {
     // =============================================================== front-end warps: next tile's encodings
     const int r = (warp - kFeWarp0) * 32 + lane;
@@ -820,7 +863,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
 // forward layer; for every backward layer li (net.bwd): io.bits[li] = relu mask to apply (input), io.packT[li] = where dZ
 // goes as the weight-gradient operand (its row sums there are the bias gradients: launch_tc_gemm a_rowsum).
 int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz_ld, const float* dout,
-                      const MlpEmit& io, int n_passes, int num_sms, int* d_err, cudaStream_t st, int64_t* launches) {
+                      const MlpEmit& io, int n_passes, int num_sms, int* d_err, cudaStream_t st, int64_t* launches, int emit_mn) {
   if (M <= 0) return 0;
   NM_CHECK(net.bwd_valid && net.d_wpack_bwd, "backward weight stream not built");
   NM_CHECK((dz_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(dz_in) & 15) == 0, "dz_in must be 16-byte aligned rows");
@@ -835,7 +878,8 @@ int launch_mlp_tc_bwd(const NetDev& net, long long M, const float* dz_in, int dz
   P.n_tiles = (M + kTileM - 1) / kTileM;
   P.err = d_err;
   P.has_emit = 1; P.emit = io;
-  P.mode = 2; P.dz_in = dz_in; P.dz_ld = dz_ld; P.dout = dout;
+  P.mode = 2; P.dz_in = dz_in; P.dz_ld = dz_ld; P.dout = dout; P.emit_mn = emit_mn;
+  static_assert(kEpiWarps * 8192u <= kPeTotal, "the pack staging blocks live in the (unused) encoding buffers");
   return launch_prepared(P, num_sms, st, launches);
 }
 

@@ -809,7 +809,9 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       io.packT[li] = W.pkt_dz[l - 1];
       if (G.layers[l - 1].relu) io.bits[li] = reinterpret_cast<uint32_t*>(W.bits[l - 1]);
     }
-    if (int e = launch_mlp_tc_bwd(net, P, dZ, Ltop.n_out, dout, io, mode.n_passes, num_sms, mode.d_err, st, launches)) return e;
+    // dZ packs as MN-major tiles through per-warp bulk stores (NM_TRAIN_DZ_MN=0: K-major tiles, 2-byte stores)
+    static const int dz_mn = [] { const char* e = getenv("NM_TRAIN_DZ_MN"); return (!e || atoi(e) != 0) ? 1 : 0; }();
+    if (int e = launch_mlp_tc_bwd(net, P, dZ, Ltop.n_out, dout, io, mode.n_passes, num_sms, mode.d_err, st, launches, dz_mn)) return e;
     for (int l = last; l >= 0; --l) {            // weight gradients dW (N, Kt) += dZ^T [act[l-1] | PE]: long-K GEMMs, fp32 atomics
       const LayerProg& L = G.layers[l];
       TcGemmParams T = tc_base();
@@ -818,13 +820,13 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       // from head_backward_kernel)
       T.a_rowsum = l < last ? g->bias + L.bias_off : nullptr;
       if (L.k_act > 0) {
-        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP};
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP, dz_mn};
         T.D = g->w + gw_off[l]; T.N = L.k_act;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
         T.a_rowsum = nullptr;
       }
       if (L.pe_src) {
-        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, pkt_pe_of(L), kbtP, kbtP};
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, pkt_pe_of(L), kbtP, kbtP, dz_mn};
         T.D = g->w + gw_off[l] + L.k_act; T.N = L.k_pe;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
       }
