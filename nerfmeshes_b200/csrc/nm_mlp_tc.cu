@@ -195,12 +195,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 
   // Mode 2 (data-gradient chain): the epilogue holds a 32-column slab, its bf16 hi/lo halves and the mask at once and spilled
   // under the 96-register launch budget (17 warps: one SM sub-partition hosts five).  Its front-end warps are idle and the
-  // issuers are light, so the register file is re-divided per warpgroup: per sub-partition 2 x 144 (epilogue) + 40 (front
-  // end) + 56 (producer / issuer) [+ 96 for the 17th warp, which is in no complete warpgroup] = the 4 (5) x 96 it was given.
+  // issuers are light, so the register file is re-divided per warpgroup: per sub-partition 2 x 160 (epilogue) + 24 (front
+  // end) + 40 (producer / issuer) [+ 96 for the 17th warp, which is in no complete warpgroup] = the 4 (5) x 96 it was given.
   if (MODE == 2) {
-    if (warp < kEpiWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
-    else if (warp < kProdWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    else if (warp < kProdWarp + 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp < kEpiWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    else if (warp < kProdWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    else if (warp < kProdWarp + 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   }
   if (warp < kEpiWarps) {
     // =============================================================== epilogue warps
@@ -315,7 +315,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #pragma unroll
                   for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                if (P.emit.packT[li] && !writes_a) {     // (layers that write the A operand emit from it after the hand-over, below)
+                if (MODE == 2 && P.emit_mn && P.emit.packT[li] && !writes_a) {
+                  // the chain's last layer (no A operand to read back): the same MN-major staging block as below, filled half
+                  // by half from the registers; the bulk stores follow the second half
+                  uint8_t* stg = smem + P.off_pe + (uint32_t)warp * 8192u;
+                  if (half == 0) {
+                    if (lane == 0) ptx::bulk_wait_group_read0();
+                    __syncwarp();
+                  }
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    uint32_t h4[4], l4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float x0 = valid ? v[c * 8 + 2 * e] : 0.f, x1 = valid ? v[c * 8 + 2 * e + 1] : 0.f;
+                      const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                      const float2 f = __bfloat1622float2(h2);
+                      const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+                      h4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                      l4[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    const uint32_t off = (uint32_t)lane * 128u + ((((uint32_t)(half * 4 + c)) ^ ((uint32_t)lane & 7u)) << 4);
+                    *reinterpret_cast<uint4*>(stg + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+                    *reinterpret_cast<uint4*>(stg + 4096u + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+                  }
+                  if (half == 1) {
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                      uint8_t* dst = P.emit.packT[li] + ((size_t)(n >> 1) * (size_t)P.emit.kbt + (size_t)(tile * 2 + (q >> 1))) * 32768u +
+                                     (size_t)(n & 1) * 8192u + (size_t)((q & 1) * 32) * 128u;
+                      ptx::bulk_s2g(dst, ptx::smem_u32(stg), 4096u);
+                      ptx::bulk_s2g(dst + 16384u, ptx::smem_u32(stg) + 4096u, 4096u);
+                      ptx::bulk_commit_group();
+                    }
+                  }
+                } else if (P.emit.packT[li] && !writes_a) {     // (layers that write the A operand emit from it after the hand-over, below)
                   const long long pt = tile * kTileM + row;
                   // element (feature f, point pt) of a tile: row f%128, 16-byte chunk ((pt%64)/8) ^ (f%8), 2-byte slot pt%8.
                   // col0 is a multiple of 32, so f%8 = j%8: one base address per j%8, the rest are immediates
