@@ -228,6 +228,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         // one chunk overlaps the next chunk's instead of adding to it.
         for (int nn = 0; nn < 2; ++nn) {
           const int n = hcol + 2 * nn;
+          // mode 2: the relu mask words (and d sigma) of this chunk come from HBM / L2 — issue the loads BEFORE waiting for the
+          // accumulator, so that their latency hides behind the MMAs instead of sitting on the chunk's conversion path
+          uint32_t mk_pre[2] = {0xffffffffu, 0xffffffffu};
+          float dsg_pre = 0.f;
+          if (MODE == 2 && L.kind == KIND_BWD && n < NC && m < P.in.M) {
+            if (L.relu) {
+              const uint2 bw = *reinterpret_cast<const uint2*>(P.emit.bits[li] + (size_t)m * (size_t)(L.n_out >> 5) + (size_t)(n * 2));
+              mk_pre[0] = bw.x; mk_pre[1] = bw.y;       // n_out is a multiple of 64: the two words of a chunk are 8-byte aligned
+            }
+            if (L.aux2) dsg_pre = P.dout[(size_t)m * 4 + 3];
+          }
           const long long tr0 = P.trace ? clock64() : 0;
           ptx::mbar_wait(bars + kBarDFull + 8 * n, gl & 1, P.err, ERR_DFULL);
           const long long tr1 = P.trace ? clock64() : 0;
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * so;
                 if (L.aux2) {
-                  const float dsg = valid ? P.dout[(size_t)m * 4 + 3] : 0.f;
+                  const float dsg = valid ? dsg_pre : 0.f;
                   const float4* w4 = reinterpret_cast<const float4*>(s_head + L.head_off + col0);
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
@@ -268,8 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                     v[4 * j + 2] = fmaf(dsg, ww.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(dsg, ww.w, v[4 * j + 3]);
                   }
                 }
-                uint32_t mk = valid ? 0xffffffffu : 0u;
-                if (L.relu && valid) mk = P.emit.bits[li][(size_t)m * (size_t)(L.n_out >> 5) + (size_t)(col0 >> 5)];
+                const uint32_t mk = valid ? (half ? mk_pre[1] : mk_pre[0]) : 0u;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = ((mk >> j) & 1u) ? v[j] : 0.f;
               } else if (MODE != 2 || L.kind != KIND_LOAD) {
