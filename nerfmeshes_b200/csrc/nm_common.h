@@ -106,6 +106,7 @@ struct MlpEmit {
   uint32_t* bits[kMaxLayers];
   float* act[kMaxLayers];
   int kbt;
+  int mn;      // packT as MN-major tiles (bulk stores from a shared-memory staging block) instead of K-major ones
 };
 
 int build_programs(const NmNetDesc& d, NetProgram* full, NetProgram* sigma);

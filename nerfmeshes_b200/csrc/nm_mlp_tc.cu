@@ -77,7 +77,8 @@ struct TcParams {
   const float* dz_in;     // (M, dz_ld) fp32: dZ of the last forward layer
   int dz_ld;
   const float* dout;      // (M, 4): compositor adjoint, column 3 = d sigma
-  int emit_mn;            // mode 2: dZ packs as MN-major tiles, written by per-warp bulk stores from a shared-memory staging block
+  int emit_mn;            // modes 1 / 2: packs as MN-major tiles, written by per-warp bulk stores from a shared-memory staging block
+  uint32_t off_stg;       //   its eight 8 KB blocks: the (unused) encoding buffers in mode 2, an own region in mode 1
   // fused compositor (mode 0, ray inputs): the last layer's (rgb, sigma) of a tile go to the front-end warps through shared
   // memory instead of to `out`; they composite every ray in sample order (nm_composite.cuh) and write the per-ray maps.
   int comp_on;
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 if (MODE == 2 && P.emit_mn && P.emit.packT[li] && !writes_a) {
                   // the chain's last layer (no A operand to read back): the same MN-major staging block as below, filled half
                   // by half from the registers; the bulk stores follow the second half
-                  uint8_t* stg = smem + P.off_pe + (uint32_t)warp * 8192u;
+                  uint8_t* stg = smem + P.off_stg + (uint32_t)warp * 8192u;
                   if (half == 0) {
                     if (lane == 0) ptx::bulk_wait_group_read0();
                     __syncwarp();
@@ -433,13 +434,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             const bool valid = m < P.in.M;
             const long long pt = tile * kTileM + row;
             const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
-            if (MODE == 2 && P.emit_mn) {
+            if (MODE >= 1 && P.emit_mn) {
               // MN-major pack (ptx::make_mnmajor_sw128_desc: a point's 64 features of a group are one 128-byte line, chunks
               // XOR-swizzled by the row).  Sixteen-byte global stores from here would touch 32 lines per instruction; instead the
               // warp lays its 32 rows x 128 B (hi, lo) out in a private shared-memory block — exactly the contiguous 4 KB the rows
               // occupy in the global tile — and one lane hands each to the bulk-copy engine.  The encoding buffers, unused by
-              // the data-gradient chain, hold the eight 8 KB blocks.
-              uint8_t* stg = smem + P.off_pe + (uint32_t)warp * 8192u;
+              // the data-gradient chain, hold the eight 8 KB blocks (mode 1: a region of its own, taken from the weight ring).
+              uint8_t* stg = smem + P.off_stg + (uint32_t)warp * 8192u;
               if (lane == 0) ptx::bulk_wait_group_read0();          // the previous chunk's stores have drained this block
               __syncwarp();
 #pragma unroll 1
@@ -455,6 +456,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 } else if (n_passes != 3) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) l16[j] = 0u;
+                }
+                if (MODE == 1) {       // fp16 hi + lo (22 bits) -> bf16 hi / lo, two features per register
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
+                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
+                    const float x0 = (fh.x + fl.x) * so, x1 = (fh.y + fl.y) * so;
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                    const float2 f = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+                    h16[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                    l16[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                  }
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -558,7 +572,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
         }
       }
     }
-    if (MODE == 2 && lane == 0) ptx::bulk_wait_group0();      // outstanding pack stores (emit_mn) before the block goes away
+    if (MODE >= 1 && lane == 0) ptx::bulk_wait_group0();      // outstanding pack stores (emit_mn) before the block goes away
   } else if (warp < kProdWarp) {
     // =============================================================== front-end warps: next tile's encodings
     const int r = (warp - kFeWarp0) * 32 + lane;
@@ -821,7 +835,7 @@ static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* l
   NM_CUDA(cudaGetDevice(&dev));
   NM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const uint32_t fixed = kPeTotal + align_up(hp.n_bias * 4, 16) + align_up((hp.n_head > 0 ? hp.n_head : 4) * 4, 16) +
-                         (128 + 512) * 4 + kBarBytes + (P.comp_on ? kCompBytes : 0u);
+                         (128 + 512) * 4 + kBarBytes + (P.comp_on ? kCompBytes : 0u) + ((P.emit_mn && P.mode != 2) ? kEpiWarps * 8192u + 1024u : 0u);
   int ns = ((int)max_smem - (int)fixed) / kStageBytes;
   if (ns > kMaxStages) ns = kMaxStages;
   if (const char* e = getenv("NM_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v < ns) ns = v; }
@@ -834,6 +848,8 @@ static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* l
   P.off_red = off; off += (128 + 512) * 4;
   P.off_bars = off; off += kBarBytes;
   P.off_comp = off; off += P.comp_on ? kCompBytes : 0u;
+  if (P.emit_mn && P.mode != 2) { off = align_up(off, 1024); P.off_stg = off; off += kEpiWarps * 8192u; }
+  else P.off_stg = P.off_pe;
   if (P.tile_group < 1) P.tile_group = 1;
   NM_CHECK((int)off <= max_smem, "shared-memory layout overflow");
 
@@ -892,7 +908,7 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.act_inv_scale = ldexpf(1.f, -act_scale_log2);
   P.n_tiles = (in.M + kTileM - 1) / kTileM;
   P.err = d_err;
-  if (emit) { P.has_emit = 1; P.emit = *emit; }
+  if (emit) { P.has_emit = 1; P.emit = *emit; P.emit_mn = emit->mn; }
   P.tile_group = 1;
   if (comp) {
     NM_CHECK(!emit && !sigma_only && in.mode == IN_RAYS && comp->S == in.S && comp->R * (long long)comp->S == in.M && comp->t == in.t,

@@ -651,6 +651,11 @@ int build_weight_packs(NetDev& net, cudaStream_t st, int64_t* launches) {
 size_t train_ws_bytes(const NetProgram& G, long long points, bool use_tc) { return carve(G, points, use_tc, nullptr).bytes; }
 
 bool train_fused(bool use_tc) { return use_tc && !train_layerwise(); }
+// NM_TRAIN_ACT_MN=1: the training forward writes its activation packs as MN-major tiles too (64 KB of staging out of the weight ring)
+int train_act_mn() {
+  static const int v = [] { const char* e = getenv("NM_TRAIN_ACT_MN"); return (e && atoi(e) != 0) ? 1 : 0; }();
+  return v;
+}
 
 // The by-products a training forward must leave in `ws` (same carving as mlp_backward) so that the backward can skip its
 // recompute launch: see MlpEmit.
@@ -658,6 +663,7 @@ void train_emit_setup(const NetProgram& G, long long P, float* ws_base, MlpEmit*
   const TrainWs W = carve(G, P, true, reinterpret_cast<uint8_t*>(ws_base));
   *E = MlpEmit{};
   E->kbt = 2 * (int)((P + 127) / 128);
+  E->mn = train_act_mn();
   for (int l = 0; l < G.n_layers; ++l) {
     const LayerProg& L = G.layers[l];
     if (l + 1 < G.n_layers) E->packT[l] = W.pkt_act[l];
@@ -820,7 +826,7 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       // from head_backward_kernel)
       T.a_rowsum = l < last ? g->bias + L.bias_off : nullptr;
       if (L.k_act > 0) {
-        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP, dz_mn};
+        T.seg[0] = TcSeg{W.pkt_dz[l], kbtP, W.pkt_act[l - 1], kbtP, kbtP, dz_mn | (train_act_mn() << 1)};
         T.D = g->w + gw_off[l]; T.N = L.k_act;
         if (int e = launch_tc_gemm(T, num_sms, st, launches)) return e;
         T.a_rowsum = nullptr;
