@@ -816,7 +816,8 @@ int mlp_backward(NetDev& net, const MlpInput& in, const float* dout, float* ws_b
       if (G.layers[l - 1].relu) io.bits[li] = reinterpret_cast<uint32_t*>(W.bits[l - 1]);
     }
     // dZ packs as MN-major tiles through per-warp bulk stores (NM_TRAIN_DZ_MN=0: K-major tiles, 2-byte stores)
-    static const int dz_mn = [] { const char* e = getenv("NM_TRAIN_DZ_MN"); return (!e || atoi(e) != 0) ? 1 : 0; }();
+    const char* dz_env = getenv("NM_TRAIN_DZ_MN");       // read per call: the tests cover both layouts
+    const int dz_mn = (!dz_env || atoi(dz_env) != 0) ? 1 : 0;
     if (int e = launch_mlp_tc_bwd(net, P, dZ, Ltop.n_out, dout, io, mode.n_passes, num_sms, mode.d_err, st, launches, dz_mn)) return e;
     for (int l = last; l >= 0; --l) {            // weight gradients dW (N, Kt) += dZ^T [act[l-1] | PE]: long-K GEMMs, fp32 atomics
       const LayerProg& L = G.layers[l];

@@ -195,6 +195,10 @@ def test_direct_and_subchunk_walks_agree(monkeypatch):
     l_dir, c_dir, f_dir = run()
     monkeypatch.setenv("NM_TRAIN_DIRECT_GB", "0")
     l_sub, c_sub, f_sub = run()
+    monkeypatch.setenv("NM_TRAIN_DZ_MN", "0")            # ... and with the dZ packs as K-major tiles (2-byte stores, K-major row sums)
+    l_k, c_k, f_k = run()
+    compare(c_k, c_dir, rel_max=2e-5, name="K-major dZ packs coarse")
+    compare(f_k, f_dir, rel_max=2e-5, name="K-major dZ packs fine")
     assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l_dir, l_sub))      # the loss is an atomic sum of block partials
     compare(c_sub, c_dir, rel_max=2e-5, name="walks coarse")
     compare(f_sub, f_dir, rel_max=2e-5, name="walks fine")
