@@ -77,6 +77,7 @@ struct TcParams {
   const float* dz_in;     // (M, dz_ld) fp32: dZ of the last forward layer
   int dz_ld;
   const float* dout;      // (M, 4): compositor adjoint, column 3 = d sigma
+  int cluster;            // 2: CTAs 2p, 2p+1 form a cluster that shares ONE weight stream (rank 0 multicasts every stage into both)
   int emit_mn;            // modes 1 / 2: packs as MN-major tiles, written by per-warp bulk stores from a shared-memory staging block
   uint32_t off_stg;       //   its eight 8 KB blocks: the (unused) encoding buffers in mode 2, an own region in mode 1
   // fused compositor (mode 0, ray inputs): the last layer's (rgb, sigma) of a tile go to the front-end warps through shared
@@ -140,7 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   // ---------------------------------------------------------------- one-time setup
   if (threadIdx.x == 0) {
     if (sbase & 1023u) { atomicExch(P.err, ERR_ALIGN); __trap(); }
-    for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(bars + kBarWFull + 8 * i, 1); ptx::mbar_init(bars + kBarWEmpty + 8 * i, 1); }
+    // a weight stage is released by its consuming issuer of EVERY CTA of the cluster (multicast commits): count = cluster size
+    for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(bars + kBarWFull + 8 * i, 1); ptx::mbar_init(bars + kBarWEmpty + 8 * i, P.cluster == 2 ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(bars + kBarPeFull + 8 * i, 128); ptx::mbar_init(bars + kBarPeEmpty + 8 * i, kIssuers); }
     ptx::mbar_init(bars + kBarDirFull, 128);
     ptx::mbar_init(bars + kBarDirEmpty, kIssuers);
@@ -186,13 +188,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   const float so = P.act_scale, si = P.act_inv_scale;
   const int n_passes = P.n_passes;
   // i-th tile of this CTA: groups of `tile_group` consecutive tiles are dealt round-robin to the CTAs (group size 1: the plain
-  // strided order).  Returns -1 past the end.
+  // strided order).  Returns -1 past the end.  In a cluster of two both CTAs must walk the weight ring the same number of
+  // times: iter_exists(i) is decided by rank 0's tile, and rank 1 runs a "ghost" iteration (ring traffic only) when its own
+  // tile of that round does not exist — which can only be its last one.
   const uint32_t Gt = (uint32_t)P.tile_group;
+  const bool cl2 = P.cluster == 2;
+  const uint32_t crank = cl2 ? ptx::cluster_ctarank() : 0u;
   auto tile_of = [&](uint32_t i) -> long long {
-    const long long g = (long long)blockIdx.x + (long long)(i / Gt) * (long long)gridDim.x;
+    const long long g = (long long)blockIdx.x + (long long)(i / Gt) * (long long)gridDim.x;     // blockIdx.x = 2 * pair + rank
     const long long t = g * (long long)Gt + (long long)(i % Gt);
     return t < P.n_tiles ? t : -1;
   };
+  auto iter_exists = [&](uint32_t i) -> bool {
+    const long long g0 = (long long)(blockIdx.x - crank) + (long long)(i / Gt) * (long long)gridDim.x;
+    return g0 * (long long)Gt + (long long)(i % Gt) < P.n_tiles;
+  };
+  if (cl2) ptx::cluster_sync_all();              // the peer's barriers are initialised before anything is multicast at them
 
   // Mode 2 (data-gradient chain): the epilogue holds a 32-column slab, its bf16 hi/lo halves and the mask at once and spilled
   // under the 96-register launch budget (17 warps: one SM sub-partition hosts five).  Its front-end warps are idle and the
@@ -702,15 +713,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       uint32_t ph = 0, issued = 0;
       const uint32_t cnt_addr = bars + kLoadedCnt;
       const uint32_t bytes = (n_passes == 3) ? (uint32_t)kStageBytes : (uint32_t)kHalfStage;
-      for (uint32_t itile = 0; tile_of(itile) >= 0; ++itile) {
+      for (uint32_t itile = 0; iter_exists(itile); ++itile) {
         for (int b = 0; b < n_blocks; ++b) {
           ptx::mbar_wait(bars + kBarWEmpty + 8 * slot, ph ^ 1, P.err, ERR_W_EMPTY);
           if (P.dbg & 4) {
             ptx::mbar_arrive(bars + kBarWFull + 8 * slot);
           } else {
+            // every CTA arms its own barrier; in a cluster rank 0 alone reads L2 and the copy lands in both CTAs (the slot is
+            // free in both: its `empty` barrier counts the consuming issuer of each)
             ptx::mbar_expect_tx(bars + kBarWFull + 8 * slot, bytes);
-            ptx::bulk_g2s(sbase + (uint32_t)slot * kStageBytes, P.wpack + (size_t)b * kStageBytes, bytes,
-                          bars + kBarWFull + 8 * slot);
+            if (!cl2) ptx::bulk_g2s(sbase + (uint32_t)slot * kStageBytes, P.wpack + (size_t)b * kStageBytes, bytes, bars + kBarWFull + 8 * slot);
+            else if (crank == 0)
+              ptx::bulk_g2s_multicast(sbase + (uint32_t)slot * kStageBytes, P.wpack + (size_t)b * kStageBytes, bytes,
+                                      bars + kBarWFull + 8 * slot, (uint16_t)3);
           }
           // Publish how many stages have been armed.  The ring's mbarriers carry one parity bit, and an issuer whose
           // consecutive blocks are more than NS apart in the schedule could otherwise look at a slot a full round early
@@ -730,7 +745,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     uint32_t ph = 0, gl = 0, it = 0, cur_pos = 0;
     unsigned trace_cursor = 0;
     const uint32_t cnt_addr = bars + kLoadedCnt;
-    for (; tile_of(it) >= 0; ++it) {
+    auto release_stage = [&](int sl) {
+      if (cl2) ptx::tc_commit_elect_multicast(bars + kBarWEmpty + 8 * sl, (uint16_t)3);
+      else ptx::tc_commit_elect(bars + kBarWEmpty + 8 * sl);
+    };
+    for (; iter_exists(it); ++it) {
+      if (tile_of(it) < 0) {
+        // ghost iteration (cluster rank 1, last round): no tile of our own, but the peer's producer multicasts this round's
+        // stages into our ring and waits for our release of each — walk our blocks' stages and hand them straight back
+        const uint32_t base_pos = it * (uint32_t)n_blocks;
+        for (int li = 0; li < n_layers; ++li) {
+          const LayerProg& L = P.net.layers[li];
+          const uint32_t fb = ((uint32_t)L.first_blk >> (8 * w)) & 0xFFu;
+          if (fb == 0xFFu) continue;
+          int b = L.blk_begin + (int)fb;
+          while (true) {
+            const BlockProg& B = P.net.blocks[b];
+            const uint32_t gpos = base_pos + (uint32_t)b;
+            slot += (int)(gpos - cur_pos);
+            cur_pos = gpos;
+            while (slot >= NS) { slot -= NS; ph ^= 1; }
+            uint32_t c;
+            do { asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(c) : "r"(cnt_addr) : "memory"); } while (c <= gpos);
+            ptx::mbar_wait(bars + kBarWFull + 8 * slot, ph, P.err, ERR_W_FULL);
+            release_stage(slot);
+            if (!B.next) break;
+            b += (int)B.next;
+          }
+        }
+        continue;
+      }
       const uint32_t buf = it & 1;
       ptx::mbar_wait(bars + kBarPeFull + 8 * buf, (it >> 1) & 1, P.err, ERR_PE_FULL);
       ptx::tc_fence_after();
@@ -800,7 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 else ptx::mma_block_ss1(d_t, a_hi, a_lo, b_hi, b_lo, idesc, acc_first, (uint32_t)B.ksteps);
               }
             }
-            ptx::tc_commit_elect(bars + kBarWEmpty + 8 * slot);
+            release_stage(slot);
             if (B.flags & 1) ptx::tc_commit_elect(bars + kBarDFull + 8 * B.nc);
             if (B.flags & 2) ptx::tc_commit_elect(bars + kBarKbFree + 8 * B.kb);
             if (P.trace && lane == 0) trace_rec(P, 1, w, b, gl, tr0, tr1, tr2, clock64(), trace_cursor);
@@ -818,6 +862,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   // ---------------------------------------------------------------- teardown
   ptx::tc_fence_before();
   __syncthreads();
+  if (cl2) ptx::cluster_sync_all();              // the peer may still be crediting our barriers / have copies in flight at us
   if (warp == kProdWarp) ptx::tmem_dealloc(tmem, 512);
 }
 
@@ -862,13 +907,31 @@ static int launch_prepared(TcParams& P, int num_sms, cudaStream_t st, int64_t* l
   }
   const long long n_groups = (P.n_tiles + P.tile_group - 1) / P.tile_group;
   long long grid = n_groups < num_sms ? n_groups : num_sms;
+  // pairs of CTAs share the weight stream when the grid allows it (NM_TC_CLUSTER=0: every CTA streams its own copy)
+  static const bool cluster_env = [] { const char* e = getenv("NM_TC_CLUSTER"); return !e || atoi(e) != 0; }();
+  P.cluster = 1;
+  if (cluster_env && grid >= 2 && !(P.dbg & 4)) {
+    grid += grid & 1;                             // an odd grid gets one more CTA: rank 1 of the last pair only runs ghosts... or a real group
+    if (grid > num_sms) grid -= 2;
+    if (grid >= 2) P.cluster = 2;
+  }
   const char* trace_path = getenv("NM_TC_TRACE");
   const size_t trace_words = 1 + 6 * (size_t)kTraceRegion * 5;
   if (trace_path) {
     NM_CUDA(cudaMalloc(&P.trace, trace_words * 8));
     NM_CUDA(cudaMemset(P.trace, 0, trace_words * 8));
   }
-  kern<<<(unsigned)grid, kThreads, off, st>>>(P);
+  if (P.cluster == 2) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = off; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    NM_CUDA(cudaLaunchKernelEx(&lc, kern, P));
+  } else {
+    kern<<<(unsigned)grid, kThreads, off, st>>>(P);
+  }
   NM_CUDA(cudaGetLastError());
   if (trace_path) {   // debugging aid: synchronous dump of CTA 0's event log
     NM_CUDA(cudaStreamSynchronize(st));

@@ -51,6 +51,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// ---- cluster of two CTAs sharing one weight stream --------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one L2 read, the same shared-memory offset written (and the same mbarrier offset credited) in every CTA of `mask`
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+
 // shared -> global bulk store (bulk async-group completion): the issuing thread commits a group and, before the shared-memory
 // source is rewritten (or the kernel exits), waits for the group's reads (or writes) to finish
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
@@ -265,6 +281,13 @@ __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+// the same arrival delivered to the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_elect_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar), "h"(mask)
       : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4
