@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   // tile of that round does not exist — which can only be its last one.
   const uint32_t Gt = (uint32_t)P.tile_group;
   const bool cl2 = P.cluster == 2;
-  const uint32_t crank = cl2 ? ptx::cluster_ctarank() : 0u;
+  const uint32_t crank = cl2 ? (blockIdx.x & 1u) : 0u;     // == %cluster_ctarank for cluster dims (2,1,1); from blockIdx it stays on the uniform datapath
   auto tile_of = [&](uint32_t i) -> long long {
     const long long g = (long long)blockIdx.x + (long long)(i / Gt) * (long long)gridDim.x;     // blockIdx.x = 2 * pair + rank
     const long long t = g * (long long)Gt + (long long)(i % Gt);
