@@ -12,7 +12,7 @@ from conftest import ROOT
 from oracle import nerf_oracle as O
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-from protocol_sim import simulate  # noqa: E402
+from protocol_sim import simulate, simulate_pair  # noqa: E402
 from test_host_logic import debug_pack  # noqa: E402
 
 
@@ -33,3 +33,16 @@ def test_simulator_catches_parity_aliasing():
     prog, _ = debug_pack(cfg, O.init_weights(cfg, 1))
     ok, _ = simulate(prog, tiles=3, NS=5, armed_counter=False)     # the pre-fix protocol, as it failed on hardware
     assert not ok
+
+
+@pytest.mark.parametrize("arch", [dict(), dict(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)])
+def test_cta_pair_sharing_one_weight_stream_is_deadlock_free(arch):
+    """P.cluster == 2: rank 0 multicasts every stage into both CTAs' rings, stages are released into both CTAs' w_empty
+    barriers by each CTA's consuming issuer (count 2); with and without rank 1's ghost iteration, for every ring depth."""
+    cfg = O.NetCfg(**{**O.NetCfg().__dict__, **arch})
+    for sigma_only in (False, True):
+        prog, _ = debug_pack(cfg, O.init_weights(cfg, 1), sigma_only)
+        for ns in (2, 3, 5, 7):
+            for ghost in (False, True):
+                ok, info = simulate_pair(prog, tiles=3, NS=ns, ghost=ghost)
+                assert ok, (ns, ghost, info)

@@ -153,6 +153,156 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
     return (not errors), dict(errors=errors[:3])
 
 
+def simulate_pair(prog, tiles, NS, ghost=False):
+    """Two CTAs of a cluster sharing ONE weight stream (nm_mlp_tc.cu, P.cluster == 2): rank 0's producer multicasts every
+    stage into both rings; each CTA's producer arms its own w_full (modelled as a second arrival: arm + copy completion); a
+    stage is released into BOTH CTAs' w_empty barriers (count 2) by the consuming issuer of each CTA.  ghost=True: rank 1 has
+    one tile less and its issuers run a ghost iteration for the last round (wait for the stage, release it).  Only the ring
+    protocol and the tile-level barriers that gate it are modelled per CTA; returns (ok, info)."""
+    L = [prog.layers[i] for i in range(prog.n_layers)]
+    uses_dir = any(L[i].pe_src == 2 for i in range(len(L)))
+    waiting, errors = {}, []
+
+    class Cta:
+        def __init__(self, r):
+            self.r = r
+            self.w_full = [Bar(f"c{r}.w_full{i}", 2) for i in range(NS)]
+            self.w_empty = [Bar(f"c{r}.w_empty{i}", 2) for i in range(NS)]
+            self.pe_full = [Bar(f"c{r}.pe_full{i}", 1) for i in range(2)]
+            self.pe_empty = [Bar(f"c{r}.pe_empty{i}", 4) for i in range(2)]
+            self.chunk = [Bar(f"c{r}.chunk{i}", 1) for i in range(4)]
+            self.d_full = [Bar(f"c{r}.d_full{i}", 4) for i in range(4)]
+            self.kb_free = [Bar(f"c{r}.kb_free{i}", 4) for i in range(4)]
+            self.dir_full, self.dir_empty = Bar(f"c{r}.dir_full", 1), Bar(f"c{r}.dir_empty", 4)
+            self.armed = 0
+            self.real = tiles - (1 if (ghost and r == 1) else 0)
+
+        def bars(self):
+            return self.w_full + self.w_empty + self.pe_full + self.pe_empty + self.chunk + self.d_full + self.kb_free + [self.dir_full, self.dir_empty]
+    C = [Cta(0), Cta(1)]
+
+    def wait(me, bar, k):
+        while not bar.done(k):
+            waiting[me] = f"{bar.name} completion #{k} (phase now {bar.phase}, pending {bar.pending})"
+            yield
+        waiting.pop(me, None)
+
+    def producer(c):
+        me = f"c{c.r}.producer"
+        g = 0
+        for t in range(tiles):                       # both ranks: the SAME number of rounds (iter_exists)
+            for b in range(prog.n_blocks):
+                slot, rnd = g % NS, g // NS
+                if rnd > 0:
+                    yield from wait(me, c.w_empty[slot], rnd - 1)
+                c.w_full[slot].arrive()              # arm (expect_tx)
+                if c.r == 0:                         # the multicast copy lands in both rings
+                    C[0].w_full[slot].arrive()
+                    C[1].w_full[slot].arrive()
+                g += 1
+                c.armed = g
+                yield
+
+    def frontend(c):
+        me = f"c{c.r}.frontend"
+        for t in range(c.real):
+            buf = t & 1
+            if t >= 2:
+                yield from wait(me, c.pe_empty[buf], t // 2 - 1)
+            c.pe_full[buf].arrive()
+            if uses_dir:
+                if t >= 1:
+                    yield from wait(me, c.dir_empty, t - 1)
+                c.dir_full.arrive()
+
+    def issuer(c, w):
+        me = f"c{c.r}.issuer{w}"
+        g = gl = 0
+        for t in range(tiles):
+            is_ghost = t >= c.real
+            buf = t & 1
+            if not is_ghost:
+                yield from wait(me, c.pe_full[buf], t // 2)
+            for li, Lp in enumerate(L):
+                waited = -1
+
+                def pass_group(gr):
+                    nonlocal waited
+                    while waited < gr:
+                        waited += 1
+                        if gl > 0:
+                            yield from wait(me, c.chunk[waited], gl - 1)
+                        if (Lp.none_d >> (4 * w + waited)) & 1:
+                            c.d_full[waited].arrive()
+                        if (Lp.none_k >> (4 * w + waited)) & 1:
+                            c.kb_free[waited].arrive()
+                for b in range(Lp.blk_begin, Lp.blk_end):
+                    B = prog.blocks[b]
+                    slot, rnd = g % NS, g // NS
+                    if (B.flags >> 4) == w:
+                        if not is_ghost:
+                            yield from pass_group(B.group)
+                            if B.src == 2:
+                                yield from wait(me, c.dir_full, t)
+                        while c.armed <= g:
+                            waiting[me] = f"armed counter > {g}"
+                            yield
+                        yield from wait(me, c.w_full[slot], rnd)
+                        if c.w_full[slot].phase != rnd + 1:
+                            errors.append(f"{me}: consumed slot {slot} for block {g} (round {rnd}) while the barrier had completed {c.w_full[slot].phase} rounds")
+                        C[0].w_empty[slot].arrive()      # multicast commit: both CTAs' barriers
+                        C[1].w_empty[slot].arrive()
+                        if not is_ghost:
+                            if B.flags & 1:
+                                c.d_full[B.nc].arrive()
+                            if B.flags & 2:
+                                c.kb_free[B.kb].arrive()
+                    g += 1
+                if not is_ghost:
+                    yield from pass_group(3)
+                    gl += 1
+            if not is_ghost:
+                c.pe_empty[buf].arrive()
+                c.dir_empty.arrive()
+
+    def epilogue(c, s_):
+        me = f"c{c.r}.epi_set{s_}"
+        gl = 0
+        for t in range(c.real):
+            for li, Lp in enumerate(L):
+                for nn in range(2):
+                    n = s_ + 2 * nn
+                    yield from wait(me, c.d_full[n], gl)
+                    yield from wait(me, c.kb_free[n], gl)
+                    c.chunk[n].arrive()
+                gl += 1
+
+    agents = {}
+    for c in C:
+        agents[f"c{c.r}.producer"] = producer(c)
+        agents[f"c{c.r}.frontend"] = frontend(c)
+        for w in range(4):
+            agents[f"c{c.r}.issuer{w}"] = issuer(c, w)
+        for s_ in range(2):
+            agents[f"c{c.r}.epi{s_}"] = epilogue(c, s_)
+    alive = dict(agents)
+    allbars = C[0].bars() + C[1].bars()
+    while alive:
+        progressed = False
+        for name in list(alive):
+            before = (tuple(b.phase for b in allbars), tuple(b.pending for b in allbars), C[0].armed, C[1].armed)
+            try:
+                next(alive[name])
+            except StopIteration:
+                del alive[name]
+                progressed = True
+                continue
+            progressed |= before != (tuple(b.phase for b in allbars), tuple(b.pending for b in allbars), C[0].armed, C[1].armed)
+        if not progressed:
+            return False, dict(waiting, errors=errors[:3])
+    return (not errors), dict(errors=errors[:3])
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiles", type=int, default=3)
