@@ -532,6 +532,7 @@ def main():
                 "workload": "lego 512^3 sigma sweep (sigma-only trunk, 982,528 FLOP/voxel; the reference discards rgb, mesh_nerf.py:73) "
                             "+ extract_iso_level + marching cubes iso=32" + (", x-slabs across ranks + mesh all_gather" if ctx.world > 1 else ""),
                 "ms_per_step": ms[0], "sigma_sweep_ms": ms[1], "iso_stats_ms": ms[2], "marching_cubes_ms": ms[3], "gather_ms": ms[4],
+                "mc_cells_per_s": (MESH_RES - 1) ** 3 / (ms[3] * 1e-3) if ms[3] > 0 else None,
                 "n_vertices": m["n_vertices"], "n_triangles": m["n_triangles"], "iso": m["iso"], "gpu_launches": int(m["launches"]),
                 "roofline": {"bound": "tensor", "kernel": "mlp_tc_kernel (grid front-end, sigma-only)",
                              "achieved": vox * FLOP_SIGMA_ONLY / (ms[1] * 1e-3) / 1e12, "peak": peak_tf * ctx.world, "unit": "TFLOP/s",
