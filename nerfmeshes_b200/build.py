@@ -16,6 +16,7 @@ LIB = os.path.join(OUT_DIR, "libnerfmeshes_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+COMMON += os.environ.get("NM_NVCC_EXTRA", "").split()        # bring-up aid: extra -D switches for A/B builds (use with --force)
 # per-file extra flags: the light render stages keep a*b+c as two roundings, like the reference's separate torch ops
 SOURCES = {
     "nm_program.cu": [],

@@ -31,11 +31,31 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or `ns` elapse — a long hint
+// means a waiting warp issues (almost) nothing instead of polling, which matters under the board's power cap
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok;
+}
+#ifndef NM_WAIT_HINT_NS
+#define NM_WAIT_HINT_NS 200000u
+#endif
 // Bounded wait: a protocol bug must become a trap with a code in *err, never a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+#if NM_WAIT_HINT_NS == 0
+  while (!mbar_try_wait(bar, parity)) {              // plain polling (the default suspend window): A/B builds only
+#else
+  while (!mbar_try_wait_hint(bar, parity, NM_WAIT_HINT_NS)) {
+#endif
     if (clock64() - t0 > 4000000000LL) {  // ~2 s
       if (err) atomicExch(err, code);
       __threadfence_system();
