@@ -4,8 +4,9 @@
 // GEMMs (gradients span fp32's exponent range; 16 significand bits per operand, ~2^-16 per product) and fp16 for the
 // forward recompute (22 bits, the forward kernel's class: its relu masks must agree with the forward's).
 //
-// ptile = one (128 operand rows) x (64 K) block: [hi | lo], each 16 KB, K-major, 128-byte swizzled — the shared-memory
-// image tcgen05.mma reads, so a ptile moves global -> shared with ONE 32 KB cp.async.bulk.  A pack is ptiles ordered
+// ptile = one (128 operand rows) x (64 K) block: [hi | lo], each 16 KB, 128-byte swizzled, K-major or (per segment and
+// operand, TcSeg.mn) MN-major — the shared-memory image tcgen05.mma reads, so a ptile moves global -> shared with ONE 32 KB
+// cp.async.bulk.  A pack is ptiles ordered
 // [row block][K block].  Packs are produced by pack_rows_kernel (K along the source's columns), pack_cols_kernel (K
 // along the source's rows: the A^T / B^T operands of the weight gradient) and, for everything inside the layer chain,
 // by this kernel's own epilogue.
@@ -16,8 +17,10 @@
 // epilogue of tile i overlaps the main loop of tile i+1; the weight gradient (K = points) splits K over one wave of
 // CTAs and reduces with vector atomics.  Barriers: full[s] (tx bytes), empty[s] (tcgen05.commit), acc_full[b]
 // (tcgen05.commit after a tile's last K block), acc_empty[b] (16 epilogue warps).  tests/test_gemm_protocol.py models
-// the protocol with one-bit parities.  The fused epilogue (bias/relu, rank-1 term, 1-bit masks in and out, row pack and
-// point-major pack of the output, bias-gradient column sums) is described in DESIGN.md section 4.4.
+// the protocol with one-bit parities.  In a split-K launch with a_rowsum the 16 epilogue warps first walk the stage ring as
+// readers and sum the rows of the staged A tiles (the bias gradient when A = dZ^T).  The fused epilogue of the layer-wise
+// walk (bias/relu, rank-1 term, 1-bit masks in and out, row pack and point-major pack of the output, column sums) is
+// described in DESIGN.md section 4.4.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 

@@ -26,6 +26,17 @@
 //   d_full[n]      (4 commits)  every issuer is done with accumulator chunk n           -> epilogue may drain it
 //   kb_free[k]     (4 commits)  every issuer is done reading activation K-block k       -> epilogue may overwrite it
 //   chunk_ready[n] (4 arrives)  chunk n drained + zeroed, K-block n of the new layer written -> issuers may use both
+//
+// Round 2:
+//   * three template modes — 0 inference; 1 training forward, whose epilogue also emits the backward's operands (relu bit
+//     masks, head activations, point-major bf16 hi/lo packs); 2 the whole data-gradient chain of the backward on a backward
+//     layer program (dZ as the A operand in TMEM, W^T streamed through the ring, MN-major packs out through per-warp bulk
+//     stores, register file re-divided with setmaxnreg)
+//   * mode 0 on ray inputs composites in the kernel: the last layer's (rgb, sigma) go to the front-end warps through shared
+//     memory (raw_full / raw_empty), which run VolumeRenderer per ray in sample order (nm_composite.cuh) — tiles are dealt in
+//     ray-aligned groups and a carry slot passes the ray cut by a tile edge to the next tile
+//   * CTA pairs (cluster of 2) share ONE weight stream: rank 0 multicasts every stage into both rings, a stage is released
+//     by multicast commits of both CTAs' issuers (w_empty counts 2), rank 1 runs ghost iterations when it has no tile
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 

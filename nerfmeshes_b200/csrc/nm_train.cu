@@ -3,14 +3,15 @@
 // through VolumeRenderer (src/nerf/modules.py:67-121), the network (src/nerf/models.py:60-80) and nothing else
 // (SamplePDF is detached, modules.py:201; sample positions do not depend on θ).
 //
-// The forward of a training step runs on the fused tcgen05 kernel (nm_mlp_tc.cu).  The backward recomputes the
-// activations layer by layer for one sub-chunk of points (kept in HBM as operand packs + 1-bit relu masks) and walks the
-// layers back with three GEMM shapes:
-//     forward     Y  = act([X | PE] W^T + b)
-//     data grad   dX = (dZ W) (+ dsigma w_alpha) * relu'
-//     weight grad dW += dZ^T [X | PE]                     (K = points: split over CTAs, fp32 atomics)
-// Default: all three on the tensor cores through tc_gemm_kernel (nm_gemm_tc.cu), whose epilogues hand the next GEMM its
-// operands.  NM_PREC_FP32: the same walk in plain fp32 FMAs on the CUDA cores (sgemm_kernel / sgemm_tn_kernel below; the
+// Default (tensor cores): the training forward is the fused kernel in its emitting mode (nm_mlp_tc.cu mode 1:
+// relu masks, head activations, point-major operand packs of every hidden activation) — for the whole chunk when its
+// workspace fits (no recompute), else per sub-chunk of points; the data-gradient chain
+//     dZ_{l-1} = (dZ_l W_l (+ dsigma w_alpha)) * relu'_{l-1}
+// of ALL layers is one more launch of that kernel (mode 2); the weight gradients
+//     dW_l += dZ_l^T [act_{l-1} | PE]                    (K = points: split over CTAs, fp32 atomics)
+// are long-K launches of tc_gemm_kernel (nm_gemm_tc.cu) on the packs, which also take the bias gradients (row sums of the
+// staged dZ^T tiles).  NM_TRAIN_LAYERWISE=1: round 1's walk, every layer's forward / data gradient as its own tc_gemm launch.
+// NM_PREC_FP32: the same walk in plain fp32 FMAs on the CUDA cores (sgemm_kernel / sgemm_tn_kernel below; the
 // reference trains in fp32, TF32 off) — the numerical yard-stick the tensor-core path is tested against.
 // Small SIMT kernels around them: encodings, the 3-/4-row heads, the compositor adjoint, the MSE gradient.
 // Gradients accumulate in the reference's (out,in) orientation (rows padded to 4 floats, grad_layout()); nm_get_grad
