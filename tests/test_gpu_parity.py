@@ -407,13 +407,15 @@ def test_eval_loop_device_resident(lego_model, tmp_path):
     close(d.cpu(), dd, 2e-6, name="eval rays vs oracle rays")
 
 
-@pytest.mark.parametrize("case", ["lego_64_128", "s96_group3", "s48_white_training_noise", "s16_coarse_only", "s33_not_eligible", "buff_192"])
+@pytest.mark.parametrize("case", ["lego_64_128", "s96_group3", "s48_white_training_noise", "s16_coarse_only", "s8_coarse_only", "s4_coarse_only",
+                                  "s33_not_eligible", "buff_192"])
 def test_fused_compositor_equals_two_kernel_path(case, monkeypatch):
     """The compositor fused into the MLP kernel (the last layer's outputs go to the front-end warps through shared memory; per-
     sample network outputs never reach HBM) against the two-kernel path (raw (R,S,4) to HBM + composite_kernel): the same
     sequential arithmetic (csrc/nm_composite.cuh) => every output map, weights and masks included, bit-identical.  Cases:
     rays of 0.5 / 1.5 tiles (lego), 0.75 tiles in groups of 3 (S=96), S=48 with a white background, training mode, jitter
-    and sigma noise (same seed), 8 rays per tile (S=16), a sample count whose group would be too long (S=33: falls back),
+    and sigma noise (same seed), 8 / 16 / 32 rays per tile (S=16, 8, 4: more ray segments than one round of the accumulator
+    lanes), a sample count whose group would be too long (S=33: falls back),
     the BuFF sampler; ragged ray counts throughout."""
     import nerfmeshes_b200 as nm
     all_out = ["rgb", "depth", "depth_raw", "acc", "disp", "weights", "mask_weights", "t_vals", "coarse_rgb", "coarse_acc", "coarse_disp",
@@ -429,7 +431,7 @@ def test_fused_compositor_equals_two_kernel_path(case, monkeypatch):
     else:
         net = O.NetCfg() if case == "lego_64_128" else O.NetCfg(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6)
         nc, nf = {"lego_64_128": (64, 128), "s96_group3": (40, 56), "s48_white_training_noise": (20, 28), "s16_coarse_only": (16, 0),
-                  "s33_not_eligible": (33, 31)}[case]
+                  "s8_coarse_only": (8, 0), "s4_coarse_only": (4, 0), "s33_not_eligible": (33, 31)}[case]      # 16 / 32 rays per tile too
         cfg = _cfg(net, net if nf else None, nc=nc, nf=nf, white=case.startswith("s48"))
         if case.startswith("s48"):
             cfg.update({"nerf.train.perturb": True, "nerf.train.radiance_field_noise_std": 0.7})
