@@ -88,6 +88,7 @@ struct TcParams {
   const float* dz_in;     // (M, dz_ld) fp32: dZ of the last forward layer
   int dz_ld;
   const float* dout;      // (M, 4): compositor adjoint, column 3 = d sigma
+  int fe_emit;            // mode 1, K-major packs: the front-end warps emit the packs of accumulator chunks 2 and 3 (emit_done barriers)
   int cluster;            // 2: CTAs 2p, 2p+1 form a cluster that shares ONE weight stream (rank 0 multicasts every stage into both)
   int emit_mn;            // modes 1 / 2: packs as MN-major tiles, written by per-warp bulk stores from a shared-memory staging block
   uint32_t off_stg;       //   its eight 8 KB blocks: the (unused) encoding buffers in mode 2, an own region in mode 1
@@ -103,7 +104,7 @@ static_assert(sizeof(TcParams) <= 4096, "TcParams must fit the 4 KB kernel-param
 // barrier slots (8 B each) relative to off_bars
 constexpr uint32_t kBarWFull = 0, kBarWEmpty = 64, kBarPeFull = 128, kBarPeEmpty = 144, kBarChunk = 160,
                    kBarDFull = 192, kBarKbFree = 224, kTmemPtr = 256, kLoadedCnt = 264, kBarDirFull = 272, kBarDirEmpty = 280,
-                   kBarRawFull = 288, kBarRawEmpty = 296, kBarBytes = 320;
+                   kBarRawFull = 288, kBarRawEmpty = 296, kBarEmitDone = 304 /* [2] */, kBarBytes = 320;
 constexpr uint32_t kCompBytes = 128 * 16 + 128 * 4 + 128 * 4 + 64;   // staged q / products, keep / T, weights, two carry slots
 
 enum : int { ERR_ALIGN = 1, ERR_W_EMPTY = 2, ERR_W_FULL = 3, ERR_PE_FULL = 4, ERR_PE_EMPTY = 5, ERR_CHUNK = 6,
@@ -159,6 +160,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     ptx::mbar_init(bars + kBarDirEmpty, kIssuers);
     ptx::mbar_init(bars + kBarRawFull, 128);
     ptx::mbar_init(bars + kBarRawEmpty, 1);
+    ptx::mbar_init(bars + kBarEmitDone, 4);
+    ptx::mbar_init(bars + kBarEmitDone + 8, 4);
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(bars + kBarChunk + 8 * i, 4);
       ptx::mbar_init(bars + kBarDFull + 8 * i, kIssuers);
@@ -216,6 +219,63 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
   };
   if (cl2) ptx::cluster_sync_all();              // the peer's barriers are initialised before anything is multicast at them
 
+  // K-major pack emission of accumulator chunk n of layer li for the 32 rows of TMEM lane quarter `lq` (this warp's quarter):
+  // the values are read back from the A operand (hi + lo 16-bit halves) and stored as the point-major bf16 hi/lo pack of the
+  // weight-gradient GEMM (rows past M as zeros).  done_bar != 0: arrive there once every TMEM read of the chunk has landed.
+  auto emit_kmajor = [&](int li, int n, long long tile, int lq, uint32_t done_bar) {
+    const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+    const long long pt = tile * kTileM + lq * 32 + lane;
+    const bool valid = pt < P.in.M;
+    const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      uint32_t h16[16], l16[16];
+      const uint32_t acol = (uint32_t)(n * 32 + half * 16);
+      NM_TMEM_LD16(tmem + lane_addr + kColAhi + acol, h16);
+      if (n_passes == 3) NM_TMEM_LD16(tmem + lane_addr + kColAlo + acol, l16);
+      ptx::tmem_wait_ld();
+      if (half == 1 && done_bar) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(done_bar);
+      }
+      const int col0 = n * 64 + half * 32;
+      if (!valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { h16[j] = 0u; l16[j] = 0u; }
+      } else if (n_passes != 3) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) l16[j] = 0u;
+      }
+      // element (feature f, point pt) of a tile: row f%128, 16-byte chunk ((pt%64)/8) ^ (f%8), 2-byte slot pt%8; col0 is a
+      // multiple of 32, so f%8 = j%8: one base address per (feature % 8), immediates for the rest; features 2j, 2j+1 = register j
+      uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
+                    (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8) {
+        uint8_t* bq = tb + ((c8 ^ (uint32_t)q8) << 4);
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int f = q8 + 8 * rr, j = f >> 1, odd = f & 1;
+          uint16_t oh, ol;
+          if (MODE == 2) {        // already bf16 hi / lo
+            oh = (uint16_t)(odd ? (h16[j] >> 16) : (h16[j] & 0xffffu));
+            ol = (uint16_t)(odd ? (l16[j] >> 16) : (l16[j] & 0xffffu));
+          } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
+            const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
+            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
+            const float x = ((odd ? fh.y : fh.x) + (odd ? fl.y : fl.x)) * so;
+            const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+            oh = __bfloat16_as_ushort(b0);
+            ol = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(b0)));
+          }
+          *reinterpret_cast<uint16_t*>(bq + f * 128) = oh;
+          *reinterpret_cast<uint16_t*>(bq + f * 128 + 16384) = ol;
+        }
+      }
+    }
+  };
+
   // Mode 2 (data-gradient chain): the epilogue holds a 32-column slab, its bf16 hi/lo halves and the mask at once and spilled
   // under the 96-register launch budget (17 warps: one SM sub-partition hosts five).  Its front-end warps are idle and the
   // issuers are light, so the register file is re-divided per warpgroup: per sub-partition 2 x 160 (epilogue) + 24 (front
@@ -234,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     uint32_t gl = 0;
     unsigned trace_cursor = 0;
     float sigma_val = 0.f;
+    uint32_t fe_events = 0;      // pack emissions of this warp's second chunk handed to the front-end warps so far (fe_emit)
     for (uint32_t it = 0;; ++it) {
       const long long tile = tile_of(it);
       if (tile < 0) break;
@@ -429,6 +490,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 if (half == 0) {
                   if (P.trace) tr2 = clock64();
                   ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
+                  // ... and the front-end warps have read the previous contents of this K block back (their latest emission)
+                  if (MODE == 1 && P.fe_emit && nn == 1 && fe_events > 0)
+                    ptx::mbar_wait(bars + kBarEmitDone + 8 * (n - 2), (fe_events - 1) & 1, P.err, ERR_RAW);
                 }
                 const uint32_t acol = (uint32_t)(n * 32 + half * 16);
                 NM_TMEM_ST16(tmem + lane_addr + kColAhi + acol, hi);
@@ -454,8 +518,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             // this warp has just written (hi + lo 16-bit halves; it stays untouched until this warp's next epilogue of chunk n)
             // and stored as the point-major bf16 hi/lo pack of the weight-gradient GEMM (rows past M as zeros).
             const bool valid = m < P.in.M;
-            const long long pt = tile * kTileM + row;
-            const uint32_t c8 = (uint32_t)((pt & 63) >> 3);
             if (MODE >= 1 && P.emit_mn) {
               // MN-major pack (ptx::make_mnmajor_sw128_desc: a point's 64 features of a group are one 128-byte line, chunks
               // XOR-swizzled by the row).  Sixteen-byte global stores from here would touch 32 lines per instruction; instead the
@@ -509,47 +571,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 ptx::bulk_s2g(dst + 16384u, ptx::smem_u32(stg) + 4096u, 4096u);
                 ptx::bulk_commit_group();
               }
-            } else
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              uint32_t h16[16], l16[16];
-              const uint32_t acol = (uint32_t)(n * 32 + half * 16);
-              NM_TMEM_LD16(tmem + lane_addr + kColAhi + acol, h16);
-              if (n_passes == 3) NM_TMEM_LD16(tmem + lane_addr + kColAlo + acol, l16);
-              ptx::tmem_wait_ld();
-              const int col0 = n * 64 + half * 32;
-              if (!valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { h16[j] = 0u; l16[j] = 0u; }
-              } else if (n_passes != 3) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) l16[j] = 0u;
-              }
-              // one base address per (feature % 8) — see the inline variant above; features 2j, 2j+1 sit in register j
-              uint8_t* tb = P.emit.packT[li] + ((size_t)(col0 >> 7) * (size_t)P.emit.kbt + (size_t)(pt >> 6)) * 32768u +
-                            (size_t)(col0 & 127) * 128u + (size_t)(pt & 7) * 2u;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                uint8_t* bq = tb + ((c8 ^ (uint32_t)q) << 4);
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                  const int f = q + 8 * rr, j = f >> 1, odd = f & 1;
-                  uint16_t oh, ol;
-                  if (MODE == 2) {        // already bf16 hi / lo
-                    oh = (uint16_t)(odd ? (h16[j] >> 16) : (h16[j] & 0xffffu));
-                    ol = (uint16_t)(odd ? (l16[j] >> 16) : (l16[j] & 0xffffu));
-                  } else {                // fp16 hi + lo (22 bits) -> bf16 hi / lo
-                    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&h16[j]));
-                    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&l16[j]));
-                    const float x = ((odd ? fh.y : fh.x) + (odd ? fl.y : fl.x)) * so;
-                    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
-                    oh = __bfloat16_as_ushort(b0);
-                    ol = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(b0)));
-                  }
-                  *reinterpret_cast<uint16_t*>(bq + f * 128) = oh;
-                  *reinterpret_cast<uint16_t*>(bq + f * 128 + 16384) = ol;
-                }
-              }
+            } else if (MODE == 1 && P.fe_emit && nn == 1) {
+              ++fe_events;                                  // the front-end warp of this lane quarter emits chunk n (2 or 3)
+            } else {
+              emit_kmajor(li, n, tile, q, 0u);
             }
           }
         }
@@ -686,6 +711,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       ptx::named_bar_sync(3, 128);                 // staging block consumed, carry visible to the next tile
       if (r == 0) ptx::mbar_arrive(bars + kBarRawEmpty);
     };
+    // fe_emit (mode 1): these warps are idle for ~95 % of a tile, the epilogue warps are what paces the training forward — so
+    // warp 8+q emits the packs of accumulator chunks 2 and 3 for TMEM lane quarter q, layer by layer, as soon as the epilogue
+    // has written that K block (chunk_ready) and before it overwrites it in the next layer (emit_done)
+    auto fe_emit_tile = [&](uint32_t itp) {
+      const long long tp = tile_of(itp);
+      uint32_t glp = itp * (uint32_t)n_layers;
+      for (int li = 0; li < n_layers; ++li, ++glp) {
+        const LayerProg& L = P.net.layers[li];
+        const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
+        if (!writes_a || !P.emit.packT[li]) continue;
+        const int NC = L.n_out >> 6;
+        for (int n = 2; n < 4 && n < NC; ++n) {
+          ptx::mbar_wait(bars + kBarChunk + 8 * n, glp & 1, P.err, ERR_CHUNK);
+          ptx::tc_fence_after();
+          emit_kmajor(li, n, tp, warp - kFeWarp0, bars + kBarEmitDone + 8 * (n - 2));
+        }
+      }
+    };
     uint32_t it = 0;
     for (;; ++it) {
       const long long tile = tile_of(it);
@@ -708,6 +751,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       positional_encoding(p, Lx, ix, fx, [&](int j, float val) { emit_to(tb, j, val); });
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bars + kBarPeFull + 8 * buf);
+      if (MODE == 1 && P.fe_emit && it > 0) fe_emit_tile(it - 1);      // the previous tile is being processed right now
       if (has_dir) {   // the view-direction tile is free once the previous tile's last layer has read it
         ptx::mbar_wait(bars + kBarDirEmpty, (it & 1) ^ 1, P.err, ERR_PE_EMPTY);
         positional_encoding(d, Ld, id, fd, [&](int j, float val) { emit_to(smem + P.off_pe + 2 * kPeBuf, j, val); });
@@ -717,6 +761,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       if (MODE == 0 && P.comp_on && it > 0) composite_tile(it - 1);     // the previous tile is finishing while this one starts
     }
     if (MODE == 0 && P.comp_on && it > 0) composite_tile(it - 1);
+    if (MODE == 1 && P.fe_emit && it > 0) fe_emit_tile(it - 1);
   } else if (warp == kProdWarp) {
     // =============================================================== weight producer
     if (lane == 0) {
@@ -982,7 +1027,11 @@ int launch_mlp_tc(const NetDev& net, bool sigma_only, int n_passes, int act_scal
   P.act_inv_scale = ldexpf(1.f, -act_scale_log2);
   P.n_tiles = (in.M + kTileM - 1) / kTileM;
   P.err = d_err;
-  if (emit) { P.has_emit = 1; P.emit = *emit; P.emit_mn = emit->mn; }
+  if (emit) {
+    P.has_emit = 1; P.emit = *emit; P.emit_mn = emit->mn;
+    static const bool fe_env = [] { const char* e = getenv("NM_TRAIN_FE_EMIT"); return e && atoi(e) != 0; }();
+    P.fe_emit = (fe_env && !emit->mn) ? 1 : 0;
+  }
   P.tile_group = 1;
   if (comp) {
     NM_CHECK(!emit && !sigma_only && in.mode == IN_RAYS && comp->S == in.S && comp->R * (long long)comp->S == in.M && comp->t == in.t,
