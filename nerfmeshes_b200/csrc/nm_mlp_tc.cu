@@ -294,7 +294,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
     uint32_t gl = 0;
     unsigned trace_cursor = 0;
     float sigma_val = 0.f;
-    uint32_t fe_events = 0;      // pack emissions of this warp's second chunk handed to the front-end warps so far (fe_emit)
     for (uint32_t it = 0;; ++it) {
       const long long tile = tile_of(it);
       if (tile < 0) break;
@@ -490,9 +489,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 if (half == 0) {
                   if (P.trace) tr2 = clock64();
                   ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
-                  // ... and the front-end warps have read the previous contents of this K block back (their latest emission)
-                  if (MODE == 1 && P.fe_emit && nn == 1 && fe_events > 0)
-                    ptx::mbar_wait(bars + kBarEmitDone + 8 * (n - 2), (fe_events - 1) & 1, P.err, ERR_RAW);
+                  // ... and the front-end warps are done with the previous layer's contents of this K block (fe_emit: they
+                  // signal emit_done once per layer, emission or not, so that both sides stay within one barrier phase)
+                  if (MODE == 1 && P.fe_emit && nn == 1 && gl > 0)
+                    ptx::mbar_wait(bars + kBarEmitDone + 8 * (n - 2), (gl - 1) & 1, P.err, ERR_RAW);
                 }
                 const uint32_t acol = (uint32_t)(n * 32 + half * 16);
                 NM_TMEM_ST16(tmem + lane_addr + kColAhi + acol, hi);
@@ -508,7 +508,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
             }
             ptx::tmem_wait_st();
           }
-          if (!(n < NC && !(P.dbg & 2) && writes_a)) ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
+          if (!(n < NC && !(P.dbg & 2) && writes_a)) {
+            ptx::mbar_wait(bars + kBarKbFree + 8 * n, gl & 1, P.err, ERR_KBFREE);
+            if (MODE == 1 && P.fe_emit && nn == 1 && gl > 0)      // no A write in this layer: keep the lockstep with the front end all the same
+              ptx::mbar_wait(bars + kBarEmitDone + 8 * (n - 2), (gl - 1) & 1, P.err, ERR_RAW);
+          }
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bars + kBarChunk + 8 * n);
@@ -572,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
                 ptx::bulk_commit_group();
               }
             } else if (MODE == 1 && P.fe_emit && nn == 1) {
-              ++fe_events;                                  // the front-end warp of this lane quarter emits chunk n (2 or 3)
+              // the front-end warp of this lane quarter emits chunk n (2 or 3)
             } else {
               emit_kmajor(li, n, tile, q, 0u);
             }
@@ -720,12 +724,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tc_kernel(const __grid_consta
       for (int li = 0; li < n_layers; ++li, ++glp) {
         const LayerProg& L = P.net.layers[li];
         const bool writes_a = (L.kind == KIND_HIDDEN) || (L.kind == KIND_SIGMA && !L.is_final);
-        if (!writes_a || !P.emit.packT[li]) continue;
         const int NC = L.n_out >> 6;
-        for (int n = 2; n < 4 && n < NC; ++n) {
+        for (int n = 2; n < 4; ++n) {
+          // every layer, emission or not: observe chunk_ready and answer with emit_done, so that neither side can run more than
+          // one phase ahead of the other on these one-parity-bit barriers
           ptx::mbar_wait(bars + kBarChunk + 8 * n, glp & 1, P.err, ERR_CHUNK);
-          ptx::tc_fence_after();
-          emit_kmajor(li, n, tp, warp - kFeWarp0, bars + kBarEmitDone + 8 * (n - 2));
+          if (writes_a && P.emit.packT[li] && n < NC) {
+            ptx::tc_fence_after();
+            emit_kmajor(li, n, tp, warp - kFeWarp0, bars + kBarEmitDone + 8 * (n - 2));
+          } else {
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bars + kBarEmitDone + 8 * (n - 2));
+          }
         }
       }
     };

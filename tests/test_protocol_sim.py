@@ -46,3 +46,16 @@ def test_cta_pair_sharing_one_weight_stream_is_deadlock_free(arch):
             for ghost in (False, True):
                 ok, info = simulate_pair(prog, tiles=3, NS=ns, ghost=ghost)
                 assert ok, (ns, ghost, info)
+
+
+def test_front_end_assisted_emission_stays_in_lockstep():
+    """fe_emit (mode 1): the front-end warps answer chunk_ready[2..3] of EVERY layer with emit_done, the epilogue waits for the
+    previous layer's emit_done before it arrives on chunk_ready — neither side more than one phase ahead on the one-bit parities
+    (an earlier version that only synchronised on layers with an emission deadlocked / aliased on the hardware)."""
+    for arch in (dict(), dict(num_layers=4, hidden_size=128, num_encoding_fn_xyz=6), dict(num_layers=3, hidden_size=128, use_viewdirs=False)):
+        cfg = O.NetCfg(**{**O.NetCfg().__dict__, **arch})
+        prog, _ = debug_pack(cfg, O.init_weights(cfg, 1))
+        for ns in (2, 5, 7):
+            for tiles in (1, 2, 4):
+                ok, info = simulate(prog, tiles=tiles, NS=ns, fe_emit=True)
+                assert ok, (arch, ns, tiles, info)

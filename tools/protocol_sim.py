@@ -30,7 +30,7 @@ class Bar:
         return (self.phase & 1) != (k & 1)   # phases away from the barrier's current phase aliases (this is what is modelled)
 
 
-def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
+def simulate(prog, tiles, NS, verbose=False, armed_counter=True, fe_emit=False):
     L = [prog.layers[i] for i in range(prog.n_layers)]
     w_full = [Bar(f"w_full{i}", 1) for i in range(NS)]
     w_empty = [Bar(f"w_empty{i}", 1) for i in range(NS)]
@@ -40,6 +40,7 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
     d_full = [Bar(f"d_full{i}", 4) for i in range(4)]
     kb_free = [Bar(f"kb_free{i}", 4) for i in range(4)]
     dir_full, dir_empty = Bar("dir_full", 1), Bar("dir_empty", 4)
+    emit_done = [Bar(f"emit_done{i}", 1) for i in range(2)]      # fe_emit (mode 1): the front end answers chunk_ready[2..3] per layer
     uses_dir = any(L[i].pe_src == 2 for i in range(len(L)))
     waiting = {}
     armed = [0]
@@ -62,16 +63,27 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
                 g += 1
                 armed[0] = g
 
+    def fe_emit_tile(T):
+        for li in range(len(L)):
+            gl = T * len(L) + li
+            for n in (2, 3):
+                yield from wait("frontend", chunk[n], gl)
+                emit_done[n - 2].arrive()
+
     def frontend():
         for t in range(tiles):
             buf = t & 1
             if t >= 2:
                 yield from wait("frontend", pe_empty[buf], t // 2 - 1)
             pe_full[buf].arrive()
+            if fe_emit and t > 0:
+                yield from fe_emit_tile(t - 1)
             if uses_dir:
                 if t >= 1:
                     yield from wait("frontend", dir_empty, t - 1)
                 dir_full.arrive()
+        if fe_emit:
+            yield from fe_emit_tile(tiles - 1)
 
     def issuer(w):
         me = f"issuer{w}"
@@ -126,6 +138,8 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
                     n = s + 2 * nn
                     yield from wait(me, d_full[n], gl)
                     yield from wait(me, kb_free[n], gl)
+                    if fe_emit and nn == 1 and gl > 0:
+                        yield from wait(me, emit_done[n - 2], gl - 1)
                     chunk[n].arrive()
                 gl += 1
 
@@ -136,16 +150,16 @@ def simulate(prog, tiles, NS, verbose=False, armed_counter=True):
     while alive:
         progressed = False
         for name in list(alive):
-            before = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]),
-                      tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]))
+            before = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + emit_done + [dir_full, dir_empty]),
+                      tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + emit_done + [dir_full, dir_empty]))
             try:
                 next(alive[name])
             except StopIteration:
                 del alive[name]
                 progressed = True
                 continue
-            after = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]),
-                     tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + [dir_full, dir_empty]))
+            after = (tuple(b.phase for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + emit_done + [dir_full, dir_empty]),
+                     tuple(b.pending for b in w_full + w_empty + pe_full + pe_empty + chunk + d_full + kb_free + emit_done + [dir_full, dir_empty]))
             progressed |= before != after
         steps += 1
         if not progressed:
