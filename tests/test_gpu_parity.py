@@ -7,8 +7,9 @@ max-abs with fp32 accumulate):
     from an fp64 evaluation of the same net, the CUDA-core fp32 kernel 3.6e-5 / 1.7e-3, the fp16-split tensor-core
     kernel 2.1e-4 / 9.0e-3 — a 22-bit operand split against fp32's 24 bits)
   * composited maps, teacher-forced samples:    <= 1e-4 (measured 8e-7 lego, 2.4e-5 fern); disparity relative 1e-4
-  * end to end (samples re-derived on device):  <= 6e-4 max, the reference's own fp32-vs-fp64 floor
-    (5.7e-4), and <= 1e-4 at the 99th percentile
+  * end to end (samples re-derived on device) on the small goldens: lego <= 1e-4 max / 5e-5 p99 (measured 2.4e-5 / 1.2e-5),
+    fern <= 2e-4 max (measured 6.6e-5); the 4096-ray goldens, where the reference's own fp32-vs-fp64 floor (SURVEY Appendix
+    D.1: 5.7e-4) shows, are asserted as distributions in test_gpu_wide_parity.py
   * index / placement work (AABB z-values, coarse t):  bit-exact
 """
 import numpy as np
@@ -186,10 +187,13 @@ def test_lego_pipeline_end_to_end(lego_model):
     close(coarse.rgb_map, g["coarse_rgb"], 1e-4, name="coarse rgb")
     close(coarse.weights, g["coarse_weights"], 1e-4, name="coarse weights")
     err = (fine.rgb_map.cpu() - g["fine_rgb"]).abs().flatten()
-    assert float(err.max()) <= 6e-4, float(err.max())
-    assert float(err.quantile(0.99)) <= 1e-4
-    close(fine.acc_map, g["fine_acc"], 6e-4, name="acc")
-    close(fine.disp_map, g["fine_disp"], 6e-4, 1e-4, name="disp")
+    # north_star's bar (<= 1e-4 max-abs) on these 96 rays: measured 2.4e-5 max / 1.2e-5 p99 (profiles/r02_parity_report.json);
+    # the kernels are deterministic, so the margin is against future arithmetic changes, not run-to-run noise.  (On thousands of
+    # rays the resampler's bucket flips make the reference's own fp32-vs-fp64 difference exceed 1e-4: test_gpu_wide_parity.py.)
+    assert float(err.max()) <= 1e-4, float(err.max())
+    assert float(err.quantile(0.99)) <= 5e-5
+    close(fine.acc_map, g["fine_acc"], 2e-5, name="acc")          # measured 1.8e-6
+    close(fine.disp_map, g["fine_disp"], 2e-5, 1e-5, name="disp")  # measured 2.4e-7
     # query() returns the fine bundle; CPU tensors go through the host-buffer C-ABI call with identical results
     q = lego_model.query((g["origin"], g["dirs"], g["bounds"]))
     assert not q.rgb_map.is_cuda and torch.equal(q.rgb_map, fine.rgb_map.cpu())
@@ -197,7 +201,9 @@ def test_lego_pipeline_end_to_end(lego_model):
     o = lego_model._engine().render_rays(g["origin"].cuda(), g["dirs"].cuda(), 2.0, 6.0, want=["t_vals", "rgb"])
     tf = o["t_vals"].cpu()
     terr = (tf - g["t_fine"]).abs().flatten()                     # a 1-ulp cdf change can move a sample across a bin:
-    assert float(terr.quantile(0.99)) <= 1e-5 and float(terr.max()) <= 0.07   # rare, bounded by one coarse interval
+    # measured: p99 9.5e-7, max 0.0317 = ONE sample moved by half a coarse interval (4/63 = 0.0635 wide); a flip can never move a
+    # sample further than one interval, which is what bounds the max
+    assert float(terr.quantile(0.99)) <= 1e-5 and float(terr.max()) <= 0.0635 + 1e-4
     assert bool((tf[:, 1:] >= tf[:, :-1]).all())                  # sortedness (size-independent property)
 
 
@@ -206,7 +212,7 @@ def test_fern_ndc_pipeline(fern_model):
     coarse, fine = fern_model.forward((g["origins"].cuda(), g["dirs"].cuda(), g["bounds"]))
     close(coarse.rgb_map, g["coarse_rgb"], 1e-4, name="coarse rgb")
     err = (fine.rgb_map.cpu() - g["fine_rgb"]).abs().flatten()
-    assert float(err.max()) <= 6e-4, float(err.max())
+    assert float(err.max()) <= 2e-4, float(err.max())               # measured 6.6e-5 on these 64 rays (|sigma| up to 2e4: §5 of DESIGN.md)
     o = fern_model._engine().render_rays(g["origins"].cuda(), g["dirs"].cuda(), 0.0, 1.0, teacher_t=g["t_fine"].cuda(),
                                          want=["rgb", "acc"])
     close(o["rgb"], g["fine_rgb"], 1e-4, name="teacher-forced rgb")
