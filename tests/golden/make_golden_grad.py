@@ -51,6 +51,31 @@ def main():
     np.savez_compressed(os.path.join(HERE, "golden_lego_grad.npz"), **out)
     print("tensors", n, "loss", lc.item(), lf.item())
 
+    # BuFF: single network on the AABB-clipped samples (model_buff.py:34-69), loss = mse(rgb_map, target) (:96-104)
+    gb = dict(np.load(os.path.join(HERE, "golden_lego_buff.npz")))
+    mb = rh.load_model("BuFFModel", "buff-synthetic-lego")
+    mb.eval()
+    ob, db = torch.from_numpy(gb["origin"]), torch.from_numpy(gb["dirs"])
+    tb = torch.rand(db.shape[0], 3, generator=torch.Generator().manual_seed(12))
+    for p in mb.parameters():
+        p.grad = None
+    bundle = mb.forward((ob[None], db, torch.from_numpy(gb["bounds"])))
+    lb = torch.nn.functional.mse_loss(bundle.rgb_map, tb)
+    lb.backward()
+    outb = {"target": tb.numpy(), "loss": lb.item()}
+    nb = 0
+    for name, p in mb.named_parameters():
+        if p.grad is None:
+            continue
+        gflat = p.grad.detach().flatten().double()
+        idx = probe_index(gflat.numel())
+        outb[f"{name}|norm"] = float(gflat.norm())
+        outb[f"{name}|sum"] = float(gflat.sum())
+        outb[f"{name}|probe"] = gflat[idx].numpy()
+        nb += 1
+    np.savez_compressed(os.path.join(HERE, "golden_buff_grad.npz"), **outb)
+    print("buff tensors", nb, "loss", lb.item(), [k for k in outb if k.endswith("|norm")][:4])
+
 
 if __name__ == "__main__":
     main()

@@ -183,3 +183,31 @@ def test_oracle_autograd_matches_the_reference_backward():
             assert float((gr[idx] - torch.from_numpy(G[f"{key}|probe"])).abs().max()) <= 1e-5 * scale + 1e-12, key
             checked += 1
     assert checked == 48
+
+
+def test_oracle_autograd_matches_the_reference_backward_buff(buff):
+    """The same pin for BuFFModel (single network on the AABB-clipped samples, loss = mse(rgb_map, target),
+    src/models/model_buff.py:34-69, 96-104): gradients of the unmodified reference on the shipped BuFF checkpoint."""
+    import os
+    from conftest import ROOT
+    g = load_npz("golden_lego_buff.npz")
+    G = dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_buff_grad.npz")))
+    sd = {k: (v.clone().float().requires_grad_(True) if k.endswith((".weight", ".bias")) else v.clone()) for k, v in buff["coarse"].items()}
+    target = torch.from_numpy(G["target"])
+    rc = O.RenderCfg(num_coarse=192, num_fine=0)
+    b, _, _ = O.buff_forward(sd, NET, rc, buff["voxels"], g["origin"][None], g["dirs"], g["bounds"][0], g["bounds"][1])
+    loss = torch.nn.functional.mse_loss(b.rgb_map, target)
+    loss.backward()
+    assert abs(loss.item() - float(G["loss"])) <= 1e-6
+    checked = 0
+    for k, v in sd.items():
+        if not v.requires_grad:
+            continue
+        key = f"model.{k}"
+        gr = v.grad.flatten().double()
+        n_ref = float(G[f"{key}|norm"])
+        idx = torch.from_numpy(np.random.RandomState(5 + gr.numel() % 9973).randint(0, gr.numel(), size=24)).long()
+        assert abs(float(gr.norm()) - n_ref) <= 1e-5 * n_ref + 1e-12, (key, float(gr.norm()), n_ref)
+        assert float((gr[idx] - torch.from_numpy(G[f"{key}|probe"])).abs().max()) <= 1e-5 * float(gr.abs().max()) + 1e-12, key
+        checked += 1
+    assert checked == 24
